@@ -1,0 +1,216 @@
+/*
+ * lintsampler_b200 — C ABI of the B200-native linear-interpolant sampler.
+ *
+ * The reference (aneeshnaik/lintsampler) is pure Python/NumPy and has no FFI
+ * of its own.  Each entry point below replaces one NumPy
+ * whole-array step of the reference's `LintSampler.sample` hot path and cites
+ * it as `file:line` relative to /root/reference/src/lintsampler.  The Python
+ * host layer (lintsampler_b200/*.py) binds these with ctypes; INTEGRATION.md
+ * shows the equivalent stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no exceptions across the boundary.
+ *   - Every `*_dev` / descriptor pointer is a DEVICE pointer owned by the
+ *     caller; the library never allocates or frees device memory.  Scratch is
+ *     caller-provided, sized by the matching `*_scratch_bytes` query.
+ *   - `stream` is a cudaStream_t passed as void*.  All work is enqueued on it;
+ *     no call synchronises the host.  Device-side findings (negative or
+ *     non-finite densities, zero total mass) are written to caller-provided
+ *     device words the caller reads after synchronising.
+ *   - Return value: LINT_OK or an error code; `lint_last_error()` returns a
+ *     thread-local message for the last non-OK return.
+ *   - Row-major (C-order) everywhere, as NumPy in the reference.
+ *   - Corner order: corner c of a k-cube is offset along dim d by bit (k-1-d)
+ *     of c (dim 0 = MSB)  [density_structures/grid.py:456-459, utils.py:37-74].
+ *   - Uniform layout: a row of k+1 uniforms; columns 0..k-1 drive the in-cell
+ *     coordinates, column k selects the cell  [lintsampler.py:269-270].
+ */
+#ifndef LINTSAMPLER_B200_H
+#define LINTSAMPLER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LINT_MAX_DIM 6          /* reference advises <= 6 dims (paper/paper.md:84) */
+#define LINT_ABI_VERSION 1
+
+typedef void *lint_stream_t;    /* cudaStream_t */
+
+enum lint_status {
+    LINT_OK = 0,
+    LINT_ERR_BAD_ARG = 1,
+    LINT_ERR_UNSUPPORTED = 2,
+    LINT_ERR_CUDA = 3
+};
+
+/* precision mode of a domain: arithmetic the in-cell solve runs in, dtype of the
+ * stored densities and dtype of the emitted samples.  The cell CDF and the
+ * cell-selecting uniform are ALWAYS fp64 / 53-bit. */
+enum lint_dtype {
+    LINT_F32 = 0,   /* densities fp32, samples fp32, stable fp32 in-cell solve   */
+    LINT_F64 = 1    /* densities fp64, samples fp64, the reference's literal fp64
+                       expression order (bit-identical to NumPy)                 */
+};
+
+/* bits of the device status word written by lint_grid_masses / lint_cells_check */
+#define LINT_FLAG_NEGATIVE   1u  /* a density < 0       [grid.py:401-402, tree.py:598-601] */
+#define LINT_FLAG_NONFINITE  2u  /* a NaN/Inf density   [grid.py:403-404, tree.py:602-605] */
+
+/* CDF construction modes for lint_cdf_build */
+enum lint_cdf_mode {
+    LINT_CDF_PARALLEL = 0,   /* deterministic tiled reduce-then-scan (throughput)       */
+    LINT_CDF_SEQUENTIAL = 1  /* NumPy-identical: pairwise m.sum(), p=m/sum, strictly
+                                sequential cumsum, /= last  [grid.py:431, utils.py:195-196] */
+};
+
+/* Rectilinear grid domain == reference DensityGrid  [grid.py:253-307]. */
+typedef struct lint_grid {
+    int32_t dim;                          /* k, 1..LINT_MAX_DIM                          */
+    int32_t dtype;                        /* enum lint_dtype                             */
+    int64_t ncells[LINT_MAX_DIM];         /* cells per dim (grid.shape)                  */
+    const void *vertex_densities_dev;     /* (n0+1,..,nk-1+1), fp32 or fp64 per dtype     */
+    const double *edges_dev[LINT_MAX_DIM];/* edges_dev[d]: n_d+1 fp64 edge coordinates   */
+    const double *cdf_dev;                /* prod(ncells) fp64, normalised inclusive CDF */
+    const uint32_t *guide_dev;            /* optional 2^guide_bits+1 entry guide table   */
+    int32_t guide_bits;                   /* 0 = no guide table                          */
+    int32_t reserved;
+} lint_grid_t;
+
+/* Flat cell list == the leaves of a reference DensityTree in list order
+ * [tree.py:334-355], or any user DensityStructure flattened by the host. */
+typedef struct lint_cells {
+    int32_t dim;
+    int32_t dtype;
+    int64_t ncells;                       /* L                                           */
+    const double *mins_dev;               /* (L,k)  leaf.x                               */
+    const double *widths_dev;             /* (L,k)  leaf.dx                              */
+    const void *corners_dev;              /* (L,2^k) leaf.corner_densities, per dtype    */
+    const double *cdf_dev;                /* (L) normalised inclusive CDF of leaf masses */
+    const uint32_t *guide_dev;
+    int32_t guide_bits;
+    int32_t reserved;
+} lint_cells_t;
+
+/* Scrambled Sobol state read from a host scipy.stats.qmc.Sobol(d=k+1, bits=32)
+ * engine (`_sv`, `_shift`, `num_generated`)  [lintsampler.py:465,515]. */
+typedef struct lint_sobol {
+    uint32_t sv[LINT_MAX_DIM + 1][32];    /* HOST: scrambled direction numbers           */
+    uint32_t shift[LINT_MAX_DIM + 1];     /* HOST: digital shift                         */
+    uint64_t first_index;                 /* index of the first point to emit            */
+} lint_sobol_t;
+
+/* Gaussian mixture sum_j w_j N(x; mu_j, Sigma_j), passed as HOST arrays:
+ *   log_norm[j] = log w_j - 0.5 log det Sigma_j - 0.5 k log(2 pi)
+ *   mean[j*k + d]
+ *   prec_chol[j*k*k + r*k + c] = U_j[r][c], upper triangular, with
+ *   Sigma_j^-1 = U_j^T U_j, so the Mahalanobis term is |U_j (x - mu_j)|^2. */
+typedef struct lint_gmm {
+    int32_t dim;
+    int32_t ncomp;                        /* 1..LINT_GMM_MAX_COMP                        */
+    const double *log_norm;
+    const double *mean;
+    const double *prec_chol;
+} lint_gmm_t;
+#define LINT_GMM_MAX_COMP 16
+
+/* ---- library ---------------------------------------------------------------- */
+int lint_abi_version(void);
+const char *lint_last_error(void);
+
+/* ---- grid build ------------------------------------------------------------- */
+
+/* Fused vertex evaluation of a built-in analytic pdf on the grid vertices;
+ * replaces the meshgrid + `pdf(edgegrid)` of grid.py:384-398 without ever
+ * materialising the (npts,k) coordinate array.  Writes g->vertex_densities_dev
+ * (cast away const) in g->dtype; densities are multiplied by `scale` first. */
+int lint_grid_eval_gmm(const lint_grid_t *g, const lint_gmm_t *gmm, double scale,
+                       lint_stream_t stream);
+
+/* Trapezoid cell masses: mean of the 2^k corner densities (summed in corner
+ * order from zero, one division by 2^k) times the cell volume ((w0*w1)*w2...)
+ * [grid.py:469-498, 501-518, 411].  masses_dev: prod(ncells) fp64.
+ * Also performs the density validity check of grid.py:401-404 on every vertex:
+ * ORs LINT_FLAG_* into *flags_dev (caller zeroes it first). */
+int lint_grid_masses(const lint_grid_t *g, double *masses_dev, uint32_t *flags_dev,
+                     lint_stream_t stream);
+
+/* Same validity check for a cell list's corner densities [tree.py:598-605]. */
+int lint_cells_check(const lint_cells_t *c, uint32_t *flags_dev, lint_stream_t stream);
+
+/* Scratch needed by lint_cdf_build / lint_sum_numpy_f64 for n values. */
+size_t lint_cdf_scratch_bytes(int64_t n);
+
+/* Bit-exact NumPy `np.sum` of a contiguous fp64 array (pairwise summation with
+ * 8 accumulators, 128-element leaves)  [grid.py:412 `np.sum(self.masses)`]. */
+int lint_sum_numpy_f64(const double *x_dev, int64_t n, double *out_dev,
+                       void *scratch_dev, size_t scratch_bytes, lint_stream_t stream);
+
+/* Normalised inclusive CDF of `masses`  [grid.py:431 + utils.py:195-196; also
+ * tree.py:335 and lintsampler.py:286-290].  total_dev receives the total mass
+ * (NumPy-identical in SEQUENTIAL mode).  cdf_dev[n-1] is exactly 1.0. */
+int lint_cdf_build(const double *masses_dev, int64_t n, int mode, double *cdf_dev,
+                   double *total_dev, void *scratch_dev, size_t scratch_bytes,
+                   lint_stream_t stream);
+
+/* Guide (index) table that shortens the searchsorted of utils.py:197 without
+ * changing its result: guide[j] = first i with cdf[i] > j / 2^guide_bits for
+ * j = 0..2^guide_bits (inclusive; last entry n-1).  guide_dev: 2^guide_bits+1. */
+int lint_guide_build(const double *cdf_dev, int64_t n, int guide_bits,
+                     uint32_t *guide_dev, lint_stream_t stream);
+
+/* ---- sampling: uniforms supplied by the caller (parity mode) ------------------ */
+
+/* == sampling._grid_sample(grid, u)  [sampling.py:97-127] on a DensityGrid:
+ * searchsorted(side='right') on u[:,k] [utils.py:197], C-order unravel
+ * [grid.py:437], 2^k corner gather [grid.py:440-467], k sequential 1-D inverse
+ * CDFs [sampling.py:41-94, 6-38], affine map [sampling.py:126].
+ * u_dev: (N,k+1) fp64.  out_dev: (N,k) in g->dtype.  cell_idx_dev: optional
+ * (N) int64 flat C-order cell index. */
+int lint_grid_sample_u(const lint_grid_t *g, const double *u_dev, int64_t N,
+                       void *out_dev, int64_t *cell_idx_dev, lint_stream_t stream);
+
+/* Same over a cell list  [tree.py:314-355 + sampling.py:123-126]. */
+int lint_cells_sample_u(const lint_cells_t *c, const double *u_dev, int64_t N,
+                        void *out_dev, int64_t *cell_idx_dev, lint_stream_t stream);
+
+/* In-cell stage only, for user-defined DensityStructure subclasses whose
+ * choose_cells ran on the host  [base.py:11-30, sampling.py:123-126].
+ * mins/maxs: (N,k) fp64; corners: (2^k,N) fp64; u: (N,k+1) fp64 (column k
+ * unused); out: (N,k) fp64. */
+int lint_incell_sample_u(int dim, int64_t N, const double *mins_dev, const double *maxs_dev,
+                         const double *corners_dev, const double *u_dev, double *out_dev,
+                         lint_stream_t stream);
+
+/* ---- sampling: device-generated uniforms --------------------------------------- */
+
+/* Philox4x32-10 stream replacing `rng.random((N,k+1))` [lintsampler.py:517]:
+ * row i of the call uses counter (offset+i) under key `seed`; successive calls
+ * continue the stream by advancing `offset` by N.  The cell-selecting uniform
+ * has 53 bits; in-cell uniforms have 53 bits (F64) or 24 bits (F32). */
+int lint_grid_sample_philox(const lint_grid_t *g, int64_t N, uint64_t seed, uint64_t offset,
+                            void *out_dev, int64_t *cell_idx_dev, lint_stream_t stream);
+int lint_cells_sample_philox(const lint_cells_t *c, int64_t N, uint64_t seed, uint64_t offset,
+                             void *out_dev, int64_t *cell_idx_dev, lint_stream_t stream);
+
+/* The uniforms the Philox samplers consume, materialised as (N,k+1) fp64 — for
+ * tests and for callers that want to replay a draw on the host. */
+int lint_philox_uniforms(int dim, int dtype, int64_t N, uint64_t seed, uint64_t offset,
+                         double *u_dev, lint_stream_t stream);
+
+/* Scrambled Sobol points by direct Gray-code index, bit-identical to
+ * scipy.stats.qmc.Sobol(d=k+1, bits=32).random(N)  [lintsampler.py:465,515]. */
+int lint_grid_sample_sobol(const lint_grid_t *g, int64_t N, const lint_sobol_t *sobol,
+                           void *out_dev, int64_t *cell_idx_dev, lint_stream_t stream);
+int lint_cells_sample_sobol(const lint_cells_t *c, int64_t N, const lint_sobol_t *sobol,
+                            void *out_dev, int64_t *cell_idx_dev, lint_stream_t stream);
+int lint_sobol_uniforms(int dim, int64_t N, const lint_sobol_t *sobol, double *u_dev,
+                        lint_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LINTSAMPLER_B200_H */

@@ -1,0 +1,641 @@
+// Grid-build kernels: analytic vertex evaluation, trapezoid cell masses,
+// NumPy-identical pairwise sum, CDF construction (parallel / NumPy-sequential),
+// guide table.  C ABI declared in include/lintsampler_b200.h.
+//
+// Reference citations are relative to /root/reference/src/lintsampler.
+#include <cstdarg>
+#include <cstdio>
+#include <cmath>
+#include "lint_device.cuh"
+
+namespace lint {
+
+std::string &last_error_slot() {
+    static thread_local std::string s;
+    return s;
+}
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    last_error_slot() = buf;
+    return code;
+}
+
+int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(LINT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return LINT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// descriptor validation shared with lint_sample.cu
+// ---------------------------------------------------------------------------
+int validate_grid(const lint_grid_t *g, bool need_cdf, uint64_t *ncells_out, uint64_t *nverts_out) {
+    if (!g) return fail(LINT_ERR_BAD_ARG, "grid descriptor is NULL");
+    if (g->dim < 1 || g->dim > LINT_MAX_DIM)
+        return fail(LINT_ERR_BAD_ARG, "grid dim %d outside 1..%d", g->dim, LINT_MAX_DIM);
+    if (g->dtype != LINT_F32 && g->dtype != LINT_F64)
+        return fail(LINT_ERR_BAD_ARG, "grid dtype %d is not LINT_F32/LINT_F64", g->dtype);
+    uint64_t nc = 1, nv = 1;
+    for (int d = 0; d < g->dim; ++d) {
+        if (g->ncells[d] < 1) return fail(LINT_ERR_BAD_ARG, "grid ncells[%d] < 1", d);
+        if (!g->edges_dev[d]) return fail(LINT_ERR_BAD_ARG, "grid edges_dev[%d] is NULL", d);
+        nc *= (uint64_t)g->ncells[d];
+        nv *= (uint64_t)g->ncells[d] + 1;
+        if (nv >= (1ull << 31))
+            return fail(LINT_ERR_UNSUPPORTED, "grids with >= 2^31 vertices are not supported");
+    }
+    if (!g->vertex_densities_dev) return fail(LINT_ERR_BAD_ARG, "grid vertex_densities_dev is NULL");
+    if (need_cdf && !g->cdf_dev) return fail(LINT_ERR_BAD_ARG, "grid cdf_dev is NULL");
+    if (g->guide_bits < 0 || g->guide_bits > 30 || (g->guide_bits > 0 && !g->guide_dev))
+        return fail(LINT_ERR_BAD_ARG, "grid guide table inconsistent (bits=%d)", g->guide_bits);
+    if (ncells_out) *ncells_out = nc;
+    if (nverts_out) *nverts_out = nv;
+    return LINT_OK;
+}
+
+template <int K>
+GridView<K> make_grid_view(const lint_grid_t *g, uint64_t ncells) {
+    GridView<K> v;
+    v.V = g->vertex_densities_dev;
+    uint32_t stride = 1;
+    for (int d = K - 1; d >= 0; --d) {
+        v.edges[d] = g->edges_dev[d];
+        v.n[d] = (uint32_t)g->ncells[d];
+        v.vstride[d] = stride;
+        stride *= (uint32_t)g->ncells[d] + 1;
+    }
+    for (int c = 0; c < (1 << K); ++c) {
+        uint32_t off = 0;
+        for (int d = 0; d < K; ++d)
+            if ((c >> (K - 1 - d)) & 1) off += v.vstride[d];
+        v.corner_off[c] = off;
+    }
+    v.table.cdf = g->cdf_dev;
+    v.table.guide = g->guide_dev;
+    v.table.guide_bits = g->guide_bits;
+    v.table.n = (uint32_t)ncells;
+    return v;
+}
+template GridView<1> make_grid_view<1>(const lint_grid_t *, uint64_t);
+template GridView<2> make_grid_view<2>(const lint_grid_t *, uint64_t);
+template GridView<3> make_grid_view<3>(const lint_grid_t *, uint64_t);
+template GridView<4> make_grid_view<4>(const lint_grid_t *, uint64_t);
+template GridView<5> make_grid_view<5>(const lint_grid_t *, uint64_t);
+template GridView<6> make_grid_view<6>(const lint_grid_t *, uint64_t);
+
+// ---------------------------------------------------------------------------
+// fused Gaussian-mixture vertex evaluation            [replaces grid.py:384-398]
+// ---------------------------------------------------------------------------
+template <int K>
+struct GmmParams {
+    int ncomp;
+    double log_norm[LINT_GMM_MAX_COMP];
+    double mean[LINT_GMM_MAX_COMP][K];
+    double U[LINT_GMM_MAX_COMP][K * (K + 1) / 2];   // upper triangle, row-major
+};
+
+template <int K, typename DensT>
+__global__ void __launch_bounds__(256)
+gmm_eval_kernel(GridView<K> g, GmmParams<K> p, double scale, uint32_t nverts, DensT *out) {
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nverts; v += gridDim.x * blockDim.x) {
+        double x[K];
+        uint32_t r = v;
+#pragma unroll
+        for (int d = K - 1; d >= 0; --d) {
+            const uint32_t nd = g.n[d] + 1;
+            uint32_t i;
+            if (d == 0) { i = r; } else { const uint32_t q = r / nd; i = r - q * nd; r = q; }
+            x[d] = __ldg(g.edges[d] + i);
+        }
+        double f = 0.0;
+        for (int j = 0; j < p.ncomp; ++j) {
+            double y[K];
+#pragma unroll
+            for (int d = 0; d < K; ++d) y[d] = x[d] - p.mean[j][d];
+            double q = 0.0;
+            int t = 0;
+#pragma unroll
+            for (int rr = 0; rr < K; ++rr) {
+                double s = 0.0;
+#pragma unroll
+                for (int cc = rr; cc < K; ++cc) s = fma(p.U[j][t++], y[cc], s);
+                q = fma(s, s, q);
+            }
+            f += exp(p.log_norm[j] - 0.5 * q);
+        }
+        out[v] = (DensT)(f * scale);
+    }
+}
+
+template <int K>
+int eval_gmm_impl(const lint_grid_t *g, const lint_gmm_t *gmm, double scale, uint64_t nverts,
+                  cudaStream_t st) {
+    GmmParams<K> p;
+    p.ncomp = gmm->ncomp;
+    for (int j = 0; j < gmm->ncomp; ++j) {
+        p.log_norm[j] = gmm->log_norm[j];
+        int t = 0;
+        for (int r = 0; r < K; ++r) {
+            p.mean[j][r] = gmm->mean[j * K + r];
+            for (int c = r; c < K; ++c) p.U[j][t++] = gmm->prec_chol[(j * K + r) * K + c];
+        }
+    }
+    GridView<K> v = make_grid_view<K>(g, 1);
+    const int threads = 256;
+    const int blocks = (int)std::min<uint64_t>((nverts + threads - 1) / threads, 148 * 32);
+    if (g->dtype == LINT_F32)
+        gmm_eval_kernel<K, float><<<blocks, threads, 0, st>>>(v, p, scale, (uint32_t)nverts,
+                                                             (float *)g->vertex_densities_dev);
+    else
+        gmm_eval_kernel<K, double><<<blocks, threads, 0, st>>>(v, p, scale, (uint32_t)nverts,
+                                                              (double *)g->vertex_densities_dev);
+    return check_launch("lint_grid_eval_gmm");
+}
+
+// ---------------------------------------------------------------------------
+// trapezoid cell masses + density validity check   [grid.py:469-518, 411, 401-404]
+// ---------------------------------------------------------------------------
+template <int K, typename DensT>
+__global__ void __launch_bounds__(256)
+cell_mass_kernel(GridView<K> g, uint32_t ncells, double *masses, uint32_t *flags) {
+    uint32_t bad = 0;
+    for (uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x; cell < ncells;
+         cell += gridDim.x * blockDim.x) {
+        double c[1 << K], lo[K], hi[K];
+        grid_fetch<K, DensT, double>(g, cell, c, lo, hi);
+        double acc = 0.0;                      // `sum = np.zeros(shape)` then += per corner
+#pragma unroll
+        for (int j = 0; j < (1 << K); ++j) {
+            acc = __dadd_rn(acc, c[j]);
+            if (c[j] < 0.0) bad |= LINT_FLAG_NEGATIVE;
+            if (!isfinite(c[j])) bad |= LINT_FLAG_NONFINITE;
+        }
+        const double mean = __dmul_rn(acc, 1.0 / (1 << K));     // exact /2^K
+        double vol = __dsub_rn(hi[0], lo[0]);                   // np.diff, then outer products
+#pragma unroll
+        for (int d = 1; d < K; ++d) vol = __dmul_rn(vol, __dsub_rn(hi[d], lo[d]));
+        masses[cell] = __dmul_rn(mean, vol);
+    }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if (bad && (threadIdx.x & 31) == 0) atomicOr(flags, bad);
+}
+
+template <int K>
+int masses_impl(const lint_grid_t *g, uint64_t ncells, double *masses, uint32_t *flags,
+                cudaStream_t st) {
+    GridView<K> v = make_grid_view<K>(g, ncells);
+    const int threads = 256;
+    const int blocks = (int)std::min<uint64_t>((ncells + threads - 1) / threads, 148 * 32);
+    if (g->dtype == LINT_F32)
+        cell_mass_kernel<K, float><<<blocks, threads, 0, st>>>(v, (uint32_t)ncells, masses, flags);
+    else
+        cell_mass_kernel<K, double><<<blocks, threads, 0, st>>>(v, (uint32_t)ncells, masses, flags);
+    return check_launch("lint_grid_masses");
+}
+
+template <typename DensT>
+__global__ void cells_check_kernel(const DensT *c, uint64_t n, uint32_t *flags) {
+    uint32_t bad = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const double v = (double)c[i];
+        if (v < 0.0) bad |= LINT_FLAG_NEGATIVE;
+        if (!isfinite(v)) bad |= LINT_FLAG_NONFINITE;
+    }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if (bad && (threadIdx.x & 31) == 0) atomicOr(flags, bad);
+}
+
+// ---------------------------------------------------------------------------
+// NumPy-identical pairwise sum                      [np.sum at grid.py:412,431]
+// ---------------------------------------------------------------------------
+// NumPy sums a contiguous fp64 array with a recursion that halves the range
+// (left half rounded down to a multiple of 8) until a block has <= 128
+// elements, which is summed with 8 interleaved accumulators.  The recursion
+// tree depends only on n.  Every node at depth D (the deepest level at which
+// all nodes still have > 128 elements) is evaluated by one thread with the
+// scalar recursion; the complete binary tree above is then folded level by
+// level, left + right, exactly as the recursion returns.
+__host__ __device__ inline uint64_t pw_left(uint64_t n) {
+    uint64_t n2 = n / 2;
+    return n2 - (n2 % 8);
+}
+
+__device__ double pw_leaf(const double *a, uint32_t n) {
+    if (n < 8) {
+        double r = -0.0;
+        for (uint32_t i = 0; i < n; ++i) r = __dadd_rn(r, a[i]);
+        return r;
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    uint32_t i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+    return res;
+}
+
+__device__ double pw_node(const double *a, uint64_t n) {
+    // explicit stack; subtree sizes here are a few hundred elements at most
+    struct Frame { const double *a; uint64_t n; int state; double left; };
+    Frame st[12];
+    int sp = 0;
+    st[0] = {a, n, 0, 0.0};
+    double ret = 0.0;
+    while (sp >= 0) {
+        Frame &f = st[sp];
+        if (f.n <= 128) { ret = pw_leaf(f.a, (uint32_t)f.n); --sp; continue; }
+        const uint64_t n2 = pw_left(f.n);
+        if (f.state == 0) { f.state = 1; st[++sp] = {f.a, n2, 0, 0.0}; }
+        else if (f.state == 1) { f.left = ret; f.state = 2; st[++sp] = {f.a + n2, f.n - n2, 0, 0.0}; }
+        else { ret = __dadd_rn(f.left, ret); --sp; }
+    }
+    return ret;
+}
+
+__global__ void pw_nodes_kernel(const double *x, uint64_t n, int depth, double *node_out) {
+    const uint32_t nnodes = 1u << depth;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nnodes; p += gridDim.x * blockDim.x) {
+        uint64_t start = 0, len = n;
+        for (int b = depth - 1; b >= 0; --b) {
+            const uint64_t n2 = pw_left(len);
+            if ((p >> b) & 1) { start += n2; len -= n2; } else { len = n2; }
+        }
+        node_out[p] = pw_node(x + start, len);
+    }
+}
+
+__global__ void pw_fold_kernel(const double *in, uint32_t nout, double *out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nout; i += gridDim.x * blockDim.x)
+        out[i] = __dadd_rn(in[2 * i], in[2 * i + 1]);
+}
+
+static int pw_depth(uint64_t n) {
+    // deepest level whose smallest node (always the left-most) still exceeds 128
+    int depth = 0;
+    uint64_t smallest = n;
+    while (smallest > 128) {
+        const uint64_t child = pw_left(smallest);
+        if (child <= 128) break;
+        smallest = child;
+        ++depth;
+    }
+    return depth;
+}
+
+static int sum_numpy_launch(const double *x, uint64_t n, double *out, double *scratch,
+                            cudaStream_t st) {
+    const int depth = pw_depth(n);
+    uint32_t nnodes = 1u << depth;
+    double *a = scratch, *b = scratch + nnodes;
+    double *dst = depth == 0 ? out : a;
+    pw_nodes_kernel<<<std::max(1u, std::min(nnodes / 128, 148u * 16)), 128, 0, st>>>(x, n, depth, dst);
+    for (int lv = depth; lv > 0; --lv) {
+        nnodes >>= 1;
+        double *o = lv == 1 ? out : b;
+        pw_fold_kernel<<<std::max(1u, std::min(nnodes / 256, 148u * 8)), 256, 0, st>>>(a, nnodes, o);
+        std::swap(a, b);
+    }
+    return check_launch("lint_sum_numpy_f64");
+}
+
+// ---------------------------------------------------------------------------
+// CDF, NumPy-sequential mode                [grid.py:431 + utils.py:195-196]
+// ---------------------------------------------------------------------------
+constexpr int SEQ_CHUNK = 1024;
+constexpr int SEQ_THREADS = 256;
+
+// One CTA.  Thread 0 carries the strictly sequential fp64 accumulation (that is
+// what np.cumsum does) over chunk c-1 while warps 1.. stage p = m / total for
+// chunk c into shared memory and stream chunk c-2 back out.
+__global__ void __launch_bounds__(SEQ_THREADS)
+cdf_sequential_kernel(const double *masses, uint64_t n, const double *total, double *cdf) {
+    __shared__ double sin[2][SEQ_CHUNK];
+    __shared__ double sout[2][SEQ_CHUNK];
+    const double tot = *total;
+    const uint64_t nchunks = (n + SEQ_CHUNK - 1) / SEQ_CHUNK;
+    double acc = 0.0;
+    for (uint64_t c = 0; c < nchunks + 2; ++c) {
+        if (threadIdx.x >= 32) {
+            const int t = threadIdx.x - 32;
+            if (c < nchunks) {                           // stage chunk c
+                const uint64_t base = c * SEQ_CHUNK;
+                for (int i = t; i < SEQ_CHUNK; i += SEQ_THREADS - 32)
+                    if (base + i < n) sin[c & 1][i] = __ddiv_rn(masses[base + i], tot);
+            }
+            if (c >= 2) {                                // drain chunk c-2
+                const uint64_t base = (c - 2) * SEQ_CHUNK;
+                for (int i = t; i < SEQ_CHUNK; i += SEQ_THREADS - 32)
+                    if (base + i < n) cdf[base + i] = sout[c & 1][i];
+            }
+        } else if (threadIdx.x == 0 && c >= 1 && c - 1 < nchunks) {   // scan chunk c-1
+            const uint64_t base = (c - 1) * SEQ_CHUNK;
+            const int m = (int)min((uint64_t)SEQ_CHUNK, n - base);
+            const double *in = sin[(c - 1) & 1];
+            double *o = sout[(c - 1) & 1];
+            int i = 0;
+            if (c == 1) { acc = in[0]; o[0] = acc; i = 1; }   // cumsum starts from p[0]
+#pragma unroll 8
+            for (; i < m; ++i) { acc = __dadd_rn(acc, in[i]); o[i] = acc; }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void cdf_normalise_kernel(double *cdf, uint64_t n) {
+    const double last = cdf[n - 1];   // element n-1 is rewritten by a later launch
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i + 1 < n;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        cdf[i] = __ddiv_rn(cdf[i], last);
+}
+__global__ void cdf_set_last_kernel(double *cdf, uint64_t n) { cdf[n - 1] = 1.0; }
+
+// ---------------------------------------------------------------------------
+// CDF, parallel mode: deterministic, monotone, zero-preserving tiled scan
+// ---------------------------------------------------------------------------
+// S_i = E_tile (+) (E_warp (+) (E_lane (+) P_i)) where P_i is the sequential
+// prefix inside a lane's run of PAR_ITEMS values and every exclusive offset is
+// *exactly* the inclusive value of the element before it.  Because fp addition
+// of non-negative numbers is monotone in each argument this gives a
+// non-decreasing sequence with S_i == S_{i-1} whenever m_i == 0 (zero-mass
+// cells stay unselectable, utils.py:197) and it is independent of scheduling,
+// unlike a decoupled look-back whose partial-sum association varies run to run
+// (the reference's determinism tests, tests/test_lintsampler.py:520-541, need
+// bit-reproducible CDFs).
+constexpr int PAR_THREADS = 256;
+constexpr int PAR_ITEMS = 8;
+constexpr int PAR_TILE = PAR_THREADS * PAR_ITEMS;
+
+// Inclusive prefix of one tile in registers; returns the tile's inclusive total
+// to thread 0 via *tile_total (shared).  x[] is replaced by E_warp(+)(E_lane(+)P_i).
+__device__ __forceinline__ double tile_scan(double (&x)[PAR_ITEMS], double *warp_tot /*[8]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 1; j < PAR_ITEMS; ++j) x[j] = __dadd_rn(x[j - 1], x[j]);
+    // chain across lanes: lane l's exclusive offset is lane l-1's inclusive total
+    double run = x[PAR_ITEMS - 1];      // becomes inclusive total through this lane
+    double excl = 0.0;
+#pragma unroll 1
+    for (int l = 1; l < 32; ++l) {
+        const double prev = __shfl_sync(0xffffffffu, run, l - 1);
+        if (lane == l) { excl = prev; run = __dadd_rn(prev, run); }
+    }
+    if (lane > 0) {
+#pragma unroll
+        for (int j = 0; j < PAR_ITEMS; ++j) x[j] = __dadd_rn(excl, x[j]);
+    }
+    if (lane == 31) warp_tot[warp] = x[PAR_ITEMS - 1];
+    __syncthreads();
+    // chain across warps
+    double wex = 0.0;
+    for (int w = 0; w < warp; ++w) wex = (w == 0) ? warp_tot[0] : __dadd_rn(wex, warp_tot[w]);
+    // note: warp_tot[w] for w>0 is that warp's *local* inclusive total; chain it
+    double tile_total = 0.0;
+    for (int w = 0; w < PAR_THREADS / 32; ++w)
+        tile_total = (w == 0) ? warp_tot[0] : __dadd_rn(tile_total, warp_tot[w]);
+    if (warp > 0) {
+#pragma unroll
+        for (int j = 0; j < PAR_ITEMS; ++j) x[j] = __dadd_rn(wex, x[j]);
+    }
+    __syncthreads();
+    return tile_total;
+}
+
+__global__ void __launch_bounds__(PAR_THREADS)
+scan_tile_totals_kernel(const double *m, uint64_t n, double *tile_tot) {
+    __shared__ double warp_tot[PAR_THREADS / 32];
+    for (uint64_t t = blockIdx.x; t * PAR_TILE < n; t += gridDim.x) {
+        double x[PAR_ITEMS];
+        const uint64_t base = t * PAR_TILE + (uint64_t)threadIdx.x * PAR_ITEMS;
+#pragma unroll
+        for (int j = 0; j < PAR_ITEMS; ++j) x[j] = base + j < n ? m[base + j] : 0.0;
+        const double tot = tile_scan(x, warp_tot);
+        if (threadIdx.x == 0) tile_tot[t] = tot;
+    }
+}
+
+// Offsets above the tile level keep the same nesting: tiles are chained inside
+// groups of PAR_GROUP tiles, groups are chained by one thread.
+//   S_i = G_group (+) (T_tile (+) x_i)
+// tile_tot[] is replaced in place by T_tile; group_off[] receives G_group.
+constexpr int PAR_GROUP = 64;
+
+__global__ void __launch_bounds__(256)
+scan_group_kernel(double *tile_tot, uint32_t ntiles, double *group_tot) {
+    const uint32_t ngroups = (ntiles + PAR_GROUP - 1) / PAR_GROUP;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gridDim.x * blockDim.x) {
+        const uint32_t lo = g * PAR_GROUP, hi = min(lo + PAR_GROUP, ntiles);
+        double run = 0.0;
+        for (uint32_t t = lo; t < hi; ++t) {
+            const double mine = tile_tot[t];
+            tile_tot[t] = run;
+            run = __dadd_rn(run, mine);          // 0.0 + x is exact for the first tile
+        }
+        group_tot[g] = run;
+    }
+}
+
+__global__ void scan_group_chain_kernel(double *group_tot, uint32_t ngroups, double *total) {
+    double run = 0.0;
+    for (uint32_t g = 0; g < ngroups; ++g) {
+        const double mine = group_tot[g];
+        group_tot[g] = run;
+        run = __dadd_rn(run, mine);
+    }
+    *total = run;
+}
+
+__global__ void __launch_bounds__(PAR_THREADS)
+scan_apply_kernel(const double *m, uint64_t n, const double *tile_off, const double *group_off,
+                  const double *total, double *cdf) {
+    __shared__ double warp_tot[PAR_THREADS / 32];
+    const double tot = *total;
+    for (uint64_t t = blockIdx.x; t * PAR_TILE < n; t += gridDim.x) {
+        double x[PAR_ITEMS];
+        const uint64_t base = t * PAR_TILE + (uint64_t)threadIdx.x * PAR_ITEMS;
+#pragma unroll
+        for (int j = 0; j < PAR_ITEMS; ++j) x[j] = base + j < n ? m[base + j] : 0.0;
+        tile_scan(x, warp_tot);
+        const double toff = tile_off[t], goff = group_off[t / PAR_GROUP];
+#pragma unroll
+        for (int j = 0; j < PAR_ITEMS; ++j) {
+            if (base + j < n) {
+                const double s = __dadd_rn(goff, __dadd_rn(toff, x[j]));
+                cdf[base + j] = __ddiv_rn(s, tot);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// guide table
+// ---------------------------------------------------------------------------
+// guide[j] = first i with cdf[i] > j/G.  Cell i owns the bins j with
+// cdf[i-1] <= j/G < cdf[i], i.e. j in [ceil(cdf[i-1]*G), ceil(cdf[i]*G)).
+// One warp walks 32 consecutive cells; short runs are written by the owning
+// lane, long runs cooperatively.
+__global__ void __launch_bounds__(256)
+guide_build_kernel(const double *cdf, uint32_t n, int bits, uint32_t *guide) {
+    const double G = (double)(1u << bits);
+    const uint32_t Gi = 1u << bits;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; (uint64_t)w * 32 < n; w += warps) {
+        const uint32_t i = w * 32 + lane;
+        uint32_t j0 = 0, j1 = 0;
+        if (i < n) {
+            const double lo = i == 0 ? 0.0 : cdf[i - 1];
+            j0 = (uint32_t)min(ceil(lo * G), G);
+            j1 = i == n - 1 ? Gi + 1 : (uint32_t)min(ceil(cdf[i] * G), G);   // last cell also owns j = G
+        }
+        const uint32_t len = j1 > j0 ? j1 - j0 : 0;
+        if (len > 0 && len <= 32)
+            for (uint32_t j = j0; j < j1; ++j) guide[j] = i;
+        uint32_t longmask = __ballot_sync(0xffffffffu, len > 32);
+        while (longmask) {
+            const int src = __ffs(longmask) - 1;
+            longmask &= longmask - 1;
+            const uint32_t a = __shfl_sync(0xffffffffu, j0, src), b = __shfl_sync(0xffffffffu, j1, src);
+            const uint32_t ci = w * 32 + src;
+            for (uint32_t j = a + lane; j < b; j += 32) guide[j] = ci;
+        }
+    }
+}
+
+}  // namespace lint
+
+using namespace lint;
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int lint_abi_version(void) { return LINT_ABI_VERSION; }
+const char *lint_last_error(void) { return last_error_slot().c_str(); }
+
+int lint_grid_eval_gmm(const lint_grid_t *g, const lint_gmm_t *gmm, double scale,
+                       lint_stream_t stream) {
+    uint64_t nc, nv;
+    if (int rc = validate_grid(g, false, &nc, &nv)) return rc;
+    if (!gmm || gmm->dim != g->dim) return fail(LINT_ERR_BAD_ARG, "gmm dim does not match grid dim");
+    if (gmm->ncomp < 1 || gmm->ncomp > LINT_GMM_MAX_COMP)
+        return fail(LINT_ERR_BAD_ARG, "gmm ncomp %d outside 1..%d", gmm->ncomp, LINT_GMM_MAX_COMP);
+    if (!gmm->log_norm || !gmm->mean || !gmm->prec_chol)
+        return fail(LINT_ERR_BAD_ARG, "gmm parameter arrays must not be NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (g->dim) {
+        case 1: return eval_gmm_impl<1>(g, gmm, scale, nv, st);
+        case 2: return eval_gmm_impl<2>(g, gmm, scale, nv, st);
+        case 3: return eval_gmm_impl<3>(g, gmm, scale, nv, st);
+        case 4: return eval_gmm_impl<4>(g, gmm, scale, nv, st);
+        case 5: return eval_gmm_impl<5>(g, gmm, scale, nv, st);
+        default: return eval_gmm_impl<6>(g, gmm, scale, nv, st);
+    }
+}
+
+int lint_grid_masses(const lint_grid_t *g, double *masses_dev, uint32_t *flags_dev,
+                     lint_stream_t stream) {
+    uint64_t nc, nv;
+    if (int rc = validate_grid(g, false, &nc, &nv)) return rc;
+    if (!masses_dev || !flags_dev) return fail(LINT_ERR_BAD_ARG, "masses_dev / flags_dev is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (g->dim) {
+        case 1: return masses_impl<1>(g, nc, masses_dev, flags_dev, st);
+        case 2: return masses_impl<2>(g, nc, masses_dev, flags_dev, st);
+        case 3: return masses_impl<3>(g, nc, masses_dev, flags_dev, st);
+        case 4: return masses_impl<4>(g, nc, masses_dev, flags_dev, st);
+        case 5: return masses_impl<5>(g, nc, masses_dev, flags_dev, st);
+        default: return masses_impl<6>(g, nc, masses_dev, flags_dev, st);
+    }
+}
+
+int lint_cells_check(const lint_cells_t *c, uint32_t *flags_dev, lint_stream_t stream) {
+    if (!c || !c->corners_dev || !flags_dev) return fail(LINT_ERR_BAD_ARG, "NULL argument");
+    if (c->dim < 1 || c->dim > LINT_MAX_DIM || c->ncells < 1)
+        return fail(LINT_ERR_BAD_ARG, "bad cell-list shape");
+    const uint64_t n = (uint64_t)c->ncells << c->dim;
+    const int blocks = (int)std::min<uint64_t>((n + 255) / 256, 148 * 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c->dtype == LINT_F32)
+        cells_check_kernel<float><<<blocks, 256, 0, st>>>((const float *)c->corners_dev, n, flags_dev);
+    else
+        cells_check_kernel<double><<<blocks, 256, 0, st>>>((const double *)c->corners_dev, n, flags_dev);
+    return check_launch("lint_cells_check");
+}
+
+size_t lint_cdf_scratch_bytes(int64_t n) {
+    if (n < 1) return 0;
+    // pairwise-sum node buffers (2 * 2^depth <= 2 * n/129 + 2) and parallel tile totals
+    const size_t nodes = 2 * ((size_t)1 << pw_depth((uint64_t)n));
+    const size_t tiles = ((size_t)n + PAR_TILE - 1) / PAR_TILE;
+    const size_t groups = (tiles + PAR_GROUP - 1) / PAR_GROUP;
+    return (nodes + tiles + groups + 8) * sizeof(double);
+}
+
+int lint_sum_numpy_f64(const double *x_dev, int64_t n, double *out_dev, void *scratch_dev,
+                       size_t scratch_bytes, lint_stream_t stream) {
+    if (!x_dev || !out_dev || n < 1) return fail(LINT_ERR_BAD_ARG, "lint_sum_numpy_f64: bad argument");
+    if (scratch_bytes < lint_cdf_scratch_bytes(n) || !scratch_dev)
+        return fail(LINT_ERR_BAD_ARG, "lint_sum_numpy_f64: scratch too small");
+    return sum_numpy_launch(x_dev, (uint64_t)n, out_dev, (double *)scratch_dev, (cudaStream_t)stream);
+}
+
+int lint_cdf_build(const double *masses_dev, int64_t n, int mode, double *cdf_dev,
+                   double *total_dev, void *scratch_dev, size_t scratch_bytes,
+                   lint_stream_t stream) {
+    if (!masses_dev || !cdf_dev || !total_dev || n < 1)
+        return fail(LINT_ERR_BAD_ARG, "lint_cdf_build: bad argument");
+    if (n >= (1ll << 31)) return fail(LINT_ERR_UNSUPPORTED, "lint_cdf_build: n >= 2^31");
+    if (scratch_bytes < lint_cdf_scratch_bytes(n) || !scratch_dev)
+        return fail(LINT_ERR_BAD_ARG, "lint_cdf_build: scratch too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t un = (uint64_t)n;
+    if (mode == LINT_CDF_SEQUENTIAL) {
+        if (int rc = sum_numpy_launch(masses_dev, un, total_dev, (double *)scratch_dev, st)) return rc;
+        cdf_sequential_kernel<<<1, SEQ_THREADS, 0, st>>>(masses_dev, un, total_dev, cdf_dev);
+        // `cdf /= cdf[-1]`: the divisor must be read before any element changes, so the
+        // last element is rewritten by a separate launch after the others
+        const int blocks = (int)std::min<uint64_t>((un + 255) / 256, 148 * 16);
+        cdf_normalise_kernel<<<blocks, 256, 0, st>>>(cdf_dev, un);
+        cdf_set_last_kernel<<<1, 1, 0, st>>>(cdf_dev, un);
+        return check_launch("lint_cdf_build(sequential)");
+    }
+    if (mode != LINT_CDF_PARALLEL) return fail(LINT_ERR_BAD_ARG, "lint_cdf_build: unknown mode %d", mode);
+    double *tile_tot = (double *)scratch_dev;
+    const uint32_t ntiles = (uint32_t)((un + PAR_TILE - 1) / PAR_TILE);
+    const int blocks = (int)std::min<uint32_t>(ntiles, 148 * 8);
+    scan_tile_totals_kernel<<<blocks, PAR_THREADS, 0, st>>>(masses_dev, un, tile_tot);
+    const uint32_t ngroups = (ntiles + PAR_GROUP - 1) / PAR_GROUP;
+    double *group_off = tile_tot + ntiles;
+    scan_group_kernel<<<(ngroups + 255) / 256, 256, 0, st>>>(tile_tot, ntiles, group_off);
+    scan_group_chain_kernel<<<1, 1, 0, st>>>(group_off, ngroups, total_dev);
+    scan_apply_kernel<<<blocks, PAR_THREADS, 0, st>>>(masses_dev, un, tile_tot, group_off, total_dev,
+                                                      cdf_dev);
+    return check_launch("lint_cdf_build(parallel)");
+}
+
+int lint_guide_build(const double *cdf_dev, int64_t n, int guide_bits, uint32_t *guide_dev,
+                     lint_stream_t stream) {
+    if (!cdf_dev || !guide_dev || n < 1 || n >= (1ll << 31))
+        return fail(LINT_ERR_BAD_ARG, "lint_guide_build: bad argument");
+    if (guide_bits < 1 || guide_bits > 30)
+        return fail(LINT_ERR_BAD_ARG, "lint_guide_build: guide_bits %d outside 1..30", guide_bits);
+    const uint64_t nwarps = ((uint64_t)n + 31) / 32;
+    const int blocks = (int)std::min<uint64_t>((nwarps + 7) / 8, 148 * 16);
+    guide_build_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cdf_dev, (uint32_t)n, guide_bits, guide_dev);
+    return check_launch("lint_guide_build");
+}
+
+}  // extern "C"

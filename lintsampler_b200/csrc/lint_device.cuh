@@ -1,0 +1,312 @@
+// Device-side building blocks of the B200 linear-interpolant sampler.
+// Everything here is header-only and shared by lint_build.cu / lint_sample.cu.
+//
+// Reference citations are relative to /root/reference/src/lintsampler.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/lintsampler_b200.h"
+
+namespace lint {
+
+// ---------------------------------------------------------------------------
+// host-side error plumbing (no exceptions cross the C ABI)
+// ---------------------------------------------------------------------------
+std::string &last_error_slot();
+int fail(int code, const char *fmt, ...);
+int check_launch(const char *what);
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter-based: one 128-bit block per call
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    constexpr uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = mulhi32(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = mulhi32(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+__host__ __device__ __forceinline__ double u53(uint32_t lo, uint32_t hi) {
+    // same construction as NumPy's Generator.random: top 53 bits * 2^-53
+    const uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;
+    return (double)v * (1.0 / 9007199254740992.0);
+}
+
+// ---------------------------------------------------------------------------
+// searchsorted(side='right'): first i in [0, n) with cdf[i] > u   [utils.py:197]
+// The guide table only narrows the bracket; the comparisons, and therefore the
+// result, are exactly those of a full binary search on the same fp64 table.
+// ---------------------------------------------------------------------------
+struct CdfView {
+    const double *cdf;
+    const uint32_t *guide;
+    uint32_t n;
+    int guide_bits;
+};
+
+__device__ __forceinline__ uint32_t search_right(const CdfView &t, double u) {
+    uint32_t lo = 0, hi = t.n - 1;
+    if (t.guide_bits > 0) {
+        // u * 2^bits is exact in fp64; u < 1 keeps j < 2^bits
+        const uint32_t G = 1u << t.guide_bits;
+        uint32_t j = (uint32_t)(u * (double)G);
+        j = j < G ? j : G - 1;
+        lo = __ldg(t.guide + j);
+        hi = __ldg(t.guide + j + 1);
+    }
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(t.cdf + mid) > u) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// ---------------------------------------------------------------------------
+// 1-D inverse CDF of a linear density   [sampling.py:6-38]
+// ---------------------------------------------------------------------------
+// fp64: the reference's literal expression, one IEEE rounding per NumPy ufunc
+// call, so the result is bit-identical to sampling.py:32-37.
+__device__ __forceinline__ double quantile_exact(double f0, double f1, double u) {
+    if (f0 == f1) return u;
+    const double a2 = __dmul_rn(f0, f0);
+    const double b2 = __dmul_rn(f1, f1);
+    const double rad = __dadd_rn(a2, __dmul_rn(__dsub_rn(b2, a2), u));
+    return __ddiv_rn(__dadd_rn(-f0, __dsqrt_rn(rad)), __dsub_rn(f1, f0));
+}
+
+// fp32: algebraically equal conjugate form (no cancellation when f0 ~ f1,
+// SURVEY.md §7.3-3); inputs are pre-normalised so the squares cannot underflow.
+__device__ __forceinline__ float quantile_fast(float f0, float f1, float u) {
+    const float rad = fmaf(u, fmaf(f1, f1, -f0 * f0), f0 * f0);
+    const float den = f0 + __fsqrt_rn(fmaxf(rad, 0.f));
+    return den > 0.f ? __fdividef((f0 + f1) * u, den) : u;
+}
+
+// ---------------------------------------------------------------------------
+// k-D multilinear-interpolant inverse CDF in the unit cube   [sampling.py:41-94]
+// ---------------------------------------------------------------------------
+// fp64 parity version: operation order identical to the oracle's
+// unit_cube_sample (= the order NumPy executes for the reference).
+template <int K>
+__device__ __forceinline__ void incell_exact(const double (&c)[1 << K], const double (&u)[K],
+                                             double (&z)[K]) {
+#pragma unroll
+    for (int d = 0; d < K; ++d) {
+        const int nlater = 1 << (K - 1 - d);   // corner bits of dims > d
+        const int nearly = 1 << d;             // corner bits of dims < d
+        double g[2];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            double total = 0.0;
+#pragma unroll
+            for (int hi = 0; hi < nearly; ++hi) {
+                const int base = (hi * 2 + b) * nlater;
+                double acc = c[base];
+#pragma unroll
+                for (int lo = 1; lo < nlater; ++lo) acc = __dadd_rn(acc, c[base + lo]);
+                if (nlater > 1) acc = __dmul_rn(acc, 1.0 / nlater);   // == division by 2^j
+#pragma unroll
+                for (int i = 0; i < d; ++i) {
+                    const int bit = (hi >> (d - 1 - i)) & 1;
+                    acc = __dmul_rn(acc, bit ? z[i] : __dsub_rn(1.0, z[i]));
+                }
+                total = (hi == 0) ? acc : __dadd_rn(total, acc);
+            }
+            g[b] = total;
+        }
+        z[d] = quantile_exact(g[0], g[1], u[d]);
+    }
+}
+
+// fp32 throughput version: condition the corner array on each coordinate as it
+// is drawn (2^K - 1 lerps in total); the 1/2^j averaging factors are dropped
+// because the 1-D quantile is scale invariant.  `c` is consumed.
+template <int K>
+__device__ __forceinline__ void incell_fast(float (&c)[1 << K], const float (&u)[K],
+                                            float (&z)[K]) {
+    // normalise by the largest corner so squares stay in range
+    float m = c[0];
+#pragma unroll
+    for (int j = 1; j < (1 << K); ++j) m = fmaxf(m, c[j]);
+    const float inv = m > 0.f ? __frcp_rn(m) : 0.f;
+#pragma unroll
+    for (int j = 0; j < (1 << K); ++j) c[j] *= inv;
+#pragma unroll
+    for (int d = 0; d < K; ++d) {
+        const int half = 1 << (K - 1 - d);     // live corners: 2*half
+        float g0 = c[0], g1 = c[half];
+#pragma unroll
+        for (int j = 1; j < half; ++j) { g0 += c[j]; g1 += c[half + j]; }
+        const float zd = quantile_fast(g0, g1, u[d]);
+        z[d] = zd;
+#pragma unroll
+        for (int j = 0; j < half; ++j) c[j] = fmaf(zd, c[half + j] - c[j], c[j]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// cell sources
+// ---------------------------------------------------------------------------
+// Rectilinear grid (reference DensityGrid).  Cell counts and vertex counts are
+// limited to < 2^31 so all index arithmetic is 32-bit.
+template <int K>
+struct GridView {
+    const void *V;
+    const double *edges[K];
+    CdfView table;
+    uint32_t n[K];                 // cells per dim
+    uint32_t vstride[K];           // vertex strides (elements)
+    uint32_t corner_off[1 << K];   // vertex offset of corner c from the cell origin
+};
+
+template <int K, typename DensT, typename T>
+__device__ __forceinline__ void grid_fetch(const GridView<K> &g, uint32_t flat, T (&c)[1 << K],
+                                           T (&lo)[K], T (&hi)[K]) {
+    // C-order unravel  [grid.py:437]
+    uint32_t r = flat, base = 0;
+#pragma unroll
+    for (int d = K - 1; d >= 0; --d) {
+        uint32_t i;
+        if (d == 0) { i = r; } else { const uint32_t q = r / g.n[d]; i = r - q * g.n[d]; r = q; }
+        base += i * g.vstride[d];
+        lo[d] = (T)__ldg(g.edges[d] + i);        // _cell_mins gather [grid.py:353]
+        hi[d] = (T)__ldg(g.edges[d] + i + 1);    // _cell_maxs gather [grid.py:354]
+    }
+    // 2^K corner gather, corner order = MSB-first bit pattern [grid.py:440-467]
+    const DensT *V = reinterpret_cast<const DensT *>(g.V);
+#pragma unroll
+    for (int j = 0; j < (1 << K); ++j) c[j] = (T)__ldg(V + base + g.corner_off[j]);
+}
+
+// Flat cell list (reference DensityTree leaves, list order)  [tree.py:334-355]
+struct CellsView {
+    const double *mins;
+    const double *widths;
+    const void *corners;
+    CdfView table;
+};
+
+template <int K, typename DensT, typename T>
+__device__ __forceinline__ void cells_fetch(const CellsView &s, uint32_t idx, T (&c)[1 << K],
+                                            T (&lo)[K], T (&hi)[K]) {
+#pragma unroll
+    for (int d = 0; d < K; ++d) {
+        const double x = __ldg(s.mins + (size_t)idx * K + d);
+        const double dx = __ldg(s.widths + (size_t)idx * K + d);
+        lo[d] = (T)x;
+        hi[d] = (T)__dadd_rn(x, dx);              // maxs = leaf.x + leaf.dx [tree.py:348]
+    }
+    const DensT *C = reinterpret_cast<const DensT *>(s.corners) + (size_t)idx * (1 << K);
+#pragma unroll
+    for (int j = 0; j < (1 << K); ++j) c[j] = (T)__ldg(C + j);
+}
+
+// ---------------------------------------------------------------------------
+// uniform sources: each yields, for row i, the cell-selecting fp64 uniform and
+// the K in-cell uniforms in arithmetic type T   [lintsampler.py:269-270]
+// ---------------------------------------------------------------------------
+template <int K>
+struct UniformsFromArray {        // caller-supplied (N, K+1) fp64  [lintsampler.py:517]
+    const double *u;
+    template <typename T>
+    __device__ __forceinline__ void get(int64_t row, double &ucell, T (&uc)[K]) const {
+        const double *p = u + row * (K + 1);
+#pragma unroll
+        for (int d = 0; d < K; ++d) uc[d] = (T)__ldg(p + d);
+        ucell = __ldg(p + K);
+    }
+};
+
+template <int K>
+struct UniformsPhilox {
+    uint2 key;
+    uint64_t offset;
+    // fp64 rows: cell uniform from words (0,1), coordinate d from words (2+2d, 3+2d)
+    __device__ __forceinline__ void get(int64_t row, double &ucell, double (&uc)[K]) const {
+        const uint64_t i = offset + (uint64_t)row;
+        constexpr int NCALL = (K + 2) / 2;
+        uint32_t w[4 * NCALL];
+#pragma unroll
+        for (int q = 0; q < NCALL; ++q) {
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), q, 0), key);
+            w[4 * q] = r.x; w[4 * q + 1] = r.y; w[4 * q + 2] = r.z; w[4 * q + 3] = r.w;
+        }
+        ucell = u53(w[0], w[1]);
+#pragma unroll
+        for (int d = 0; d < K; ++d) uc[d] = u53(w[2 + 2 * d], w[3 + 2 * d]);
+    }
+    // fp32 rows: cell uniform from words (0,1); 24-bit coordinates: d=0,1 from the
+    // top bits of words 2,3; d=2 from the otherwise unused low bytes of words
+    // 2, 3 and 0; d=3..5 from a second block.
+    __device__ __forceinline__ void get(int64_t row, double &ucell, float (&uc)[K]) const {
+        const uint64_t i = offset + (uint64_t)row;
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0, 0), key);
+        ucell = u53(r.x, r.y);
+        constexpr float S = 1.0f / 16777216.0f;
+        uc[0] = (float)(r.z >> 8) * S;
+        if (K > 1) uc[1 % K] = (float)(r.w >> 8) * S;
+        if (K > 2) uc[2 % K] = (float)(((r.z & 0xffu) << 16) | ((r.w & 0xffu) << 8) | (r.x & 0xffu)) * S;
+        if (K > 3) {
+            const uint4 s = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 1, 0), key);
+            uc[3 % K] = (float)(s.x >> 8) * S;
+            if (K > 4) uc[4 % K] = (float)(s.y >> 8) * S;
+            if (K > 5) uc[5 % K] = (float)(s.z >> 8) * S;
+        }
+    }
+};
+
+template <int K>
+struct UniformsSobol {            // scipy Sobol(d=K+1, bits=32), direct Gray-code index
+    uint32_t sv[K + 1][32];
+    uint32_t shift[K + 1];
+    uint64_t first;
+    template <typename T>
+    __device__ __forceinline__ void get(int64_t row, double &ucell, T (&uc)[K]) const {
+        const uint64_t n = first + (uint64_t)row;
+        uint32_t gray = (uint32_t)(n ^ (n >> 1));
+        uint32_t x[K + 1];
+#pragma unroll
+        for (int j = 0; j <= K; ++j) x[j] = shift[j];
+        while (gray) {
+            const int b = __ffs(gray) - 1;
+            gray &= gray - 1;
+#pragma unroll
+            for (int j = 0; j <= K; ++j) x[j] ^= sv[j][b];
+        }
+        // scipy scales the 32-bit integers by 2^-32 in fp64
+#pragma unroll
+        for (int d = 0; d < K; ++d) uc[d] = (T)((double)x[d] * (1.0 / 4294967296.0));
+        ucell = (double)x[K] * (1.0 / 4294967296.0);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// affine map into the cell   [sampling.py:126]
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double affine(double lo, double hi, double z) {
+    return __dadd_rn(lo, __dmul_rn(__dsub_rn(hi, lo), z));
+}
+__device__ __forceinline__ float affine(float lo, float hi, float z) {
+    return fmaf(hi - lo, z, lo);
+}
+
+template <int K> __device__ __forceinline__ void incell(double (&c)[1 << K], const double (&u)[K], double (&z)[K]) { incell_exact<K>(c, u, z); }
+template <int K> __device__ __forceinline__ void incell(float (&c)[1 << K], const float (&u)[K], float (&z)[K]) { incell_fast<K>(c, u, z); }
+
+}  // namespace lint

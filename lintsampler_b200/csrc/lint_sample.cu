@@ -1,0 +1,315 @@
+// Sampling kernels: cell selection (searchsorted on the fp64 CDF), corner
+// gather, k-D multilinear inverse CDF, affine map — one fused kernel per
+// (cell source, uniform source, dim, precision).  C ABI in
+// include/lintsampler_b200.h.
+//
+// Reference citations are relative to /root/reference/src/lintsampler.
+#include <algorithm>
+#include "lint_device.cuh"
+
+namespace lint {
+
+int validate_grid(const lint_grid_t *g, bool need_cdf, uint64_t *ncells_out, uint64_t *nverts_out);
+template <int K> GridView<K> make_grid_view(const lint_grid_t *g, uint64_t ncells);
+
+// ---------------------------------------------------------------------------
+// cell-source adaptors
+// ---------------------------------------------------------------------------
+template <int K, typename DensT>
+struct GridSource {
+    GridView<K> g;
+    __device__ __forceinline__ uint32_t choose(double u) const {
+        return g.table.n == 1 ? 0u : search_right(g.table, u);   // grid.py:427-428 shortcut
+    }
+    template <typename T>
+    __device__ __forceinline__ void fetch(uint32_t idx, T (&c)[1 << K], T (&lo)[K], T (&hi)[K]) const {
+        grid_fetch<K, DensT, T>(g, idx, c, lo, hi);
+    }
+};
+
+template <int K, typename DensT>
+struct ListSource {
+    CellsView s;
+    __device__ __forceinline__ uint32_t choose(double u) const { return search_right(s.table, u); }
+    template <typename T>
+    __device__ __forceinline__ void fetch(uint32_t idx, T (&c)[1 << K], T (&lo)[K], T (&hi)[K]) const {
+        cells_fetch<K, DensT, T>(s, idx, c, lo, hi);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// the fused per-sample kernel   [sampling.py:97-127]
+// ---------------------------------------------------------------------------
+constexpr int SAMPLE_THREADS = 256;
+
+template <int K, typename T, typename Source, typename Uniforms>
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+sample_kernel(Source src, Uniforms unif, int64_t N, T *__restrict__ out,
+              int64_t *__restrict__ cell_idx) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < N; row += stride) {
+        double ucell;
+        T u[K];
+        unif.get(row, ucell, u);
+        const uint32_t idx = src.choose(ucell);           // grid.choose_cells(u[..., -1])
+        T c[1 << K], lo[K], hi[K], z[K];
+        src.fetch(idx, c, lo, hi);
+        incell<K>(c, u, z);                               // _unitsample_kd(*corners, u=u[..., :-1])
+#pragma unroll
+        for (int d = 0; d < K; ++d) out[row * K + d] = affine(lo[d], hi[d], z[d]);
+        if (cell_idx) cell_idx[row] = (int64_t)idx;
+    }
+}
+
+template <int K, typename T, typename Source, typename Uniforms>
+int launch_sample(const Source &src, const Uniforms &unif, int64_t N, void *out, int64_t *cell_idx,
+                  cudaStream_t st, const char *what) {
+    if (N == 0) return LINT_OK;
+    const int64_t want = (N + SAMPLE_THREADS - 1) / SAMPLE_THREADS;
+    const int blocks = (int)std::min<int64_t>(want, 148 * 64);
+    sample_kernel<K, T, Source, Uniforms><<<blocks, SAMPLE_THREADS, 0, st>>>(src, unif, N, (T *)out, cell_idx);
+    return check_launch(what);
+}
+
+// ---------------------------------------------------------------------------
+// dispatch helpers
+// ---------------------------------------------------------------------------
+template <int K, typename UnifMaker>
+int grid_dispatch_k(const lint_grid_t *g, uint64_t ncells, int64_t N, void *out, int64_t *cell_idx,
+                    cudaStream_t st, const UnifMaker &mk, const char *what) {
+    if (g->dtype == LINT_F32) {
+        GridSource<K, float> src{make_grid_view<K>(g, ncells)};
+        return launch_sample<K, float>(src, mk.template make<K>(), N, out, cell_idx, st, what);
+    }
+    GridSource<K, double> src{make_grid_view<K>(g, ncells)};
+    return launch_sample<K, double>(src, mk.template make<K>(), N, out, cell_idx, st, what);
+}
+
+template <typename UnifMaker>
+int grid_dispatch(const lint_grid_t *g, int64_t N, void *out, int64_t *cell_idx, lint_stream_t stream,
+                  const UnifMaker &mk, const char *what) {
+    uint64_t nc, nv;
+    if (int rc = validate_grid(g, true, &nc, &nv)) return rc;
+    if (N < 0 || (N > 0 && !out)) return fail(LINT_ERR_BAD_ARG, "%s: bad N / out_dev", what);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (g->dim) {
+        case 1: return grid_dispatch_k<1>(g, nc, N, out, cell_idx, st, mk, what);
+        case 2: return grid_dispatch_k<2>(g, nc, N, out, cell_idx, st, mk, what);
+        case 3: return grid_dispatch_k<3>(g, nc, N, out, cell_idx, st, mk, what);
+        case 4: return grid_dispatch_k<4>(g, nc, N, out, cell_idx, st, mk, what);
+        case 5: return grid_dispatch_k<5>(g, nc, N, out, cell_idx, st, mk, what);
+        default: return grid_dispatch_k<6>(g, nc, N, out, cell_idx, st, mk, what);
+    }
+}
+
+static int validate_cells(const lint_cells_t *c) {
+    if (!c) return fail(LINT_ERR_BAD_ARG, "cell-list descriptor is NULL");
+    if (c->dim < 1 || c->dim > LINT_MAX_DIM)
+        return fail(LINT_ERR_BAD_ARG, "cell-list dim %d outside 1..%d", c->dim, LINT_MAX_DIM);
+    if (c->dtype != LINT_F32 && c->dtype != LINT_F64)
+        return fail(LINT_ERR_BAD_ARG, "cell-list dtype %d is not LINT_F32/LINT_F64", c->dtype);
+    if (c->ncells < 1 || c->ncells >= (1ll << 31))
+        return fail(LINT_ERR_BAD_ARG, "cell-list ncells outside 1..2^31-1");
+    if (!c->mins_dev || !c->widths_dev || !c->corners_dev || !c->cdf_dev)
+        return fail(LINT_ERR_BAD_ARG, "cell-list device pointer is NULL");
+    if (c->guide_bits < 0 || c->guide_bits > 30 || (c->guide_bits > 0 && !c->guide_dev))
+        return fail(LINT_ERR_BAD_ARG, "cell-list guide table inconsistent (bits=%d)", c->guide_bits);
+    return LINT_OK;
+}
+
+static CellsView make_cells_view(const lint_cells_t *c) {
+    CellsView v;
+    v.mins = c->mins_dev;
+    v.widths = c->widths_dev;
+    v.corners = c->corners_dev;
+    v.table.cdf = c->cdf_dev;
+    v.table.guide = c->guide_dev;
+    v.table.guide_bits = c->guide_bits;
+    v.table.n = (uint32_t)c->ncells;
+    return v;
+}
+
+template <int K, typename UnifMaker>
+int cells_dispatch_k(const lint_cells_t *c, int64_t N, void *out, int64_t *cell_idx, cudaStream_t st,
+                     const UnifMaker &mk, const char *what) {
+    if (c->dtype == LINT_F32) {
+        ListSource<K, float> src{make_cells_view(c)};
+        return launch_sample<K, float>(src, mk.template make<K>(), N, out, cell_idx, st, what);
+    }
+    ListSource<K, double> src{make_cells_view(c)};
+    return launch_sample<K, double>(src, mk.template make<K>(), N, out, cell_idx, st, what);
+}
+
+template <typename UnifMaker>
+int cells_dispatch(const lint_cells_t *c, int64_t N, void *out, int64_t *cell_idx, lint_stream_t stream,
+                   const UnifMaker &mk, const char *what) {
+    if (int rc = validate_cells(c)) return rc;
+    if (N < 0 || (N > 0 && !out)) return fail(LINT_ERR_BAD_ARG, "%s: bad N / out_dev", what);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (c->dim) {
+        case 1: return cells_dispatch_k<1>(c, N, out, cell_idx, st, mk, what);
+        case 2: return cells_dispatch_k<2>(c, N, out, cell_idx, st, mk, what);
+        case 3: return cells_dispatch_k<3>(c, N, out, cell_idx, st, mk, what);
+        case 4: return cells_dispatch_k<4>(c, N, out, cell_idx, st, mk, what);
+        case 5: return cells_dispatch_k<5>(c, N, out, cell_idx, st, mk, what);
+        default: return cells_dispatch_k<6>(c, N, out, cell_idx, st, mk, what);
+    }
+}
+
+struct ArrayMaker {
+    const double *u;
+    template <int K> UniformsFromArray<K> make() const { return UniformsFromArray<K>{u}; }
+};
+struct PhiloxMaker {
+    uint64_t seed, offset;
+    template <int K> UniformsPhilox<K> make() const {
+        return UniformsPhilox<K>{make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), offset};
+    }
+};
+struct SobolMaker {
+    const lint_sobol_t *s;
+    template <int K> UniformsSobol<K> make() const {
+        UniformsSobol<K> u;
+        for (int j = 0; j <= K; ++j) {
+            for (int b = 0; b < 32; ++b) u.sv[j][b] = s->sv[j][b];
+            u.shift[j] = s->shift[j];
+        }
+        u.first = s->first_index;
+        return u;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// in-cell stage only (generic DensityStructure)   [sampling.py:123-126]
+// ---------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+incell_kernel(int64_t N, const double *mins, const double *maxs, const double *corners,
+              const double *u, double *out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < N; row += stride) {
+        double c[1 << K], uu[K], z[K];
+#pragma unroll
+        for (int j = 0; j < (1 << K); ++j) c[j] = corners[(int64_t)j * N + row];
+#pragma unroll
+        for (int d = 0; d < K; ++d) uu[d] = u[row * (K + 1) + d];
+        incell_exact<K>(c, uu, z);
+#pragma unroll
+        for (int d = 0; d < K; ++d)
+            out[row * K + d] = affine(mins[row * K + d], maxs[row * K + d], z[d]);
+    }
+}
+
+template <int K, typename T, typename Uniforms>
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+uniforms_kernel(Uniforms unif, int64_t N, double *out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < N; row += stride) {
+        double ucell;
+        T u[K];
+        unif.get(row, ucell, u);
+#pragma unroll
+        for (int d = 0; d < K; ++d) out[row * (K + 1) + d] = (double)u[d];
+        out[row * (K + 1) + K] = ucell;
+    }
+}
+
+template <int K, typename Maker>
+int uniforms_dispatch_k(int dtype, int64_t N, const Maker &mk, double *out, cudaStream_t st) {
+    if (N == 0) return LINT_OK;
+    const int blocks = (int)std::min<int64_t>((N + SAMPLE_THREADS - 1) / SAMPLE_THREADS, 148 * 32);
+    auto u = mk.template make<K>();
+    if (dtype == LINT_F32)
+        uniforms_kernel<K, float, decltype(u)><<<blocks, SAMPLE_THREADS, 0, st>>>(u, N, out);
+    else
+        uniforms_kernel<K, double, decltype(u)><<<blocks, SAMPLE_THREADS, 0, st>>>(u, N, out);
+    return check_launch("uniforms");
+}
+
+template <typename Maker>
+int uniforms_dispatch(int dim, int dtype, int64_t N, const Maker &mk, double *out, lint_stream_t stream) {
+    if (dim < 1 || dim > LINT_MAX_DIM) return fail(LINT_ERR_BAD_ARG, "dim %d outside 1..%d", dim, LINT_MAX_DIM);
+    if (dtype != LINT_F32 && dtype != LINT_F64) return fail(LINT_ERR_BAD_ARG, "bad dtype %d", dtype);
+    if (N < 0 || (N > 0 && !out)) return fail(LINT_ERR_BAD_ARG, "bad N / u_dev");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dim) {
+        case 1: return uniforms_dispatch_k<1>(dtype, N, mk, out, st);
+        case 2: return uniforms_dispatch_k<2>(dtype, N, mk, out, st);
+        case 3: return uniforms_dispatch_k<3>(dtype, N, mk, out, st);
+        case 4: return uniforms_dispatch_k<4>(dtype, N, mk, out, st);
+        case 5: return uniforms_dispatch_k<5>(dtype, N, mk, out, st);
+        default: return uniforms_dispatch_k<6>(dtype, N, mk, out, st);
+    }
+}
+
+}  // namespace lint
+
+using namespace lint;
+
+extern "C" {
+
+int lint_grid_sample_u(const lint_grid_t *g, const double *u_dev, int64_t N, void *out_dev,
+                       int64_t *cell_idx_dev, lint_stream_t stream) {
+    if (N > 0 && !u_dev) return fail(LINT_ERR_BAD_ARG, "lint_grid_sample_u: u_dev is NULL");
+    return grid_dispatch(g, N, out_dev, cell_idx_dev, stream, ArrayMaker{u_dev}, "lint_grid_sample_u");
+}
+
+int lint_cells_sample_u(const lint_cells_t *c, const double *u_dev, int64_t N, void *out_dev,
+                        int64_t *cell_idx_dev, lint_stream_t stream) {
+    if (N > 0 && !u_dev) return fail(LINT_ERR_BAD_ARG, "lint_cells_sample_u: u_dev is NULL");
+    return cells_dispatch(c, N, out_dev, cell_idx_dev, stream, ArrayMaker{u_dev}, "lint_cells_sample_u");
+}
+
+int lint_incell_sample_u(int dim, int64_t N, const double *mins_dev, const double *maxs_dev,
+                         const double *corners_dev, const double *u_dev, double *out_dev,
+                         lint_stream_t stream) {
+    if (dim < 1 || dim > LINT_MAX_DIM)
+        return fail(LINT_ERR_BAD_ARG, "lint_incell_sample_u: dim %d outside 1..%d", dim, LINT_MAX_DIM);
+    if (N < 0) return fail(LINT_ERR_BAD_ARG, "lint_incell_sample_u: N < 0");
+    if (N == 0) return LINT_OK;
+    if (!mins_dev || !maxs_dev || !corners_dev || !u_dev || !out_dev)
+        return fail(LINT_ERR_BAD_ARG, "lint_incell_sample_u: NULL device pointer");
+    const int blocks = (int)std::min<int64_t>((N + SAMPLE_THREADS - 1) / SAMPLE_THREADS, 148 * 32);
+    cudaStream_t st = (cudaStream_t)stream;
+#define LINT_CASE(KK) case KK: incell_kernel<KK><<<blocks, SAMPLE_THREADS, 0, st>>>(N, mins_dev, maxs_dev, corners_dev, u_dev, out_dev); break;
+    switch (dim) { LINT_CASE(1) LINT_CASE(2) LINT_CASE(3) LINT_CASE(4) LINT_CASE(5) LINT_CASE(6) }
+#undef LINT_CASE
+    return check_launch("lint_incell_sample_u");
+}
+
+int lint_grid_sample_philox(const lint_grid_t *g, int64_t N, uint64_t seed, uint64_t offset,
+                            void *out_dev, int64_t *cell_idx_dev, lint_stream_t stream) {
+    return grid_dispatch(g, N, out_dev, cell_idx_dev, stream, PhiloxMaker{seed, offset},
+                         "lint_grid_sample_philox");
+}
+
+int lint_cells_sample_philox(const lint_cells_t *c, int64_t N, uint64_t seed, uint64_t offset,
+                             void *out_dev, int64_t *cell_idx_dev, lint_stream_t stream) {
+    return cells_dispatch(c, N, out_dev, cell_idx_dev, stream, PhiloxMaker{seed, offset},
+                          "lint_cells_sample_philox");
+}
+
+int lint_philox_uniforms(int dim, int dtype, int64_t N, uint64_t seed, uint64_t offset,
+                         double *u_dev, lint_stream_t stream) {
+    return uniforms_dispatch(dim, dtype, N, PhiloxMaker{seed, offset}, u_dev, stream);
+}
+
+int lint_grid_sample_sobol(const lint_grid_t *g, int64_t N, const lint_sobol_t *sobol, void *out_dev,
+                           int64_t *cell_idx_dev, lint_stream_t stream) {
+    if (!sobol) return fail(LINT_ERR_BAD_ARG, "lint_grid_sample_sobol: sobol is NULL");
+    return grid_dispatch(g, N, out_dev, cell_idx_dev, stream, SobolMaker{sobol}, "lint_grid_sample_sobol");
+}
+
+int lint_cells_sample_sobol(const lint_cells_t *c, int64_t N, const lint_sobol_t *sobol, void *out_dev,
+                            int64_t *cell_idx_dev, lint_stream_t stream) {
+    if (!sobol) return fail(LINT_ERR_BAD_ARG, "lint_cells_sample_sobol: sobol is NULL");
+    return cells_dispatch(c, N, out_dev, cell_idx_dev, stream, SobolMaker{sobol}, "lint_cells_sample_sobol");
+}
+
+int lint_sobol_uniforms(int dim, int64_t N, const lint_sobol_t *sobol, double *u_dev,
+                        lint_stream_t stream) {
+    if (!sobol) return fail(LINT_ERR_BAD_ARG, "lint_sobol_uniforms: sobol is NULL");
+    return uniforms_dispatch(dim, LINT_F64, N, SobolMaker{sobol}, u_dev, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,254 @@
+"""``DensityGrid``: rectilinear-grid domain, device resident.
+
+Host-side mirror of the reference class (density_structures/grid.py:6-518):
+same constructor, attributes, exceptions and ``choose_cells`` contract.  The
+vertex densities, cell masses, cell CDF and guide table live in HBM as torch
+tensors; every array step of the reference is one C-ABI kernel call.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi, _device
+from .base import DensityStructure
+from .pdfs import GaussianMixture
+
+
+def _is_flat_sequence(obj):
+    """True for a sequence whose first element is not itself a sequence."""
+    return hasattr(obj, "__len__") and not hasattr(obj[0], "__len__")
+
+
+class DensityGrid(DensityStructure):
+    """Rectilinear (not necessarily uniform) k-D grid with the pdf evaluated on
+    its vertices.
+
+    Parameters (as the reference, grid.py:253)
+    ----------
+    edges : 1-D sequence (k = 1) or tuple of k 1-D sequences of cell edges.
+    pdf : callable returning the (unnormalised) density; a
+        ``lintsampler_b200.GaussianMixture`` is evaluated by a fused kernel.
+    vectorizedpdf, pdf_args, pdf_kwargs : as the reference.
+
+    Keyword-only extensions (defaults reproduce the reference)
+    ----------
+    dtype : np.float64 (default) or np.float32 — storage of the vertex
+        densities, arithmetic of the in-cell solve and dtype of the samples.
+        The cell CDF is fp64 either way.
+    device : torch CUDA device (default: current device).
+    cdf_mode : "parallel" (default) or "sequential" (bit-identical to NumPy's
+        ``cumsum``; slower, used for exact parity).
+    pdf_on_device : if True the vectorised ``pdf`` is called with a torch CUDA
+        tensor of shape (npts, k) and must return a torch tensor.
+    """
+
+    def __init__(self, edges, pdf, vectorizedpdf=False, pdf_args=(), pdf_kwargs={},
+                 *, dtype=np.float64, device=None, cdf_mode="parallel", pdf_on_device=False):
+        # --- domain parsing: one flat sequence, or a tuple of them  [grid.py:256-285]
+        if _is_flat_sequence(edges):
+            arrays = [np.array(edges)]
+        elif isinstance(edges, tuple) and _is_flat_sequence(edges[0]):
+            arrays = [np.array(e) for e in edges]
+        else:
+            raise TypeError(
+                "DensityGrid: the evaluation domain must be a single 1D iterable "
+                "or a tuple of 1D iterables.")
+        for arr in arrays:                                     # [grid.py:288-296]
+            if np.any(np.diff(arr) <= 0):
+                raise ValueError("DensityGrid: Edges not monotically increasing.")
+            if not np.all(np.isfinite(arr)):
+                raise ValueError("DensityGrid: Edges not finite-valued.")
+        self._dim = len(arrays)
+        if self._dim > _capi.LINT_MAX_DIM:
+            raise ValueError(f"DensityGrid: at most {_capi.LINT_MAX_DIM} dimensions are supported")
+        self.edgearrays = arrays
+        self._edgeshape = tuple(len(a) for a in arrays)
+        self._mins = np.array([a[0] for a in arrays])
+        self._maxs = np.array([a[-1] for a in arrays])
+        self.shape = tuple(n - 1 for n in self._edgeshape)
+        self.ncells = np.prod(self.shape)
+        self.dtype = _device.check_dtype(dtype)
+        self.cdf_mode = cdf_mode
+        self._device_arg = device
+        self._host_densities = None
+        self._masses_host = None
+        self._evaluate_pdf(pdf, vectorizedpdf, pdf_args, pdf_kwargs, pdf_on_device)
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def dim(self):
+        return self._dim
+
+    @property
+    def mins(self):
+        return self._mins
+
+    @property
+    def maxs(self):
+        return self._maxs
+
+    @property
+    def total_mass(self):
+        return self._total_mass
+
+    @property
+    def vertex_densities(self):
+        """(n0+1, ..., nk-1+1) NumPy array of vertex densities (fp64)."""
+        if self._host_densities is None:
+            self._host_densities = self._V.cpu().numpy().astype(np.float64).reshape(self._edgeshape)
+        return self._host_densities
+
+    @property
+    def masses(self):
+        """Cell masses, shape ``self.shape`` (NumPy, fp64)  [grid.py:411]."""
+        if self._masses_host is None:
+            self._masses_host = self._masses.cpu().numpy().reshape(self.shape)
+        return self._masses_host
+
+    # ------------------------------------------------------------------ build
+    def _evaluate_pdf(self, pdf, vectorizedpdf, pdf_args, pdf_kwargs, pdf_on_device):
+        """Vertex evaluation [grid.py:358-404] then the device build."""
+        npts = int(np.prod(self._edgeshape))
+        fused = isinstance(pdf, GaussianMixture) and not pdf_args and not pdf_kwargs
+        if fused and pdf.dim != self._dim:
+            raise ValueError("DensityGrid: GaussianMixture dimensionality does not match the grid")
+        densities = None
+        dev_densities = None
+        if fused:
+            pass                                    # evaluated by lint_grid_eval_gmm below
+        elif vectorizedpdf and pdf_on_device:
+            import torch
+            dev = _device.require_cuda(self._device_arg)
+            axes = [torch.as_tensor(np.asarray(a, dtype=np.float64), device=dev) for a in self.edgearrays]
+            if self._dim > 1:
+                pts = torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1).reshape(npts, self._dim)
+            else:
+                pts = axes[0]
+            f = pdf(pts, *pdf_args, **pdf_kwargs)
+            if not isinstance(f, torch.Tensor):
+                raise TypeError("DensityGrid: with pdf_on_device=True the pdf must return a torch tensor")
+            if f.numel() != npts:
+                raise ValueError("DensityGrid: pdf returned an array of the wrong size")
+            dev_densities = f.to(device=dev, dtype=torch.float64).reshape(npts)
+        else:
+            if self._dim > 1:
+                mesh = np.stack(np.meshgrid(*self.edgearrays, indexing='ij'), axis=-1)
+                pts = mesh.reshape(npts, self._dim)
+            else:
+                pts = self.edgearrays[0]
+            if vectorizedpdf:
+                densities = np.array(pdf(pts, *pdf_args, **pdf_kwargs), dtype=np.float64)
+            else:
+                densities = np.zeros(npts, dtype=np.float64)
+                for i in range(npts):
+                    densities[i] = pdf(pts[i], *pdf_args, **pdf_kwargs)
+            # validity, on the host because the values are already here  [grid.py:401-404]
+            if np.any(densities < 0):
+                raise ValueError("DensityGrid: Densities can't be negative")
+            if not np.all(np.isfinite(densities)):
+                raise ValueError("DensityGrid: Detected non-finite density")
+            densities = densities.reshape(self._edgeshape)      # ValueError on a bad shape
+            self._host_densities = densities
+        self._build_device(pdf if fused else None, densities, dev_densities)
+
+    def _build_device(self, gmm, densities, dev_densities):
+        import torch
+        dev = _device.require_cuda(self._device_arg)
+        self.device = dev
+        tdt = _device.torch_dtype(self.dtype)
+        npts = int(np.prod(self._edgeshape))
+        ncells = int(self.ncells)
+        self._edges_t = [torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=dev)
+                         for a in self.edgearrays]
+        if densities is not None:
+            self._V = torch.as_tensor(np.ascontiguousarray(densities).reshape(npts), device=dev).to(tdt)
+        elif dev_densities is not None:
+            self._V = dev_densities.to(tdt).contiguous()
+        else:
+            self._V = torch.empty(npts, dtype=tdt, device=dev)
+        self._cdf = None
+        self._guide = None
+        self._guide_bits = 0
+        st = _device.stream_ptr(dev)
+        desc = self._descriptor()
+        if gmm is not None:
+            gs, keep = gmm._as_struct()
+            _capi.call("lint_grid_eval_gmm", C.byref(desc), C.byref(gs), 1.0, st)
+            del keep
+        self._masses = torch.empty(ncells, dtype=torch.float64, device=dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        _capi.call("lint_grid_masses", C.byref(desc), _device.ptr(self._masses), _device.ptr(flags), st)
+        bad = int(flags.item())
+        if bad & _capi.LINT_FLAG_NEGATIVE:                     # [grid.py:401-402]
+            raise ValueError("DensityGrid: Densities can't be negative")
+        if bad & _capi.LINT_FLAG_NONFINITE:                    # [grid.py:403-404]
+            raise ValueError("DensityGrid: Detected non-finite density")
+        self._cdf, self._guide, self._guide_bits, self._total_mass = _device.build_cdf(
+            self._masses, self.cdf_mode, dev)
+
+    def _descriptor(self):
+        d = _capi.LintGrid()
+        d.dim = self._dim
+        d.dtype = _device.lint_dtype(self.dtype)
+        for i, n in enumerate(self.shape):
+            d.ncells[i] = n
+            d.edges_dev[i] = self._edges_t[i].data_ptr()
+        d.vertex_densities_dev = self._V.data_ptr()
+        d.cdf_dev = self._cdf.data_ptr() if self._cdf is not None else None
+        d.guide_dev = self._guide.data_ptr() if self._guide is not None else None
+        d.guide_bits = self._guide_bits
+        return d
+
+    # ------------------------------------------------------------------ sampling entry points
+    def _sample_u(self, u_t, want_cells=False):
+        """(N,k+1) fp64 device uniforms -> (N,k) device samples  [sampling.py:97-127]."""
+        import torch
+        N = u_t.shape[0]
+        out = torch.empty((N, self._dim), dtype=_device.torch_dtype(self.dtype), device=self.device)
+        cells = torch.empty(N, dtype=torch.int64, device=self.device) if want_cells else None
+        desc = self._descriptor()
+        _capi.call("lint_grid_sample_u", C.byref(desc), _device.ptr(u_t), N, _device.ptr(out),
+                   _device.ptr(cells), _device.stream_ptr(self.device))
+        return (out, cells) if want_cells else out
+
+    def _sample_philox(self, N, seed, offset, want_cells=False, out=None):
+        import torch
+        if out is None:
+            out = torch.empty((N, self._dim), dtype=_device.torch_dtype(self.dtype), device=self.device)
+        cells = torch.empty(N, dtype=torch.int64, device=self.device) if want_cells else None
+        desc = self._descriptor()
+        _capi.call("lint_grid_sample_philox", C.byref(desc), N, C.c_uint64(seed), C.c_uint64(offset),
+                   _device.ptr(out), _device.ptr(cells), _device.stream_ptr(self.device))
+        return (out, cells) if want_cells else out
+
+    def _sample_sobol(self, N, sobol_struct, want_cells=False):
+        import torch
+        out = torch.empty((N, self._dim), dtype=_device.torch_dtype(self.dtype), device=self.device)
+        cells = torch.empty(N, dtype=torch.int64, device=self.device) if want_cells else None
+        desc = self._descriptor()
+        _capi.call("lint_grid_sample_sobol", C.byref(desc), N, C.byref(sobol_struct), _device.ptr(out),
+                   _device.ptr(cells), _device.stream_ptr(self.device))
+        return (out, cells) if want_cells else out
+
+    # ------------------------------------------------------------------ DensityStructure API
+    def choose_cells(self, u):
+        """Host-facing cell choice with the reference's return contract
+        [grid.py:325-356]: ``(mins (N,k), maxs (N,k), corners 2^k-tuple of (N,))``.
+        The search itself runs on the device."""
+        import torch
+        u = np.asarray(u, dtype=np.float64).reshape(-1)
+        N = len(u)
+        k = self._dim
+        ufull = np.zeros((N, k + 1))
+        ufull[:, -1] = u
+        _, cells = self._sample_u(torch.as_tensor(ufull, device=self.device), want_cells=True)
+        flat = cells.cpu().numpy()
+        multi = np.unravel_index(flat, self.shape)
+        mins = np.stack([self.edgearrays[d][multi[d]] for d in range(k)], axis=-1)
+        maxs = np.stack([self.edgearrays[d][multi[d] + 1] for d in range(k)], axis=-1)
+        V = self.vertex_densities
+        corners = []
+        for c in range(2 ** k):
+            off = [(c >> (k - 1 - d)) & 1 for d in range(k)]
+            corners.append(V[tuple(multi[d] + off[d] for d in range(k))])
+        return mins, maxs, tuple(corners)

@@ -1,0 +1,328 @@
+"""``LintSampler``: the user-facing sampler, drop-in for the reference class
+(reference lintsampler.py:11-518): same constructor, ``sample(N)`` /
+``reset_domain`` semantics, attributes, exceptions, warnings and return shapes.
+
+All per-sample work runs in fused CUDA kernels through the C ABI.  What differs
+from the reference is confined to keyword-only options whose defaults keep the
+reference's observable behaviour:
+
+``rng_backend``
+    ``"philox"`` (default) draws the uniforms on the device (Philox4x32-10 keyed
+    by the seed, counter advanced per call); ``"numpy"`` draws them on the host
+    with the very ``Generator`` calls of the reference (lintsampler.py:517, 311)
+    so that ``sample(N)`` reproduces the reference bit for bit.
+``dtype``
+    precision for domains this sampler builds itself from ``pdf`` + edges.
+``return_tensor``
+    return the device-resident ``torch`` tensor instead of a NumPy array.
+"""
+import ctypes as C
+from warnings import warn
+
+import numpy as np
+from scipy.stats.qmc import QMCEngine, Sobol
+
+from . import _capi, _device
+from .base import DensityStructure
+from .grid import DensityGrid, _is_flat_sequence
+
+
+def rng_backend_is_philox(sampler):
+    return sampler.rng_backend == "philox"
+
+
+def _boxes_overlap(a_lo, a_hi, b_lo, b_hi):
+    """Axis-aligned boxes overlap unless separated along some axis [utils.py:156-176]."""
+    return not np.any((a_hi <= b_lo) | (b_hi <= a_lo))
+
+
+class LintSampler:
+    """Linear-interpolant sampler for density functions on grids / trees.
+
+    Parameters (as the reference, lintsampler.py:201-205)
+    ----------
+    domain : ``DensityStructure`` | list of them | edges | tuple of edges |
+        list of edges / tuples of edges
+    pdf, vectorizedpdf, pdf_args, pdf_kwargs : density callable and its options
+    seed : None | int | ``numpy.random.Generator``
+    qmc : use quasi-Monte Carlo (scrambled Sobol by default)
+    qmc_engine : optional ``scipy.stats.qmc.QMCEngine`` of dimension k+1
+    """
+
+    def __init__(self, domain, pdf=None, vectorizedpdf=False, pdf_args=(), pdf_kwargs={},
+                 seed=None, qmc=False, qmc_engine=None,
+                 *, rng_backend="philox", dtype=np.float64, device=None, cdf_mode="parallel",
+                 return_tensor=False):
+        if pdf:                                                 # truthiness, then callable
+            if not callable(pdf):                               # [lintsampler.py:208-213]
+                raise TypeError("LintSampler.__init__: Given PDF is not callable.")
+        elif vectorizedpdf or pdf_args or pdf_kwargs:
+            warn("LintSampler.__init__: PDF configuration setting given but no PDF provided.")
+        if rng_backend not in ("philox", "numpy"):
+            raise ValueError("LintSampler: rng_backend must be 'philox' or 'numpy'")
+        self.pdf = pdf
+        self.vectorizedpdf = vectorizedpdf
+        self.pdf_args = pdf_args
+        self.pdf_kwargs = pdf_kwargs
+        self.rng_backend = rng_backend
+        self.return_tensor = return_tensor
+        self._dtype = _device.check_dtype(dtype)
+        self._device_arg = device
+        self._cdf_mode = cdf_mode
+        self._set_grids(domain)
+        self._set_random_state(seed, qmc, qmc_engine)
+
+    # ------------------------------------------------------------------ domains
+    def reset_domain(self, domain):
+        """Swap the domain(s), keeping pdf and random state [lintsampler.py:323-336]."""
+        self._set_grids(domain)
+
+    def _make_grid(self, edges):
+        return DensityGrid(edges, self.pdf, vectorizedpdf=self.vectorizedpdf, pdf_args=self.pdf_args,
+                           pdf_kwargs=self.pdf_kwargs, dtype=self._dtype, device=self._device_arg,
+                           cdf_mode=self._cdf_mode)
+
+    def _set_grids(self, domain):
+        """Normalise ``domain`` into ``self.grids`` [lintsampler.py:339-436]."""
+        prebuilt_msg = ("LintSampler.__set_grids: Pre-constructed DensityStructure provided, "
+                        "so `pdf` parameter is redundant.")
+        no_pdf_msg = "LintSampler._set_grids: No PDF provided and no pre-constructed DensityStructure."
+        mixed_msg = "LintSampler._set_grids: List members of different types"
+        if isinstance(domain, DensityStructure):
+            grids = [domain]
+            if self.pdf:
+                warn(prebuilt_msg)
+        elif isinstance(domain, list) and all(isinstance(g, DensityStructure) for g in domain):
+            if not all(isinstance(g, type(domain[0])) for g in domain):
+                raise TypeError(mixed_msg)
+            grids = domain
+            if self.pdf:
+                warn(prebuilt_msg)
+        elif isinstance(domain, list) and not _is_flat_sequence(domain):
+            if not self.pdf:
+                raise ValueError(no_pdf_msg)
+            if not all(isinstance(g, type(domain[0])) for g in domain):
+                raise TypeError(mixed_msg)
+            grids = [self._make_grid(edges) for edges in domain]
+        else:
+            if not self.pdf:
+                raise ValueError(no_pdf_msg)
+            grids = [self._make_grid(domain)]
+        dim = grids[0].dim
+        for g in grids[1:]:
+            if g.dim != dim:
+                raise ValueError(
+                    f"LintSampler._set_grids: Grids have mismatched dimensions: {g.dim} and {dim}")
+        for i in range(len(grids) - 1):
+            for j in range(i + 1, len(grids)):
+                if _boxes_overlap(grids[i].mins, grids[i].maxs, grids[j].mins, grids[j].maxs):
+                    raise ValueError(f"LintSampler._set_grids: Grids {i} and {j} spatially overlapping.")
+        self.grids = grids
+        self.ngrids = len(grids)
+        self.dim = dim
+
+    # ------------------------------------------------------------------ random state
+    def _set_random_state(self, seed, qmc, qmc_engine):
+        """[lintsampler.py:438-498]; plus the device Philox key/counter."""
+        self.qmc = qmc
+        self.rng = np.random.default_rng(seed)               # TypeError for e.g. seed=42.5
+        if qmc:
+            if qmc_engine is None:
+                qmc_engine = Sobol(d=self.dim + 1, bits=32, seed=seed)
+            elif isinstance(qmc_engine, QMCEngine):
+                if qmc_engine.d != self.dim + 1:
+                    raise ValueError(
+                        f"LintSampler.__init__: qmc_engine inconsistent: expected {self.dim + 1}.")
+                if seed is not None:
+                    warn("LintSampler.__init__: pre-condigured qmc_engine provided, so given random "
+                         "seed won't be used except for final array shuffle.")
+            else:
+                raise TypeError("qmc_engine must be QMCEngine instance or None")
+        elif qmc_engine is not None:
+            warn("LintSampler.__init__: provided qmc_engine won't be used as qmc switched off.")
+        self.qmc_engine = qmc_engine
+        # device stream: 64-bit Philox key.  An int seed is the key; a caller's
+        # Generator is shared and consumed, as the reference shares it
+        # (lintsampler.py:72-77,458); None draws fresh entropy.
+        if isinstance(seed, (int, np.integer)) and 0 <= int(seed) < 2 ** 64:
+            self._philox_key = int(seed)
+        elif isinstance(seed, np.random.Generator) and rng_backend_is_philox(self):
+            self._philox_key = int(seed.integers(0, 2 ** 64, dtype=np.uint64))
+        else:
+            ss = seed if isinstance(seed, np.random.SeedSequence) else np.random.SeedSequence(
+                seed if isinstance(seed, (int, np.integer, type(None))) else None)
+            self._philox_key = int(ss.generate_state(1, np.uint64)[0])
+        self._philox_offset = 0
+
+    # ------------------------------------------------------------------ uniform sources
+    def _device(self):
+        return _device.require_cuda(self._device_arg)
+
+    def _sobol_on_device(self):
+        """A scipy Sobol engine with 32-bit output can be replayed on the device
+        by direct index; anything else is drawn on the host."""
+        e = self.qmc_engine
+        return (type(e) is Sobol and getattr(e, "bits", None) == 32
+                and getattr(e, "_sv", None) is not None and e._sv.dtype == np.uint32
+                and e._sv.shape == (self.dim + 1, 32))
+
+    def _sobol_precheck(self, n):
+        """The checks scipy's ``Sobol.random`` would make for this draw (the
+        reference's tests expect its non-power-of-two UserWarning)."""
+        e = self.qmc_engine
+        if e.num_generated + n > e.maxn:
+            raise ValueError(
+                f"At most 2**{e.bits}={e.maxn} distinct points can be generated. "
+                f"{e.num_generated} points have been previously generated, then: "
+                f"n={e.num_generated}+{n}={e.num_generated + n}. Consider increasing `bits`.")
+        if e.num_generated == 0 and n & (n - 1):
+            warn("The balance properties of Sobol' points require n to be a power of 2.")
+
+    def _sobol_struct(self):
+        e = self.qmc_engine
+        s = _capi.LintSobol()
+        for j in range(self.dim + 1):
+            for b in range(32):
+                s.sv[j][b] = int(e._sv[j, b])
+            s.shift[j] = int(e._shift[j])
+        s.first_index = int(e.num_generated)
+        return s
+
+    def _host_uniforms(self, n):
+        """[lintsampler.py:500-518] on the host, uploaded."""
+        import torch
+        if self.qmc:
+            u = self.qmc_engine.random(n)
+        else:
+            u = self.rng.random((n, self.dim + 1))
+        return torch.as_tensor(np.ascontiguousarray(u, dtype=np.float64), device=self._device())
+
+    def _device_uniforms(self, n):
+        """The (n,k+1) matrix the fused device samplers would consume, materialised
+        (needed only for lists of domains, where rows must be routed by value)."""
+        import torch
+        dev = self._device()
+        u = torch.empty((n, self.dim + 1), dtype=torch.float64, device=dev)
+        if self.qmc:
+            self._sobol_precheck(n)
+            s = self._sobol_struct()
+            _capi.call("lint_sobol_uniforms", self.dim, n, C.byref(s), _device.ptr(u),
+                       _device.stream_ptr(dev))
+            self.qmc_engine.fast_forward(n)
+        else:
+            _capi.call("lint_philox_uniforms", self.dim, _device.lint_dtype(self._domain_dtype()), n,
+                       C.c_uint64(self._philox_key), C.c_uint64(self._philox_offset), _device.ptr(u),
+                       _device.stream_ptr(dev))
+            self._philox_offset += n
+        return u
+
+    def _domain_dtype(self):
+        return np.dtype(getattr(self.grids[0], "dtype", np.float64))
+
+    def _uses_host_uniforms(self):
+        if self.qmc:
+            return not self._sobol_on_device()
+        return self.rng_backend == "numpy"
+
+    # ------------------------------------------------------------------ sampling
+    def _sample_domain_u(self, grid, u_t):
+        """One domain, uniforms given on the device  [sampling.py:97-127]."""
+        import torch
+        if hasattr(grid, "_sample_u"):
+            return grid._sample_u(u_t)
+        # generic DensityStructure: its own choose_cells on the host, then the
+        # in-cell stage on the device
+        u_host = u_t.cpu().numpy()
+        mins, maxs, corners = grid.choose_cells(u_host[:, -1])
+        dev = self._device()
+        n = u_t.shape[0]
+        k = self.dim
+        mins_t = torch.as_tensor(np.ascontiguousarray(mins, dtype=np.float64).reshape(n, k), device=dev)
+        maxs_t = torch.as_tensor(np.ascontiguousarray(maxs, dtype=np.float64).reshape(n, k), device=dev)
+        corn_t = torch.as_tensor(np.ascontiguousarray(np.stack(corners), dtype=np.float64), device=dev)
+        out = torch.empty((n, k), dtype=torch.float64, device=dev)
+        _capi.call("lint_incell_sample_u", k, n, _device.ptr(mins_t), _device.ptr(maxs_t),
+                   _device.ptr(corn_t), _device.ptr(u_t), _device.ptr(out), _device.stream_ptr(dev))
+        return out
+
+    def _sample_single(self, grid, n):
+        """Single domain: fused kernel with device-generated uniforms where possible."""
+        native = hasattr(grid, "_sample_philox")
+        if self._uses_host_uniforms() or not native:
+            u = self._host_uniforms(n) if self._uses_host_uniforms() else self._device_uniforms(n)
+            return self._sample_domain_u(grid, u)
+        if self.qmc:
+            self._sobol_precheck(n)
+            s = self._sobol_struct()
+            x = grid._sample_sobol(n, s)
+            self.qmc_engine.fast_forward(n)
+            return x
+        x = grid._sample_philox(n, self._philox_key, self._philox_offset)
+        self._philox_offset += n
+        return x
+
+    def _sample_multi(self, n):
+        """List of domains  [lintsampler.py:281-307]: domain chosen by the same
+        uniform that then (rescaled) chooses the cell; rows grouped by domain."""
+        import torch
+        u = self._host_uniforms(n) if self._uses_host_uniforms() else self._device_uniforms(n)
+        masses = np.array([g.total_mass for g in self.grids])
+        p = masses / masses.sum()
+        c = p.cumsum()
+        cdf_t = torch.as_tensor(c / c[-1], device=u.device)
+        bounds = np.append(0, p.cumsum())
+        choice = torch.searchsorted(cdf_t, u[:, -1].contiguous(), right=True)
+        parts = []
+        for i, grid in enumerate(self.grids):
+            rows = (choice == i).nonzero(as_tuple=True)[0]
+            if rows.numel():
+                usub = u[rows].clone()
+                usub[:, -1] = (usub[:, -1] - bounds[i]) / (bounds[i + 1] - bounds[i])
+                parts.append(self._sample_domain_u(grid, usub).to(torch.float64))
+        return torch.cat(parts, dim=0)
+
+    def sample(self, N=None):
+        """Draw ``N`` samples (one if ``N`` is None)  [lintsampler.py:233-321].
+
+        Returns a scalar / (k,) for ``N=None``; (N,) in 1-D; (N,k) otherwise.
+        """
+        if N is not None:
+            if not isinstance(N, int):
+                raise TypeError(f"LintSampler.sample: Expected int N, got {type(N)}")
+            if N <= 0:
+                raise ValueError(f"LintSampler.sample: Expected positive N, got {N}")
+        n = N if N else 1
+        if self.ngrids == 1:
+            X = self._sample_single(self.grids[0], n)
+        else:
+            X = self._sample_multi(n)
+        X = self._finalise_order(X, N)
+        if self.return_tensor:
+            if not N:
+                return X[0, 0] if self.dim == 1 else X[0]
+            return X.squeeze() if self.dim == 1 else X
+        X = X.cpu().numpy()
+        if N and self._host_shuffle():
+            self.rng.shuffle(X, axis=0)                         # [lintsampler.py:310-311]
+        if not N and self.dim == 1:
+            return X.item()
+        if not N:
+            return X[0]
+        if self.dim == 1:
+            return X.squeeze()
+        return X
+
+    # ------------------------------------------------------------------ row order
+    def _host_shuffle(self):
+        """The reference shuffles the rows of every multi-sample draw with
+        ``rng.shuffle`` (lintsampler.py:309-311).  With ``rng_backend="numpy"``
+        that exact call is replayed on the host.  With device-generated
+        independent Philox rows from a single domain the rows are already
+        exchangeable and the shuffle is skipped; quasi-random or domain-grouped
+        rows are permuted on the host with ``self.rng`` as in the reference."""
+        if self.rng_backend == "numpy":
+            return True
+        return self.qmc or self.ngrids > 1
+
+    def _finalise_order(self, X, N):
+        return X

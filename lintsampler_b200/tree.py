@@ -1,0 +1,462 @@
+"""``DensityTree``: adaptive 2^k-tree domain.
+
+Host-side mirror of the reference class (density_structures/tree.py:10-541):
+same constructor, ``refine`` / ``get_leaf_at_pos`` / ``choose_cells`` contract,
+exceptions, warnings and — crucially — the same *leaf order*, because the order
+of ``tree.leaves`` defines the leaf CDF (tree.py:335-338).
+
+Construction and Romberg refinement are sequential, user-pdf-bound host logic
+(SURVEY.md §2 row 4 keeps them on the host); this implementation batches the
+pdf evaluations of every cell opened in a sweep and keeps per-leaf data in flat
+arrays.  Sampling runs on the device over the flattened leaf table
+(``lint_cells_sample_*``).
+"""
+import ctypes as C
+from warnings import warn
+
+import numpy as np
+
+from . import _capi, _device
+from .base import DensityStructure
+
+
+class TreeCell:
+    """One node of the tree (reference ``_TreeCell``, tree.py:544-703).
+
+    Attributes kept API-compatible with the reference: ``parent``, ``idx``,
+    ``level``, ``x`` (origin position), ``dx`` (extent), ``vol``,
+    ``corner_densities`` (2^k, corner order), ``mass_raw``,
+    ``romberg_estimates``, ``mass_romberg``, ``children`` (tuple or None).
+    ``origin`` holds the integer lattice coordinates of the cell at its level.
+    """
+    __slots__ = ("parent", "idx", "level", "origin", "x", "dx", "vol", "corner_densities",
+                 "mass_raw", "romberg_estimates", "mass_romberg", "children")
+
+    def __init__(self, parent, idx, level, origin):
+        self.parent = parent
+        self.idx = idx
+        self.level = level
+        self.origin = origin
+        self.children = None
+
+
+def _unit_corners(k):
+    """(2^k, k) corner offsets, dim 0 = most significant bit  [utils.py:37-74]."""
+    c = np.arange(2 ** k)[:, None]
+    return (c >> (k - 1 - np.arange(k))[None, :]) & 1
+
+
+class _VertexEvaluator:
+    """Evaluates the pdf on lattice vertices ``mins + c * (maxs-mins)/2^level``
+    with an optional cache keyed by the vertex's coarsest (level, coords)
+    representation (the reference's ``_GridCache``, tree.py:707-929)."""
+
+    def __init__(self, mins, maxs, pdf, vectorized, args, kwargs, usecache):
+        self.mins, self.maxs = mins, maxs
+        self.pdf, self.vectorized, self.args, self.kwargs = pdf, vectorized, args, kwargs
+        self.usecache = usecache
+        self.k = len(mins)
+        self.cache = {}
+
+    def positions(self, coords, level):
+        return self.mins + coords * ((self.maxs - self.mins) / 2 ** level)   # tree.py:866-867
+
+    def _call(self, pos):
+        """pdf on an (n,k) batch of positions -> (n,) fp64."""
+        n = len(pos)
+        if self.k == 1:
+            pos = pos[..., 0]                                   # tree.py:813-814
+        if self.vectorized:
+            out = np.empty(n, dtype=np.float64)
+            try:
+                out[:] = self.pdf(pos, *self.args, **self.kwargs)   # NumPy assignment rules, as
+            except TypeError:                                       # the reference (tree.py:816-822)
+                raise ValueError("DensityTree: pdf function does not return appropriate shape.")
+            return out
+        out = np.empty(n, dtype=np.float64)
+        for i in range(n):
+            try:
+                out[i] = self.pdf(pos[i], *self.args, **self.kwargs)
+            except TypeError:
+                raise ValueError("DensityTree: pdf function does not return appropriate shape.")
+        return out
+
+    def eval(self, coords, level):
+        """Densities at integer lattice ``coords`` (n,k) of refinement ``level``."""
+        coords = np.asarray(coords, dtype=np.int64)
+        n = len(coords)
+        if not self.usecache:
+            return self._call(self.positions(coords, level))
+        # canonical representation: halve while every coordinate is even
+        cc = coords.copy()
+        lev = np.full(n, level, dtype=np.int64)
+        while True:
+            m = (lev > 0) & np.all(cc % 2 == 0, axis=1)
+            if not m.any():
+                break
+            cc[m] //= 2
+            lev[m] -= 1
+        keys = [(int(l),) + tuple(int(v) for v in row) for l, row in zip(lev, cc)]
+        out = np.empty(n, dtype=np.float64)
+        missing = {}
+        for i, key in enumerate(keys):
+            v = self.cache.get(key)
+            if v is None:
+                missing.setdefault(key, []).append(i)
+            else:
+                out[i] = v
+        if missing:
+            first = np.array([ix[0] for ix in missing.values()])
+            vals = self._call(self.positions(coords[first], level))
+            for (key, ix), v in zip(missing.items(), vals):
+                self.cache[key] = v
+                out[ix] = v
+        return out
+
+
+class DensityTree(DensityStructure):
+    """Tree-like domain over the box ``[mins, maxs]``.
+
+    Parameters (as the reference, tree.py:228-232)
+    ----------
+    mins, maxs : scalars (1-D) or length-k sequences.
+    pdf, vectorizedpdf, pdf_args, pdf_kwargs : as ``DensityGrid``.
+    min_openings : number of full openings at construction.
+    usecache : memoise pdf evaluations on shared vertices.
+    batch : evaluate all vertices of a cell's children in one vectorised call.
+
+    Keyword-only extensions: ``dtype``, ``device``, ``cdf_mode`` as ``DensityGrid``.
+    """
+
+    def __init__(self, mins, maxs, pdf, vectorizedpdf=False, pdf_args=(), pdf_kwargs={},
+                 min_openings=1, usecache=True, batch=False,
+                 *, dtype=np.float64, device=None, cdf_mode="parallel"):
+        if not hasattr(mins, "__len__"):
+            mins, maxs = np.array([mins]), np.array([maxs])
+        else:
+            mins, maxs = np.array(mins), np.array(maxs)
+        if len(maxs) != len(mins):
+            raise ValueError("DensityTree.__init__: mins and maxs have different lengths.")
+        for arr in (mins, maxs):                                # tree.py:248-262
+            if arr.ndim != 1:
+                raise ValueError("DensityTree.__init__: Need 1D array of minima/maxima.")
+            if np.any((maxs - mins) <= 0):
+                raise ValueError("DensityTree.__init__: Coordinates not monotically increasing.")
+            if not np.all(np.isfinite(arr)):
+                raise ValueError("DensityTree.__init__: Coordinates not finite-valued.")
+        if len(mins) > _capi.LINT_MAX_DIM:
+            raise ValueError(f"DensityTree: at most {_capi.LINT_MAX_DIM} dimensions are supported")
+        if batch and usecache:
+            warn("DensityTree.__init__: `usecache` set to True but cache not used if `batch=True`")
+        self._mins, self._maxs, self._dim = mins, maxs, len(mins)
+        self.usecache, self.batch = usecache, batch
+        self.dtype = _device.check_dtype(dtype)
+        self.cdf_mode = cdf_mode
+        self._device_arg = device
+        self._table = None          # device leaf table, rebuilt lazily
+        self._corners01 = _unit_corners(self._dim)
+        self._eval = _VertexEvaluator(mins, maxs, pdf, vectorizedpdf or batch, pdf_args, pdf_kwargs,
+                                      usecache and not batch)
+        self.root = TreeCell(None, 0, 0, np.zeros(self._dim, dtype=np.int64))
+        self._finish_cells([self.root])
+        leaves = [self.root]
+        for _ in range(min_openings):                           # tree.py:285-291
+            self._open(leaves)
+            leaves = [child for leaf in leaves for child in leaf.children]
+        self.leaves = leaves
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def dim(self):
+        return self._dim
+
+    @property
+    def mins(self):
+        return self._mins
+
+    @property
+    def maxs(self):
+        return self._maxs
+
+    @property
+    def _leaf_masses(self):
+        return np.array([leaf.mass_raw for leaf in self.leaves])
+
+    @property
+    def total_mass(self):
+        return np.sum(self._leaf_masses)
+
+    # ------------------------------------------------------------------ construction
+    def _open(self, cells):
+        """Create the 2^k children of every cell in ``cells`` (tree.py:615-647),
+        evaluating all their corner densities in one batch."""
+        k = self._dim
+        for cell in cells:
+            kids = []
+            for j in range(2 ** k):
+                kids.append(TreeCell(cell, cell.idx * 2 ** k + j, cell.level + 1,
+                                     2 * cell.origin + self._corners01[j]))
+            cell.children = tuple(kids)
+        self._finish_cells([kid for cell in cells for kid in cell.children])
+        self._table = None
+
+    def _finish_cells(self, cells):
+        """Evaluate corner densities, trapezoid mass and Romberg estimates."""
+        k = self._dim
+        nc = 2 ** k
+        span = self._maxs - self._mins
+        # corner densities, one pdf batch per refinement level present
+        by_level = {}
+        for cell in cells:
+            by_level.setdefault(cell.level, []).append(cell)
+        for level, group in by_level.items():
+            lattice = (np.stack([c.origin for c in group])[:, None, :]
+                       + self._corners01[None, :, :]).reshape(-1, k)
+            f = self._eval.eval(lattice, level).reshape(len(group), nc)
+            if np.any(f < 0):                                   # tree.py:598-601
+                raise ValueError("DensityTree: Densities can't be negative")
+            if not np.all(np.isfinite(f)):                      # tree.py:602-605
+                raise ValueError("DensityTree: Detected non-finite density")
+            dx = span / 2 ** level
+            vol = np.prod(dx)
+            mass = vol * (np.sum(f, axis=1) / nc)               # vol * average  [tree.py:608]
+            for cell, fc, m in zip(group, f, mass):
+                cell.dx = dx
+                cell.vol = vol
+                cell.x = self._mins + cell.origin * dx
+                cell.corner_densities = fc
+                cell.mass_raw = m
+        # Romberg estimates: siblings share their whole ancestor chain
+        done = set()
+        for cell in cells:
+            if id(cell) in done:
+                continue
+            sibs = [cell] if cell.parent is None else [c for c in cell.parent.children]
+            for s in sibs:
+                done.add(id(s))
+            self._romberg(sibs)
+
+    def _romberg(self, sibs):
+        """Richardson-extrapolated masses of sibling cells  [tree.py:649-703].
+
+        ``raws[:, 0]`` is each cell's own trapezoid mass; ``raws[:, j]`` is the
+        mass its j-th ancestor's multilinear interpolant assigns to it (value
+        at the cell's midpoint times the cell volume)."""
+        k = self._dim
+        level = sibs[0].level
+        n = len(sibs)
+        raws = np.empty((n, level + 1))
+        raws[:, 0] = [s.mass_raw for s in sibs]
+        origins = np.stack([s.origin for s in sibs]).astype(np.float64)
+        anc = sibs[0]
+        for j in range(1, level + 1):
+            anc = anc.parent
+            # midpoint of each cell in the ancestor's unit cube (dyadic, exact)
+            mid = (origins + 0.5) / 2 ** j - anc.origin
+            w = np.stack((1 - mid[:, 0], mid[:, 0]), axis=-1)
+            for d in range(1, k):
+                rd = np.stack((1 - mid[:, d], mid[:, d]), axis=-1)
+                w = (w[:, :, None] * rd[:, None, :]).reshape(n, -1)
+            fmid = np.sum(anc.corner_densities[None, :] * w, axis=1)
+            raws[:, j] = fmid * anc.vol / 2 ** (j * k)
+        est = np.empty((n, level + 1))
+        est[:, 0] = raws[:, 0]
+        cur = raws.copy()
+        for i in range(level):
+            cur = cur[:, :-1] - np.diff(cur, axis=1) / (4 ** (i + 1) - 1)
+            est[:, i + 1] = cur[:, 0]
+        for s, e in zip(sibs, est):
+            s.romberg_estimates = list(e)
+            s.mass_romberg = e[-1]
+
+    @staticmethod
+    def _leaf_error(leaf):
+        e = leaf.romberg_estimates
+        return np.abs(e[-1] - e[-2])
+
+    # ------------------------------------------------------------------ refinement
+    def refine(self, tree_tol, leaf_tol=0.01, leaf_mass_contribution_tol=0.01, verbose=False):
+        """Open leaves with large Romberg mass-error estimates  [tree.py:357-488].
+
+        Stage 1 repeatedly opens every leaf whose last Romberg correction exceeds
+        ``leaf_tol`` of its mass (ignoring leaves lighter than
+        ``leaf_mass_contribution_tol`` times the mean leaf); stage 2 repeatedly
+        opens the single worst leaf until the tree-wide fractional error drops
+        below ``tree_tol``.
+        """
+        if len(self.leaves) == 1:
+            raise RuntimeError(
+                "DensityTree.refine: Romberg refinement needs at least two tree levels "
+                "to estimate mass errors. Instantiate tree with min_openings>0.")
+        if verbose:
+            print(f"Pre-loop: {len(self.leaves)} leaves on tree. Total mass={self.total_mass}")
+
+        m_rom = np.array([leaf.mass_romberg for leaf in self.leaves])
+        errs = np.array([self._leaf_error(leaf) for leaf in self.leaves])
+        sweep = 0
+        while True:
+            sweep += 1
+            sel = np.where((errs > leaf_tol * m_rom)
+                           & (m_rom > leaf_mass_contribution_tol * np.nanmean(m_rom)))[0]
+            if len(sel):
+                opened = [self.leaves[i] for i in sel[::-1]]       # reversed index order
+                keep = np.ones(len(self.leaves), dtype=bool)
+                keep[sel] = False
+                self._open(opened)
+                fresh = [kid for cell in opened for kid in cell.children]
+                self.leaves = [leaf for leaf, kp in zip(self.leaves, keep) if kp] + fresh
+                m_rom = np.concatenate((m_rom[keep], [c.mass_romberg for c in fresh]))
+                errs = np.concatenate((errs[keep], [self._leaf_error(c) for c in fresh]))
+            if verbose:
+                print(f"End of leaf iteration {sweep}: {len(self.leaves)} leaves on tree. "
+                      f"Total mass={np.sum(m_rom)}, with mean leaf mass={np.nanmean(m_rom)}")
+            if not len(sel):
+                break
+
+        m_rom = np.array([leaf.mass_romberg for leaf in self.leaves])
+        m_raw = np.array([leaf.mass_raw for leaf in self.leaves])
+        it = 0
+        while True:
+            it += 1
+            m_tot = np.sum(m_rom)
+            sq = (m_rom - m_raw) ** 2
+            err_tot = np.sqrt(np.sum(sq))
+            if err_tot / m_tot < tree_tol:
+                break
+            worst = int(np.argmax(sq))
+            cell = self.leaves.pop(worst)
+            self._open([cell])
+            self.leaves += list(cell.children)
+            m_rom = np.concatenate((np.delete(m_rom, worst), [c.mass_romberg for c in cell.children]))
+            m_raw = np.concatenate((np.delete(m_raw, worst), [c.mass_raw for c in cell.children]))
+            if verbose:
+                print(f"End of tree iteration {it}: {len(self.leaves)} leaves on tree. "
+                      f"Total mass={m_tot}. Fractional error={err_tot / m_tot}.")
+        self._table = None
+
+    def get_leaf_at_pos(self, pos):
+        """Leaf containing ``pos``  [tree.py:490-541]."""
+        pos = np.array([pos]) if not hasattr(pos, "__len__") else np.array(pos)
+        if pos.shape != (self._dim,):
+            raise ValueError(
+                f"DensityTree.get_leaf_at_pos: Shape of input pos: {pos.shape} does not make sense.")
+        r = (pos - self._mins) / (self._maxs - self._mins)
+        if not np.all((r >= 0) & (r <= 1)):
+            raise ValueError("DensityTree.get_leaf_at_pos: Requested pos falls outside tree.")
+        cell = self.root
+        weights = 2 ** np.arange(self._dim)[::-1]
+        while cell.children:
+            upper = (r > 0.5).astype(int)
+            cell = cell.children[int(upper.dot(weights))]
+            r = 2 * r - upper
+        return cell
+
+    # ------------------------------------------------------------------ device leaf table
+    def leaf_table(self):
+        """Host arrays ``(x (L,k), dx (L,k), corners (L,2^k), mass (L,))`` in leaf order."""
+        L, k = len(self.leaves), self._dim
+        x = np.array([leaf.x for leaf in self.leaves], dtype=np.float64).reshape(L, k)
+        dx = np.array([leaf.dx for leaf in self.leaves], dtype=np.float64).reshape(L, k)
+        cd = np.array([leaf.corner_densities for leaf in self.leaves], dtype=np.float64).reshape(L, 2 ** k)
+        m = np.array([leaf.mass_raw for leaf in self.leaves], dtype=np.float64)
+        return x, dx, cd, m
+
+    def _ensure_device(self):
+        if self._table is not None:
+            return self._table
+        self._table = _CellTable(*self.leaf_table(), dtype=self.dtype, device=self._device_arg,
+                                 cdf_mode=self.cdf_mode)
+        self.device = self._table.device
+        return self._table
+
+    def _sample_u(self, u_t, want_cells=False):
+        return self._ensure_device().sample_u(u_t, want_cells)
+
+    def _sample_philox(self, N, seed, offset, want_cells=False, out=None):
+        return self._ensure_device().sample_philox(N, seed, offset, want_cells, out)
+
+    def _sample_sobol(self, N, sobol_struct, want_cells=False):
+        return self._ensure_device().sample_sobol(N, sobol_struct, want_cells)
+
+    def choose_cells(self, u):
+        """Reference return contract  [tree.py:314-355]; the search runs on the device."""
+        import torch
+        table = self._ensure_device()
+        u = np.asarray(u, dtype=np.float64).reshape(-1)
+        ufull = np.zeros((len(u), self._dim + 1))
+        ufull[:, -1] = u
+        _, cells = table.sample_u(torch.as_tensor(ufull, device=table.device), want_cells=True)
+        idx = cells.cpu().numpy()
+        x, dx, cd, _ = self.leaf_table()
+        return x[idx], x[idx] + dx[idx], tuple(cd[idx].T)
+
+
+class _CellTable:
+    """Device copy of a flat cell list + its CDF/guide table (``lint_cells_t``)."""
+
+    def __init__(self, mins, widths, corners, masses, dtype, device, cdf_mode):
+        import torch
+        dev = _device.require_cuda(device)
+        self.device = dev
+        self.dtype = np.dtype(dtype)
+        self.dim = mins.shape[1]
+        self.ncells = mins.shape[0]
+        tdt = _device.torch_dtype(dtype)
+        self._mins = torch.as_tensor(np.ascontiguousarray(mins), device=dev)
+        self._widths = torch.as_tensor(np.ascontiguousarray(widths), device=dev)
+        self._corners = torch.as_tensor(np.ascontiguousarray(corners), device=dev).to(tdt).contiguous()
+        self._masses = torch.as_tensor(np.ascontiguousarray(masses), device=dev)
+        self._cdf = None
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        desc = self.descriptor(need_cdf=False)
+        _capi.call("lint_cells_check", C.byref(desc), _device.ptr(flags), _device.stream_ptr(dev))
+        bad = int(flags.item())
+        if bad & _capi.LINT_FLAG_NEGATIVE:
+            raise ValueError("Cell list: Densities can't be negative")
+        if bad & _capi.LINT_FLAG_NONFINITE:
+            raise ValueError("Cell list: Detected non-finite density")
+        self._cdf, self._guide, self._guide_bits, self.total_mass = _device.build_cdf(
+            self._masses, cdf_mode, dev)
+
+    def descriptor(self, need_cdf=True):
+        d = _capi.LintCells()
+        d.dim = self.dim
+        d.dtype = _device.lint_dtype(self.dtype)
+        d.ncells = self.ncells
+        d.mins_dev = self._mins.data_ptr()
+        d.widths_dev = self._widths.data_ptr()
+        d.corners_dev = self._corners.data_ptr()
+        if need_cdf:
+            d.cdf_dev = self._cdf.data_ptr()
+            d.guide_dev = self._guide.data_ptr()
+            d.guide_bits = self._guide_bits
+        return d
+
+    def _alloc(self, N, want_cells, out=None):
+        import torch
+        if out is None:
+            out = torch.empty((N, self.dim), dtype=_device.torch_dtype(self.dtype), device=self.device)
+        cells = torch.empty(N, dtype=torch.int64, device=self.device) if want_cells else None
+        return out, cells
+
+    def sample_u(self, u_t, want_cells=False):
+        N = u_t.shape[0]
+        out, cells = self._alloc(N, want_cells)
+        desc = self.descriptor()
+        _capi.call("lint_cells_sample_u", C.byref(desc), _device.ptr(u_t), N, _device.ptr(out),
+                   _device.ptr(cells), _device.stream_ptr(self.device))
+        return (out, cells) if want_cells else out
+
+    def sample_philox(self, N, seed, offset, want_cells=False, out=None):
+        out, cells = self._alloc(N, want_cells, out)
+        desc = self.descriptor()
+        _capi.call("lint_cells_sample_philox", C.byref(desc), N, C.c_uint64(seed), C.c_uint64(offset),
+                   _device.ptr(out), _device.ptr(cells), _device.stream_ptr(self.device))
+        return (out, cells) if want_cells else out
+
+    def sample_sobol(self, N, sobol_struct, want_cells=False):
+        out, cells = self._alloc(N, want_cells)
+        desc = self.descriptor()
+        _capi.call("lint_cells_sample_sobol", C.byref(desc), N, C.byref(sobol_struct), _device.ptr(out),
+                   _device.ptr(cells), _device.stream_ptr(self.device))
+        return (out, cells) if want_cells else out

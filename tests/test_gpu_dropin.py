@@ -1,0 +1,265 @@
+"""GPU tests at the drop-in boundary: ``LintSampler(...).sample(N)`` against the
+real reference's outputs (golden) and the reference's own behavioural contract
+(shapes, determinism, statistics — modelled on the reference's tests/)."""
+import warnings
+
+import numpy as np
+import pytest
+from scipy import stats
+from scipy.stats.qmc import Halton, Sobol
+
+import pdfs
+from conftest import load_golden, golden_edges
+from oracle import lint_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lb():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import lintsampler_b200
+    return lintsampler_b200
+
+
+PDFS = {
+    "c1_readme_1d": (pdfs.readme_gmm_1d, False),
+    "g1d_nonuniform": (pdfs.GMM(*pdfs.gmm_params(1, seed=3)), True),
+    "g2d_fullcov": (pdfs.GMM(*pdfs.gmm_params(2, seed=1, full_cov=True)), True),
+    "g3d_iso": (pdfs.GMM(*pdfs.gmm_params(3, seed=0)), True),
+    "g3d_holes": (pdfs.bump_with_holes, True),
+    "g2d_flat": (pdfs.flat_pdf, True),
+    "g2d_onecell": (pdfs.GMM(*pdfs.gmm_params(2, seed=4)), True),
+    "g4d_iso": (pdfs.GMM(*pdfs.gmm_params(4, seed=2, smin=0.5, smax=0.9)), True),
+    "g6d_iso": (pdfs.GMM(*pdfs.gmm_params(6, seed=6, smin=0.7, smax=1.1)), True),
+    "g5d_sobol": (pdfs.GMM(*pdfs.gmm_params(5, seed=0, smin=0.5, smax=0.9)), True),
+    "g2d_sobol": (pdfs.GMM(*pdfs.gmm_params(2, seed=1, full_cov=True)), True),
+}
+
+
+def _domain(g):
+    e = golden_edges(g)
+    return tuple(e) if len(e) > 1 else e[0]
+
+
+# ----------------------------------------------------------------------------- exact reproduction of the reference
+@pytest.mark.parametrize("name", list(PDFS))
+def test_sample_reproduces_reference_exactly(lb, name):
+    """Same pdf, domain and seed as the golden run of the real reference; host
+    PCG64 stream (or scipy-identical device Sobol), NumPy-order CDF: the final,
+    shuffled output of sample(N) is bit-identical."""
+    g = load_golden(name)
+    pdf, vec = PDFS[name]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        s = lb.LintSampler(_domain(g), pdf=pdf, vectorizedpdf=vec, seed=int(g["seed"]),
+                           qmc=bool(g["qmc"]), rng_backend="numpy", cdf_mode="sequential")
+        x = s.sample(int(g["N"]))
+    assert np.array_equal(np.atleast_1d(x).reshape(g["x_final"].shape), g["x_final"])
+
+
+@pytest.mark.parametrize("name,pdf,kw,ref", [
+    ("t3d_open3", pdfs.GMM(*pdfs.gmm_params(3, seed=0)), dict(min_openings=3), None),
+    ("t3d_refined", pdfs.GMM(*pdfs.gmm_params(3, K=8, seed=0, smin=0.1, smax=0.4)),
+     dict(min_openings=3), dict(tree_tol=2e-2, leaf_tol=2e-2)),
+    ("t2d_refined", pdfs.GMM(*pdfs.gmm_params(2, seed=1, full_cov=True)), dict(min_openings=2),
+     dict(tree_tol=1e-3)),
+    ("t1d_refined", pdfs.GMM(*pdfs.gmm_params(1, seed=3)), dict(min_openings=2),
+     dict(tree_tol=1e-4, leaf_tol=1e-3)),
+])
+def test_tree_sample_reproduces_reference_exactly(lb, name, pdf, kw, ref):
+    g = load_golden(name)
+    mins, maxs = g["mins"], g["maxs"]
+    if len(mins) == 1:
+        mins, maxs = float(mins[0]), float(maxs[0])
+    tree = lb.DensityTree(mins, maxs, pdf, vectorizedpdf=True, cdf_mode="sequential", **kw)
+    if ref:
+        tree.refine(**ref)
+    x = lb.LintSampler(tree, seed=int(g["seed"]), rng_backend="numpy").sample(int(g["N"]))
+    assert np.array_equal(np.atleast_1d(x).reshape(g["x_final"].shape), g["x_final"])
+
+
+@pytest.mark.parametrize("name,qmc", [("m2d_quadrants", False), ("m1d_halves", False),
+                                      ("m2d_quadrants_sobol", True)])
+def test_multi_domain_reproduces_reference_exactly(lb, name, qmc):
+    g = load_golden(name)
+    k, nd = int(g["k"]), int(g["ndomains"])
+    pdf = (pdfs.GMM(*pdfs.gmm_params(2, seed=1, full_cov=True)) if k == 2
+           else pdfs.GMM(*pdfs.gmm_params(1, seed=3)))
+    doms = []
+    for i in range(nd):
+        e = [g[f"dom{i}_edges{d}"] for d in range(k)]
+        doms.append(tuple(e) if k > 1 else e[0])
+    s = lb.LintSampler(doms, pdf=pdf, vectorizedpdf=True, seed=int(g["seed"]), qmc=qmc,
+                       rng_backend="numpy", cdf_mode="sequential")
+    assert np.array_equal(np.array([gr.total_mass for gr in s.grids]), g["domain_masses"])
+    x = s.sample(int(g["N"]))
+    assert np.array_equal(np.atleast_1d(x).reshape(g["x_final"].shape), g["x_final"])
+
+
+# ----------------------------------------------------------------------------- statistics of the device stream
+def _ks_all_dims(x, y):
+    return min(stats.ks_2samp(x[:, d], y[:, d]).pvalue for d in range(x.shape[1]))
+
+
+@pytest.mark.parametrize("name", ["g1d_nonuniform", "g2d_fullcov", "g3d_iso", "g4d_iso"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_philox_samples_match_reference_distribution(lb, name, dtype):
+    """KS per coordinate and chi^2 over cells against samples drawn by the oracle
+    (== the reference) with an independent NumPy stream."""
+    g = load_golden(name)
+    k = int(g["k"])
+    pdf, vec = PDFS[name]
+    N = 200_000
+    grid = lb.DensityGrid(_domain(g), pdf, vectorizedpdf=vec, dtype=dtype)
+    x = lb.LintSampler(grid, seed=123).sample(N).reshape(N, k).astype(np.float64)
+    u = np.random.default_rng(999).random((N, k + 1))
+    x_ref = O.grid_sample(golden_edges(g), g["vertex_densities"], u)
+    assert _ks_all_dims(x, x_ref) > 1e-4
+    # chi^2 of cell occupancy against the exact cell probabilities
+    edges = golden_edges(g)
+    idx = [np.clip(np.searchsorted(edges[d], x[:, d], side="right") - 1, 0, len(edges[d]) - 2)
+           for d in range(k)]
+    counts = np.bincount(np.ravel_multi_index(idx, tuple(len(e) - 1 for e in edges)),
+                         minlength=g["masses"].size)
+    p = (g["masses"] / g["masses"].sum()).ravel()
+    big = p * N >= 20
+    obs = np.append(counts[big], counts[~big].sum())
+    exp = np.append(p[big], p[~big].sum()) * N
+    keep = exp > 0
+    chi2 = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum()
+    assert stats.chi2.sf(chi2, keep.sum() - 1) > 1e-4
+
+
+def test_gaussian_moments_grid_and_tree(lb):
+    """Model: reference tests/test_lintsampler.py:569-657 (moments to 1 decimal)."""
+    mu, cov = np.array([1.5, -0.5]), np.array([[1.0, 1.2], [1.2, 1.8]])
+    pdf = stats.multivariate_normal(mean=mu, cov=cov).pdf
+    e = (np.linspace(-12, 12, 513), np.linspace(-12, 12, 513))
+    x = lb.LintSampler(e, pdf=pdf, vectorizedpdf=True, seed=42).sample(2 ** 18)
+    assert np.all(np.round(x.mean(axis=0), 1) == mu)
+    assert np.all(np.round(np.cov(x.T), 1) == cov)
+    tree = lb.DensityTree([-12, -12], [12, 12], pdf, vectorizedpdf=True, min_openings=4)
+    tree.refine(1e-3)
+    x = lb.LintSampler(tree, seed=42).sample(2 ** 18)
+    assert np.all(np.round(x.mean(axis=0), 1) == mu)
+    assert np.all(np.round(np.cov(x.T), 1) == cov)
+    xq = lb.LintSampler(e, pdf=pdf, vectorizedpdf=True, seed=42, qmc=True).sample(2 ** 18)
+    assert np.all(np.round(xq.mean(axis=0), 1) == mu)
+
+
+def test_two_component_mixture_on_disjoint_grids(lb):
+    """Model: reference tests/test_lintsampler.py:737-830 (weights by domain)."""
+    def pdf(x):
+        return 0.3 * stats.norm.pdf(x, -5, 1.0) + 0.7 * stats.norm.pdf(x, 5, 0.5)
+    doms = [np.linspace(-10, -1, 257), np.linspace(1, 10, 257)]
+    for qmc in (False, True):
+        x = lb.LintSampler(doms, pdf=pdf, vectorizedpdf=True, seed=7, qmc=qmc).sample(2 ** 17)
+        assert round((x < 0).mean(), 2) == 0.3
+        assert round(x[x < 0].mean(), 1) == -5.0 and round(x[x > 0].std(), 1) == 0.5
+
+
+# ----------------------------------------------------------------------------- shapes, determinism, state
+@pytest.mark.parametrize("qmc", [False, True])
+def test_output_shapes(lb, qmc):
+    """Model: reference tests/test_lintsampler.py:356-514 and SURVEY §8b quirks."""
+    g1 = np.linspace(-10, 10, 65)
+    g2 = (np.linspace(-10, 10, 65), np.linspace(-5, 5, 33))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        s1 = lb.LintSampler(g1, pdf=stats.norm.pdf, vectorizedpdf=True, qmc=qmc)
+        s2 = lb.LintSampler(g2, pdf=stats.multivariate_normal(np.zeros(2), np.eye(2)).pdf,
+                            vectorizedpdf=True, qmc=qmc)
+        assert isinstance(s1.sample(), float)
+        assert s1.sample(16).shape == (16,)
+        assert s1.sample(1).shape == ()
+        assert s2.sample().shape == (2,)
+        assert s2.sample(16).shape == (16, 2)
+        assert s2.sample(1).shape == (1, 2)
+        t1 = lb.DensityTree(-10, 10, stats.norm.pdf, vectorizedpdf=True, min_openings=3)
+        assert lb.LintSampler(t1, qmc=qmc).sample(8).shape == (8,)
+
+
+@pytest.mark.parametrize("qmc", [False, True])
+@pytest.mark.parametrize("backend", ["philox", "numpy"])
+def test_same_seed_same_samples(lb, qmc, backend):
+    """Model: reference tests/test_lintsampler.py:520-541."""
+    g2 = (np.linspace(-10, 10, 65), np.linspace(-5, 5, 33))
+    pdf = stats.multivariate_normal(np.zeros(2), np.eye(2)).pdf
+    a = lb.LintSampler(g2, pdf=pdf, vectorizedpdf=True, seed=42, qmc=qmc, rng_backend=backend)
+    b = lb.LintSampler(g2, pdf=pdf, vectorizedpdf=True, seed=42, qmc=qmc, rng_backend=backend)
+    xa, xb = a.sample(1024), b.sample(1024)
+    assert np.all(xa == xb)
+    # the stream continues rather than restarts
+    assert not np.array_equal(xa, a.sample(1024))
+    a = lb.LintSampler(g2, pdf=pdf, vectorizedpdf=True, seed=np.random.default_rng(42), qmc=qmc,
+                       rng_backend=backend)
+    b = lb.LintSampler(g2, pdf=pdf, vectorizedpdf=True, seed=np.random.default_rng(42), qmc=qmc,
+                       rng_backend=backend)
+    assert np.all(a.sample(1024) == b.sample(1024))
+
+
+def test_user_qmc_engine_reset_replays(lb):
+    """Model: reference tests/test_lintsampler.py:544-552; a Halton engine goes
+    through the host path, a 32-bit Sobol engine through the device path."""
+    g2 = (np.linspace(-10, 10, 65), np.linspace(-5, 5, 33))
+    pdf = stats.multivariate_normal(np.zeros(2), np.eye(2)).pdf
+    for eng in (Halton(d=3, seed=1), Sobol(d=3, bits=32, seed=1), Sobol(d=3, seed=1)):
+        s = lb.LintSampler(g2, pdf=pdf, vectorizedpdf=True, qmc=True, qmc_engine=eng)
+        x1 = s.sample(256)
+        s.rng = np.random.default_rng(0)
+        eng.reset()
+        s.rng = np.random.default_rng(0)
+        x2 = s.sample(256)
+        assert sorted(map(tuple, x1)) == sorted(map(tuple, x2))
+
+
+def test_reset_domain_keeps_random_state(lb):
+    g1 = np.linspace(-10, 10, 65)
+    s = lb.LintSampler(g1, pdf=stats.norm.pdf, vectorizedpdf=True, seed=3)
+    s.sample(100)
+    off = s._philox_offset
+    s.reset_domain(np.linspace(-5, 5, 33))
+    assert s._philox_offset == off and s.grids[0].ncells == 32
+    assert s.sample(10).shape == (10,)
+
+
+def test_sobol_non_power_of_two_warns(lb):
+    """Model: reference tests/test_lintsampler.py:177-181."""
+    g1 = np.linspace(-10, 10, 65)
+    s = lb.LintSampler(g1, pdf=stats.norm.pdf, vectorizedpdf=True, qmc=True)
+    with pytest.warns(UserWarning):
+        s.sample(10)
+
+
+def test_user_defined_density_structure(lb):
+    """A user subclass of the ABC keeps working: its choose_cells runs on the
+    host, the in-cell stage on the device (reference base.py:4-81)."""
+    class TwoCells(lb.DensityStructure):
+        dim, mins, maxs, total_mass = 1, np.array([0.0]), np.array([2.0]), 1.0
+
+        def choose_cells(self, u):
+            right = u >= 0.25
+            lo = np.where(right, 1.0, 0.0)[:, None]
+            return lo, lo + 1.0, (np.where(right, 1.0, 0.0), np.where(right, 1.0, 1.0))
+
+    x = lb.LintSampler(TwoCells(), seed=1).sample(20000)
+    assert x.shape == (20000,) and x.min() >= 0 and x.max() <= 2
+    assert abs((x >= 1).mean() - 0.75) < 0.02
+
+
+def test_device_tensor_return(lb):
+    import torch
+    g3 = tuple(np.linspace(-4, 4, 33) for _ in range(3))
+    gm = lb.GaussianMixture(*_gm3())
+    s = lb.LintSampler(g3, pdf=gm, vectorizedpdf=True, seed=5, dtype=np.float32, return_tensor=True)
+    x = s.sample(100000)
+    assert isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.shape == (100000, 3)
+    assert float(x.min()) >= -4 and float(x.max()) <= 4
+
+
+def _gm3():
+    w, mu, cov = pdfs.gmm_params(3, seed=0)
+    return w, mu, cov

@@ -1,0 +1,341 @@
+"""GPU parity tests, kernel level: every C-ABI entry point against the CPU oracle
+and the golden vectors produced by the real reference.  Bit-exact unless a
+tolerance is written in the test."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, golden_edges
+from oracle import lint_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GRID_CASES = ["c1_readme_1d", "g1d_nonuniform", "g2d_fullcov", "g3d_iso", "g3d_holes",
+              "g2d_flat", "g2d_onecell", "g4d_iso", "g5d_sobol", "g6d_iso", "g2d_sobol"]
+TREE_CASES = ["t3d_open3", "t3d_refined", "t2d_refined", "t2d_batch", "t1d_refined"]
+
+
+@pytest.fixture(scope="module")
+def lb():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import lintsampler_b200
+    return lintsampler_b200
+
+
+def _grid_from_golden(lb, g, **kw):
+    """DensityGrid over the golden vertex densities (pdf = table lookup)."""
+    edges = golden_edges(g)
+    V = g["vertex_densities"]
+    dom = tuple(edges) if len(edges) > 1 else edges[0]
+    return lb.DensityGrid(dom, lambda pts: V.reshape(-1), vectorizedpdf=True, **kw)
+
+
+def _dev(a):
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(a), device="cuda")
+
+
+# ----------------------------------------------------------------------------- build
+@pytest.mark.parametrize("name", GRID_CASES)
+def test_masses_total_cdf_bit_exact(lb, name):
+    g = load_golden(name)
+    grid = _grid_from_golden(lb, g, cdf_mode="sequential")
+    assert np.array_equal(grid.masses, g["masses"])
+    assert grid.total_mass == g["total_mass"]
+    assert np.array_equal(grid._cdf.cpu().numpy(), g["cdf"])
+
+
+@pytest.mark.parametrize("n", [1, 5, 8, 9, 127, 128, 129, 255, 256, 257, 1000, 4097, 65536,
+                               100003, 1 << 20, (1 << 22) + 12345])
+def test_sum_numpy_bit_exact(lb, n):
+    import torch
+    from lintsampler_b200 import _capi, _device
+    rng = np.random.default_rng(n)
+    a = rng.random(n) * np.exp(rng.normal(size=n) * 5)
+    x = _dev(a)
+    nbytes = _capi.load().lint_cdf_scratch_bytes(n)
+    scratch = torch.empty(max(nbytes, 8), dtype=torch.uint8, device="cuda")
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    _capi.call("lint_sum_numpy_f64", _device.ptr(x), n, _device.ptr(out), _device.ptr(scratch), nbytes,
+               _device.stream_ptr(x.device))
+    assert out.item() == np.sum(a)
+    if n <= 4097:
+        assert out.item() == O.numpy_pairwise_sum_emulated(a)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 2047, 2048, 2049, 70000, 1 << 21])
+@pytest.mark.parametrize("mode", ["sequential", "parallel"])
+def test_cdf_modes(lb, n, mode):
+    from lintsampler_b200 import _device
+    rng = np.random.default_rng(n)
+    m = rng.random(n) * np.exp(rng.normal(size=n) * 4)
+    m[rng.random(n) < 0.3] = 0.0                       # zero-mass cells: flat CDF runs
+    if m.sum() == 0:
+        m[0] = 1.0
+    cdf, guide, bits, total = _device.build_cdf(_dev(m), mode, _dev(m).device)
+    cdf = cdf.cpu().numpy()
+    ref = O.cdf_from_masses(m)
+    if mode == "sequential":
+        assert np.array_equal(cdf, ref)
+        assert total == np.sum(m)
+    else:
+        # tiled scan rounds differently from a sequential one; tolerance 1e-12
+        assert np.max(np.abs(cdf - ref)) < 1e-12
+        assert abs(total / np.sum(m) - 1) < 1e-13
+    assert cdf[-1] == 1.0
+    assert np.all(np.diff(cdf) >= 0)
+    zero = np.flatnonzero(m == 0)
+    zero = zero[zero > 0]
+    assert np.array_equal(cdf[zero], cdf[zero - 1])    # zero-mass cells stay unselectable
+    # guide table == searchsorted of the same table at j / G
+    G = 1 << bits
+    gt = guide.cpu().numpy().astype(np.int64)
+    want = np.minimum(cdf.searchsorted(np.arange(G + 1) / G, side="right"), n - 1)
+    assert np.array_equal(gt, want)
+
+
+def test_parallel_cdf_is_deterministic(lb):
+    from lintsampler_b200 import _device
+    rng = np.random.default_rng(0)
+    m = _dev(rng.random(3_000_001))
+    a = _device.build_cdf(m, "parallel", m.device)[0].cpu().numpy()
+    for _ in range(3):
+        assert np.array_equal(a, _device.build_cdf(m, "parallel", m.device)[0].cpu().numpy())
+
+
+def test_density_validity_flags(lb):
+    e = (np.linspace(0, 1, 9), np.linspace(0, 1, 7))
+    import torch
+
+    def neg(p):
+        f = torch.ones(p.shape[0], dtype=torch.float64, device=p.device)
+        f[5] = -1.0
+        return f
+
+    def nan(p):
+        f = torch.ones(p.shape[0], dtype=torch.float64, device=p.device)
+        f[-1] = float("nan")
+        return f
+
+    with pytest.raises(ValueError):
+        lb.DensityGrid(e, neg, vectorizedpdf=True, pdf_on_device=True)
+    with pytest.raises(ValueError):
+        lb.DensityGrid(e, nan, vectorizedpdf=True, pdf_on_device=True)
+    with pytest.raises(ValueError):          # all-zero density: documented deviation
+        lb.DensityGrid(e, lambda p: np.zeros(len(p)), vectorizedpdf=True)
+
+
+@pytest.mark.parametrize("k,full", [(1, False), (2, True), (3, False), (3, True), (5, False), (6, True)])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fused_gmm_vertex_eval(lb, k, full, dtype):
+    import pdfs
+    w, mu, cov = pdfs.gmm_params(k, K=5, seed=k, full_cov=full, smin=0.5, smax=0.9)
+    rng = np.random.default_rng(k)
+    edges = tuple(np.sort(rng.uniform(-4, 4, n)) for n in (9, 7, 8, 5, 6, 4)[:k])
+    dom = edges if k > 1 else edges[0]
+    grid = lb.DensityGrid(dom, lb.GaussianMixture(w, mu, cov), vectorizedpdf=True, dtype=dtype)
+    mesh = np.stack(np.meshgrid(*edges, indexing="ij"), axis=-1)
+    ref = O.gmm_pdf(mesh if k > 1 else edges[0], w, mu, cov)
+    # exp() differs from NumPy's by <= 1 ulp: tolerance 1e-12 (fp64) / fp32 rounding 1e-6
+    np.testing.assert_allclose(grid.vertex_densities, ref, rtol=1e-12 if dtype == np.float64 else 1e-6)
+
+
+# ----------------------------------------------------------------------------- sampling, fed the reference's u
+@pytest.mark.parametrize("name", GRID_CASES)
+def test_grid_sample_u_bit_exact(lb, name):
+    g = load_golden(name)
+    grid = _grid_from_golden(lb, g, cdf_mode="sequential")
+    x, cells = grid._sample_u(_dev(g["u"]), want_cells=True)
+    assert np.array_equal(cells.cpu().numpy(), g["flat"])
+    assert np.array_equal(x.cpu().numpy(), g["x_pre"])
+
+
+@pytest.mark.parametrize("name", ["g2d_fullcov", "g3d_iso", "g3d_holes", "g5d_sobol"])
+def test_grid_sample_u_parallel_cdf_mismatches_explained(lb, name):
+    """With the GPU-built parallel CDF a pick may differ from the reference only
+    when u lies between the two tables' values of a boundary between the picks
+    (parity mode B); unexplained mismatches must be zero."""
+    g = load_golden(name)
+    grid = _grid_from_golden(lb, g, cdf_mode="parallel")
+    cdf_gpu = grid._cdf.cpu().numpy()
+    cdf_ref = g["cdf"]
+    u = g["u"][:, -1]
+    _, cells = grid._sample_u(_dev(g["u"]), want_cells=True)
+    cells = cells.cpu().numpy()
+    assert np.array_equal(cells, cdf_gpu.searchsorted(u, side="right"))   # exact on its own table
+    bad = np.flatnonzero(cells != g["flat"])
+    unexplained = 0
+    for i in bad:
+        lo, hi = sorted((cells[i], g["flat"][i]))
+        b = np.arange(lo, hi)
+        inside = (np.minimum(cdf_gpu[b], cdf_ref[b]) <= u[i]) & (u[i] < np.maximum(cdf_gpu[b], cdf_ref[b]))
+        unexplained += not inside.any()
+    assert unexplained == 0
+    assert len(bad) <= max(1, len(u) // 1000)
+
+
+@pytest.mark.parametrize("name", ["g1d_nonuniform", "g2d_fullcov", "g3d_iso", "g4d_iso", "g5d_sobol", "g6d_iso"])
+def test_grid_sample_u_fp32(lb, name):
+    """fp32 mode: densities stored in fp32, fp64 CDF/cell uniform.  Cell picks are
+    exact against the oracle run on the same fp32-rounded densities; coordinates
+    agree to 1e-4 of the cell width (north_star tolerance for fp32)."""
+    g = load_golden(name)
+    edges = golden_edges(g)
+    V32 = g["vertex_densities"].astype(np.float32)
+    dom = tuple(edges) if len(edges) > 1 else edges[0]
+    grid = lb.DensityGrid(dom, lambda p: V32.reshape(-1).astype(np.float64), vectorizedpdf=True,
+                          dtype=np.float32, cdf_mode="sequential")
+    x_ref, flat_ref = O.grid_sample(edges, V32.astype(np.float64), g["u"], return_cells=True)
+    x, cells = grid._sample_u(_dev(g["u"]), want_cells=True)
+    assert x.dtype.is_floating_point and x.element_size() == 4
+    assert np.array_equal(cells.cpu().numpy(), flat_ref)
+    multi = np.unravel_index(flat_ref, tuple(len(e) - 1 for e in edges))
+    width = np.stack([np.diff(edges[d])[multi[d]] for d in range(len(edges))], axis=-1)
+    err = np.abs(x.cpu().numpy().astype(np.float64) - x_ref) / width
+    assert err.max() < 1e-4, err.max()
+
+
+@pytest.mark.parametrize("name", TREE_CASES)
+def test_cells_sample_u_bit_exact(lb, name):
+    from lintsampler_b200.tree import _CellTable
+    g = load_golden(name)
+    table = _CellTable(g["leaf_x"], g["leaf_dx"], g["leaf_corners"], g["leaf_mass"], np.float64,
+                       None, "sequential")
+    assert table.total_mass == g["total_mass"]
+    x, cells = table.sample_u(_dev(g["u"]), want_cells=True)
+    assert np.array_equal(cells.cpu().numpy(), g["leaf_choice"])
+    assert np.array_equal(x.cpu().numpy(), g["x_pre"])
+
+
+def test_incell_kernel_known_answers(lb):
+    import torch
+    from lintsampler_b200 import _capi, _device
+    g = load_golden("incell_kernels")
+    for k in range(1, 7):
+        corners, u = g[f"corners{k}"], g[f"u{k}"]
+        n = u.shape[0]
+        ufull = np.concatenate([u, np.zeros((n, 1))], axis=1)
+        out = torch.empty((n, k), dtype=torch.float64, device="cuda")
+        _capi.call("lint_incell_sample_u", k, n, _device.ptr(_dev(np.zeros((n, k)))),
+                   _device.ptr(_dev(np.ones((n, k)))), _device.ptr(_dev(corners)),
+                   _device.ptr(_dev(ufull)), _device.ptr(out), _device.stream_ptr(out.device))
+        # mins=0, maxs=1: x = 0 + (1-0)*z = z exactly
+        assert np.array_equal(out.cpu().numpy(), g[f"z{k}"])
+
+
+# ----------------------------------------------------------------------------- device uniform streams
+def _philox4x32_10(ctr, key):
+    """NumPy Philox4x32-10 (Salmon et al. 2011) — test-side restatement of the
+    stream definition in include/lintsampler_b200.h."""
+    c = [np.asarray(x, dtype=np.uint64) for x in ctr]
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> np.uint64(32)) ^ c[1] ^ k0) & mask, p1 & mask,
+             ((p0 >> np.uint64(32)) ^ c[3] ^ k1) & mask, p0 & mask]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return c
+
+
+def test_philox_known_answer_vectors():
+    # Random123 kat_vectors, philox4x32-10
+    r = _philox4x32_10([0, 0, 0, 0], [0, 0])
+    assert [int(x) for x in r] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    r = _philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2)
+    assert [int(x) for x in r] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    r = _philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0])
+    assert [int(x) for x in r] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def _philox_rows(k, dtype, N, seed, offset):
+    i = np.arange(offset, offset + N, dtype=np.uint64)
+    lo, hi = i & np.uint64(0xFFFFFFFF), i >> np.uint64(32)
+    key = [seed & 0xFFFFFFFF, seed >> 32]
+    z = np.zeros(N, dtype=np.uint64)
+
+    def u53(a, b):
+        return ((((b << np.uint64(32)) | a) >> np.uint64(11)).astype(np.float64)) * 2.0 ** -53
+    u = np.empty((N, k + 1))
+    if dtype == np.float64:
+        w = []
+        for q in range((k + 2) // 2):
+            w += _philox4x32_10([lo, hi, z + np.uint64(q), z], key)
+        u[:, k] = u53(w[0], w[1])
+        for d in range(k):
+            u[:, d] = u53(w[2 + 2 * d], w[3 + 2 * d])
+    else:
+        r = _philox4x32_10([lo, hi, z, z], key)
+        s = _philox4x32_10([lo, hi, z + np.uint64(1), z], key)
+        u[:, k] = u53(r[0], r[1])
+        S = 2.0 ** -24
+        cols = [(r[2] >> np.uint64(8)), (r[3] >> np.uint64(8)),
+                ((r[2] & np.uint64(255)) << np.uint64(16)) | ((r[3] & np.uint64(255)) << np.uint64(8))
+                | (r[0] & np.uint64(255)),
+                s[0] >> np.uint64(8), s[1] >> np.uint64(8), s[2] >> np.uint64(8)]
+        for d in range(k):
+            u[:, d] = cols[d].astype(np.float64) * S
+    return u
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_philox_uniform_stream_definition(lb, k, dtype):
+    import torch
+    from lintsampler_b200 import _capi, _device
+    N, seed, offset = 4099, 0x1234567890ABCDEF, (1 << 32) - 1000     # counter carries into the high word
+    u = torch.empty((N, k + 1), dtype=torch.float64, device="cuda")
+    _capi.call("lint_philox_uniforms", k, _device.lint_dtype(dtype), N, C.c_uint64(seed),
+               C.c_uint64(offset), _device.ptr(u), _device.stream_ptr(u.device))
+    assert np.array_equal(u.cpu().numpy(), _philox_rows(k, dtype, N, seed, offset))
+
+
+@pytest.mark.parametrize("name", ["g1d_nonuniform", "g2d_fullcov", "g3d_iso", "g4d_iso", "g6d_iso"])
+def test_philox_sampler_equals_oracle_on_its_own_uniforms(lb, name):
+    import torch
+    from lintsampler_b200 import _capi, _device
+    g = load_golden(name)
+    k = int(g["k"])
+    grid = _grid_from_golden(lb, g, cdf_mode="sequential")
+    N, seed, offset = 50000, 77, 123456789
+    x, cells = grid._sample_philox(N, seed, offset, want_cells=True)
+    u = torch.empty((N, k + 1), dtype=torch.float64, device="cuda")
+    _capi.call("lint_philox_uniforms", k, _capi.LINT_F64, N, C.c_uint64(seed), C.c_uint64(offset),
+               _device.ptr(u), _device.stream_ptr(u.device))
+    x_ref, flat_ref = O.grid_sample(golden_edges(g), g["vertex_densities"], u.cpu().numpy(),
+                                    cdf=g["cdf"], return_cells=True)
+    assert np.array_equal(cells.cpu().numpy(), flat_ref)
+    assert np.array_equal(x.cpu().numpy(), x_ref)
+    # stream continuation: two half calls == one call
+    xa = grid._sample_philox(N // 2, seed, offset)
+    xb = grid._sample_philox(N - N // 2, seed, offset + N // 2)
+    assert torch.equal(torch.cat([xa, xb]), x)
+
+
+@pytest.mark.parametrize("name", ["g5d_sobol", "g2d_sobol"])
+def test_sobol_stream_and_sampler_bit_exact(lb, name):
+    import torch
+    from lintsampler_b200 import _capi, _device
+    g = load_golden(name)
+    k, N = int(g["k"]), int(g["N"])
+    s = _capi.LintSobol()
+    for j in range(k + 1):
+        for b in range(32):
+            s.sv[j][b] = int(g["sobol_sv"][j, b])
+        s.shift[j] = int(g["sobol_shift"][j])
+    s.first_index = 0
+    u = torch.empty((N, k + 1), dtype=torch.float64, device="cuda")
+    _capi.call("lint_sobol_uniforms", k, N, C.byref(s), _device.ptr(u), _device.stream_ptr(u.device))
+    assert np.array_equal(u.cpu().numpy(), g["u"])          # == scipy Sobol.random(N)
+    grid = _grid_from_golden(lb, g, cdf_mode="sequential")
+    x, cells = grid._sample_sobol(N, s, want_cells=True)
+    assert np.array_equal(cells.cpu().numpy(), g["flat"])
+    assert np.array_equal(x.cpu().numpy(), g["x_pre"])
+    s.first_index = 1500                                     # continuation
+    x2 = grid._sample_sobol(N - 1500, s)
+    assert np.array_equal(x2.cpu().numpy(), g["x_pre"][1500:])

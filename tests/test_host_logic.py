@@ -1,0 +1,277 @@
+"""CPU-only tests: host-side mirror of the reference interface (argument
+validation, exception and warning types — modelled on the reference's
+tests/test_lintsampler.py:76-350 and tests/test_densitytree.py:10-194), the
+tree builder against golden leaf tables from the real reference, and the C-ABI
+library's exported symbols.  No kernel is launched here."""
+import os
+import re
+import warnings
+
+import numpy as np
+import pytest
+from scipy.stats import norm, multivariate_normal
+from scipy.stats.qmc import Sobol
+
+import pdfs
+from conftest import load_golden, ROOT
+import lintsampler_b200 as lb
+from lintsampler_b200 import _capi
+
+X = np.linspace(-10, 10, 65)
+Y = np.linspace(-5, 5, 33)
+PDF2 = multivariate_normal(np.zeros(2), np.eye(2)).pdf
+
+
+def _no_gpu():
+    import torch
+    return not torch.cuda.is_available()
+
+
+# ----------------------------------------------------------------------------- C ABI
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "lintsampler_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|size_t|const char \*)\s*\*?(lint_\w+)\s*\(", hdr, flags=re.M))
+    assert declared == set(_capi.PROTOTYPES), declared ^ set(_capi.PROTOTYPES)
+    lib = _capi.load()                       # resolves each symbol or raises
+    assert lib.lint_abi_version() == 1
+    assert lib.lint_cdf_scratch_bytes(1 << 24) > 0
+
+
+def test_abi_rejects_bad_arguments_without_a_gpu():
+    import ctypes as C
+    lib = _capi.load()
+    assert lib.lint_grid_masses(None, None, None, None) == 1          # LINT_ERR_BAD_ARG
+    assert b"NULL" in lib.lint_last_error()
+    g = _capi.LintGrid()
+    g.dim = 9
+    assert lib.lint_grid_sample_u(C.byref(g), None, 0, None, None, None) == 1
+    assert b"dim" in lib.lint_last_error()
+    with pytest.raises(_capi.LintError):
+        _capi.call("lint_guide_build", None, 10, 4, None, None)
+
+
+def test_product_fails_loudly_without_a_device():
+    if not _no_gpu():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        lb.DensityGrid(X, norm.pdf, vectorizedpdf=True)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "lintsampler_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("no CPU fallback", ""), fn
+
+
+# ----------------------------------------------------------------------------- density validation (before any device work)
+def _neg1(x):
+    return -norm.pdf(x)
+
+
+def _neg2(x):
+    return -multivariate_normal(mean=np.ones(2), cov=np.eye(2)).pdf(x)
+
+
+@pytest.mark.parametrize("pdf,cells", [(_neg1, X), (_neg2, (X, Y))])
+@pytest.mark.parametrize("vec", [True, False])
+def test_negative_density_raises(pdf, cells, vec):
+    with pytest.raises(ValueError):
+        lb.LintSampler(domain=cells, pdf=pdf, vectorizedpdf=vec)
+
+
+def _nan_vec_1d(x):
+    f = np.ones_like(x)
+    f[x < 0] = np.nan
+    return f
+
+
+def _nan_vec_kd(x):
+    f = np.ones(x.shape[:-1])
+    f[x[..., 0] < 0] = np.nan
+    return f
+
+
+@pytest.mark.parametrize("pdf,cells,vec", [
+    (lambda x: np.nan if x < 0 else 1.0, X, False),
+    (_nan_vec_1d, X, True),
+    (lambda x: np.nan if x[0] < 0 else 1.0, (X, Y), False),
+    (_nan_vec_kd, (X, Y), True),
+])
+def test_nonfinite_density_raises(pdf, cells, vec):
+    with pytest.raises(ValueError):
+        lb.LintSampler(domain=cells, pdf=pdf, vectorizedpdf=vec)
+
+
+@pytest.mark.parametrize("pdf,cells,vec", [
+    (lambda x: np.ones(10), X, False),
+    (lambda x: 1.0, X, True),
+    (lambda x: np.ones((len(x), 2)), X, True),
+    (lambda x: np.ones(2), (X, Y), False),
+    (lambda x: 1.0, (X, Y), True),
+    (lambda x: np.ones((len(x), 2)), (X, Y), True),
+])
+def test_bad_density_shape_raises(pdf, cells, vec):
+    with pytest.raises(ValueError):
+        lb.LintSampler(domain=cells, pdf=pdf, vectorizedpdf=vec)
+
+
+def test_pdf_argument_checks():
+    with pytest.raises(TypeError):
+        lb.LintSampler(X, pdf=3.0)
+    with pytest.raises(ValueError):
+        lb.LintSampler(X)
+    with pytest.raises(ValueError):
+        lb.LintSampler([X[:33], X[32:]])
+    with pytest.raises(ValueError), pytest.warns(UserWarning):
+        lb.LintSampler(X, vectorizedpdf=True)
+
+
+# ----------------------------------------------------------------------------- domain validation
+@pytest.mark.parametrize("bad", [
+    np.array([1.0, 1.5, 1.5, 2.0]), np.ones(10), np.array([9.0, 8.0, 10.0, 12.0]),
+    np.array([1.0, 1.5, np.nan]), np.array([1.0, 1.5, np.inf]),
+])
+def test_bad_edges_raise(bad):
+    with pytest.raises(ValueError):
+        lb.LintSampler(bad, pdf=norm.pdf, vectorizedpdf=True)
+    with pytest.raises(ValueError):
+        lb.LintSampler((X, bad), pdf=PDF2, vectorizedpdf=True)
+    with pytest.raises(ValueError):
+        lb.DensityGrid((bad, Y), PDF2, vectorizedpdf=True)
+
+
+def test_nonsense_domains_raise():
+    with pytest.raises(TypeError):
+        lb.DensityGrid(17.0, norm.pdf)
+    with pytest.raises(TypeError):
+        lb.DensityGrid([[X, Y]], PDF2)
+    with pytest.raises(TypeError):
+        lb.LintSampler([X, (X, Y)], pdf=norm.pdf, vectorizedpdf=True)
+
+
+def test_seed_and_N_validation_messages():
+    with pytest.raises(TypeError):
+        np.random.default_rng(42.5)          # the reference relies on NumPy for this (lintsampler.py:458)
+
+
+# ----------------------------------------------------------------------------- tree: validation + structure (host only)
+def test_tree_argument_validation():
+    with pytest.raises(ValueError):
+        lb.DensityTree([0, 0], [1, 1, 1], PDF2)
+    with pytest.raises(ValueError):
+        lb.DensityTree([[0, 0]], [[1, 1]], PDF2)
+    with pytest.raises(ValueError):
+        lb.DensityTree([0, 2], [1, 1], PDF2)
+    with pytest.raises(ValueError):
+        lb.DensityTree([0, 0], [1, np.inf], PDF2)
+    with pytest.raises(ValueError):
+        lb.DensityTree(-10, 10, _neg1, vectorizedpdf=True)
+    with pytest.raises(ValueError):
+        lb.DensityTree(-10, 10, _nan_vec_1d, vectorizedpdf=True)
+    with pytest.raises(ValueError):
+        lb.DensityTree(-10, 10, lambda x: np.ones((len(x), 2)), vectorizedpdf=True)
+    with pytest.warns(UserWarning):
+        lb.DensityTree([-5, -5], [5, 5], PDF2, vectorizedpdf=True, batch=True, usecache=True)
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+@pytest.mark.parametrize("openings", [0, 1, 2, 3])
+@pytest.mark.parametrize("batch", [False, True])
+def test_tree_leaf_count(dim, openings, batch):
+    pdf = multivariate_normal(np.zeros(dim), np.eye(dim)).pdf
+    t = lb.DensityTree(-5 * np.ones(dim), 5 * np.ones(dim), pdf, vectorizedpdf=True,
+                       min_openings=openings, usecache=not batch, batch=batch)
+    assert len(t.leaves) == 2 ** (dim * openings)
+
+
+def test_tree_refine_needs_two_levels_and_verbose_prints(capfd):
+    t = lb.DensityTree([-5, -5], [5, 5], PDF2, vectorizedpdf=True, min_openings=0)
+    with pytest.raises(RuntimeError):
+        t.refine(1e-2)
+    t = lb.DensityTree([-5, -5], [5, 5], PDF2, vectorizedpdf=True, min_openings=2)
+    t.refine(1e-2, verbose=True)
+    assert "Pre-loop" in capfd.readouterr().out
+
+
+def test_tree_get_leaf_at_pos():
+    t = lb.DensityTree([-5, -5], [5, 5], PDF2, vectorizedpdf=True, min_openings=2)
+    t.refine(1e-2)
+    with pytest.raises(ValueError):
+        t.get_leaf_at_pos(np.array([0.0, 0.0, 0.0]))
+    with pytest.raises(ValueError):
+        t.get_leaf_at_pos(np.array([0.0, 7.0]))
+    pos = np.array([1.02, -3.74])
+    leaf = t.get_leaf_at_pos(pos)
+    assert leaf.children is None and leaf in t.leaves
+    assert np.all(pos >= leaf.x) and np.all(pos <= leaf.x + leaf.dx)
+    t1 = lb.DensityTree(-10, 10, norm.pdf, vectorizedpdf=True, min_openings=3)
+    assert t1.get_leaf_at_pos(0.3).level == 3
+
+
+CASES = {
+    "t3d_open3": (pdfs.GMM(*pdfs.gmm_params(3, seed=0)), dict(min_openings=3), None),
+    "t3d_refined": (pdfs.GMM(*pdfs.gmm_params(3, K=8, seed=0, smin=0.1, smax=0.4)),
+                    dict(min_openings=3), dict(tree_tol=2e-2, leaf_tol=2e-2)),
+    "t2d_refined": (pdfs.GMM(*pdfs.gmm_params(2, seed=1, full_cov=True)), dict(min_openings=2),
+                    dict(tree_tol=1e-3)),
+    "t2d_batch": (pdfs.GMM(*pdfs.gmm_params(2, seed=2)), dict(min_openings=3, batch=True, usecache=False),
+                  dict(tree_tol=5e-3)),
+    "t1d_refined": (pdfs.GMM(*pdfs.gmm_params(1, seed=3)), dict(min_openings=2),
+                    dict(tree_tol=1e-4, leaf_tol=1e-3)),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("vectorized", [True, False])
+def test_tree_builder_reproduces_reference_leaf_table(name, vectorized):
+    """Leaf ORDER, levels, origins, corner densities, trapezoid and Romberg masses
+    are bit-identical to the real reference's tree (golden), whichever way the
+    pdf is evaluated."""
+    pdf, kw, ref = CASES[name]
+    if kw.get("batch") and not vectorized:
+        pytest.skip("batch mode always calls the pdf vectorised")
+    g = load_golden(name)
+    mins, maxs = g["mins"], g["maxs"]
+    if len(mins) == 1:
+        mins, maxs = float(mins[0]), float(maxs[0])
+    t = lb.DensityTree(mins, maxs, pdf, vectorizedpdf=vectorized, **kw)
+    if ref:
+        t.refine(**ref)
+    x, dx, cd, m = t.leaf_table()
+    assert np.array_equal(np.array([leaf.level for leaf in t.leaves]), g["leaf_level"])
+    assert np.array_equal(np.array([leaf.idx for leaf in t.leaves]), g["leaf_idx"])
+    assert np.array_equal(x, g["leaf_x"]) and np.array_equal(dx, g["leaf_dx"])
+    # a vectorised einsum and a per-point call may differ in the last bit
+    if vectorized:
+        assert np.array_equal(cd, g["leaf_corners"]) and np.array_equal(m, g["leaf_mass"])
+        assert np.array_equal(np.array([leaf.mass_romberg for leaf in t.leaves]), g["leaf_mass_romberg"])
+    else:
+        np.testing.assert_allclose(cd, g["leaf_corners"], rtol=1e-12)
+    assert t.total_mass == pytest.approx(float(g["total_mass"]), rel=1e-12)
+
+
+def test_tree_cache_saves_evaluations():
+    calls = [0]
+
+    def pdf(x):
+        calls[0] += len(x)
+        return PDF2(x)
+    lb.DensityTree([-5, -5], [5, 5], pdf, vectorizedpdf=True, min_openings=4, usecache=True)
+    assert calls[0] == 17 * 17                # every lattice vertex exactly once
+    calls[0] = 0
+    lb.DensityTree([-5, -5], [5, 5], pdf, vectorizedpdf=True, min_openings=4, usecache=False)
+    assert calls[0] > 17 * 17
+
+
+# ----------------------------------------------------------------------------- GaussianMixture host evaluation
+@pytest.mark.parametrize("k,full", [(1, False), (2, True), (3, True), (6, False)])
+def test_gaussian_mixture_host_call_matches_scipy(k, full):
+    w, mu, cov = pdfs.gmm_params(k, K=3, seed=k, full_cov=full)
+    gm = lb.GaussianMixture(w, mu, cov)
+    x = np.random.default_rng(0).normal(size=(50, k))
+    ref = sum(w[j] * multivariate_normal(mu[j], cov[j]).pdf(x) for j in range(3))
+    np.testing.assert_allclose(gm(x if k > 1 else x[:, 0]), ref, rtol=1e-11)
+    with pytest.raises(ValueError):
+        lb.GaussianMixture(w, mu)
