@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): samples/s for a 256^3 3-D DensityGrid,
+N = 1e9 samples per GPU, fp32 samples / fp64 CDF, synthetic K=4 Gaussian mixture.
+
+    python bench.py --gpus N --steps K --warmup W            # this build
+    python bench.py --impl reference ...                      # CPU reference arm
+
+One "step" = the whole hot path on one batch: cell masses -> cell CDF -> guide
+table -> N fused Philox/search/gather/inverse-CDF samples written to HBM, with
+the vertex densities already resident in HBM.  `value` counts the samples of
+all ranks over the max-over-ranks device time.  `e2e` is the same step driven
+through the public API from host buffers: pinned vertex densities copied in,
+samples copied out to pinned host memory, both inside the timed region.
+
+Prints exactly one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GRID_N = 256          # cells per dimension (C3 in SURVEY.md §8)
+DIM = 3
+N_SAMPLES = 1_000_000_000
+SEED = 1
+
+
+def synthetic_c3():
+    """SURVEY.md §8(d) C3 generator: all draws from default_rng(0), in this order."""
+    rng = np.random.default_rng(0)
+    means = rng.uniform(-2, 2, size=(4, DIM))
+    sig = rng.uniform(0.3, 0.8, size=4)
+    w = rng.dirichlet(np.ones(4))
+    edges = tuple(np.linspace(-4, 4, GRID_N + 1) for _ in range(DIM))
+    return edges, w, means, sig
+
+
+def algorithmic_bytes(n_samples, dens_bytes=4, out_bytes=4):
+    """B_mass + B_scan + B_sample."""
+    V = (GRID_N + 1) ** DIM
+    Cn = GRID_N ** DIM
+    b_mass = V * dens_bytes + Cn * 8
+    b_scan = 2 * Cn * 8
+    b_sample = n_samples * DIM * out_bytes
+    return b_mass, b_scan, b_sample
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                     "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names)
+                   if any(len(r) > 2 + j and r[2 + j].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU legs (oracle)
+def _cpu_worker(args):
+    seed, n, edges, V, cdf = args
+    from oracle import lint_oracle as O
+    u = np.random.default_rng(seed).random((n, DIM + 1))
+    x = O.grid_sample(edges, V, u, cdf=cdf)
+    return float(x[0, 0])
+
+
+def cpu_baseline_port(n_cpu=3_000_000):
+    """The oracle (NumPy port of the reference's algorithm) on ONE host core, on a
+    bounded sample of the same workload: CDF rebuild + uniforms + _grid_sample."""
+    from oracle import lint_oracle as O
+    edges, w, means, sig = synthetic_c3()
+    mesh = np.stack(np.meshgrid(*edges, indexing="ij"), axis=-1)
+    V = O.gmm_pdf(mesh, w, means, sig[:, None, None] ** 2 * np.eye(DIM)[None])
+    del mesh
+    masses = O.cell_masses(edges, V)
+    t0 = time.perf_counter()
+    cdf = O.cdf_from_masses(masses)                 # the reference redoes this on every call
+    u = np.random.default_rng(SEED).random((n_cpu, DIM + 1))
+    x = O.grid_sample(edges, V, u, cdf=cdf)
+    t1 = time.perf_counter()
+    np.random.default_rng(SEED).shuffle(x, axis=0)  # the reference's final rng.shuffle
+    t2 = time.perf_counter()
+    return {"value": n_cpu / (t1 - t0), "unit": "samples/s", "cores": 1, "kind": "port",
+            "sample": f"{n_cpu} samples of the same 256^3 grid: CDF rebuild + PCG64 uniforms + "
+                      f"_grid_sample (oracle/lint_oracle.py) in {t1 - t0:.2f} s on 1 core; with the "
+                      f"reference's final rng.shuffle {n_cpu / (t2 - t0):.3g} samples/s"}
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's own CPU algorithm (the oracle port — the
+    reference is pure NumPy and cannot travel to the GPU box) on all host cores:
+    one process per core, each sampling its share of a bounded batch."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle import lint_oracle as O
+    edges, w, means, sig = synthetic_c3()
+    mesh = np.stack(np.meshgrid(*edges, indexing="ij"), axis=-1)
+    V = O.gmm_pdf(mesh, w, means, sig[:, None, None] ** 2 * np.eye(DIM)[None])
+    del mesh
+    cdf = O.cdf_from_masses(O.cell_masses(edges, V))
+    cores = min(len(os.sched_getaffinity(0)), 64)
+    per = 400_000
+    n_step = cores * per
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        def step(s):
+            pool.map(_cpu_worker, [(1000 * s + c, per, edges, V, cdf) for c in range(cores)])
+        for s in range(args.warmup):
+            step(s)
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            step(100 + s)
+        dt = (time.perf_counter() - t0) / args.steps
+    val = n_step / dt
+    line = {
+        "impl": "reference", "metric": "samples/s", "value": val, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "C3: 3-D DensityGrid 256^3, K=4 isotropic GMM on [-4,4]^3",
+                   "samples_per_step": n_step, "note": "bounded sample of the N=1e9 workload"},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_step} samples/step ({per} per process), uniforms + "
+                                   "searchsorted + corner gather + in-cell inverse CDF; CDF prebuilt"},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import lintsampler_b200 as lb
+    from lintsampler_b200 import distributed as lbd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    edges, w, means, sig = synthetic_c3()
+    gmm = lb.GaussianMixture(w, means, sigmas=sig)
+    n_local = args.samples
+    # domain: the whole grid at world 1, this rank's equal-mass shard otherwise
+    shard = lbd.ShardedGrid(edges, gmm, dtype=np.float32, device=dev,
+                            rank=rank, world=world, group=dist.group.WORLD if world > 1 else None)
+    out = torch.empty((n_local, DIM), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i, ev=None):
+        shard.enqueue_build()                       # masses -> CDF -> guide (+ tiny all-gather)
+        if ev:
+            ev[0].record(stream)
+        shard.sample_philox_into(out, seed=SEED, offset=i * n_local * world)
+        if ev:
+            ev[1].record(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        t_beg.record(stream)
+        for i in range(args.steps):
+            step(args.warmup + i, evs[i])
+        t_end.record(stream)
+        barrier()
+    ms_total = t_beg.elapsed_time(t_end)
+    ms_sample = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    t = torch.tensor([ms_total, ms_sample], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_sample = t.tolist()
+    ms_step = ms_total / args.steps
+    value = n_local * world / (ms_step * 1e-3)
+
+    # ---- e2e: public API, host buffers in and out, N=1 GPU semantics per rank
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, lb, edges, gmm, dev, world)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        b_mass, b_scan, b_sample = algorithmic_bytes(n_local)
+        achieved = b_sample / (ms_sample * 1e-3) / 1e9
+        line = {
+            "metric": "samples/s", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": "C3: 3-D DensityGrid 256^3 (257^3 fp32 vertex densities, fp64 CDF), "
+                            "K=4 isotropic GMM on [-4,4]^3, N=%d samples per GPU per step" % n_local,
+                "samples_per_gpu": n_local, "l2": "outputs (12 GB/step) and tables (>260 MB) exceed L2",
+                "sharding": shard.describe(), "order": "rows in draw order (iid Philox rows, exchangeable)",
+            },
+            "roofline": {
+                "bound": "hbm", "kernel": "sample_kernel<3,float,GridSource,UniformsPhilox>",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
+                "traffic": None, "ms_per_launch": ms_sample,
+                "step_frac_of_hbm_roofline": (b_mass + b_scan + b_sample) / (ms_step * 1e-3) / 1e9 / peak,
+            },
+            "clocks": clocks.summary(),
+            "gpu_launches": shard.launches_per_step() * args.steps,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_port()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, lb, edges, gmm, dev, world):
+    import torch
+    import torch.distributed as dist
+    n = args.samples
+    steps = max(1, min(args.steps, 3))
+    # host inputs: pinned fp32 vertex densities (evaluated once, outside the timed region)
+    g0 = lb.DensityGrid(edges, gmm, vectorizedpdf=True, dtype=np.float32, device=dev)
+    v_host = torch.empty(g0._V.numel(), dtype=torch.float32, pin_memory=True)
+    v_host.copy_(g0._V)
+    out_host = torch.empty((n, DIM), dtype=torch.float32, pin_memory=True)
+    sampler = lb.LintSampler(g0, seed=SEED, dtype=np.float32)
+    torch.cuda.synchronize(dev)
+
+    def one():
+        g0.update_densities(v_host, check=False)            # H2D + masses + CDF + guide
+        sampler.sample_to_host(n, out=out_host)              # sample + D2H, pipelined
+    one()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize(dev)
+    dt = (time.perf_counter() - t0) / steps
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    assert np.isfinite(out_host[-1].numpy()).all()
+    return {"value": n * world / dt, "unit": "samples/s", "h2d_bytes_per_step": int(v_host.numel() * 4),
+            "d2h_bytes_per_step": int(n * DIM * 4), "ms_per_step": dt * 1e3, "steps": steps,
+            "api": "DensityGrid.update_densities(pinned) + LintSampler.sample_to_host(N, out=pinned)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--samples", type=int, default=N_SAMPLES, help="samples per GPU per step")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

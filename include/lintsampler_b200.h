@@ -190,11 +190,16 @@ int lint_incell_sample_u(int dim, int64_t N, const double *mins_dev, const doubl
 /* Philox4x32-10 stream replacing `rng.random((N,k+1))` [lintsampler.py:517]:
  * row i of the call uses counter (offset+i) under key `seed`; successive calls
  * continue the stream by advancing `offset` by N.  The cell-selecting uniform
- * has 53 bits; in-cell uniforms have 53 bits (F64) or 24 bits (F32). */
+ * has 53 bits; in-cell uniforms have 53 bits (F64) or 24 bits (F32).
+ * [u_lo, u_hi) is the stratum of the cell-selecting uniform this call draws
+ * from: (0, 1) for the whole domain; a rank of a sharded run passes its own
+ * slice of the CDF, which is the u-rescaling of lintsampler.py:306 inverted. */
 int lint_grid_sample_philox(const lint_grid_t *g, int64_t N, uint64_t seed, uint64_t offset,
-                            void *out_dev, int64_t *cell_idx_dev, lint_stream_t stream);
+                            double u_lo, double u_hi, void *out_dev, int64_t *cell_idx_dev,
+                            lint_stream_t stream);
 int lint_cells_sample_philox(const lint_cells_t *c, int64_t N, uint64_t seed, uint64_t offset,
-                             void *out_dev, int64_t *cell_idx_dev, lint_stream_t stream);
+                             double u_lo, double u_hi, void *out_dev, int64_t *cell_idx_dev,
+                             lint_stream_t stream);
 
 /* The uniforms the Philox samplers consume, materialised as (N,k+1) fp64 — for
  * tests and for callers that want to replay a draw on the host. */

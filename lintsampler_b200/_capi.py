@@ -76,8 +76,10 @@ PROTOTYPES = {
     "lint_grid_sample_u": (C.c_int, [C.POINTER(LintGrid), _P, _I64, _P, _P, _P]),
     "lint_cells_sample_u": (C.c_int, [C.POINTER(LintCells), _P, _I64, _P, _P, _P]),
     "lint_incell_sample_u": (C.c_int, [C.c_int, _I64, _P, _P, _P, _P, _P, _P]),
-    "lint_grid_sample_philox": (C.c_int, [C.POINTER(LintGrid), _I64, _U64, _U64, _P, _P, _P]),
-    "lint_cells_sample_philox": (C.c_int, [C.POINTER(LintCells), _I64, _U64, _U64, _P, _P, _P]),
+    "lint_grid_sample_philox": (C.c_int, [C.POINTER(LintGrid), _I64, _U64, _U64, C.c_double, C.c_double,
+                                          _P, _P, _P]),
+    "lint_cells_sample_philox": (C.c_int, [C.POINTER(LintCells), _I64, _U64, _U64, C.c_double, C.c_double,
+                                           _P, _P, _P]),
     "lint_philox_uniforms": (C.c_int, [C.c_int, C.c_int, _I64, _U64, _U64, _P, _P]),
     "lint_grid_sample_sobol": (C.c_int, [C.POINTER(LintGrid), _I64, C.POINTER(LintSobol), _P, _P, _P]),
     "lint_cells_sample_sobol": (C.c_int, [C.POINTER(LintCells), _I64, C.POINTER(LintSobol), _P, _P, _P]),

@@ -237,6 +237,10 @@ template <int K>
 struct UniformsPhilox {
     uint2 key;
     uint64_t offset;
+    double u_lo, u_span;           // cell-uniform stratum [u_lo, u_lo + u_span); (0, 1) = whole domain
+    __device__ __forceinline__ double stratum(double r) const {
+        return __dadd_rn(u_lo, __dmul_rn(u_span, r));   // exact identity for (0, 1)
+    }
     // fp64 rows: cell uniform from words (0,1), coordinate d from words (2+2d, 3+2d)
     __device__ __forceinline__ void get(int64_t row, double &ucell, double (&uc)[K]) const {
         const uint64_t i = offset + (uint64_t)row;
@@ -247,7 +251,7 @@ struct UniformsPhilox {
             const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), q, 0), key);
             w[4 * q] = r.x; w[4 * q + 1] = r.y; w[4 * q + 2] = r.z; w[4 * q + 3] = r.w;
         }
-        ucell = u53(w[0], w[1]);
+        ucell = stratum(u53(w[0], w[1]));
 #pragma unroll
         for (int d = 0; d < K; ++d) uc[d] = u53(w[2 + 2 * d], w[3 + 2 * d]);
     }
@@ -257,7 +261,7 @@ struct UniformsPhilox {
     __device__ __forceinline__ void get(int64_t row, double &ucell, float (&uc)[K]) const {
         const uint64_t i = offset + (uint64_t)row;
         const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0, 0), key);
-        ucell = u53(r.x, r.y);
+        ucell = stratum(u53(r.x, r.y));
         constexpr float S = 1.0f / 16777216.0f;
         uc[0] = (float)(r.z >> 8) * S;
         if (K > 1) uc[1 % K] = (float)(r.w >> 8) * S;

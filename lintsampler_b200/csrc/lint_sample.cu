@@ -162,10 +162,18 @@ struct ArrayMaker {
 };
 struct PhiloxMaker {
     uint64_t seed, offset;
+    double u_lo = 0.0, u_hi = 1.0;
     template <int K> UniformsPhilox<K> make() const {
-        return UniformsPhilox<K>{make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), offset};
+        return UniformsPhilox<K>{make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), offset,
+                                 u_lo, u_hi - u_lo};
     }
 };
+
+static int check_stratum(double u_lo, double u_hi, const char *what) {
+    if (!(u_lo >= 0.0) || !(u_hi <= 1.0) || !(u_lo < u_hi))
+        return fail(LINT_ERR_BAD_ARG, "%s: stratum [%g, %g) is not inside [0, 1]", what, u_lo, u_hi);
+    return LINT_OK;
+}
 struct SobolMaker {
     const lint_sobol_t *s;
     template <int K> UniformsSobol<K> make() const {
@@ -278,20 +286,24 @@ int lint_incell_sample_u(int dim, int64_t N, const double *mins_dev, const doubl
 }
 
 int lint_grid_sample_philox(const lint_grid_t *g, int64_t N, uint64_t seed, uint64_t offset,
-                            void *out_dev, int64_t *cell_idx_dev, lint_stream_t stream) {
-    return grid_dispatch(g, N, out_dev, cell_idx_dev, stream, PhiloxMaker{seed, offset},
+                            double u_lo, double u_hi, void *out_dev, int64_t *cell_idx_dev,
+                            lint_stream_t stream) {
+    if (int rc = check_stratum(u_lo, u_hi, "lint_grid_sample_philox")) return rc;
+    return grid_dispatch(g, N, out_dev, cell_idx_dev, stream, PhiloxMaker{seed, offset, u_lo, u_hi},
                          "lint_grid_sample_philox");
 }
 
 int lint_cells_sample_philox(const lint_cells_t *c, int64_t N, uint64_t seed, uint64_t offset,
-                             void *out_dev, int64_t *cell_idx_dev, lint_stream_t stream) {
-    return cells_dispatch(c, N, out_dev, cell_idx_dev, stream, PhiloxMaker{seed, offset},
+                             double u_lo, double u_hi, void *out_dev, int64_t *cell_idx_dev,
+                             lint_stream_t stream) {
+    if (int rc = check_stratum(u_lo, u_hi, "lint_cells_sample_philox")) return rc;
+    return cells_dispatch(c, N, out_dev, cell_idx_dev, stream, PhiloxMaker{seed, offset, u_lo, u_hi},
                           "lint_cells_sample_philox");
 }
 
 int lint_philox_uniforms(int dim, int dtype, int64_t N, uint64_t seed, uint64_t offset,
                          double *u_dev, lint_stream_t stream) {
-    return uniforms_dispatch(dim, dtype, N, PhiloxMaker{seed, offset}, u_dev, stream);
+    return uniforms_dispatch(dim, dtype, N, PhiloxMaker{seed, offset, 0.0, 1.0}, u_dev, stream);
 }
 
 int lint_grid_sample_sobol(const lint_grid_t *g, int64_t N, const lint_sobol_t *sobol, void *out_dev,

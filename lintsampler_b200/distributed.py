@@ -1,0 +1,121 @@
+"""Multi-GPU sampling: one process per GPU, the domain sharded by contiguous
+ranges of the flat (dim-0-major) cell index — i.e. by slabs of the grid.
+
+The reference has no distributed code; its nearest construct is the list of
+domains (lintsampler.py:281-307): a domain is chosen with probability
+proportional to its mass and the cell-selecting uniform is rescaled into the
+domain's CDF interval.  A sharded run is exactly that with one domain per
+rank: rank g owns the cells whose CDF interval intersects its stratum
+``[b_g, b_{g+1})`` of the cell-selecting uniform and samples ``N_g`` rows with
+``u_cell`` drawn from that stratum.
+
+Strata are cut at equal mass (``b_g = g / world``) rather than at equal plane
+counts, because per-rank work is proportional to the shard's *mass*, not its
+cell count; a slab cut by plane index leaves the ranks that own the tails of
+the density idle.  The per-shard masses are exchanged with one NCCL all-gather
+of 8 bytes per rank per build, and ``N`` is split multinomially over them with a
+seed shared by all ranks, so no sample data ever crosses NVLink.
+"""
+import numpy as np
+
+from . import _device
+from .grid import DensityGrid
+
+
+def split_counts(n_total, shard_masses, seed):
+    """``(N_0..N_{G-1}) ~ Multinomial(N, M / sum M)`` drawn identically on every
+    rank from a shared seed (lintsampler.py:286-290 draws the same split one
+    row at a time through ``_choice``)."""
+    p = np.asarray(shard_masses, dtype=np.float64)
+    p = p / p.sum()
+    return np.random.default_rng(seed).multinomial(int(n_total), p)
+
+
+def equal_mass_strata(world):
+    """Stratum boundaries of the cell-selecting uniform, one stratum per rank."""
+    return np.arange(world + 1, dtype=np.float64) / world
+
+
+class ShardedGrid:
+    """A ``DensityGrid`` whose sampling work is sharded over ``world`` ranks.
+
+    Every rank holds the (small) vertex-density table and builds the cell CDF;
+    rank ``g`` samples only the cells of its equal-mass stratum.  With
+    ``world == 1`` this is a plain ``DensityGrid``.
+    """
+
+    def __init__(self, edges, pdf, *, dtype=np.float64, device=None, rank=0, world=1,
+                 group=None, vectorizedpdf=True, cdf_mode="parallel"):
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.grid = DensityGrid(edges, pdf, vectorizedpdf=vectorizedpdf, dtype=dtype, device=device,
+                                cdf_mode=cdf_mode)
+        self.device = self.grid.device
+        self.bounds = equal_mass_strata(self.world)
+        self.shard_masses = None
+        self._gather_buf = None
+        self.exchange_masses()
+
+    # -- build -------------------------------------------------------------
+    def enqueue_build(self):
+        """Cell masses -> CDF -> guide table on the current stream, then the
+        all-gather of the per-shard masses (asynchronous; no host sync)."""
+        self.grid._enqueue_build()
+        self._enqueue_gather()
+
+    def _stratum_mass_tensor(self):
+        """This rank's shard mass as a device scalar: (b_{g+1} - b_g) * total."""
+        lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+        return self.grid._total * (hi - lo)
+
+    def _enqueue_gather(self):
+        import torch
+        mine = self._stratum_mass_tensor()
+        if self._gather_buf is None:
+            self._gather_buf = torch.empty(self.world, dtype=torch.float64, device=self.device)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self._gather_buf, mine, group=self.group)   # NCCL, 8 B / rank
+        else:
+            self._gather_buf.copy_(mine)
+
+    def exchange_masses(self):
+        """Synchronous version: returns the per-shard masses as a NumPy array."""
+        self._enqueue_gather()
+        self.shard_masses = self._gather_buf.cpu().numpy().copy()
+        return self.shard_masses
+
+    # -- sampling ------------------------------------------------------------
+    def sample_philox_into(self, out, seed, offset):
+        """Fill the device tensor ``out`` (n, k) with this rank's rows.  Row i of
+        rank g uses Philox counter ``offset + g * n + i`` so ranks never share a
+        counter."""
+        n = out.shape[0]
+        lo, hi = float(self.bounds[self.rank]), float(self.bounds[self.rank + 1])
+        self.grid._sample_philox(n, seed, offset + self.rank * n, out=out, stratum=(lo, hi))
+        return out
+
+    def sample(self, n_total, seed, offset=0):
+        """Draw this rank's share of ``n_total`` samples (multinomial split with a
+        shared seed); returns a device tensor (N_g, k)."""
+        import torch
+        counts = split_counts(n_total, self.exchange_masses(), seed)
+        n = int(counts[self.rank])
+        start = int(counts[:self.rank].sum())
+        out = torch.empty((n, self.grid.dim), dtype=_device.torch_dtype(self.grid.dtype),
+                          device=self.device)
+        if n:
+            lo, hi = float(self.bounds[self.rank]), float(self.bounds[self.rank + 1])
+            self.grid._sample_philox(n, seed, offset + start, out=out, stratum=(lo, hi))
+        return out, counts
+
+    # -- reporting -------------------------------------------------------------
+    def launches_per_step(self):
+        """Kernels of this library launched by enqueue_build + one sampling call:
+        masses 1, parallel CDF 4, guide 1, sampler 1."""
+        return 7
+
+    def describe(self):
+        if self.world == 1:
+            return "single GPU"
+        return (f"{self.world} ranks, equal-mass strata of the flat cell CDF (contiguous dim-0-major "
+                "cell ranges); one 8-byte-per-rank NCCL all-gather of shard masses per build")

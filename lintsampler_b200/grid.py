@@ -19,6 +19,16 @@ def _is_flat_sequence(obj):
     return hasattr(obj, "__len__") and not hasattr(obj[0], "__len__")
 
 
+class _TensorDensities:
+    """Marker wrapping pre-evaluated vertex densities held in a torch tensor."""
+
+    def __init__(self, t):
+        self.t = t
+
+    def __call__(self, *a, **k):
+        raise TypeError("pre-evaluated densities are not callable")
+
+
 class DensityGrid(DensityStructure):
     """Rectilinear (not necessarily uniform) k-D grid with the pdf evaluated on
     its vertices.
@@ -74,6 +84,23 @@ class DensityGrid(DensityStructure):
         self._masses_host = None
         self._evaluate_pdf(pdf, vectorizedpdf, pdf_args, pdf_kwargs, pdf_on_device)
 
+    @classmethod
+    def from_densities(cls, edges, densities, *, dtype=np.float64, device=None,
+                       cdf_mode="parallel"):
+        """Grid over vertex densities that were already evaluated: ``densities`` is
+        an array (NumPy, or a torch tensor in host/pinned/device memory) of shape
+        ``(n0+1, ..., nk-1+1)`` (or flat).  Same validation as the constructor;
+        the density checks of grid.py:401-404 run on the device."""
+        import torch
+        if isinstance(densities, torch.Tensor):
+            self = cls.__new__(cls)
+            cls.__init__(self, edges, _TensorDensities(densities), vectorizedpdf=True,
+                         dtype=dtype, device=device, cdf_mode=cdf_mode, pdf_on_device=True)
+            return self
+        table = np.asarray(densities, dtype=np.float64)
+        return cls(edges, lambda pts: table.reshape(-1), vectorizedpdf=True, dtype=dtype,
+                   device=device, cdf_mode=cdf_mode)
+
     # ------------------------------------------------------------------ properties
     @property
     def dim(self):
@@ -116,6 +143,12 @@ class DensityGrid(DensityStructure):
         dev_densities = None
         if fused:
             pass                                    # evaluated by lint_grid_eval_gmm below
+        elif isinstance(pdf, _TensorDensities):
+            import torch
+            dev = _device.require_cuda(self._device_arg)
+            if pdf.t.numel() != npts:
+                raise ValueError("DensityGrid: densities have the wrong size for these edges")
+            dev_densities = pdf.t.reshape(npts).to(device=dev, non_blocking=True)
         elif vectorizedpdf and pdf_on_device:
             import torch
             dev = _device.require_cuda(self._device_arg)
@@ -171,20 +204,72 @@ class DensityGrid(DensityStructure):
         self._guide_bits = 0
         st = _device.stream_ptr(dev)
         desc = self._descriptor()
+        self._gmm = gmm
         if gmm is not None:
             gs, keep = gmm._as_struct()
             _capi.call("lint_grid_eval_gmm", C.byref(desc), C.byref(gs), 1.0, st)
             del keep
         self._masses = torch.empty(ncells, dtype=torch.float64, device=dev)
-        flags = torch.zeros(1, dtype=torch.int32, device=dev)
-        _capi.call("lint_grid_masses", C.byref(desc), _device.ptr(self._masses), _device.ptr(flags), st)
-        bad = int(flags.item())
+        self._flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._cdf = torch.empty(ncells, dtype=torch.float64, device=dev)
+        self._total = torch.empty(1, dtype=torch.float64, device=dev)
+        self._guide_bits_planned = _device.default_guide_bits(ncells)
+        self._guide = torch.empty((1 << self._guide_bits_planned) + 1, dtype=torch.int32, device=dev)
+        nbytes = _capi.load().lint_cdf_scratch_bytes(ncells)
+        self._scratch = torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device=dev)
+        self._enqueue_build()
+        self._check_build()
+
+    def _enqueue_build(self):
+        """Cell masses -> CDF -> guide table, enqueued on the current stream with no
+        host synchronisation (grid.py:411-412, 431; utils.py:195-196).  Seven kernel
+        launches in parallel-CDF mode."""
+        dev = self.device
+        st = _device.stream_ptr(dev)
+        ncells = int(self.ncells)
+        mode = {"parallel": _capi.LINT_CDF_PARALLEL, "sequential": _capi.LINT_CDF_SEQUENTIAL}.get(self.cdf_mode)
+        if mode is None:
+            raise ValueError(f"cdf_mode must be 'parallel' or 'sequential', got {self.cdf_mode!r}")
+        self._guide_bits = 0
+        desc = self._descriptor()
+        self._flags.zero_()
+        _capi.call("lint_grid_masses", C.byref(desc), _device.ptr(self._masses), _device.ptr(self._flags), st)
+        _capi.call("lint_cdf_build", _device.ptr(self._masses), ncells, mode, _device.ptr(self._cdf),
+                   _device.ptr(self._total), _device.ptr(self._scratch), self._scratch.numel(), st)
+        _capi.call("lint_guide_build", _device.ptr(self._cdf), ncells, self._guide_bits_planned,
+                   _device.ptr(self._guide), st)
+        self._guide_bits = self._guide_bits_planned
+        self._masses_host = None
+
+    def update_densities(self, densities, check=True):
+        """Replace the vertex densities (same edges) and rebuild masses, CDF and
+        guide table on the current stream.  ``densities`` may be a NumPy array or
+        a torch tensor in host (ideally pinned) or device memory.  With
+        ``check=False`` nothing synchronises the host; the validity flags are
+        then read by the next checked call."""
+        import torch
+        npts = self._V.numel()
+        t = densities if isinstance(densities, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(densities))
+        if t.numel() != npts:
+            raise ValueError("DensityGrid.update_densities: wrong number of vertex densities")
+        self._V.copy_(t.reshape(npts), non_blocking=True)       # H2D (+ cast) on the current stream
+        self._host_densities = None
+        self._enqueue_build()
+        if check:
+            self._check_build()
+
+    def _check_build(self):
+        bad = int(self._flags.item())                          # synchronises
         if bad & _capi.LINT_FLAG_NEGATIVE:                     # [grid.py:401-402]
             raise ValueError("DensityGrid: Densities can't be negative")
         if bad & _capi.LINT_FLAG_NONFINITE:                    # [grid.py:403-404]
             raise ValueError("DensityGrid: Detected non-finite density")
-        self._cdf, self._guide, self._guide_bits, self._total_mass = _device.build_cdf(
-            self._masses, self.cdf_mode, dev)
+        self._total_mass = float(self._total.item())
+        if not (self._total_mass > 0.0) or not np.isfinite(self._total_mass):
+            raise ValueError(
+                "DensityGrid: total mass of the grid is not positive and finite "
+                f"({self._total_mass}); cannot build a cell CDF")
 
     def _descriptor(self):
         d = _capi.LintGrid()
@@ -211,14 +296,14 @@ class DensityGrid(DensityStructure):
                    _device.ptr(cells), _device.stream_ptr(self.device))
         return (out, cells) if want_cells else out
 
-    def _sample_philox(self, N, seed, offset, want_cells=False, out=None):
+    def _sample_philox(self, N, seed, offset, want_cells=False, out=None, stratum=(0.0, 1.0)):
         import torch
         if out is None:
             out = torch.empty((N, self._dim), dtype=_device.torch_dtype(self.dtype), device=self.device)
         cells = torch.empty(N, dtype=torch.int64, device=self.device) if want_cells else None
         desc = self._descriptor()
         _capi.call("lint_grid_sample_philox", C.byref(desc), N, C.c_uint64(seed), C.c_uint64(offset),
-                   _device.ptr(out), _device.ptr(cells), _device.stream_ptr(self.device))
+                   C.c_double(stratum[0]), C.c_double(stratum[1]), _device.ptr(out), _device.ptr(cells), _device.stream_ptr(self.device))
         return (out, cells) if want_cells else out
 
     def _sample_sobol(self, N, sobol_struct, want_cells=False):

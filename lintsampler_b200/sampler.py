@@ -312,6 +312,56 @@ class LintSampler:
             return X.squeeze()
         return X
 
+    def sample_to_host(self, N, out=None, chunk=1 << 26):
+        """Draw ``N`` samples straight into host memory, overlapping the sampling
+        kernel of one chunk with the device->host copy of the previous one.
+
+        ``out``: optional pinned host ``torch`` tensor of shape (N, k) in the
+        domain's dtype; allocated (pinned) when omitted.  Returns the host tensor
+        (``.numpy()`` gives a zero-copy NumPy view).  Only for a single native
+        domain with the device Philox stream, whose rows are exchangeable, so no
+        shuffle pass is needed (see ``_host_shuffle``)."""
+        import torch
+        if not isinstance(N, int):
+            raise TypeError(f"LintSampler.sample_to_host: Expected int N, got {type(N)}")
+        if N <= 0:
+            raise ValueError(f"LintSampler.sample_to_host: Expected positive N, got {N}")
+        grid = self.grids[0]
+        if self.ngrids != 1 or self.qmc or self.rng_backend != "philox" or not hasattr(grid, "_sample_philox"):
+            raise ValueError("LintSampler.sample_to_host: needs one native domain and the Philox stream")
+        dev = self._device()
+        tdt = _device.torch_dtype(self._domain_dtype())
+        if out is None:
+            out = torch.empty((N, self.dim), dtype=tdt, pin_memory=True)
+        if tuple(out.shape) != (N, self.dim) or out.dtype != tdt or out.is_cuda:
+            raise ValueError("LintSampler.sample_to_host: `out` must be a host tensor of shape (N, k) "
+                             "in the domain's dtype")
+        chunk = min(int(chunk), N)
+        if getattr(self, "_stage", None) is None or self._stage[0].shape[0] < chunk \
+                or self._stage[0].dtype != tdt:
+            self._stage = [torch.empty((chunk, self.dim), dtype=tdt, device=dev) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
+        main = torch.cuda.current_stream(dev)
+        done = 0
+        i = 0
+        while done < N:
+            n = min(chunk, N - done)
+            buf = self._stage[i & 1]
+            main.wait_event(self._stage_free[i & 1])            # previous copy out of this buffer
+            grid._sample_philox(n, self._philox_key, self._philox_offset, out=buf[:n])
+            self._philox_offset += n
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(ready)
+                out[done:done + n].copy_(buf[:n], non_blocking=True)
+                self._stage_free[i & 1].record(self._copy_stream)
+            done += n
+            i += 1
+        main.wait_stream(self._copy_stream)
+        return out
+
     # ------------------------------------------------------------------ row order
     def _host_shuffle(self):
         """The reference shuffles the rows of every multi-sample draw with

@@ -372,8 +372,8 @@ class DensityTree(DensityStructure):
     def _sample_u(self, u_t, want_cells=False):
         return self._ensure_device().sample_u(u_t, want_cells)
 
-    def _sample_philox(self, N, seed, offset, want_cells=False, out=None):
-        return self._ensure_device().sample_philox(N, seed, offset, want_cells, out)
+    def _sample_philox(self, N, seed, offset, want_cells=False, out=None, stratum=(0.0, 1.0)):
+        return self._ensure_device().sample_philox(N, seed, offset, want_cells, out, stratum)
 
     def _sample_sobol(self, N, sobol_struct, want_cells=False):
         return self._ensure_device().sample_sobol(N, sobol_struct, want_cells)
@@ -447,11 +447,11 @@ class _CellTable:
                    _device.ptr(cells), _device.stream_ptr(self.device))
         return (out, cells) if want_cells else out
 
-    def sample_philox(self, N, seed, offset, want_cells=False, out=None):
+    def sample_philox(self, N, seed, offset, want_cells=False, out=None, stratum=(0.0, 1.0)):
         out, cells = self._alloc(N, want_cells, out)
         desc = self.descriptor()
         _capi.call("lint_cells_sample_philox", C.byref(desc), N, C.c_uint64(seed), C.c_uint64(offset),
-                   _device.ptr(out), _device.ptr(cells), _device.stream_ptr(self.device))
+                   C.c_double(stratum[0]), C.c_double(stratum[1]), _device.ptr(out), _device.ptr(cells), _device.stream_ptr(self.device))
         return (out, cells) if want_cells else out
 
     def sample_sobol(self, N, sobol_struct, want_cells=False):
