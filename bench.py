@@ -190,8 +190,13 @@ def run_b200(args):
     gmm = lb.GaussianMixture(w, means, sigmas=sig)
     n_local = args.samples
     # domain: the whole grid at world 1, this rank's equal-mass shard otherwise
-    shard = lbd.ShardedGrid(edges, gmm, dtype=np.float32, device=dev,
-                            rank=rank, world=world, group=dist.group.WORLD if world > 1 else None)
+    grid_kw = {}
+    if args.guide_bits is not None:
+        grid_kw["guide_bits"] = args.guide_bits
+    if args.no_records:
+        grid_kw["cell_records"] = False
+    shard = lbd.ShardedGrid(edges, gmm, dtype=np.float32, device=dev, rank=rank, world=world,
+                            group=dist.group.WORLD if world > 1 else None, **grid_kw)
     out = torch.empty((n_local, DIM), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream(dev)
 
@@ -318,6 +323,8 @@ def main():
     ap.add_argument("--samples", type=int, default=N_SAMPLES, help="samples per GPU per step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--guide-bits", type=int, default=None, help="tuning: log2 guide-table size")
+    ap.add_argument("--no-records", action="store_true", help="tuning: gather corners from the vertex array")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -78,6 +78,9 @@ typedef struct lint_grid {
     const uint32_t *guide_dev;            /* optional 2^guide_bits+1 entry guide table   */
     int32_t guide_bits;                   /* 0 = no guide table                          */
     int32_t reserved;
+    const void *cell_records_dev;         /* optional (prod(ncells), 2^k) per-cell corner
+                                             densities in corner order (lint_grid_records);
+                                             NULL = gather corners from vertex_densities   */
 } lint_grid_t;
 
 /* Flat cell list == the leaves of a reference DensityTree in list order
@@ -138,6 +141,13 @@ int lint_grid_eval_gmm(const lint_grid_t *g, const lint_gmm_t *gmm, double scale
 int lint_grid_masses(const lint_grid_t *g, double *masses_dev, uint32_t *flags_dev,
                      lint_stream_t stream);
 
+/* Per-cell corner records: for every cell, its 2^k corner densities contiguous in
+ * corner order — the gather of grid.py:440-467 done once per build instead of
+ * once per sample, so a sample reads one record (one 32-byte sector at k=3 fp32)
+ * instead of 2^(k-1) scattered vertex pairs.  records_dev: prod(ncells)*2^k
+ * values in g->dtype.  Optional: set g->cell_records_dev to use them. */
+int lint_grid_records(const lint_grid_t *g, void *records_dev, lint_stream_t stream);
+
 /* Same validity check for a cell list's corner densities [tree.py:598-605]. */
 int lint_cells_check(const lint_cells_t *c, uint32_t *flags_dev, lint_stream_t stream);
 
@@ -157,8 +167,10 @@ int lint_cdf_build(const double *masses_dev, int64_t n, int mode, double *cdf_de
                    lint_stream_t stream);
 
 /* Guide (index) table that shortens the searchsorted of utils.py:197 without
- * changing its result: guide[j] = first i with cdf[i] > j / 2^guide_bits for
- * j = 0..2^guide_bits (inclusive; last entry n-1).  guide_dev: 2^guide_bits+1. */
+ * changing its result: guide[j] & 0x7fffffff = first i with cdf[i] > j / 2^guide_bits
+ * for j = 0..2^guide_bits (inclusive; last entry n-1); bit 31 is set when
+ * guide[j+1] names the same cell, i.e. the entry alone answers every query in the
+ * bin.  guide_dev: 2^guide_bits+1 entries. */
 int lint_guide_build(const double *cdf_dev, int64_t n, int guide_bits,
                      uint32_t *guide_dev, lint_stream_t stream);
 

@@ -27,6 +27,7 @@ class LintGrid(C.Structure):
         ("cdf_dev", C.c_void_p),
         ("guide_dev", C.c_void_p),
         ("guide_bits", C.c_int32), ("reserved", C.c_int32),
+        ("cell_records_dev", C.c_void_p),
     ]
 
 
@@ -68,6 +69,7 @@ PROTOTYPES = {
     "lint_last_error": (C.c_char_p, []),
     "lint_grid_eval_gmm": (C.c_int, [C.POINTER(LintGrid), C.POINTER(LintGmm), C.c_double, _P]),
     "lint_grid_masses": (C.c_int, [C.POINTER(LintGrid), _P, _P, _P]),
+    "lint_grid_records": (C.c_int, [C.POINTER(LintGrid), _P, _P]),
     "lint_cells_check": (C.c_int, [C.POINTER(LintCells), _P, _P]),
     "lint_cdf_scratch_bytes": (C.c_size_t, [_I64]),
     "lint_sum_numpy_f64": (C.c_int, [_P, _I64, _P, _P, C.c_size_t, _P]),

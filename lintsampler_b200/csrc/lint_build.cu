@@ -58,17 +58,38 @@ int validate_grid(const lint_grid_t *g, bool need_cdf, uint64_t *ncells_out, uin
     return LINT_OK;
 }
 
+// Shared-memory budget for the staged edge arrays (elements of the arithmetic type)
+constexpr uint32_t MAX_STAGED_EDGES = 4096;
+
 template <int K>
-GridView<K> make_grid_view(const lint_grid_t *g, uint64_t ncells) {
+GridView<K> make_grid_view(const lint_grid_t *g, uint64_t ncells, bool stage_edges) {
     GridView<K> v;
     v.V = g->vertex_densities_dev;
-    uint32_t stride = 1;
+    v.rec = g->cell_records_dev;
+    uint32_t stride = 1, eoff = 0;
     for (int d = K - 1; d >= 0; --d) {
         v.edges[d] = g->edges_dev[d];
         v.n[d] = (uint32_t)g->ncells[d];
         v.vstride[d] = stride;
         stride *= (uint32_t)g->ncells[d] + 1;
+        // magic division by n[d] for dividends < 2^31 (Granlund & Montgomery):
+        // L = ceil(log2 n), m = floor(2^(31+L) / n) + 1, q = (r * m) >> (31 + L)
+        const uint32_t n = v.n[d];
+        if (n >= 2) {
+            uint32_t L = 0;
+            while ((1ull << L) < n) ++L;
+            v.div_m[d] = (uint32_t)(((1ull << (31 + L)) / n) + 1);
+            v.div_s[d] = L - 1;
+        } else {
+            v.div_m[d] = 0;
+            v.div_s[d] = 0;
+        }
     }
+    for (int d = 0; d < K; ++d) {
+        v.edge_off[d] = eoff;
+        eoff += v.n[d] + 1;
+    }
+    v.edge_total = (stage_edges && eoff <= MAX_STAGED_EDGES) ? eoff : 0;
     for (int c = 0; c < (1 << K); ++c) {
         uint32_t off = 0;
         for (int d = 0; d < K; ++d)
@@ -81,12 +102,12 @@ GridView<K> make_grid_view(const lint_grid_t *g, uint64_t ncells) {
     v.table.n = (uint32_t)ncells;
     return v;
 }
-template GridView<1> make_grid_view<1>(const lint_grid_t *, uint64_t);
-template GridView<2> make_grid_view<2>(const lint_grid_t *, uint64_t);
-template GridView<3> make_grid_view<3>(const lint_grid_t *, uint64_t);
-template GridView<4> make_grid_view<4>(const lint_grid_t *, uint64_t);
-template GridView<5> make_grid_view<5>(const lint_grid_t *, uint64_t);
-template GridView<6> make_grid_view<6>(const lint_grid_t *, uint64_t);
+template GridView<1> make_grid_view<1>(const lint_grid_t *, uint64_t, bool);
+template GridView<2> make_grid_view<2>(const lint_grid_t *, uint64_t, bool);
+template GridView<3> make_grid_view<3>(const lint_grid_t *, uint64_t, bool);
+template GridView<4> make_grid_view<4>(const lint_grid_t *, uint64_t, bool);
+template GridView<5> make_grid_view<5>(const lint_grid_t *, uint64_t, bool);
+template GridView<6> make_grid_view<6>(const lint_grid_t *, uint64_t, bool);
 
 // ---------------------------------------------------------------------------
 // fused Gaussian-mixture vertex evaluation            [replaces grid.py:384-398]
@@ -145,7 +166,7 @@ int eval_gmm_impl(const lint_grid_t *g, const lint_gmm_t *gmm, double scale, uin
             for (int c = r; c < K; ++c) p.U[j][t++] = gmm->prec_chol[(j * K + r) * K + c];
         }
     }
-    GridView<K> v = make_grid_view<K>(g, 1);
+    GridView<K> v = make_grid_view<K>(g, 1, false);
     const int threads = 256;
     const int blocks = (int)std::min<uint64_t>((nverts + threads - 1) / threads, 148 * 32);
     if (g->dtype == LINT_F32)
@@ -167,7 +188,7 @@ cell_mass_kernel(GridView<K> g, uint32_t ncells, double *masses, uint32_t *flags
     for (uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x; cell < ncells;
          cell += gridDim.x * blockDim.x) {
         double c[1 << K], lo[K], hi[K];
-        grid_fetch<K, DensT, double>(g, cell, c, lo, hi);
+        grid_fetch<K, DensT, double>(g, (const double *)nullptr, cell, c, lo, hi);
         double acc = 0.0;                      // `sum = np.zeros(shape)` then += per corner
 #pragma unroll
         for (int j = 0; j < (1 << K); ++j) {
@@ -188,7 +209,8 @@ cell_mass_kernel(GridView<K> g, uint32_t ncells, double *masses, uint32_t *flags
 template <int K>
 int masses_impl(const lint_grid_t *g, uint64_t ncells, double *masses, uint32_t *flags,
                 cudaStream_t st) {
-    GridView<K> v = make_grid_view<K>(g, ncells);
+    GridView<K> v = make_grid_view<K>(g, ncells, false);
+    v.rec = nullptr;                       // masses always come from the vertex array
     const int threads = 256;
     const int blocks = (int)std::min<uint64_t>((ncells + threads - 1) / threads, 148 * 32);
     if (g->dtype == LINT_F32)
@@ -196,6 +218,43 @@ int masses_impl(const lint_grid_t *g, uint64_t ncells, double *masses, uint32_t 
     else
         cell_mass_kernel<K, double><<<blocks, threads, 0, st>>>(v, (uint32_t)ncells, masses, flags);
     return check_launch("lint_grid_masses");
+}
+
+// ---------------------------------------------------------------------------
+// per-cell corner records: the 2^K corner densities of every cell laid out
+// contiguously, so the sampler reads one record instead of 2^(K-1) scattered
+// vertex pairs  [layout for grid.py:440-467]
+// ---------------------------------------------------------------------------
+template <int K, typename DensT>
+__global__ void __launch_bounds__(256)
+cell_records_kernel(GridView<K> g, uint32_t ncells, DensT *rec) {
+    for (uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x; cell < ncells;
+         cell += gridDim.x * blockDim.x) {
+        uint32_t i[K];
+        grid_unravel<K>(g, cell, i);
+        uint32_t base = 0;
+#pragma unroll
+        for (int d = 0; d < K; ++d) base += i[d] * g.vstride[d];
+        const DensT *V = reinterpret_cast<const DensT *>(g.V);
+        DensT v[1 << K];
+#pragma unroll
+        for (int j = 0; j < (1 << K); ++j) v[j] = __ldg(V + base + g.corner_off[j]);
+        DensT *dst = rec + (size_t)cell * (1 << K);
+#pragma unroll
+        for (int j = 0; j < (1 << K); ++j) dst[j] = v[j];
+    }
+}
+
+template <int K>
+int records_impl(const lint_grid_t *g, uint64_t ncells, void *rec, cudaStream_t st) {
+    GridView<K> v = make_grid_view<K>(g, ncells, false);
+    const int threads = 256;
+    const int blocks = (int)std::min<uint64_t>((ncells + threads - 1) / threads, 148 * 32);
+    if (g->dtype == LINT_F32)
+        cell_records_kernel<K, float><<<blocks, threads, 0, st>>>(v, (uint32_t)ncells, (float *)rec);
+    else
+        cell_records_kernel<K, double><<<blocks, threads, 0, st>>>(v, (uint32_t)ncells, (double *)rec);
+    return check_launch("lint_grid_records");
 }
 
 template <typename DensT>
@@ -481,7 +540,8 @@ scan_apply_kernel(const double *m, uint64_t n, const double *tile_off, const dou
 // ---------------------------------------------------------------------------
 // guide table
 // ---------------------------------------------------------------------------
-// guide[j] = first i with cdf[i] > j/G.  Cell i owns the bins j with
+// guide[j] = first i with cdf[i] > j/G (bit 31: the bin lies wholly inside that
+// cell, i.e. guide[j+1] is the same cell).  Cell i owns the bins j with
 // cdf[i-1] <= j/G < cdf[i], i.e. j in [ceil(cdf[i-1]*G), ceil(cdf[i]*G)).
 // One warp walks 32 consecutive cells; short runs are written by the owning
 // lane, long runs cooperatively.
@@ -500,15 +560,16 @@ guide_build_kernel(const double *cdf, uint32_t n, int bits, uint32_t *guide) {
             j1 = i == n - 1 ? Gi + 1 : (uint32_t)min(ceil(cdf[i] * G), G);   // last cell also owns j = G
         }
         const uint32_t len = j1 > j0 ? j1 - j0 : 0;
+        // every bin but the cell's last lies wholly inside the cell: flag it
         if (len > 0 && len <= 32)
-            for (uint32_t j = j0; j < j1; ++j) guide[j] = i;
+            for (uint32_t j = j0; j < j1; ++j) guide[j] = j + 1 < j1 ? (i | GUIDE_SAME) : i;
         uint32_t longmask = __ballot_sync(0xffffffffu, len > 32);
         while (longmask) {
             const int src = __ffs(longmask) - 1;
             longmask &= longmask - 1;
             const uint32_t a = __shfl_sync(0xffffffffu, j0, src), b = __shfl_sync(0xffffffffu, j1, src);
             const uint32_t ci = w * 32 + src;
-            for (uint32_t j = a + lane; j < b; j += 32) guide[j] = ci;
+            for (uint32_t j = a + lane; j < b; j += 32) guide[j] = j + 1 < b ? (ci | GUIDE_SAME) : ci;
         }
     }
 }
@@ -558,6 +619,21 @@ int lint_grid_masses(const lint_grid_t *g, double *masses_dev, uint32_t *flags_d
         case 4: return masses_impl<4>(g, nc, masses_dev, flags_dev, st);
         case 5: return masses_impl<5>(g, nc, masses_dev, flags_dev, st);
         default: return masses_impl<6>(g, nc, masses_dev, flags_dev, st);
+    }
+}
+
+int lint_grid_records(const lint_grid_t *g, void *records_dev, lint_stream_t stream) {
+    uint64_t nc, nv;
+    if (int rc = validate_grid(g, false, &nc, &nv)) return rc;
+    if (!records_dev) return fail(LINT_ERR_BAD_ARG, "lint_grid_records: records_dev is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (g->dim) {
+        case 1: return records_impl<1>(g, nc, records_dev, st);
+        case 2: return records_impl<2>(g, nc, records_dev, st);
+        case 3: return records_impl<3>(g, nc, records_dev, st);
+        case 4: return records_impl<4>(g, nc, records_dev, st);
+        case 5: return records_impl<5>(g, nc, records_dev, st);
+        default: return records_impl<6>(g, nc, records_dev, st);
     }
 }
 

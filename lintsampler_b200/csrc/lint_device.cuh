@@ -60,6 +60,11 @@ struct CdfView {
     int guide_bits;
 };
 
+// Guide entries carry a flag in bit 31: set when the whole bin lies inside one
+// cell (guide[j] == guide[j+1]), in which case the entry IS the answer and no
+// second load is needed — the common case for every cell wider than a bin.
+constexpr uint32_t GUIDE_SAME = 0x80000000u;
+
 __device__ __forceinline__ uint32_t search_right(const CdfView &t, double u) {
     uint32_t lo = 0, hi = t.n - 1;
     if (t.guide_bits > 0) {
@@ -67,8 +72,10 @@ __device__ __forceinline__ uint32_t search_right(const CdfView &t, double u) {
         const uint32_t G = 1u << t.guide_bits;
         uint32_t j = (uint32_t)(u * (double)G);
         j = j < G ? j : G - 1;
-        lo = __ldg(t.guide + j);
-        hi = __ldg(t.guide + j + 1);
+        const uint32_t e = __ldg(t.guide + j);
+        lo = e & ~GUIDE_SAME;
+        if (e & GUIDE_SAME) return lo;
+        hi = __ldg(t.guide + j + 1) & ~GUIDE_SAME;
     }
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
@@ -167,31 +174,88 @@ __device__ __forceinline__ void incell_fast(float (&c)[1 << K], const float (&u)
 // limited to < 2^31 so all index arithmetic is 32-bit.
 template <int K>
 struct GridView {
-    const void *V;
+    const void *V;                 // vertex densities, C order
+    const void *rec;               // optional per-cell corner records (ncells, 2^K), or NULL
     const double *edges[K];
     CdfView table;
     uint32_t n[K];                 // cells per dim
+    uint32_t div_m[K], div_s[K];   // q = umulhi(r, div_m) >> div_s  ==  r / n[d]  for r < 2^31
     uint32_t vstride[K];           // vertex strides (elements)
+    uint32_t edge_off[K];          // offset of dim d's edges in the shared-memory copy
+    uint32_t edge_total;           // sum(n[d] + 1); 0 = do not stage edges in shared memory
     uint32_t corner_off[1 << K];   // vertex offset of corner c from the cell origin
 };
 
-template <int K, typename DensT, typename T>
-__device__ __forceinline__ void grid_fetch(const GridView<K> &g, uint32_t flat, T (&c)[1 << K],
-                                           T (&lo)[K], T (&hi)[K]) {
-    // C-order unravel  [grid.py:437]
-    uint32_t r = flat, base = 0;
+// C-order unravel of a flat cell index  [grid.py:437]; exact for flat < 2^31
+template <int K>
+__device__ __forceinline__ void grid_unravel(const GridView<K> &g, uint32_t flat, uint32_t (&i)[K]) {
+    uint32_t r = flat;
 #pragma unroll
-    for (int d = K - 1; d >= 0; --d) {
-        uint32_t i;
-        if (d == 0) { i = r; } else { const uint32_t q = r / g.n[d]; i = r - q * g.n[d]; r = q; }
-        base += i * g.vstride[d];
-        lo[d] = (T)__ldg(g.edges[d] + i);        // _cell_mins gather [grid.py:353]
-        hi[d] = (T)__ldg(g.edges[d] + i + 1);    // _cell_maxs gather [grid.py:354]
+    for (int d = K - 1; d > 0; --d) {
+        const uint32_t q = g.n[d] == 1 ? r : (__umulhi(r, g.div_m[d]) >> g.div_s[d]);
+        i[d] = r - q * g.n[d];
+        r = q;
     }
-    // 2^K corner gather, corner order = MSB-first bit pattern [grid.py:440-467]
-    const DensT *V = reinterpret_cast<const DensT *>(g.V);
+    i[0] = r;
+}
+
+// Cell box + 2^K corner densities of cell `flat`.  `sedges` is the CTA's
+// shared-memory copy of the edge arrays in arithmetic type T (or unused when
+// g.edge_total == 0).
+template <int K, typename DensT, typename T>
+__device__ __forceinline__ void grid_fetch(const GridView<K> &g, const T *sedges, uint32_t flat,
+                                           T (&c)[1 << K], T (&lo)[K], T (&hi)[K]) {
+    uint32_t i[K];
+    grid_unravel<K>(g, flat, i);
+    if (g.edge_total) {
 #pragma unroll
-    for (int j = 0; j < (1 << K); ++j) c[j] = (T)__ldg(V + base + g.corner_off[j]);
+        for (int d = 0; d < K; ++d) {
+            lo[d] = sedges[g.edge_off[d] + i[d]];          // _cell_mins gather [grid.py:353]
+            hi[d] = sedges[g.edge_off[d] + i[d] + 1];      // _cell_maxs gather [grid.py:354]
+        }
+    } else {
+#pragma unroll
+        for (int d = 0; d < K; ++d) {
+            lo[d] = (T)__ldg(g.edges[d] + i[d]);
+            hi[d] = (T)__ldg(g.edges[d] + i[d] + 1);
+        }
+    }
+    // 2^K corner densities, corner order = MSB-first bit pattern [grid.py:440-467]
+    if (g.rec) {
+        // one contiguous record per cell: a single 32 B sector for K=3 fp32
+        constexpr int NB = (1 << K) * (int)sizeof(DensT);
+        const char *p = reinterpret_cast<const char *>(g.rec) + (size_t)flat * NB;
+        DensT v[1 << K];
+        if constexpr (NB % 16 == 0) {
+#pragma unroll
+            for (int q = 0; q < NB / 16; ++q)
+                reinterpret_cast<uint4 *>(v)[q] = __ldg(reinterpret_cast<const uint4 *>(p) + q);
+        } else {
+#pragma unroll
+            for (int q = 0; q < NB / 8; ++q)
+                reinterpret_cast<uint2 *>(v)[q] = __ldg(reinterpret_cast<const uint2 *>(p) + q);
+        }
+#pragma unroll
+        for (int j = 0; j < (1 << K); ++j) c[j] = (T)v[j];
+    } else {
+        uint32_t base = 0;
+#pragma unroll
+        for (int d = 0; d < K; ++d) base += i[d] * g.vstride[d];
+        const DensT *V = reinterpret_cast<const DensT *>(g.V);
+#pragma unroll
+        for (int j = 0; j < (1 << K); ++j) c[j] = (T)__ldg(V + base + g.corner_off[j]);
+    }
+}
+
+// Stage the edge arrays into shared memory (converted to T) once per CTA.
+template <int K, typename T>
+__device__ __forceinline__ void grid_stage_edges(const GridView<K> &g, T *sedges) {
+    if (!g.edge_total) return;
+#pragma unroll
+    for (int d = 0; d < K; ++d)
+        for (uint32_t j = threadIdx.x; j <= g.n[d]; j += blockDim.x)
+            sedges[g.edge_off[d] + j] = (T)__ldg(g.edges[d] + j);
+    __syncthreads();
 }
 
 // Flat cell list (reference DensityTree leaves, list order)  [tree.py:334-355]

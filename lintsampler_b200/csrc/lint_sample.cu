@@ -10,7 +10,7 @@
 namespace lint {
 
 int validate_grid(const lint_grid_t *g, bool need_cdf, uint64_t *ncells_out, uint64_t *nverts_out);
-template <int K> GridView<K> make_grid_view(const lint_grid_t *g, uint64_t ncells);
+template <int K> GridView<K> make_grid_view(const lint_grid_t *g, uint64_t ncells, bool stage_edges);
 
 // ---------------------------------------------------------------------------
 // cell-source adaptors
@@ -18,21 +18,29 @@ template <int K> GridView<K> make_grid_view(const lint_grid_t *g, uint64_t ncell
 template <int K, typename DensT>
 struct GridSource {
     GridView<K> g;
+    __host__ size_t smem_bytes(size_t elem) const { return (size_t)g.edge_total * elem; }
+    template <typename T>
+    __device__ __forceinline__ void prepare(T *smem) const { grid_stage_edges<K, T>(g, smem); }
     __device__ __forceinline__ uint32_t choose(double u) const {
         return g.table.n == 1 ? 0u : search_right(g.table, u);   // grid.py:427-428 shortcut
     }
     template <typename T>
-    __device__ __forceinline__ void fetch(uint32_t idx, T (&c)[1 << K], T (&lo)[K], T (&hi)[K]) const {
-        grid_fetch<K, DensT, T>(g, idx, c, lo, hi);
+    __device__ __forceinline__ void fetch(const T *smem, uint32_t idx, T (&c)[1 << K], T (&lo)[K],
+                                          T (&hi)[K]) const {
+        grid_fetch<K, DensT, T>(g, smem, idx, c, lo, hi);
     }
 };
 
 template <int K, typename DensT>
 struct ListSource {
     CellsView s;
+    __host__ size_t smem_bytes(size_t) const { return 0; }
+    template <typename T>
+    __device__ __forceinline__ void prepare(T *) const {}
     __device__ __forceinline__ uint32_t choose(double u) const { return search_right(s.table, u); }
     template <typename T>
-    __device__ __forceinline__ void fetch(uint32_t idx, T (&c)[1 << K], T (&lo)[K], T (&hi)[K]) const {
+    __device__ __forceinline__ void fetch(const T *, uint32_t idx, T (&c)[1 << K], T (&lo)[K],
+                                          T (&hi)[K]) const {
         cells_fetch<K, DensT, T>(s, idx, c, lo, hi);
     }
 };
@@ -46,6 +54,9 @@ template <int K, typename T, typename Source, typename Uniforms>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 sample_kernel(Source src, Uniforms unif, int64_t N, T *__restrict__ out,
               int64_t *__restrict__ cell_idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *smem = reinterpret_cast<T *>(smem_raw);
+    src.prepare(smem);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < N; row += stride) {
         double ucell;
@@ -53,7 +64,7 @@ sample_kernel(Source src, Uniforms unif, int64_t N, T *__restrict__ out,
         unif.get(row, ucell, u);
         const uint32_t idx = src.choose(ucell);           // grid.choose_cells(u[..., -1])
         T c[1 << K], lo[K], hi[K], z[K];
-        src.fetch(idx, c, lo, hi);
+        src.fetch(smem, idx, c, lo, hi);
         incell<K>(c, u, z);                               // _unitsample_kd(*corners, u=u[..., :-1])
 #pragma unroll
         for (int d = 0; d < K; ++d) out[row * K + d] = affine(lo[d], hi[d], z[d]);
@@ -67,7 +78,8 @@ int launch_sample(const Source &src, const Uniforms &unif, int64_t N, void *out,
     if (N == 0) return LINT_OK;
     const int64_t want = (N + SAMPLE_THREADS - 1) / SAMPLE_THREADS;
     const int blocks = (int)std::min<int64_t>(want, 148 * 64);
-    sample_kernel<K, T, Source, Uniforms><<<blocks, SAMPLE_THREADS, 0, st>>>(src, unif, N, (T *)out, cell_idx);
+    sample_kernel<K, T, Source, Uniforms><<<blocks, SAMPLE_THREADS, src.smem_bytes(sizeof(T)), st>>>(
+        src, unif, N, (T *)out, cell_idx);
     return check_launch(what);
 }
 
@@ -78,10 +90,10 @@ template <int K, typename UnifMaker>
 int grid_dispatch_k(const lint_grid_t *g, uint64_t ncells, int64_t N, void *out, int64_t *cell_idx,
                     cudaStream_t st, const UnifMaker &mk, const char *what) {
     if (g->dtype == LINT_F32) {
-        GridSource<K, float> src{make_grid_view<K>(g, ncells)};
+        GridSource<K, float> src{make_grid_view<K>(g, ncells, true)};
         return launch_sample<K, float>(src, mk.template make<K>(), N, out, cell_idx, st, what);
     }
-    GridSource<K, double> src{make_grid_view<K>(g, ncells)};
+    GridSource<K, double> src{make_grid_view<K>(g, ncells, true)};
     return launch_sample<K, double>(src, mk.template make<K>(), N, out, cell_idx, st, what);
 }
 

@@ -45,10 +45,10 @@ class ShardedGrid:
     """
 
     def __init__(self, edges, pdf, *, dtype=np.float64, device=None, rank=0, world=1,
-                 group=None, vectorizedpdf=True, cdf_mode="parallel"):
+                 group=None, vectorizedpdf=True, cdf_mode="parallel", **grid_kw):
         self.rank, self.world, self.group = int(rank), int(world), group
         self.grid = DensityGrid(edges, pdf, vectorizedpdf=vectorizedpdf, dtype=dtype, device=device,
-                                cdf_mode=cdf_mode)
+                                cdf_mode=cdf_mode, **grid_kw)
         self.device = self.grid.device
         self.bounds = equal_mass_strata(self.world)
         self.shard_masses = None
@@ -111,8 +111,8 @@ class ShardedGrid:
     # -- reporting -------------------------------------------------------------
     def launches_per_step(self):
         """Kernels of this library launched by enqueue_build + one sampling call:
-        masses 1, parallel CDF 4, guide 1, sampler 1."""
-        return 7
+        masses 1, cell records 1, parallel CDF 4, guide 1, sampler 1."""
+        return 8 if self.grid._rec is not None else 7
 
     def describe(self):
         if self.world == 1:

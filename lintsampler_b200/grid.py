@@ -50,10 +50,14 @@ class DensityGrid(DensityStructure):
         ``cumsum``; slower, used for exact parity).
     pdf_on_device : if True the vectorised ``pdf`` is called with a torch CUDA
         tensor of shape (npts, k) and must return a torch tensor.
+    guide_bits : log2 of the guide-table size (default: about one bin per cell).
+    cell_records : keep a per-cell copy of the 2^k corner densities so a sample
+        reads one contiguous record (default: on when it needs < 8 GiB).
     """
 
     def __init__(self, edges, pdf, vectorizedpdf=False, pdf_args=(), pdf_kwargs={},
-                 *, dtype=np.float64, device=None, cdf_mode="parallel", pdf_on_device=False):
+                 *, dtype=np.float64, device=None, cdf_mode="parallel", pdf_on_device=False,
+                 guide_bits=None, cell_records=None):
         # --- domain parsing: one flat sequence, or a tuple of them  [grid.py:256-285]
         if _is_flat_sequence(edges):
             arrays = [np.array(edges)]
@@ -80,6 +84,8 @@ class DensityGrid(DensityStructure):
         self.dtype = _device.check_dtype(dtype)
         self.cdf_mode = cdf_mode
         self._device_arg = device
+        self._guide_bits_arg = guide_bits
+        self._cell_records_arg = cell_records
         self._host_densities = None
         self._masses_host = None
         self._evaluate_pdf(pdf, vectorizedpdf, pdf_args, pdf_kwargs, pdf_on_device)
@@ -213,7 +219,11 @@ class DensityGrid(DensityStructure):
         self._flags = torch.zeros(1, dtype=torch.int32, device=dev)
         self._cdf = torch.empty(ncells, dtype=torch.float64, device=dev)
         self._total = torch.empty(1, dtype=torch.float64, device=dev)
-        self._guide_bits_planned = _device.default_guide_bits(ncells)
+        self._guide_bits_planned = (int(self._guide_bits_arg) if self._guide_bits_arg is not None
+                                    else _device.default_guide_bits(ncells))
+        rec_bytes = ncells * (2 ** self._dim) * np.dtype(self.dtype).itemsize
+        want_rec = self._cell_records_arg if self._cell_records_arg is not None else rec_bytes < (8 << 30)
+        self._rec = torch.empty(ncells * 2 ** self._dim, dtype=tdt, device=dev) if want_rec else None
         self._guide = torch.empty((1 << self._guide_bits_planned) + 1, dtype=torch.int32, device=dev)
         nbytes = _capi.load().lint_cdf_scratch_bytes(ncells)
         self._scratch = torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device=dev)
@@ -222,8 +232,7 @@ class DensityGrid(DensityStructure):
 
     def _enqueue_build(self):
         """Cell masses -> CDF -> guide table, enqueued on the current stream with no
-        host synchronisation (grid.py:411-412, 431; utils.py:195-196).  Seven kernel
-        launches in parallel-CDF mode."""
+        host synchronisation (grid.py:411-412, 431; utils.py:195-196)."""
         dev = self.device
         st = _device.stream_ptr(dev)
         ncells = int(self.ncells)
@@ -234,6 +243,8 @@ class DensityGrid(DensityStructure):
         desc = self._descriptor()
         self._flags.zero_()
         _capi.call("lint_grid_masses", C.byref(desc), _device.ptr(self._masses), _device.ptr(self._flags), st)
+        if self._rec is not None:
+            _capi.call("lint_grid_records", C.byref(desc), _device.ptr(self._rec), st)
         _capi.call("lint_cdf_build", _device.ptr(self._masses), ncells, mode, _device.ptr(self._cdf),
                    _device.ptr(self._total), _device.ptr(self._scratch), self._scratch.numel(), st)
         _capi.call("lint_guide_build", _device.ptr(self._cdf), ncells, self._guide_bits_planned,
@@ -282,6 +293,8 @@ class DensityGrid(DensityStructure):
         d.cdf_dev = self._cdf.data_ptr() if self._cdf is not None else None
         d.guide_dev = self._guide.data_ptr() if self._guide is not None else None
         d.guide_bits = self._guide_bits
+        rec = getattr(self, "_rec", None)
+        d.cell_records_dev = rec.data_ptr() if rec is not None else None
         return d
 
     # ------------------------------------------------------------------ sampling entry points

@@ -92,9 +92,11 @@ def test_cdf_modes(lb, n, mode):
     assert np.array_equal(cdf[zero], cdf[zero - 1])    # zero-mass cells stay unselectable
     # guide table == searchsorted of the same table at j / G
     G = 1 << bits
-    gt = guide.cpu().numpy().astype(np.int64)
+    raw = guide.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    gt, same = raw & 0x7FFFFFFF, (raw >> 31).astype(bool)
     want = np.minimum(cdf.searchsorted(np.arange(G + 1) / G, side="right"), n - 1)
     assert np.array_equal(gt, want)
+    assert np.array_equal(same[:-1], want[:-1] == want[1:])   # bit 31: bin wholly inside one cell
 
 
 def test_parallel_cdf_is_deterministic(lb):
