@@ -325,7 +325,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--guide-bits", type=int, default=None, help="tuning: log2 guide-table size")
     ap.add_argument("--no-records", action="store_true", help="tuning: gather corners from the vertex array")
+    ap.add_argument("--grid-n", type=int, default=None, help="tuning: cells per dim (default 256)")
     args = ap.parse_args()
+    if args.grid_n:
+        global GRID_N
+        GRID_N = args.grid_n
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)

@@ -65,8 +65,49 @@ struct CdfView {
 // second load is needed — the common case for every cell wider than a bin.
 constexpr uint32_t GUIDE_SAME = 0x80000000u;
 
-__device__ __forceinline__ uint32_t search_right(const CdfView &t, double u) {
-    uint32_t lo = 0, hi = t.n - 1;
+// 256-bit non-coherent loads (sm_100+): one request, one 32-byte sector
+__device__ __forceinline__ void ldg256(const double *p, double (&v)[4]) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void ldg256(const float *p, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]),
+                   "=f"(v[7]) : "l"(p));
+}
+
+// First i in [lo, hi] with cdf[i] > u, given that cdf[hi] > u.  Long brackets are
+// halved by binary search; short ones are resolved by 32-byte windows of four
+// consecutive CDF entries (one sector, one request) so the common case costs a
+// single memory round trip instead of log2(range) dependent ones.
+__device__ __forceinline__ uint32_t search_bracket(const CdfView &t, double u, uint32_t lo, uint32_t hi) {
+    while (hi - lo > 8) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(t.cdf + mid) > u) hi = mid; else lo = mid + 1;
+    }
+    while (lo < hi) {
+        const uint32_t a = lo & ~3u;
+        if (a + 4 > t.n) {                       // ragged tail of the table: scalar probes
+            if (__ldg(t.cdf + lo) > u) return lo;
+            ++lo;
+            continue;
+        }
+        double w[4];
+        ldg256(t.cdf + a, w);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t i = a + q;
+            if (i >= lo && i < hi && w[q] > u) return i;
+        }
+        lo = a + 4 < hi ? a + 4 : hi;
+    }
+    return lo;
+}
+
+// Guide lookup: bracket [lo, hi] of the answer, lo == hi when the bin is flagged.
+__device__ __forceinline__ void guide_bracket(const CdfView &t, double u, uint32_t &lo, uint32_t &hi) {
+    lo = 0;
+    hi = t.n - 1;
     if (t.guide_bits > 0) {
         // u * 2^bits is exact in fp64; u < 1 keeps j < 2^bits
         const uint32_t G = 1u << t.guide_bits;
@@ -74,14 +115,14 @@ __device__ __forceinline__ uint32_t search_right(const CdfView &t, double u) {
         j = j < G ? j : G - 1;
         const uint32_t e = __ldg(t.guide + j);
         lo = e & ~GUIDE_SAME;
-        if (e & GUIDE_SAME) return lo;
-        hi = __ldg(t.guide + j + 1) & ~GUIDE_SAME;
+        hi = (e & GUIDE_SAME) ? lo : (__ldg(t.guide + j + 1) & ~GUIDE_SAME);
     }
-    while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (__ldg(t.cdf + mid) > u) hi = mid; else lo = mid + 1;
-    }
-    return lo;
+}
+
+__device__ __forceinline__ uint32_t search_right(const CdfView &t, double u) {
+    uint32_t lo, hi;
+    guide_bracket(t, u, lo, hi);
+    return lo < hi ? search_bracket(t, u, lo, hi) : lo;
 }
 
 // ---------------------------------------------------------------------------
@@ -99,10 +140,22 @@ __device__ __forceinline__ double quantile_exact(double f0, double f1, double u)
 
 // fp32: algebraically equal conjugate form (no cancellation when f0 ~ f1,
 // SURVEY.md §7.3-3); inputs are pre-normalised so the squares cannot underflow.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ float quantile_fast(float f0, float f1, float u) {
     const float rad = fmaf(u, fmaf(f1, f1, -f0 * f0), f0 * f0);
-    const float den = f0 + __fsqrt_rn(fmaxf(rad, 0.f));
-    return den > 0.f ? __fdividef((f0 + f1) * u, den) : u;
+    const float den = f0 + sqrt_approx(fmaxf(rad, 0.f));
+    // den == 0 only when both ends of the segment carry no density: uniform draw
+    return den > 0.f ? (f0 + f1) * u * rcp_approx(den) : u;
 }
 
 // ---------------------------------------------------------------------------
@@ -151,7 +204,7 @@ __device__ __forceinline__ void incell_fast(float (&c)[1 << K], const float (&u)
     float m = c[0];
 #pragma unroll
     for (int j = 1; j < (1 << K); ++j) m = fmaxf(m, c[j]);
-    const float inv = m > 0.f ? __frcp_rn(m) : 0.f;
+    const float inv = m > 0.f ? rcp_approx(m) : 0.f;
 #pragma unroll
     for (int j = 0; j < (1 << K); ++j) c[j] *= inv;
 #pragma unroll
@@ -224,9 +277,14 @@ __device__ __forceinline__ void grid_fetch(const GridView<K> &g, const T *sedges
     if (g.rec) {
         // one contiguous record per cell: a single 32 B sector for K=3 fp32
         constexpr int NB = (1 << K) * (int)sizeof(DensT);
-        const char *p = reinterpret_cast<const char *>(g.rec) + (size_t)flat * NB;
+        const DensT *p = reinterpret_cast<const DensT *>(g.rec) + (size_t)flat * (1 << K);
         DensT v[1 << K];
-        if constexpr (NB % 16 == 0) {
+        if constexpr (NB % 32 == 0) {
+            constexpr int PER = 32 / (int)sizeof(DensT);
+#pragma unroll
+            for (int q = 0; q < NB / 32; ++q)
+                ldg256(p + q * PER, *reinterpret_cast<DensT(*)[PER]>(v + q * PER));
+        } else if constexpr (NB % 16 == 0) {
 #pragma unroll
             for (int q = 0; q < NB / 16; ++q)
                 reinterpret_cast<uint4 *>(v)[q] = __ldg(reinterpret_cast<const uint4 *>(p) + q);
@@ -373,6 +431,11 @@ __device__ __forceinline__ double affine(double lo, double hi, double z) {
 __device__ __forceinline__ float affine(float lo, float hi, float z) {
     return fmaf(hi - lo, z, lo);
 }
+
+// streaming (evict-first) stores for the sample rows: 12 GB of output must not
+// evict the guide table and cell records from L2
+__device__ __forceinline__ void store_stream(float *p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void store_stream(double *p, double v) { __stcs(p, v); }
 
 template <int K> __device__ __forceinline__ void incell(double (&c)[1 << K], const double (&u)[K], double (&z)[K]) { incell_exact<K>(c, u, z); }
 template <int K> __device__ __forceinline__ void incell(float (&c)[1 << K], const float (&u)[K], float (&z)[K]) { incell_fast<K>(c, u, z); }

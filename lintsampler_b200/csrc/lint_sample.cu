@@ -21,8 +21,12 @@ struct GridSource {
     __host__ size_t smem_bytes(size_t elem) const { return (size_t)g.edge_total * elem; }
     template <typename T>
     __device__ __forceinline__ void prepare(T *smem) const { grid_stage_edges<K, T>(g, smem); }
-    __device__ __forceinline__ uint32_t choose(double u) const {
-        return g.table.n == 1 ? 0u : search_right(g.table, u);   // grid.py:427-428 shortcut
+    __device__ __forceinline__ void bracket(double u, uint32_t &lo, uint32_t &hi) const {
+        if (g.table.n == 1) { lo = hi = 0; return; }             // grid.py:427-428 shortcut
+        guide_bracket(g.table, u, lo, hi);
+    }
+    __device__ __forceinline__ uint32_t resolve(double u, uint32_t lo, uint32_t hi) const {
+        return search_bracket(g.table, u, lo, hi);
     }
     template <typename T>
     __device__ __forceinline__ void fetch(const T *smem, uint32_t idx, T (&c)[1 << K], T (&lo)[K],
@@ -37,7 +41,12 @@ struct ListSource {
     __host__ size_t smem_bytes(size_t) const { return 0; }
     template <typename T>
     __device__ __forceinline__ void prepare(T *) const {}
-    __device__ __forceinline__ uint32_t choose(double u) const { return search_right(s.table, u); }
+    __device__ __forceinline__ void bracket(double u, uint32_t &lo, uint32_t &hi) const {
+        guide_bracket(s.table, u, lo, hi);
+    }
+    __device__ __forceinline__ uint32_t resolve(double u, uint32_t lo, uint32_t hi) const {
+        return search_bracket(s.table, u, lo, hi);
+    }
     template <typename T>
     __device__ __forceinline__ void fetch(const T *, uint32_t idx, T (&c)[1 << K], T (&lo)[K],
                                           T (&hi)[K]) const {
@@ -50,25 +59,55 @@ struct ListSource {
 // ---------------------------------------------------------------------------
 constexpr int SAMPLE_THREADS = 256;
 
+// Rows per thread per iteration.  The chain guide -> CDF window -> cell record is
+// three dependent memory round trips per row; issuing it for several independent
+// rows at once is what hides the latency (the tables are L2/HBM resident and
+// randomly addressed, so there is no locality to exploit instead).
+template <typename T> struct RowsPerThread { static constexpr int value = 1; };
+
 template <int K, typename T, typename Source, typename Uniforms>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 sample_kernel(Source src, Uniforms unif, int64_t N, T *__restrict__ out,
               int64_t *__restrict__ cell_idx) {
+    constexpr int R = RowsPerThread<T>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *smem = reinterpret_cast<T *>(smem_raw);
     src.prepare(smem);
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < N; row += stride) {
-        double ucell;
-        T u[K];
-        unif.get(row, ucell, u);
-        const uint32_t idx = src.choose(ucell);           // grid.choose_cells(u[..., -1])
-        T c[1 << K], lo[K], hi[K], z[K];
-        src.fetch(smem, idx, c, lo, hi);
-        incell<K>(c, u, z);                               // _unitsample_kd(*corners, u=u[..., :-1])
+    const int64_t tile = (int64_t)SAMPLE_THREADS * R;
+    for (int64_t base = (int64_t)blockIdx.x * tile; base < N; base += (int64_t)gridDim.x * tile) {
+        double ucell[R];
+        T u[R][K];
+        uint32_t lo[R], hi[R];
+        bool live[R];
+        // stage 1: uniforms and guide brackets for all rows (independent loads in flight)
 #pragma unroll
-        for (int d = 0; d < K; ++d) out[row * K + d] = affine(lo[d], hi[d], z[d]);
-        if (cell_idx) cell_idx[row] = (int64_t)idx;
+        for (int r = 0; r < R; ++r) {
+            const int64_t row = base + (int64_t)r * SAMPLE_THREADS + threadIdx.x;
+            live[r] = row < N;
+            unif.get(live[r] ? row : 0, ucell[r], u[r]);
+            src.bracket(ucell[r], lo[r], hi[r]);           // grid.choose_cells(u[..., -1])
+        }
+        // stage 2: resolve the brackets that span more than one cell
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (lo[r] < hi[r]) lo[r] = src.resolve(ucell[r], lo[r], hi[r]);
+        // stage 3: cell boxes and corner densities
+        T c[R][1 << K], xlo[R][K], xhi[R][K];
+#pragma unroll
+        for (int r = 0; r < R; ++r) src.fetch(smem, lo[r], c[r], xlo[r], xhi[r]);
+        // stage 4: in-cell inverse CDF, affine map, streaming stores
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            T z[K];
+            incell<K>(c[r], u[r], z);                      // _unitsample_kd(*corners, u=u[..., :-1])
+            const int64_t row = base + (int64_t)r * SAMPLE_THREADS + threadIdx.x;
+            if (live[r]) {
+#pragma unroll
+                for (int d = 0; d < K; ++d)
+                    store_stream(out + row * K + d, affine(xlo[r][d], xhi[r][d], z[d]));
+                if (cell_idx) __stcs(reinterpret_cast<long long *>(cell_idx) + row, (long long)lo[r]);
+            }
+        }
     }
 }
 
@@ -76,8 +115,9 @@ template <int K, typename T, typename Source, typename Uniforms>
 int launch_sample(const Source &src, const Uniforms &unif, int64_t N, void *out, int64_t *cell_idx,
                   cudaStream_t st, const char *what) {
     if (N == 0) return LINT_OK;
-    const int64_t want = (N + SAMPLE_THREADS - 1) / SAMPLE_THREADS;
-    const int blocks = (int)std::min<int64_t>(want, 148 * 64);
+    const int64_t tile = (int64_t)SAMPLE_THREADS * RowsPerThread<T>::value;
+    const int64_t want = (N + tile - 1) / tile;
+    const int blocks = (int)std::min<int64_t>(want, 148 * 32);
     sample_kernel<K, T, Source, Uniforms><<<blocks, SAMPLE_THREADS, src.smem_bytes(sizeof(T)), st>>>(
         src, unif, N, (T *)out, cell_idx);
     return check_launch(what);

@@ -31,6 +31,35 @@ def split_counts(n_total, shard_masses, seed):
     return np.random.default_rng(seed).multinomial(int(n_total), p)
 
 
+def all_gather_masses(local_mass, world, group=None, out=None):
+    """All-gather one fp64 scalar per rank (NCCL on device tensors, gloo on CPU
+    tensors): the per-shard masses.  Returns a (world,) tensor on the same
+    device; asynchronous with respect to the host for device tensors."""
+    import torch
+    local_mass = local_mass.reshape(1).to(torch.float64)
+    if out is None:
+        out = torch.empty(world, dtype=torch.float64, device=local_mass.device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(out, local_mass, group=group)
+    else:
+        out.copy_(local_mass)
+    return out
+
+
+def route_rows(u_cell, bounds):
+    """Parity-mode routing of caller-supplied uniforms: rank of each row and its
+    cell uniform rescaled into that rank's stratum, exactly the list-of-domains
+    arithmetic of lintsampler.py:290-306 (``_choice`` on the normalised
+    cumulative masses, then ``(u - start) / (end - start)``)."""
+    u_cell = np.asarray(u_cell, dtype=np.float64)
+    p = np.diff(np.asarray(bounds, dtype=np.float64))
+    c = p.cumsum()
+    rank = (c / c[-1]).searchsorted(u_cell, side="right")
+    edges = np.append(0, p.cumsum())
+    return rank, (u_cell - edges[rank]) / (edges[rank + 1] - edges[rank])
+
+
 def equal_mass_strata(world):
     """Stratum boundaries of the cell-selecting uniform, one stratum per rank."""
     return np.arange(world + 1, dtype=np.float64) / world
@@ -68,15 +97,9 @@ class ShardedGrid:
         return self.grid._total * (hi - lo)
 
     def _enqueue_gather(self):
-        import torch
-        mine = self._stratum_mass_tensor()
-        if self._gather_buf is None:
-            self._gather_buf = torch.empty(self.world, dtype=torch.float64, device=self.device)
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_gather_into_tensor(self._gather_buf, mine, group=self.group)   # NCCL, 8 B / rank
-        else:
-            self._gather_buf.copy_(mine)
+        # NCCL all-gather, 8 bytes per rank
+        self._gather_buf = all_gather_masses(self._stratum_mass_tensor(), self.world, self.group,
+                                             self._gather_buf)
 
     def exchange_masses(self):
         """Synchronous version: returns the per-shard masses as a NumPy array."""
