@@ -204,7 +204,10 @@ def run_b200(args):
         shard.enqueue_build()                       # masses -> CDF -> guide (+ tiny all-gather)
         if ev:
             ev[0].record(stream)
-        shard.sample_philox_into(out, seed=SEED, offset=i * n_local * world)
+        if args.order == "cell":
+            shard.sample_cellmajor_into(out, seed=SEED, offset=i * n_local * world)
+        else:
+            shard.sample_philox_into(out, seed=SEED, offset=i * n_local * world)
         if ev:
             ev[1].record(stream)
 
@@ -321,6 +324,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--samples", type=int, default=N_SAMPLES, help="samples per GPU per step")
+    ap.add_argument("--order", default="cell", choices=["cell", "draw"],
+                    help="cell: rows grouped by cell (throughput mode); draw: u-driven per-sample search")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--guide-bits", type=int, default=None, help="tuning: log2 guide-table size")

@@ -227,6 +227,29 @@ int lint_cells_sample_sobol(const lint_cells_t *c, int64_t N, const lint_sobol_t
 int lint_sobol_uniforms(int dim, int64_t N, const lint_sobol_t *sobol, double *u_dev,
                         lint_stream_t stream);
 
+/* ---- sampling: cell-major throughput mode ----------------------------------------- */
+
+/* N i.i.d. draws as a multiset, emitted grouped by cell (C order of the flat cell
+ * index) instead of in draw order.  The per-cell counts are an exact
+ * Multinomial(N, p) draw (binomial splitting over the CDF of grid.py:431 /
+ * utils.py:195-196 — the distribution `_choice` realises one row at a time,
+ * utils.py:179-198); each cell's rows are then drawn from its k-linear
+ * interpolant (sampling.py:41-94, 126) with the box and corners loaded once per
+ * cell.  No per-sample search or gather.  Row order is NOT exchangeable: apply a
+ * row permutation (lintsampler.py:309-311) when the caller relies on it.
+ * Philox4x32-10 keyed by `seed`; `offset` separates successive calls.
+ * [u_lo, u_hi) restricts the draw to a stratum of the cell CDF exactly as in
+ * lint_grid_sample_philox ((0, 1) = whole domain; a cell straddling a stratum
+ * boundary is shared in proportion to the overlap).
+ * N < 2^32, fewer than 2^30 cells.  Scratch: lint_cellmajor_scratch_bytes. */
+size_t lint_cellmajor_scratch_bytes(int64_t ncells, int64_t N);
+int lint_grid_sample_cellmajor(const lint_grid_t *g, int64_t N, uint64_t seed, uint64_t offset,
+                               double u_lo, double u_hi, void *scratch_dev, size_t scratch_bytes, void *out_dev,
+                               int64_t *cell_idx_dev, lint_stream_t stream);
+int lint_cells_sample_cellmajor(const lint_cells_t *c, int64_t N, uint64_t seed, uint64_t offset,
+                                double u_lo, double u_hi, void *scratch_dev, size_t scratch_bytes, void *out_dev,
+                                int64_t *cell_idx_dev, lint_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

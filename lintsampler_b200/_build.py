@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 OUT = os.path.join(OUT_DIR, "liblintsampler_b200.so")
-SOURCES = ["lint_build.cu", "lint_sample.cu"]
+SOURCES = ["lint_build.cu", "lint_sample.cu", "lint_cellmajor.cu"]
 HEADERS = ["lint_device.cuh", os.path.join("..", "..", "include", "lintsampler_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

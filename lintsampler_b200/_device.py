@@ -88,3 +88,14 @@ def build_cdf(masses_t, mode, device):
     guide = torch.empty((1 << bits) + 1, dtype=torch.int32, device=device)
     _capi.call("lint_guide_build", ptr(cdf), n, bits, ptr(guide), st)
     return cdf, guide, bits, total_mass
+
+
+def cellmajor_scratch(owner, ncells, N):
+    """Scratch buffer for the cell-major sampler, cached on ``owner`` and grown on demand."""
+    import torch
+    nbytes = int(_capi.load().lint_cellmajor_scratch_bytes(ncells, N))
+    buf = getattr(owner, "_cm_scratch", None)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=owner.device)
+        owner._cm_scratch = buf
+    return buf, nbytes

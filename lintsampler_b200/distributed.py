@@ -108,6 +108,13 @@ class ShardedGrid:
         return self.shard_masses
 
     # -- sampling ------------------------------------------------------------
+    def sample_cellmajor_into(self, out, seed, offset):
+        """Throughput mode: this rank's rows grouped by cell (see DensityGrid._sample_cellmajor)."""
+        n = out.shape[0]
+        lo, hi = float(self.bounds[self.rank]), float(self.bounds[self.rank + 1])
+        self.grid._sample_cellmajor(n, seed, offset + self.rank * n, out=out, stratum=(lo, hi))
+        return out
+
     def sample_philox_into(self, out, seed, offset):
         """Fill the device tensor ``out`` (n, k) with this rank's rows.  Row i of
         rank g uses Philox counter ``offset + g * n + i`` so ranks never share a

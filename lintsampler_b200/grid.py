@@ -319,6 +319,20 @@ class DensityGrid(DensityStructure):
                    C.c_double(stratum[0]), C.c_double(stratum[1]), _device.ptr(out), _device.ptr(cells), _device.stream_ptr(self.device))
         return (out, cells) if want_cells else out
 
+    def _sample_cellmajor(self, N, seed, offset, want_cells=False, out=None, stratum=(0.0, 1.0)):
+        """Throughput mode: rows grouped by cell (C order); exact multinomial cell
+        counts, no per-sample search (``lint_grid_sample_cellmajor``)."""
+        import torch
+        if out is None:
+            out = torch.empty((N, self._dim), dtype=_device.torch_dtype(self.dtype), device=self.device)
+        cells = torch.empty(N, dtype=torch.int64, device=self.device) if want_cells else None
+        scratch, nbytes = _device.cellmajor_scratch(self, int(self.ncells), N)
+        desc = self._descriptor()
+        _capi.call("lint_grid_sample_cellmajor", C.byref(desc), N, C.c_uint64(seed), C.c_uint64(offset),
+                   C.c_double(stratum[0]), C.c_double(stratum[1]), _device.ptr(scratch), nbytes, _device.ptr(out), _device.ptr(cells),
+                   _device.stream_ptr(self.device))
+        return (out, cells) if want_cells else out
+
     def _sample_sobol(self, N, sobol_struct, want_cells=False):
         import torch
         out = torch.empty((N, self._dim), dtype=_device.torch_dtype(self.dtype), device=self.device)

@@ -15,6 +15,12 @@ reference's observable behaviour:
     precision for domains this sampler builds itself from ``pdf`` + edges.
 ``return_tensor``
     return the device-resident ``torch`` tensor instead of a NumPy array.
+``order``
+    ``"draw"`` (default): rows in draw order, exchangeable like the reference's
+    shuffled output.  ``"cell"``: the throughput mode — the same i.i.d. sample as a
+    multiset (exact multinomial cell counts), but rows are emitted grouped by
+    cell; an order of magnitude faster on large grids.  Only for the device
+    Philox stream.
 """
 import ctypes as C
 from warnings import warn
@@ -52,7 +58,7 @@ class LintSampler:
     def __init__(self, domain, pdf=None, vectorizedpdf=False, pdf_args=(), pdf_kwargs={},
                  seed=None, qmc=False, qmc_engine=None,
                  *, rng_backend="philox", dtype=np.float64, device=None, cdf_mode="parallel",
-                 return_tensor=False):
+                 return_tensor=False, order="draw"):
         if pdf:                                                 # truthiness, then callable
             if not callable(pdf):                               # [lintsampler.py:208-213]
                 raise TypeError("LintSampler.__init__: Given PDF is not callable.")
@@ -60,6 +66,11 @@ class LintSampler:
             warn("LintSampler.__init__: PDF configuration setting given but no PDF provided.")
         if rng_backend not in ("philox", "numpy"):
             raise ValueError("LintSampler: rng_backend must be 'philox' or 'numpy'")
+        if order not in ("draw", "cell"):
+            raise ValueError("LintSampler: order must be 'draw' or 'cell'")
+        if order == "cell" and (qmc or rng_backend != "philox"):
+            raise ValueError("LintSampler: order='cell' needs the device Philox stream (no qmc)")
+        self.order = order
         self.pdf = pdf
         self.vectorizedpdf = vectorizedpdf
         self.pdf_args = pdf_args
@@ -257,7 +268,10 @@ class LintSampler:
             x = grid._sample_sobol(n, s)
             self.qmc_engine.fast_forward(n)
             return x
-        x = grid._sample_philox(n, self._philox_key, self._philox_offset)
+        if self.order == "cell" and hasattr(grid, "_sample_cellmajor"):
+            x = grid._sample_cellmajor(n, self._philox_key, self._philox_offset)
+        else:
+            x = grid._sample_philox(n, self._philox_key, self._philox_offset)
         self._philox_offset += n
         return x
 

@@ -378,6 +378,9 @@ class DensityTree(DensityStructure):
     def _sample_sobol(self, N, sobol_struct, want_cells=False):
         return self._ensure_device().sample_sobol(N, sobol_struct, want_cells)
 
+    def _sample_cellmajor(self, N, seed, offset, want_cells=False, out=None, stratum=(0.0, 1.0)):
+        return self._ensure_device().sample_cellmajor(N, seed, offset, want_cells, out, stratum)
+
     def choose_cells(self, u):
         """Reference return contract  [tree.py:314-355]; the search runs on the device."""
         import torch
@@ -452,6 +455,16 @@ class _CellTable:
         desc = self.descriptor()
         _capi.call("lint_cells_sample_philox", C.byref(desc), N, C.c_uint64(seed), C.c_uint64(offset),
                    C.c_double(stratum[0]), C.c_double(stratum[1]), _device.ptr(out), _device.ptr(cells), _device.stream_ptr(self.device))
+        return (out, cells) if want_cells else out
+
+    def sample_cellmajor(self, N, seed, offset, want_cells=False, out=None, stratum=(0.0, 1.0)):
+        """Rows grouped by leaf (list order); ``lint_cells_sample_cellmajor``."""
+        out, cells = self._alloc(N, want_cells, out)
+        scratch, nbytes = _device.cellmajor_scratch(self, self.ncells, N)
+        desc = self.descriptor()
+        _capi.call("lint_cells_sample_cellmajor", C.byref(desc), N, C.c_uint64(seed), C.c_uint64(offset),
+                   C.c_double(stratum[0]), C.c_double(stratum[1]), _device.ptr(scratch), nbytes, _device.ptr(out), _device.ptr(cells),
+                   _device.stream_ptr(self.device))
         return (out, cells) if want_cells else out
 
     def sample_sobol(self, N, sobol_struct, want_cells=False):

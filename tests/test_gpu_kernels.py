@@ -344,3 +344,107 @@ def test_sobol_stream_and_sampler_bit_exact(lb, name):
     s.first_index = 1500                                     # continuation
     x2 = grid._sample_sobol(N - 1500, s)
     assert np.array_equal(x2.cpu().numpy(), g["x_pre"][1500:])
+
+
+# ----------------------------------------------------------------------------- cell-major throughput mode
+@pytest.mark.parametrize("name,dtype", [
+    ("g1d_nonuniform", np.float64), ("g2d_fullcov", np.float64), ("g3d_iso", np.float64),
+    ("g3d_holes", np.float64), ("g4d_iso", np.float64), ("g6d_iso", np.float64),
+    ("g1d_nonuniform", np.float32), ("g2d_fullcov", np.float32), ("g3d_iso", np.float32),
+    ("g4d_iso", np.float32), ("g6d_iso", np.float32),
+    # g3d_holes is fp64-only: on its exactly symmetric cells g0 and g1 differ by rounding
+    # noise and the reference's literal quantile (sampling.py:37) collapses z onto the cell
+    # faces; the fp64 kernels reproduce that bit for bit, the stable fp32
+    # formula deliberately does not, so the two distributions differ there
+])
+def test_cellmajor_structure_and_distribution(lb, name, dtype):
+    """Rows grouped by cell in C order, every row inside its cell, counts sum to N and
+    follow Multinomial(N, p) (chi^2), zero-mass cells never drawn, per-coordinate KS
+    against oracle samples, determinism."""
+    from scipy import stats
+    g = load_golden(name)
+    edges = golden_edges(g)
+    k = int(g["k"])
+    V = g["vertex_densities"]
+    dom = tuple(edges) if k > 1 else edges[0]
+    grid = lb.DensityGrid(dom, lambda p: V.reshape(-1), vectorizedpdf=True, dtype=dtype)
+    N = 300_000
+    x, cells = grid._sample_cellmajor(N, 11, 0, want_cells=True)
+    x2, cells2 = grid._sample_cellmajor(N, 11, 0, want_cells=True)
+    import torch
+    assert torch.equal(x, x2) and torch.equal(cells, cells2)                 # deterministic
+    x3 = grid._sample_cellmajor(N, 11, N)
+    assert not torch.equal(x, x3)                                            # offset decorrelates calls
+    x, cells = x.cpu().numpy().astype(np.float64), cells.cpu().numpy()
+    assert x.shape == (N, k) and np.all(np.diff(cells) >= 0)                 # grouped, C order
+    shape = tuple(len(e) - 1 for e in edges)
+    multi = np.unravel_index(cells, shape)
+    tol = 1e-6 if dtype == np.float32 else 0.0
+    for d in range(k):
+        lo, hi = edges[d][multi[d]], edges[d][multi[d] + 1]
+        assert np.all(x[:, d] >= lo - tol * (hi - lo)) and np.all(x[:, d] <= hi + tol * (hi - lo))
+    p = (g["masses"] / g["masses"].sum()).ravel()
+    counts = np.bincount(cells, minlength=p.size)
+    assert counts.sum() == N and np.all(counts[p == 0] == 0)
+    big = p * N >= 20
+    obs = np.append(counts[big], counts[~big].sum())
+    exp = np.append(p[big], p[~big].sum()) * N
+    keep = exp > 0
+    chi2 = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum()
+    assert stats.chi2.sf(chi2, keep.sum() - 1) > 1e-4
+    u = np.random.default_rng(5).random((N, k + 1))
+    x_ref = O.grid_sample(edges, V, u)
+    for d in range(k):
+        assert stats.ks_2samp(x[:, d], x_ref[:, d]).pvalue > 1e-4
+
+
+def test_cellmajor_counts_are_exactly_multinomial(lb):
+    """Dispersion test of the binomial-splitting counts in both sampler regimes
+    (BINV for small means, BTRS for large): z-scores of repeated draws must have
+    zero mean and unit variance, and counts of different cells must be negatively
+    correlated as in a multinomial."""
+    import torch
+    from scipy import stats
+    e = np.linspace(0, 1, 9)
+    dens = np.array([1, 3, 0.2, 5, 0.01, 2, 8, 1, 4.0])
+    grid = lb.DensityGrid(e, lambda p: dens, vectorizedpdf=True)
+    p = grid.masses / grid.masses.sum()
+    for N in (200, 20_000_000):
+        reps = 200
+        z = np.empty((reps, 8))
+        for r in range(reps):
+            _, cells = grid._sample_cellmajor(N, 3, r * N, want_cells=True)
+            c = torch.bincount(cells, minlength=8).cpu().numpy()
+            assert c.sum() == N
+            z[r] = (c - N * p) / np.sqrt(N * p * (1 - p))
+        for j in range(8):
+            s2 = (z[:, j] ** 2).sum()                     # ~ chi^2(reps) if mean 0 and variance 1
+            assert stats.chi2.cdf(s2, reps) > 1e-4 and stats.chi2.sf(s2, reps) > 1e-4, (N, j, s2 / reps)
+        rho = np.corrcoef(z[:, 3], z[:, 6])[0, 1]
+        expect = -np.sqrt(p[3] * p[6] / ((1 - p[3]) * (1 - p[6])))
+        assert abs(rho - expect) < 0.25, (rho, expect)
+
+
+@pytest.mark.parametrize("name", ["t3d_refined", "t2d_refined", "t1d_refined"])
+def test_cellmajor_tree_leaves(lb, name):
+    from scipy import stats
+    from lintsampler_b200.tree import _CellTable
+    g = load_golden(name)
+    table = _CellTable(g["leaf_x"], g["leaf_dx"], g["leaf_corners"], g["leaf_mass"], np.float64,
+                       None, "parallel")
+    N = 200_000
+    x, cells = table.sample_cellmajor(N, 5, 0, want_cells=True)
+    x, cells = x.cpu().numpy(), cells.cpu().numpy()
+    assert np.all(np.diff(cells) >= 0)
+    assert np.all(x >= g["leaf_x"][cells]) and np.all(x <= g["leaf_x"][cells] + g["leaf_dx"][cells])
+    p = g["leaf_mass"] / g["leaf_mass"].sum()
+    counts = np.bincount(cells, minlength=p.size)
+    big = p * N >= 20
+    obs = np.append(counts[big], counts[~big].sum())
+    exp = np.append(p[big], p[~big].sum()) * N
+    chi2 = ((obs - exp) ** 2 / exp).sum()
+    assert stats.chi2.sf(chi2, len(obs) - 1) > 1e-4
+    u = np.random.default_rng(8).random((N, x.shape[1] + 1))
+    x_ref = O.cells_sample(g["leaf_x"], g["leaf_dx"], g["leaf_corners"], g["leaf_mass"], u)
+    for d in range(x.shape[1]):
+        assert stats.ks_2samp(x[:, d], x_ref[:, d]).pvalue > 1e-4
