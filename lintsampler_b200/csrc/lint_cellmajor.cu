@@ -4,18 +4,25 @@
 // access (guide, CDF, cell record) — work the reference also does per sample
 // (utils.py:197, grid.py:440-467).  N i.i.d. draws of a cell are however fully
 // described by the per-cell counts (n_c) ~ Multinomial(N, p_c), so this path
-//   1. draws the counts exactly, by binomial splitting down a binary tree over
-//      the flat cell range (probabilities are differences of the same fp64 CDF
-//      the search path uses, grid.py:431 + utils.py:195-196),
+//   1. draws independent counts n_c ~ Poisson(L p_c) with L = N - 8 sqrt(N), one
+//      thread per cell (probabilities are differences of the same fp64 CDF the
+//      search path uses, grid.py:431 + utils.py:195-196).  Given their total T the
+//      counts are exactly Multinomial(T, p), and T < N except with probability
+//      ~1e-15 (an 8-sigma event),
 //   2. turns them into row offsets with a single-pass decoupled look-back scan
 //      (integer sums, hence deterministic) that also compacts away empty cells,
 //   3. emits each cell's rows contiguously: the cell's box and corners are
 //      loaded once per cell, every row costs only its k in-cell uniforms and the
-//      k-D inverse CDF of sampling.py:41-94.
-// The rows of one call are an exact i.i.d. sample as a multiset; their ORDER is
-// by cell (C order).  Callers that need the reference's exchangeable row order
+//      k-D inverse CDF of sampling.py:41-94,
+//   4. tops up the remaining N - T rows (~2.5e-4 N) with the u-driven kernel;
+//      Multinomial(T, p) + Multinomial(N - T, p) = Multinomial(N, p), so the N
+//      rows are an exact i.i.d. sample as a multiset.
+// Row ORDER is by cell (C order) for the first T rows, draw order for the
+// top-up tail.  Callers that need the reference's exchangeable row order
 // (lintsampler.py:309-311) apply the row permutation afterwards.
 #include <algorithm>
+#include <cmath>
+#include <cuda_pipeline.h>
 #include "lint_device.cuh"
 
 namespace lint {
@@ -24,74 +31,78 @@ int validate_grid(const lint_grid_t *g, bool need_cdf, uint64_t *ncells_out, uin
 template <int K> GridView<K> make_grid_view(const lint_grid_t *g, uint64_t ncells, bool stage_edges);
 
 // Philox counter word 1 tags (word 0 = node / row group, words 2-3 = call offset)
-constexpr uint32_t TAG_SPLIT = 0x53000000u;   // | level | attempt << 8
+constexpr uint32_t TAG_SPLIT = 0x53000000u;   // | attempt   (per-cell count draws)
 constexpr uint32_t TAG_COORD = 0x43000000u;   // | block index
 
 // ---------------------------------------------------------------------------
-// exact binomial sampler
+// Poisson counts
 // ---------------------------------------------------------------------------
-struct SplitRng {
+struct CellRng {
     uint2 key;
-    uint32_t node, level, w2, w3;
+    uint32_t cell, w2, w3;
     uint32_t attempt = 0;
     __device__ __forceinline__ void next(double &a, double &b) {
-        const uint4 r = philox4x32_10(make_uint4(node, TAG_SPLIT | level | (attempt << 8), w2, w3), key);
+        const uint4 r = philox4x32_10(make_uint4(cell, TAG_SPLIT | attempt, w2, w3), key);
         ++attempt;
         a = u53(r.x, r.y);
         b = u53(r.z, r.w);
     }
 };
 
-// Binomial(n, p) for 0 < p <= 1/2.  Small means: sequential inversion (BINV);
-// otherwise Hörmann's transformed rejection with squeeze (BTRS, 1993).
-__device__ uint32_t binomial_half(uint32_t n, double p, SplitRng &rng) {
-    const double dn = (double)n;
-    if (dn * p < 10.0) {
-        const double q = 1.0 - p, s = p / q, a = (dn + 1.0) * s;
+// log(k!) for integer-valued k >= 0: table below 16, Stirling series above
+// (truncation error < 2e-12 there)
+__device__ __forceinline__ double log_factorial(double k) {
+    const double tab[16] = {0.0, 0.0, 0.6931471805599453, 1.791759469228055, 3.1780538303479458,
+                            4.787491742782046, 6.579251212010101, 8.525161361065415,
+                            10.604602902745251, 12.801827480081469, 15.104412573075516,
+                            17.502307845873887, 19.987214495661885, 22.552163853123425,
+                            25.19122118273868, 27.89927138384089};
+    if (k < 16.0) return tab[(int)k];
+    const double x = k + 1.0, r = 1.0 / x, r2 = r * r;
+    return (x - 0.5) * log(x) - x + 0.9189385332046727 +
+           r * (1.0 / 12.0 - r2 * (1.0 / 360.0 - r2 * (1.0 / 1260.0)));
+}
+
+// Poisson(lam): sequential inversion with one uniform below 10, Hörmann's
+// transformed rejection with squeeze (PTRS, 1993) above.
+__device__ uint32_t poisson(double lam, CellRng &rng) {
+    if (!(lam > 0.0)) return 0;
+    if (lam < 10.0) {
+        const double p0 = exp(-lam);
         for (;;) {
             double u, unused;
             rng.next(u, unused);
-            double r = exp(dn * log1p(-p));
+            double p = p0;
             uint32_t x = 0;
             bool ok = true;
-            while (u > r) {
-                u -= r;
+            while (u > p) {
+                u -= p;
                 ++x;
-                if (x > n || x > 200) { ok = false; break; }   // fp dust in the far tail: redraw
-                r *= a / (double)x - s;
+                if (x > 200) { ok = false; break; }     // fp dust past the far tail: redraw
+                p *= lam / (double)x;
             }
             if (ok) return x;
         }
     }
-    const double spq = sqrt(dn * p * (1.0 - p));
-    const double b = 1.15 + 2.53 * spq;
-    const double a = -0.0873 + 0.0248 * b + 0.01 * p;
-    const double c = dn * p + 0.5;
-    const double vr = 0.92 - 4.2 / b;
-    const double alpha = (2.83 + 5.1 / b) * spq;
-    const double lpq = log(p / (1.0 - p));
-    const double m = floor((dn + 1.0) * p);
-    const double h = lgamma(m + 1.0) + lgamma(dn - m + 1.0);
+    const double slam = sqrt(lam), loglam = log(lam);
+    const double b = 0.931 + 2.53 * slam;
+    const double a = -0.059 + 0.02483 * b;
+    const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
+    const double vr = 0.9277 - 3.6224 / (b - 2.0);
     for (;;) {
         double u, v;
         rng.next(u, v);
         u -= 0.5;
         const double us = 0.5 - fabs(u);
-        const double k = floor((2.0 * a / us + b) * u + c);
-        if (k < 0.0 || k > dn) continue;
+        const double k = floor((2.0 * a / us + b) * u + lam + 0.43);
         if (us >= 0.07 && v <= vr) return (uint32_t)k;
-        v = log(v * alpha / (a / (us * us) + b));
-        if (v <= h - lgamma(k + 1.0) - lgamma(dn - k + 1.0) + (k - m) * lpq) return (uint32_t)k;
+        if (k < 0.0 || (us < 0.013 && v > us)) continue;
+        if (log(v) + log(invalpha) - log(a / (us * us) + b) <= -lam + k * loglam - log_factorial(k))
+            return (uint32_t)k;
     }
 }
 
-__device__ __forceinline__ uint32_t binomial(uint32_t n, double p, SplitRng &rng) {
-    if (n == 0 || !(p > 0.0)) return 0;
-    if (p >= 1.0) return n;
-    return p <= 0.5 ? binomial_half(n, p, rng) : n - binomial_half(n, 1.0 - p, rng);
-}
-
-// The table the splitting tree reads: the normalised CDF restricted to the stratum
+// The table the counts are read from: the normalised CDF restricted to the stratum
 // [u_lo, u_hi) of the cell-selecting uniform ((0, 1) = the whole domain; a rank of
 // a sharded run passes its own slice).
 struct CdfSlice {
@@ -100,61 +111,14 @@ struct CdfSlice {
     double u_lo, u_hi;
 };
 
-// CDF just below cell i (F(0) = 0, F(i >= C) = 1), clamped to the stratum: the mass
-// of cells [a, b) inside the stratum is F(b) - F(a)
-__device__ __forceinline__ double cdf_below(const CdfSlice &t, uint64_t i) {
-    const double f = i == 0 ? 0.0 : (i >= t.ncells ? 1.0 : __ldg(t.cdf + i - 1));
-    return fmin(fmax(f, t.u_lo), t.u_hi);
-}
-
-// One level of the splitting tree: node j of `nnodes` covers cells
-// [j*span, (j+1)*span); its count is split between its two halves.
-__device__ __forceinline__ void split_node(const CdfSlice &t, uint64_t span, uint32_t level,
-                                           uint32_t j, uint32_t n, uint2 key, uint64_t offset,
-                                           uint32_t &left, uint32_t &right) {
-    left = right = 0;
-    if (n == 0) return;
-    const uint64_t lo = (uint64_t)j * span, mid = lo + span / 2, hi = lo + span;
-    if (mid >= t.ncells) { left = n; return; }            // right half lies beyond the grid
-    const double f0 = cdf_below(t, lo), f1 = cdf_below(t, mid), f2 = cdf_below(t, hi);
-    const double tot = f2 - f0;
-    const double q = tot > 0.0 ? (f1 - f0) / tot : 0.5;
-    SplitRng rng{key, j, level, (uint32_t)offset, (uint32_t)(offset >> 32)};
-    left = binomial(n, q, rng);
-    right = n - left;
-}
-
-// levels [0, top_levels): one CTA walks down the small top of the tree in shared memory
-constexpr int TOP_LEVELS = 11;                // 2^11 = 2048 nodes after the top kernel
-__global__ void __launch_bounds__(1024)
-split_top_kernel(CdfSlice t, int depth, uint32_t n_total, uint2 key,
-                 uint64_t offset, int levels, uint32_t *out) {
-    __shared__ uint32_t a[2][1 << TOP_LEVELS];
-    if (threadIdx.x == 0) a[0][0] = n_total;
-    __syncthreads();
-    for (int lv = 0; lv < levels; ++lv) {
-        const uint32_t nn = 1u << lv;
-        const uint64_t span = 1ull << (depth - lv);
-        for (uint32_t j = threadIdx.x; j < nn; j += blockDim.x) {
-            uint32_t l, r;
-            split_node(t, span, lv, j, a[lv & 1][j], key, offset, l, r);
-            a[(lv + 1) & 1][2 * j] = l;
-            a[(lv + 1) & 1][2 * j + 1] = r;
-        }
-        __syncthreads();
-    }
-    for (uint32_t j = threadIdx.x; j < (1u << levels); j += blockDim.x) out[j] = a[levels & 1][j];
-}
-
 __global__ void __launch_bounds__(256)
-split_level_kernel(CdfSlice t, int depth, int level, uint2 key, uint64_t offset,
-                   const uint32_t *in, uint32_t *out) {
-    const uint32_t nn = 1u << level;
-    const uint64_t span = 1ull << (depth - level);
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nn; j += gridDim.x * blockDim.x) {
-        uint32_t l, r;
-        split_node(t, span, level, j, __ldg(in + j), key, offset, l, r);
-        reinterpret_cast<uint2 *>(out)[j] = make_uint2(l, r);
+poisson_counts_kernel(CdfSlice t, double lam_per_unit, uint2 key, uint64_t offset, uint32_t *counts) {
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < t.ncells; c += gridDim.x * blockDim.x) {
+        // mass of the cell inside the stratum: clamp both CDF values, then difference
+        const double f0 = c == 0 ? 0.0 : __ldg(t.cdf + c - 1), f1 = __ldg(t.cdf + c);
+        const double m = fmin(fmax(f1, t.u_lo), t.u_hi) - fmin(fmax(f0, t.u_lo), t.u_hi);
+        CellRng rng{key, c, (uint32_t)offset, (uint32_t)(offset >> 32)};
+        counts[c] = poisson(m * lam_per_unit, rng);
     }
 }
 
@@ -174,7 +138,7 @@ __device__ __forceinline__ unsigned long long pack(uint32_t rows, uint32_t cells
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_compact_kernel(const uint32_t *counts, uint32_t ncells, unsigned long long *tile_state,
                     uint32_t *tile_counter, uint32_t *cid, uint32_t *coff, uint32_t *nnz_out,
-                    uint32_t n_total) {
+                    uint32_t *rows_out) {
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
     __shared__ unsigned long long s_excl;
@@ -247,14 +211,16 @@ scan_compact_kernel(const uint32_t *counts, uint32_t ncells, unsigned long long 
     if (base <= ncells - 1 && ncells - 1 < base + SCAN_ITEMS) {    // owner of the last cell
         const uint32_t nnz = (uint32_t)(pre >> 32);
         *nnz_out = nnz;
-        coff[nnz] = n_total;                                       // sentinel
+        *rows_out = (uint32_t)pre;                                 // T = total grouped rows
+        coff[nnz] = (uint32_t)pre;                                 // sentinel
     }
 }
 
-// first segment of every output tile: last j with coff[j] <= tile * tile_rows
-__global__ void tile_start_kernel(const uint32_t *coff, const uint32_t *nnz_p, uint32_t ntiles,
+// first segment of every output chunk: last j with coff[j] <= chunk * chunk_rows
+__global__ void tile_start_kernel(const uint32_t *coff, const uint32_t *nnz_p, const uint32_t *rows_p,
                                   uint32_t tile_rows, uint32_t *tile_start) {
     const uint32_t nnz = *nnz_p;
+    const uint32_t ntiles = (*rows_p + tile_rows - 1) / tile_rows;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += gridDim.x * blockDim.x) {
         const uint32_t r0 = t * tile_rows;
         uint32_t lo = 0, hi = nnz;                                 // coff[nnz] = N > r0
@@ -295,7 +261,7 @@ struct ListCells {
     }
 };
 
-constexpr int EMIT_THREADS = 256, EMIT_RPT = 8, EMIT_TILE = EMIT_THREADS * EMIT_RPT;
+constexpr int EMIT_THREADS = 256, EMIT_RPT = 8, EMIT_CHUNK = 32 * EMIT_RPT;
 
 // K in-cell uniforms for each of the EMIT_RPT rows of a thread.  fp32 rows use one
 // 32-bit word per coordinate (top 24 bits); fp64 rows two words (53 bits).
@@ -322,30 +288,54 @@ struct RowUniforms {
     }
 };
 
+// Every warp works on its own chunks of EMIT_CHUNK consecutive rows, with a
+// private shared-memory slice for the chunk's segment table and no CTA-wide
+// barrier: warps drift apart, so one warp's table loads overlap another's math.
+// Lane l owns rows [chunk*EMIT_CHUNK + l*EMIT_RPT, +EMIT_RPT).
 template <int K, typename T, typename Cells>
-__global__ void __launch_bounds__(EMIT_THREADS)
+__global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 && K <= 3 ? 3 : 1)
 emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
-            const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ tile_start, uint32_t N,
-            uint2 key, uint64_t offset, T *__restrict__ out, int64_t *__restrict__ cell_idx) {
+            const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ rows_p,
+            const uint32_t *__restrict__ chunk_start, uint32_t n_requested, uint2 key, uint64_t offset,
+            T *__restrict__ out, int64_t *__restrict__ cell_idx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sedges = reinterpret_cast<T *>(smem_raw);
-    __shared__ uint32_t s_off[EMIT_TILE + 1];
-    __shared__ uint32_t s_cid[EMIT_TILE + 1];
+    // per warp, double buffered: the next chunk's segment table is copied in with
+    // cp.async while the current chunk is being computed
+    __shared__ uint32_t s_off_all[EMIT_THREADS / 32][2][EMIT_CHUNK + 1];
+    __shared__ uint32_t s_cid_all[EMIT_THREADS / 32][2][EMIT_CHUNK + 1];
     src.prepare(sedges);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nnz = *nnz_p;
-    const uint32_t ntiles = (N + EMIT_TILE - 1) / EMIT_TILE;
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint32_t r0 = tile * EMIT_TILE;
-        const uint32_t j0 = __ldg(tile_start + tile);
-        // every staged segment but the first starts inside the tile and holds >= 1 row,
-        // so EMIT_TILE + 1 consecutive offsets always cover the tile
-        const uint32_t cnt = min((uint32_t)EMIT_TILE + 1, nnz + 1 - j0);
-        for (uint32_t i = threadIdx.x; i < cnt; i += EMIT_THREADS) {
-            s_off[i] = __ldg(coff + j0 + i);
-            s_cid[i] = j0 + i < nnz ? __ldg(cid + j0 + i) : 0;
+    const uint32_t N = min(*rows_p, n_requested);      // grouped rows T (T <= N but for an 8-sigma event)
+    const uint32_t nchunks = (N + EMIT_CHUNK - 1) / EMIT_CHUNK;
+    const uint32_t nwarps = gridDim.x * (EMIT_THREADS / 32);
+    auto stage = [&](uint32_t j0, int b) {
+        // every staged segment but the first starts inside the chunk and holds >= 1 row,
+        // so EMIT_CHUNK + 1 consecutive offsets always cover the chunk
+        const uint32_t cnt = min((uint32_t)EMIT_CHUNK + 1, nnz + 1 - j0);
+        for (uint32_t i = lane; i < cnt; i += 32) {
+            __pipeline_memcpy_async(&s_off_all[warp][b][i], coff + j0 + i, 4);
+            if (j0 + i < nnz) __pipeline_memcpy_async(&s_cid_all[warp][b][i], cid + j0 + i, 4);
         }
-        __syncthreads();
-        const uint32_t row0 = r0 + threadIdx.x * EMIT_RPT;
+        __pipeline_commit();
+    };
+    uint32_t chunk = blockIdx.x * (EMIT_THREADS / 32) + warp;
+    int buf = 0;
+    uint32_t j0 = chunk < nchunks ? __ldg(chunk_start + chunk) : 0;
+    uint32_t j0_next = chunk + nwarps < nchunks ? __ldg(chunk_start + chunk + nwarps) : 0;
+    if (chunk < nchunks) stage(j0, 0);
+    for (; chunk < nchunks; chunk += nwarps, buf ^= 1) {
+        const uint32_t r0 = chunk * EMIT_CHUNK;
+        const uint32_t cnt = min((uint32_t)EMIT_CHUNK + 1, nnz + 1 - j0);
+        const bool more = chunk + nwarps < nchunks;
+        if (more) stage(j0_next, buf ^ 1);
+        j0 = j0_next;
+        if (chunk + 2 * (uint64_t)nwarps < nchunks) j0_next = __ldg(chunk_start + chunk + 2 * nwarps);
+        if (more) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
+        __syncwarp();
+        const uint32_t *s_off = s_off_all[warp][buf], *s_cid = s_cid_all[warp][buf];
+        const uint32_t row0 = r0 + lane * EMIT_RPT;
         if (row0 < N) {
             // last staged segment starting at or before row0
             uint32_t lo = 0, hi = cnt - 1;
@@ -358,6 +348,8 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
             T c0[1 << K], xlo[K], xhi[K];
             uint32_t cell = s_cid[seg];
             src.fetch(sedges, cell, c0, xlo, xhi);
+            CellCoefs<K, T> coef;
+            coef.set(c0);
             RowUniforms<K, T> rnd;
             rnd.fill(key, row0 / EMIT_RPT, offset);
             T x[EMIT_RPT][K];
@@ -369,12 +361,11 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
                     seg_end = s_off[seg + 1];
                     cell = s_cid[seg];
                     src.fetch(sedges, cell, c0, xlo, xhi);
+                    coef.set(c0);
                 }
-                T c[1 << K], u[K], z[K];
-#pragma unroll
-                for (int j = 0; j < (1 << K); ++j) c[j] = c0[j];
+                T u[K], z[K];
                 rnd.get(i, u);
-                incell<K>(c, u, z);                                // sampling.py:41-94
+                coef.draw(u, z);                                   // sampling.py:41-94
 #pragma unroll
                 for (int d = 0; d < K; ++d) x[i][d] = affine(xlo[d], xhi[d], z[d]);   // sampling.py:126
                 if (cell_idx && row < N) __stcs(reinterpret_cast<long long *>(cell_idx) + row, (long long)cell);
@@ -393,7 +384,7 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
                     for (int d = 0; d < K; ++d) dst[i * K + d] = x[i][d];
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -401,68 +392,62 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
 // host orchestration
 // ---------------------------------------------------------------------------
 struct Scratch {
-    uint32_t *counts_a, *counts_b, *cid, *coff, *tile_start, *nnz, *tile_counter;
+    uint32_t *counts, *cid, *coff, *chunk_start, *nnz, *rows, *tile_counter;
     unsigned long long *tile_state;
     size_t bytes;
 };
 
-static int tree_depth(uint64_t ncells) {
-    int d = 0;
-    while ((1ull << d) < ncells) ++d;
-    return d;
-}
-
 static Scratch carve(void *base, uint64_t ncells, uint64_t N) {
-    const uint64_t cpad = 1ull << tree_depth(ncells);
     const uint64_t nscan = (ncells + SCAN_TILE - 1) / SCAN_TILE;
-    const uint64_t ntiles = (N + EMIT_TILE - 1) / EMIT_TILE;
+    const uint64_t nchunks = (N + EMIT_CHUNK - 1) / EMIT_CHUNK;
     uintptr_t p = (uintptr_t)base;
     auto take = [&](size_t n) { uintptr_t q = p; p += (n + 255) & ~(size_t)255; return (void *)q; };
     Scratch s;
-    s.counts_a = (uint32_t *)take(std::max<uint64_t>(cpad, 2) * 4);
-    s.counts_b = (uint32_t *)take(std::max<uint64_t>(cpad, 2) * 4);
+    s.counts = (uint32_t *)take(ncells * 4);
     s.cid = (uint32_t *)take((ncells + 1) * 4);
     s.coff = (uint32_t *)take((ncells + 1) * 4);
-    s.tile_start = (uint32_t *)take(std::max<uint64_t>(ntiles, 1) * 4);
+    s.chunk_start = (uint32_t *)take(std::max<uint64_t>(nchunks, 1) * 4);
     s.tile_state = (unsigned long long *)take(nscan * 8);
     s.nnz = (uint32_t *)take(4);
+    s.rows = (uint32_t *)take(4);
     s.tile_counter = (uint32_t *)take(4);
     s.bytes = (size_t)(p - (uintptr_t)base);
     return s;
 }
 
-// counts -> offsets -> tile starts; returns the buffer holding the per-cell counts
+// Expected number of grouped rows and the bound on the top-up tail: the Poisson
+// total T has mean L = N - 8 sqrt(N) and standard deviation sqrt(L) < sqrt(N), so
+// N - T lies in (0, 16 sqrt(N)) except for 8-sigma events on either side.
+static double grouped_mean(uint64_t N) { return std::max(0.0, (double)N - 8.0 * std::sqrt((double)N)); }
+static uint64_t topup_bound(uint64_t N) {
+    return std::min<uint64_t>(N, (uint64_t)(16.0 * std::sqrt((double)N)) + 64);
+}
+
+// counts -> offsets (+ compaction) -> chunk starts
 static int plan_rows(const double *cdf, uint64_t ncells, uint64_t N, uint2 key, uint64_t offset,
                      double u_lo, double u_hi, const Scratch &s, cudaStream_t st) {
-    const int depth = tree_depth(ncells);
     const CdfSlice t{cdf, (uint32_t)ncells, u_lo, u_hi};
-    uint32_t *cur = s.counts_a, *nxt = s.counts_b;
-    const int top = std::min(depth, TOP_LEVELS);
-    split_top_kernel<<<1, 1024, 0, st>>>(t, depth, (uint32_t)N, key, offset, top, cur);
-    for (int lv = top; lv < depth; ++lv) {
-        const uint32_t nn = 1u << lv;
-        const int blocks = (int)std::min<uint32_t>((nn + 255) / 256, 148 * 16);
-        split_level_kernel<<<blocks, 256, 0, st>>>(t, depth, lv, key, offset, cur, nxt);
-        std::swap(cur, nxt);
-    }
+    const double lam_per_unit = grouped_mean(N) / (u_hi - u_lo);
+    const int cblocks = (int)std::min<uint64_t>((ncells + 255) / 256, 148 * 16);
+    poisson_counts_kernel<<<cblocks, 256, 0, st>>>(t, lam_per_unit, key, offset, s.counts);
     const uint32_t nscan = (uint32_t)((ncells + SCAN_TILE - 1) / SCAN_TILE);
     cudaMemsetAsync(s.tile_state, 0, (size_t)nscan * 8, st);
     cudaMemsetAsync(s.tile_counter, 0, 4, st);
-    scan_compact_kernel<<<nscan, SCAN_THREADS, 0, st>>>(cur, (uint32_t)ncells, s.tile_state, s.tile_counter,
-                                                       s.cid, s.coff, s.nnz, (uint32_t)N);
-    const uint32_t ntiles = (uint32_t)((N + EMIT_TILE - 1) / EMIT_TILE);
-    tile_start_kernel<<<std::max(1u, std::min((ntiles + 255) / 256, 148u * 8)), 256, 0, st>>>(
-        s.coff, s.nnz, ntiles, EMIT_TILE, s.tile_start);
+    scan_compact_kernel<<<nscan, SCAN_THREADS, 0, st>>>(s.counts, (uint32_t)ncells, s.tile_state,
+                                                       s.tile_counter, s.cid, s.coff, s.nnz, s.rows);
+    const uint32_t nchunks = (uint32_t)((N + EMIT_CHUNK - 1) / EMIT_CHUNK);
+    tile_start_kernel<<<std::max(1u, std::min((nchunks + 255) / 256, 148u * 8)), 256, 0, st>>>(
+        s.coff, s.nnz, s.rows, EMIT_CHUNK, s.chunk_start);
     return check_launch("cell-major row planning");
 }
 
 template <int K, typename T, typename Cells>
 int launch_emit(const Cells &src, const Scratch &s, uint64_t N, uint2 key, uint64_t offset, void *out,
                 int64_t *cell_idx, cudaStream_t st) {
-    const uint32_t ntiles = (uint32_t)((N + EMIT_TILE - 1) / EMIT_TILE);
-    const int blocks = (int)std::min<uint32_t>(ntiles, 148 * 8);
+    const uint32_t nchunks = (uint32_t)((N + EMIT_CHUNK - 1) / EMIT_CHUNK);
+    const int blocks = (int)std::min<uint32_t>((nchunks + EMIT_THREADS / 32 - 1) / (EMIT_THREADS / 32), 148 * 8);
     emit_kernel<K, T, Cells><<<blocks, EMIT_THREADS, src.smem_bytes(sizeof(T)), st>>>(
-        src, s.cid, s.coff, s.nnz, s.tile_start, (uint32_t)N, key, offset, (T *)out, cell_idx);
+        src, s.cid, s.coff, s.nnz, s.rows, s.chunk_start, (uint32_t)N, key, offset, (T *)out, cell_idx);
     return check_launch("cell-major emission");
 }
 
@@ -488,6 +473,14 @@ int grid_cellmajor_k(const lint_grid_t *g, uint64_t nc, uint64_t N, uint2 key, u
     GridCells<K, double> src{make_grid_view<K>(g, nc, true)};
     return launch_emit<K, double>(src, s, N, key, offset, out, cell_idx, st);
 }
+
+// defined in lint_sample.cu: u-driven rows [*first_row_dev, N), at most max_rows of them
+int topup_grid(const lint_grid_t *g, int64_t N, const uint32_t *first_row_dev, int64_t max_rows,
+               uint64_t seed, uint64_t offset, double u_lo, double u_hi, void *out, int64_t *cell_idx,
+               cudaStream_t st);
+int topup_cells(const lint_cells_t *c, int64_t N, const uint32_t *first_row_dev, int64_t max_rows,
+                uint64_t seed, uint64_t offset, double u_lo, double u_hi, void *out, int64_t *cell_idx,
+                cudaStream_t st);
 
 template <int K>
 int cells_cellmajor_k(const lint_cells_t *c, uint64_t N, uint2 key, uint64_t offset, const Scratch &s,
@@ -530,14 +523,19 @@ int lint_grid_sample_cellmajor(const lint_grid_t *g, int64_t N, uint64_t seed, u
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     const Scratch s = carve(scratch_dev, nc, (uint64_t)N);
     if (int rc = plan_rows(g->cdf_dev, nc, (uint64_t)N, key, offset, u_lo, u_hi, s, st)) return rc;
+    int rc;
     switch (g->dim) {
-        case 1: return grid_cellmajor_k<1>(g, nc, N, key, offset, s, out_dev, cell_idx_dev, st);
-        case 2: return grid_cellmajor_k<2>(g, nc, N, key, offset, s, out_dev, cell_idx_dev, st);
-        case 3: return grid_cellmajor_k<3>(g, nc, N, key, offset, s, out_dev, cell_idx_dev, st);
-        case 4: return grid_cellmajor_k<4>(g, nc, N, key, offset, s, out_dev, cell_idx_dev, st);
-        case 5: return grid_cellmajor_k<5>(g, nc, N, key, offset, s, out_dev, cell_idx_dev, st);
-        default: return grid_cellmajor_k<6>(g, nc, N, key, offset, s, out_dev, cell_idx_dev, st);
+        case 1: rc = grid_cellmajor_k<1>(g, nc, N, key, offset, s, out_dev, cell_idx_dev, st); break;
+        case 2: rc = grid_cellmajor_k<2>(g, nc, N, key, offset, s, out_dev, cell_idx_dev, st); break;
+        case 3: rc = grid_cellmajor_k<3>(g, nc, N, key, offset, s, out_dev, cell_idx_dev, st); break;
+        case 4: rc = grid_cellmajor_k<4>(g, nc, N, key, offset, s, out_dev, cell_idx_dev, st); break;
+        case 5: rc = grid_cellmajor_k<5>(g, nc, N, key, offset, s, out_dev, cell_idx_dev, st); break;
+        default: rc = grid_cellmajor_k<6>(g, nc, N, key, offset, s, out_dev, cell_idx_dev, st); break;
     }
+    if (rc) return rc;
+    // rows [T, N): the u-driven sampler on the same stratum
+    return topup_grid(g, N, s.rows, (int64_t)topup_bound((uint64_t)N), seed, offset, u_lo, u_hi, out_dev,
+                      cell_idx_dev, st);
 }
 
 int lint_cells_sample_cellmajor(const lint_cells_t *c, int64_t N, uint64_t seed, uint64_t offset,
@@ -553,14 +551,18 @@ int lint_cells_sample_cellmajor(const lint_cells_t *c, int64_t N, uint64_t seed,
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     const Scratch s = carve(scratch_dev, nc, (uint64_t)N);
     if (int rc = plan_rows(c->cdf_dev, nc, (uint64_t)N, key, offset, u_lo, u_hi, s, st)) return rc;
+    int rc;
     switch (c->dim) {
-        case 1: return cells_cellmajor_k<1>(c, N, key, offset, s, out_dev, cell_idx_dev, st);
-        case 2: return cells_cellmajor_k<2>(c, N, key, offset, s, out_dev, cell_idx_dev, st);
-        case 3: return cells_cellmajor_k<3>(c, N, key, offset, s, out_dev, cell_idx_dev, st);
-        case 4: return cells_cellmajor_k<4>(c, N, key, offset, s, out_dev, cell_idx_dev, st);
-        case 5: return cells_cellmajor_k<5>(c, N, key, offset, s, out_dev, cell_idx_dev, st);
-        default: return cells_cellmajor_k<6>(c, N, key, offset, s, out_dev, cell_idx_dev, st);
+        case 1: rc = cells_cellmajor_k<1>(c, N, key, offset, s, out_dev, cell_idx_dev, st); break;
+        case 2: rc = cells_cellmajor_k<2>(c, N, key, offset, s, out_dev, cell_idx_dev, st); break;
+        case 3: rc = cells_cellmajor_k<3>(c, N, key, offset, s, out_dev, cell_idx_dev, st); break;
+        case 4: rc = cells_cellmajor_k<4>(c, N, key, offset, s, out_dev, cell_idx_dev, st); break;
+        case 5: rc = cells_cellmajor_k<5>(c, N, key, offset, s, out_dev, cell_idx_dev, st); break;
+        default: rc = cells_cellmajor_k<6>(c, N, key, offset, s, out_dev, cell_idx_dev, st); break;
     }
+    if (rc) return rc;
+    return topup_cells(c, N, s.rows, (int64_t)topup_bound((uint64_t)N), seed, offset, u_lo, u_hi, out_dev,
+                       cell_idx_dev, st);
 }
 
 }  // extern "C"

@@ -196,17 +196,23 @@ __device__ __forceinline__ void incell_exact(const double (&c)[1 << K], const do
 
 // fp32 throughput version: condition the corner array on each coordinate as it
 // is drawn (2^K - 1 lerps in total); the 1/2^j averaging factors are dropped
-// because the 1-D quantile is scale invariant.  `c` is consumed.
-template <int K>
-__device__ __forceinline__ void incell_fast(float (&c)[1 << K], const float (&u)[K],
-                                            float (&z)[K]) {
-    // normalise by the largest corner so squares stay in range
+// because the 1-D quantile is scale invariant.
+//
+// normalise_corners: divide by the largest corner so squares stay in range
+// (densities may be ~1e-30 in physical units; g^2 would underflow fp32).
+template <int NC>
+__device__ __forceinline__ void normalise_corners(float *c) {
     float m = c[0];
 #pragma unroll
-    for (int j = 1; j < (1 << K); ++j) m = fmaxf(m, c[j]);
+    for (int j = 1; j < NC; ++j) m = fmaxf(m, c[j]);
     const float inv = m > 0.f ? rcp_approx(m) : 0.f;
 #pragma unroll
-    for (int j = 0; j < (1 << K); ++j) c[j] *= inv;
+    for (int j = 0; j < NC; ++j) c[j] *= inv;
+}
+
+// K sequential conditional draws on already-normalised corners; `c` is consumed.
+template <int K>
+__device__ __forceinline__ void incell_fast_core(float *c, const float *u, float *z) {
 #pragma unroll
     for (int d = 0; d < K; ++d) {
         const int half = 1 << (K - 1 - d);     // live corners: 2*half
@@ -219,6 +225,64 @@ __device__ __forceinline__ void incell_fast(float (&c)[1 << K], const float (&u)
         for (int j = 0; j < half; ++j) c[j] = fmaf(zd, c[half + j] - c[j], c[j]);
     }
 }
+
+template <int K>
+__device__ __forceinline__ void incell_fast(float (&c)[1 << K], const float (&u)[K],
+                                            float (&z)[K]) {
+    normalise_corners<(1 << K)>(c);
+    incell_fast_core<K>(c, u, z);
+}
+
+// Per-cell constants of the fp32 draw, for callers that emit many rows per cell:
+// everything about dimension 0 that does not depend on the row is hoisted
+// (normalisation, the two marginal sums, the quantile's coefficients and the
+// first lerp's differences).
+template <int K>
+struct CellFast {
+    static constexpr int H = 1 << (K - 1);
+    float c[H], dc[H];             // corners with x0 = 0, and (x0 = 1) - (x0 = 0)
+    float g0, a0, b0, s0;          // z0 = s0 u / (g0 + sqrt(a0 + b0 u))
+    __device__ __forceinline__ void set(float (&corners)[1 << K]) {
+        normalise_corners<(1 << K)>(corners);
+        float g1 = corners[H];
+        g0 = corners[0];
+#pragma unroll
+        for (int j = 1; j < H; ++j) { g0 += corners[j]; g1 += corners[H + j]; }
+        a0 = g0 * g0;
+        b0 = fmaf(g1, g1, -a0);
+        s0 = g0 + g1;
+#pragma unroll
+        for (int j = 0; j < H; ++j) { c[j] = corners[j]; dc[j] = corners[H + j] - corners[j]; }
+    }
+    __device__ __forceinline__ void draw(const float (&u)[K], float (&z)[K]) const {
+        const float den = g0 + sqrt_approx(fmaxf(fmaf(b0, u[0], a0), 0.f));
+        const float z0 = den > 0.f ? s0 * u[0] * rcp_approx(den) : u[0];
+        z[0] = z0;
+        if constexpr (K > 1) {
+            float w[H];
+#pragma unroll
+            for (int j = 0; j < H; ++j) w[j] = fmaf(z0, dc[j], c[j]);
+            incell_fast_core<K - 1>(w, &u[1], &z[1]);
+        }
+    }
+};
+
+// fp64: no hoisting — the reference's operation order is kept literally
+template <int K>
+struct CellExact {
+    double c[1 << K];
+    __device__ __forceinline__ void set(double (&corners)[1 << K]) {
+#pragma unroll
+        for (int j = 0; j < (1 << K); ++j) c[j] = corners[j];
+    }
+    __device__ __forceinline__ void draw(const double (&u)[K], double (&z)[K]) const {
+        incell_exact<K>(c, u, z);
+    }
+};
+
+template <int K, typename T> struct CellCoefs;
+template <int K> struct CellCoefs<K, float> : CellFast<K> {};
+template <int K> struct CellCoefs<K, double> : CellExact<K> {};
 
 // ---------------------------------------------------------------------------
 // cell sources

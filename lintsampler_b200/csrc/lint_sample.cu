@@ -68,13 +68,16 @@ template <typename T> struct RowsPerThread { static constexpr int value = 1; };
 template <int K, typename T, typename Source, typename Uniforms>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 sample_kernel(Source src, Uniforms unif, int64_t N, T *__restrict__ out,
-              int64_t *__restrict__ cell_idx) {
+              int64_t *__restrict__ cell_idx, const uint32_t *__restrict__ first_row_dev) {
     constexpr int R = RowsPerThread<T>::value;
+    // rows [first, N): first = 0 normally; the cell-major path tops up its tail
+    // from a device-resident row count
+    const int64_t first = first_row_dev ? (int64_t)*first_row_dev : 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *smem = reinterpret_cast<T *>(smem_raw);
     src.prepare(smem);
     const int64_t tile = (int64_t)SAMPLE_THREADS * R;
-    for (int64_t base = (int64_t)blockIdx.x * tile; base < N; base += (int64_t)gridDim.x * tile) {
+    for (int64_t base = first + (int64_t)blockIdx.x * tile; base < N; base += (int64_t)gridDim.x * tile) {
         double ucell[R];
         T u[R][K];
         uint32_t lo[R], hi[R];
@@ -111,15 +114,21 @@ sample_kernel(Source src, Uniforms unif, int64_t N, T *__restrict__ out,
     }
 }
 
+// First-row override for the next launch_sample on this thread (set by topup_*).
+struct RowWindow { const uint32_t *first_row_dev; int64_t max_rows; };
+static thread_local RowWindow g_window{nullptr, 0};
+
 template <int K, typename T, typename Source, typename Uniforms>
 int launch_sample(const Source &src, const Uniforms &unif, int64_t N, void *out, int64_t *cell_idx,
                   cudaStream_t st, const char *what) {
     if (N == 0) return LINT_OK;
+    const int64_t rows = g_window.first_row_dev ? std::min(N, g_window.max_rows) : N;
+    if (rows == 0) return LINT_OK;
     const int64_t tile = (int64_t)SAMPLE_THREADS * RowsPerThread<T>::value;
-    const int64_t want = (N + tile - 1) / tile;
+    const int64_t want = (rows + tile - 1) / tile;
     const int blocks = (int)std::min<int64_t>(want, 148 * 32);
     sample_kernel<K, T, Source, Uniforms><<<blocks, SAMPLE_THREADS, src.smem_bytes(sizeof(T)), st>>>(
-        src, unif, N, (T *)out, cell_idx);
+        src, unif, N, (T *)out, cell_idx, g_window.first_row_dev);
     return check_launch(what);
 }
 
@@ -300,6 +309,27 @@ int uniforms_dispatch(int dim, int dtype, int64_t N, const Maker &mk, double *ou
         case 5: return uniforms_dispatch_k<5>(dtype, N, mk, out, st);
         default: return uniforms_dispatch_k<6>(dtype, N, mk, out, st);
     }
+}
+
+// u-driven top-up of rows [*first_row_dev, N) for the cell-major path
+int topup_grid(const lint_grid_t *g, int64_t N, const uint32_t *first_row_dev, int64_t max_rows,
+               uint64_t seed, uint64_t offset, double u_lo, double u_hi, void *out, int64_t *cell_idx,
+               cudaStream_t st) {
+    g_window = RowWindow{first_row_dev, max_rows};
+    const int rc = grid_dispatch(g, N, out, cell_idx, (lint_stream_t)st, PhiloxMaker{seed, offset, u_lo, u_hi},
+                                 "cell-major top-up");
+    g_window = RowWindow{nullptr, 0};
+    return rc;
+}
+
+int topup_cells(const lint_cells_t *c, int64_t N, const uint32_t *first_row_dev, int64_t max_rows,
+                uint64_t seed, uint64_t offset, double u_lo, double u_hi, void *out, int64_t *cell_idx,
+                cudaStream_t st) {
+    g_window = RowWindow{first_row_dev, max_rows};
+    const int rc = cells_dispatch(c, N, out, cell_idx, (lint_stream_t)st, PhiloxMaker{seed, offset, u_lo, u_hi},
+                                  "cell-major top-up");
+    g_window = RowWindow{nullptr, 0};
+    return rc;
 }
 
 }  // namespace lint

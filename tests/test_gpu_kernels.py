@@ -376,7 +376,8 @@ def test_cellmajor_structure_and_distribution(lb, name, dtype):
     x3 = grid._sample_cellmajor(N, 11, N)
     assert not torch.equal(x, x3)                                            # offset decorrelates calls
     x, cells = x.cpu().numpy().astype(np.float64), cells.cpu().numpy()
-    assert x.shape == (N, k) and np.all(np.diff(cells) >= 0)                 # grouped, C order
+    tail = int(16 * np.sqrt(N)) + 64          # rows past the grouped part come from the u-driven top-up
+    assert x.shape == (N, k) and np.all(np.diff(cells[:N - tail]) >= 0)      # grouped, C order
     shape = tuple(len(e) - 1 for e in edges)
     multi = np.unravel_index(cells, shape)
     tol = 1e-6 if dtype == np.float32 else 0.0
@@ -399,10 +400,12 @@ def test_cellmajor_structure_and_distribution(lb, name, dtype):
 
 
 def test_cellmajor_counts_are_exactly_multinomial(lb):
-    """Dispersion test of the binomial-splitting counts in both sampler regimes
-    (BINV for small means, BTRS for large): z-scores of repeated draws must have
-    zero mean and unit variance, and counts of different cells must be negatively
-    correlated as in a multinomial."""
+    """Dispersion test of the per-cell counts (Poisson counts conditioned by the
+    u-driven top-up to total N) in both Poisson regimes (inversion for small means,
+    PTRS for large): z-scores of repeated draws must have zero mean and unit
+    variance, and counts of different cells must be negatively correlated as in a
+    multinomial (independent Poisson counts would show zero correlation and an
+    un-conditioned total)."""
     import torch
     from scipy import stats
     e = np.linspace(0, 1, 9)
@@ -435,7 +438,7 @@ def test_cellmajor_tree_leaves(lb, name):
     N = 200_000
     x, cells = table.sample_cellmajor(N, 5, 0, want_cells=True)
     x, cells = x.cpu().numpy(), cells.cpu().numpy()
-    assert np.all(np.diff(cells) >= 0)
+    assert np.all(np.diff(cells[:N - int(16 * np.sqrt(N)) - 64]) >= 0)
     assert np.all(x >= g["leaf_x"][cells]) and np.all(x <= g["leaf_x"][cells] + g["leaf_dx"][cells])
     p = g["leaf_mass"] / g["leaf_mass"].sum()
     counts = np.bincount(cells, minlength=p.size)
