@@ -261,20 +261,23 @@ struct ListCells {
     }
 };
 
-constexpr int EMIT_THREADS = 256, EMIT_RPT = 8, EMIT_CHUNK = 32 * EMIT_RPT;
+constexpr int EMIT_THREADS = 256, EMIT_CHUNK = 256, EMIT_U = 4;
 
-// K in-cell uniforms for each of the EMIT_RPT rows of a thread.  fp32 rows use one
-// 32-bit word per coordinate (top 24 bits); fp64 rows two words (53 bits).
-template <int K, typename T>
-struct RowUniforms {
-    static constexpr int WORDS = K * EMIT_RPT * (sizeof(T) == 8 ? 2 : 1);
+// In-cell uniforms of a group of R rows of one lane: R*K coordinates from
+// ceil(R*K*words/4) Philox blocks.  fp32 rows use one 32-bit word per coordinate
+// (top 24 bits); fp64 rows two words (53 bits).  The counter names the group's
+// first row, `sub` separates the multi-row groups (0) from single rows (1).
+template <int K, typename T, int R>
+struct GroupUniforms {
+    static constexpr int WORDS = K * R * (sizeof(T) == 8 ? 2 : 1);
     static constexpr int CALLS = (WORDS + 3) / 4;
     uint32_t w[4 * CALLS];
-    __device__ __forceinline__ void fill(uint2 key, uint32_t rowgroup, uint64_t offset) {
+    __device__ __forceinline__ void fill(uint2 key, uint32_t first_row, uint32_t sub, uint64_t offset) {
 #pragma unroll
         for (int q = 0; q < CALLS; ++q) {
             const uint4 r = philox4x32_10(
-                make_uint4(rowgroup, TAG_COORD | q, (uint32_t)offset, (uint32_t)(offset >> 32)), key);
+                make_uint4(first_row, TAG_COORD | (sub << 16) | q, (uint32_t)offset, (uint32_t)(offset >> 32)),
+                key);
             w[4 * q] = r.x; w[4 * q + 1] = r.y; w[4 * q + 2] = r.z; w[4 * q + 3] = r.w;
         }
     }
@@ -288,24 +291,40 @@ struct RowUniforms {
     }
 };
 
+template <int K, typename T>
+__device__ __forceinline__ void emit_row(const CellCoefs<K, T> &coef, const T (&xlo)[K], const T (&xhi)[K],
+                                         const T (&u)[K], uint32_t row, uint32_t cell,
+                                         T *__restrict__ out, int64_t *__restrict__ cell_idx) {
+    T z[K];
+    coef.draw(u, z);                                               // sampling.py:41-94
+#pragma unroll
+    for (int d = 0; d < K; ++d)
+        store_stream(out + (size_t)row * K + d, affine(xlo[d], xhi[d], z[d]));   // sampling.py:126
+    if (cell_idx) __stcs(reinterpret_cast<long long *>(cell_idx) + row, (long long)cell);
+}
+
 // Every warp works on its own chunks of EMIT_CHUNK consecutive rows, with a
-// private shared-memory slice for the chunk's segment table and no CTA-wide
-// barrier: warps drift apart, so one warp's table loads overlap another's math.
-// Lane l owns rows [chunk*EMIT_CHUNK + l*EMIT_RPT, +EMIT_RPT).
+// private, double-buffered shared-memory copy of the chunk's segment table and no
+// CTA-wide barrier.  Inside a chunk the warp walks the segments (= non-empty
+// cells) in order, with lanes mapped to consecutive rows:
+//   * 32*EMIT_U rows inside one cell: the cell's box and corners are loaded once
+//     (all lanes the same address) and every lane draws EMIT_U rows from
+//     straight-line code — no per-row bookkeeping, coalesced stores;
+//   * 32 rows inside one cell: the same with one row per lane;
+//   * 32 rows spanning several cells: each lane finds its own cell in the staged
+//     table (the cost of this path is bounded however small the cells are).
 template <int K, typename T, typename Cells>
-__global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 && K <= 3 ? 3 : 1)
+__global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 && K <= 3 ? 4 : 1)
 emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
             const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ rows_p,
             const uint32_t *__restrict__ chunk_start, uint32_t n_requested, uint2 key, uint64_t offset,
             T *__restrict__ out, int64_t *__restrict__ cell_idx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sedges = reinterpret_cast<T *>(smem_raw);
-    // per warp, double buffered: the next chunk's segment table is copied in with
-    // cp.async while the current chunk is being computed
     __shared__ uint32_t s_off_all[EMIT_THREADS / 32][2][EMIT_CHUNK + 1];
     __shared__ uint32_t s_cid_all[EMIT_THREADS / 32][2][EMIT_CHUNK + 1];
     src.prepare(sedges);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nnz = *nnz_p;
     const uint32_t N = min(*rows_p, n_requested);      // grouped rows T (T <= N but for an 8-sigma event)
     const uint32_t nchunks = (N + EMIT_CHUNK - 1) / EMIT_CHUNK;
@@ -326,8 +345,8 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
     uint32_t j0_next = chunk + nwarps < nchunks ? __ldg(chunk_start + chunk + nwarps) : 0;
     if (chunk < nchunks) stage(j0, 0);
     for (; chunk < nchunks; chunk += nwarps, buf ^= 1) {
-        const uint32_t r0 = chunk * EMIT_CHUNK;
-        const uint32_t cnt = min((uint32_t)EMIT_CHUNK + 1, nnz + 1 - j0);
+        const uint32_t r0 = chunk * EMIT_CHUNK, r1 = min(r0 + EMIT_CHUNK, N);
+        const uint32_t cnt = min((uint32_t)EMIT_CHUNK + 1, nnz + 1 - j0);   // staged offsets of this chunk
         const bool more = chunk + nwarps < nchunks;
         if (more) stage(j0_next, buf ^ 1);
         j0 = j0_next;
@@ -335,53 +354,71 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
         if (more) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
         __syncwarp();
         const uint32_t *s_off = s_off_all[warp][buf], *s_cid = s_cid_all[warp][buf];
-        const uint32_t row0 = r0 + lane * EMIT_RPT;
-        if (row0 < N) {
-            // last staged segment starting at or before row0
-            uint32_t lo = 0, hi = cnt - 1;
-            while (lo < hi) {
-                const uint32_t mid = lo + ((hi - lo + 1) >> 1);
-                if (s_off[mid] <= row0) lo = mid; else hi = mid - 1;
-            }
-            uint32_t seg = lo;
-            uint32_t seg_end = s_off[seg + 1];
-            T c0[1 << K], xlo[K], xhi[K];
-            uint32_t cell = s_cid[seg];
-            src.fetch(sedges, cell, c0, xlo, xhi);
-            CellCoefs<K, T> coef;
-            coef.set(c0);
-            RowUniforms<K, T> rnd;
-            rnd.fill(key, row0 / EMIT_RPT, offset);
-            T x[EMIT_RPT][K];
-#pragma unroll
-            for (int i = 0; i < EMIT_RPT; ++i) {
-                const uint32_t row = row0 + i;
-                if (row >= seg_end && row < N) {                   // next non-empty cell
-                    ++seg;
-                    seg_end = s_off[seg + 1];
-                    cell = s_cid[seg];
+
+        uint32_t j = 0;                                  // warp-uniform segment cursor
+        uint32_t row = r0;
+        uint32_t loaded = 0xffffffffu;                   // segment whose cell the registers hold
+        T xlo[K], xhi[K];
+        CellCoefs<K, T> coef;
+        uint32_t cell = 0;
+        while (row < r1) {
+            while (s_off[j + 1] <= row) ++j;             // segment containing `row`
+            const uint32_t seg_end = min(s_off[j + 1], r1);
+            if (seg_end - row >= 32u || seg_end == r1) {
+                // ---- rows [row, ...) of one cell, lanes = consecutive rows
+                if (loaded != j) {
+                    T c0[1 << K];
+                    cell = s_cid[j];
                     src.fetch(sedges, cell, c0, xlo, xhi);
                     coef.set(c0);
+                    loaded = j;
                 }
-                T u[K], z[K];
-                rnd.get(i, u);
-                coef.draw(u, z);                                   // sampling.py:41-94
+                while (seg_end - row >= 32u * EMIT_U) {
+                    const uint32_t first = row + lane;
+                    GroupUniforms<K, T, EMIT_U> rnd;
+                    rnd.fill(key, first, 0, offset);
 #pragma unroll
-                for (int d = 0; d < K; ++d) x[i][d] = affine(xlo[d], xhi[d], z[d]);   // sampling.py:126
-                if (cell_idx && row < N) __stcs(reinterpret_cast<long long *>(cell_idx) + row, (long long)cell);
-            }
-            // EMIT_RPT consecutive rows per thread: K * EMIT_RPT contiguous values
-            T *dst = out + (size_t)row0 * K;
-            if (row0 + EMIT_RPT <= N) {
-                constexpr int VEC = 16 / (int)sizeof(T);
-                static_assert((K * EMIT_RPT) % VEC == 0, "row group must be a whole number of 16-byte stores");
-                const T *flat = &x[0][0];
-#pragma unroll
-                for (int v = 0; v < K * EMIT_RPT / VEC; ++v)
-                    __stcs(reinterpret_cast<float4 *>(dst) + v, reinterpret_cast<const float4 *>(flat)[v]);
+                    for (int t = 0; t < EMIT_U; ++t) {
+                        T u[K];
+                        rnd.get(t, u);
+                        emit_row<K, T>(coef, xlo, xhi, u, first + 32u * t, cell, out, cell_idx);
+                    }
+                    row += 32u * EMIT_U;
+                }
+                while (row < seg_end && (seg_end - row >= 32u || seg_end == r1)) {
+                    const uint32_t r = row + lane;
+                    if (r < seg_end) {
+                        GroupUniforms<K, T, 1> rnd;
+                        rnd.fill(key, r, 1, offset);
+                        T u[K];
+                        rnd.get(0, u);
+                        emit_row<K, T>(coef, xlo, xhi, u, r, cell, out, cell_idx);
+                    }
+                    row = min(row + 32u, seg_end);
+                }
             } else {
-                for (int i = 0; i < EMIT_RPT && row0 + i < N; ++i)
-                    for (int d = 0; d < K; ++d) dst[i * K + d] = x[i][d];
+                // ---- the next 32 rows span several cells: one row per lane, own cell each.
+                // Segments hold >= 1 row, so lane l's segment is within [j, j + l].
+                const uint32_t r = row + lane;
+                const uint32_t lim = min(row + 32u, r1);
+                if (r < lim) {
+                    uint32_t lo = j, hi = min(j + lane, cnt - 2);
+                    while (lo < hi) {
+                        const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+                        if (s_off[mid] <= r) lo = mid; else hi = mid - 1;
+                    }
+                    T c0[1 << K];
+                    cell = s_cid[lo];
+                    src.fetch(sedges, cell, c0, xlo, xhi);
+                    coef.set(c0);
+                    GroupUniforms<K, T, 1> rnd;
+                    rnd.fill(key, r, 1, offset);
+                    T u[K];
+                    rnd.get(0, u);
+                    emit_row<K, T>(coef, xlo, xhi, u, r, cell, out, cell_idx);
+                }
+                loaded = 0xffffffffu;
+                row = lim;
             }
         }
         __syncwarp();
