@@ -261,7 +261,7 @@ struct ListCells {
     }
 };
 
-constexpr int EMIT_THREADS = 256, EMIT_CHUNK = 256, EMIT_U = 4;
+constexpr int EMIT_THREADS = 256, EMIT_CHUNK = 2048, EMIT_U = 4;
 
 // In-cell uniforms of a group of R rows of one lane: R*K coordinates from
 // ceil(R*K*words/4) Philox blocks.  fp32 rows use one 32-bit word per coordinate
@@ -303,16 +303,20 @@ __device__ __forceinline__ void emit_row(const CellCoefs<K, T> &coef, const T (&
     if (cell_idx) __stcs(reinterpret_cast<long long *>(cell_idx) + row, (long long)cell);
 }
 
-// Every warp works on its own chunks of EMIT_CHUNK consecutive rows, with a
-// private, double-buffered shared-memory copy of the chunk's segment table and no
-// CTA-wide barrier.  Inside a chunk the warp walks the segments (= non-empty
-// cells) in order, with lanes mapped to consecutive rows:
+// Every warp works on its own chunks of EMIT_CHUNK consecutive rows and walks the
+// segments (= non-empty cells) that intersect the chunk in order, through a small
+// private shared-memory window of the segment table (EMIT_WIN entries, refilled
+// as the walk advances; the next chunk's first window is prefetched with cp.async
+// while the current chunk is computed).  No CTA-wide barrier.  Lanes map to
+// consecutive rows:
 //   * 32*EMIT_U rows inside one cell: the cell's box and corners are loaded once
 //     (all lanes the same address) and every lane draws EMIT_U rows from
 //     straight-line code — no per-row bookkeeping, coalesced stores;
 //   * 32 rows inside one cell: the same with one row per lane;
-//   * 32 rows spanning several cells: each lane finds its own cell in the staged
-//     table (the cost of this path is bounded however small the cells are).
+//   * 32 rows spanning several cells: each lane finds its own cell in the window
+//     (the cost of this path is bounded however small the cells are).
+constexpr int EMIT_WIN = 64;
+
 template <int K, typename T, typename Cells>
 __global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 && K <= 3 ? 4 : 1)
 emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
@@ -321,21 +325,20 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
             T *__restrict__ out, int64_t *__restrict__ cell_idx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sedges = reinterpret_cast<T *>(smem_raw);
-    __shared__ uint32_t s_off_all[EMIT_THREADS / 32][2][EMIT_CHUNK + 1];
-    __shared__ uint32_t s_cid_all[EMIT_THREADS / 32][2][EMIT_CHUNK + 1];
+    __shared__ uint32_t s_off_all[EMIT_THREADS / 32][2][EMIT_WIN];
+    __shared__ uint32_t s_cid_all[EMIT_THREADS / 32][2][EMIT_WIN];
     src.prepare(sedges);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nnz = *nnz_p;
     const uint32_t N = min(*rows_p, n_requested);      // grouped rows T (T <= N but for an 8-sigma event)
     const uint32_t nchunks = (N + EMIT_CHUNK - 1) / EMIT_CHUNK;
     const uint32_t nwarps = gridDim.x * (EMIT_THREADS / 32);
-    auto stage = [&](uint32_t j0, int b) {
-        // every staged segment but the first starts inside the chunk and holds >= 1 row,
-        // so EMIT_CHUNK + 1 consecutive offsets always cover the chunk
-        const uint32_t cnt = min((uint32_t)EMIT_CHUNK + 1, nnz + 1 - j0);
-        for (uint32_t i = lane; i < cnt; i += 32) {
-            __pipeline_memcpy_async(&s_off_all[warp][b][i], coff + j0 + i, 4);
-            if (j0 + i < nnz) __pipeline_memcpy_async(&s_cid_all[warp][b][i], cid + j0 + i, 4);
+    // window entry i of buffer b <- segment jb + i (offsets exist for 0..nnz, cells for 0..nnz-1)
+    auto prefetch = [&](uint32_t jb, int b) {
+#pragma unroll
+        for (uint32_t i = lane; i < EMIT_WIN; i += 32) {
+            if (jb + i <= nnz) __pipeline_memcpy_async(&s_off_all[warp][b][i], coff + jb + i, 4);
+            if (jb + i < nnz) __pipeline_memcpy_async(&s_cid_all[warp][b][i], cid + jb + i, 4);
         }
         __pipeline_commit();
     };
@@ -343,32 +346,48 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
     int buf = 0;
     uint32_t j0 = chunk < nchunks ? __ldg(chunk_start + chunk) : 0;
     uint32_t j0_next = chunk + nwarps < nchunks ? __ldg(chunk_start + chunk + nwarps) : 0;
-    if (chunk < nchunks) stage(j0, 0);
+    if (chunk < nchunks) prefetch(j0, 0);
     for (; chunk < nchunks; chunk += nwarps, buf ^= 1) {
         const uint32_t r0 = chunk * EMIT_CHUNK, r1 = min(r0 + EMIT_CHUNK, N);
-        const uint32_t cnt = min((uint32_t)EMIT_CHUNK + 1, nnz + 1 - j0);   // staged offsets of this chunk
         const bool more = chunk + nwarps < nchunks;
-        if (more) stage(j0_next, buf ^ 1);
+        if (more) prefetch(j0_next, buf ^ 1);
+        uint32_t jbase = j0;                             // segment held in window slot 0
         j0 = j0_next;
         if (chunk + 2 * (uint64_t)nwarps < nchunks) j0_next = __ldg(chunk_start + chunk + 2 * nwarps);
         if (more) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
         __syncwarp();
-        const uint32_t *s_off = s_off_all[warp][buf], *s_cid = s_cid_all[warp][buf];
+        uint32_t *s_off = s_off_all[warp][buf], *s_cid = s_cid_all[warp][buf];
+        // offset of segment j (j > nnz: +inf); callers keep j - jbase < EMIT_WIN
+        auto off = [&](uint32_t j) { return j <= nnz ? s_off[j - jbase] : 0xffffffffu; };
+        auto refill = [&](uint32_t jb) {                 // slide the window so that slot 0 = segment jb
+            __syncwarp();
+#pragma unroll
+            for (uint32_t i = lane; i < EMIT_WIN; i += 32) {
+                if (jb + i <= nnz) s_off[i] = __ldg(coff + jb + i);
+                if (jb + i < nnz) s_cid[i] = __ldg(cid + jb + i);
+            }
+            jbase = jb;
+            __syncwarp();
+        };
 
-        uint32_t j = 0;                                  // warp-uniform segment cursor
+        uint32_t j = jbase;                              // warp-uniform segment cursor
         uint32_t row = r0;
         uint32_t loaded = 0xffffffffu;                   // segment whose cell the registers hold
         T xlo[K], xhi[K];
         CellCoefs<K, T> coef;
         uint32_t cell = 0;
         while (row < r1) {
-            while (s_off[j + 1] <= row) ++j;             // segment containing `row`
-            const uint32_t seg_end = min(s_off[j + 1], r1);
+            for (;;) {                                   // segment containing `row`
+                if (j + 1 - jbase >= EMIT_WIN) refill(j);
+                if (off(j + 1) > row) break;
+                ++j;
+            }
+            const uint32_t seg_end = min(off(j + 1), r1);
             if (seg_end - row >= 32u || seg_end == r1) {
                 // ---- rows [row, ...) of one cell, lanes = consecutive rows
                 if (loaded != j) {
                     T c0[1 << K];
-                    cell = s_cid[j];
+                    cell = s_cid[j - jbase];
                     src.fetch(sedges, cell, c0, xlo, xhi);
                     coef.set(c0);
                     loaded = j;
@@ -399,16 +418,17 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
             } else {
                 // ---- the next 32 rows span several cells: one row per lane, own cell each.
                 // Segments hold >= 1 row, so lane l's segment is within [j, j + l].
+                if (j + 33 - jbase >= EMIT_WIN) refill(j);
                 const uint32_t r = row + lane;
                 const uint32_t lim = min(row + 32u, r1);
                 if (r < lim) {
-                    uint32_t lo = j, hi = min(j + lane, cnt - 2);
+                    uint32_t lo = j, hi = min(j + lane, nnz - 1);
                     while (lo < hi) {
                         const uint32_t mid = lo + ((hi - lo + 1) >> 1);
-                        if (s_off[mid] <= r) lo = mid; else hi = mid - 1;
+                        if (s_off[mid - jbase] <= r) lo = mid; else hi = mid - 1;
                     }
                     T c0[1 << K];
-                    cell = s_cid[lo];
+                    cell = s_cid[lo - jbase];
                     src.fetch(sedges, cell, c0, xlo, xhi);
                     coef.set(c0);
                     GroupUniforms<K, T, 1> rnd;
