@@ -76,7 +76,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         self._t.start()
@@ -191,6 +191,10 @@ def run_b200(args):
     n_local = args.samples
     # domain: the whole grid at world 1, this rank's equal-mass shard otherwise
     grid_kw = {}
+    if args.order == "cell":
+        # the grouped emitter loads each cell once, so it needs neither per-cell records
+        # nor a fine guide table (only the ~2.5e-4 N top-up rows search the CDF)
+        grid_kw.update(cell_records=False, guide_bits=16)
     if args.guide_bits is not None:
         grid_kw["guide_bits"] = args.guide_bits
     if args.no_records:
@@ -200,11 +204,11 @@ def run_b200(args):
     out = torch.empty((n_local, DIM), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream(dev)
 
-    def step(i, ev=None):
+    def step(i, ev=None, order=None):
         shard.enqueue_build()                       # masses -> CDF -> guide (+ tiny all-gather)
         if ev:
             ev[0].record(stream)
-        if args.order == "cell":
+        if (order or args.order) == "cell":
             shard.sample_cellmajor_into(out, seed=SEED, offset=i * n_local * world)
         else:
             shard.sample_philox_into(out, seed=SEED, offset=i * n_local * world)
@@ -238,6 +242,31 @@ def run_b200(args):
     ms_step = ms_total / args.steps
     value = n_local * world / (ms_step * 1e-3)
 
+    # the other row order, for the record (2 steps, same workload)
+    other = "draw" if args.order == "cell" else "cell"
+    other_line = None
+    if not args.no_other:
+        # its own tables: the u-driven kernel wants per-cell records and a fine guide table
+        shard.grid.__dict__.pop("_cm_scratch", None)
+        okw = dict(cell_records=False, guide_bits=16) if other == "cell" else dict(guide_bits=22)
+        shard_main, shard = shard, lbd.ShardedGrid(edges, gmm, dtype=np.float32, device=dev, rank=rank,
+                                                   world=world, group=dist.group.WORLD if world > 1 else None,
+                                                   **okw)
+        step(0, order=other)
+        barrier()
+        o_beg, o_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o_beg.record(stream)
+        for i in range(2):
+            step(100 + i, order=other)
+        o_end.record(stream)
+        barrier()
+        t2 = torch.tensor([o_beg.elapsed_time(o_end) / 2], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        other_line = {"order": other, "value": n_local * world / (float(t2.item()) * 1e-3),
+                      "ms_per_step": float(t2.item()), "steps": 2}
+        shard = shard_main
+
     # ---- e2e: public API, host buffers in and out, N=1 GPU semantics per rank
     e2e = None
     if not args.no_e2e:
@@ -261,18 +290,27 @@ def run_b200(args):
                 "workload": "C3: 3-D DensityGrid 256^3 (257^3 fp32 vertex densities, fp64 CDF), "
                             "K=4 isotropic GMM on [-4,4]^3, N=%d samples per GPU per step" % n_local,
                 "samples_per_gpu": n_local, "l2": "outputs (12 GB/step) and tables (>260 MB) exceed L2",
-                "sharding": shard.describe(), "order": "rows in draw order (iid Philox rows, exchangeable)",
+                "sharding": shard.describe(),
+                "order": ("rows grouped by cell: exact multinomial cell counts (Poisson counts + u-driven "
+                          "top-up), i.i.d. as a multiset, NOT exchangeable in row order"
+                          if args.order == "cell" else
+                          "rows in draw order (i.i.d. Philox rows, exchangeable like the reference's shuffle)"),
             },
             "roofline": {
-                "bound": "hbm", "kernel": "sample_kernel<3,float,GridSource,UniformsPhilox>",
+                "bound": "hbm",
+                "kernel": ("emit_kernel<3,float,GridCells<3,float>> incl. its row planning (poisson_counts, "
+                           "scan_compact, tile_start) and the sample_kernel top-up" if args.order == "cell"
+                           else "sample_kernel<3,float,GridSource<3,float>,UniformsPhilox<3>>"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
                 "traffic": None, "ms_per_launch": ms_sample,
                 "step_frac_of_hbm_roofline": (b_mass + b_scan + b_sample) / (ms_step * 1e-3) / 1e9 / peak,
             },
             "clocks": clocks.summary(),
-            "gpu_launches": shard.launches_per_step() * args.steps,
+            "gpu_launches": shard.launches_per_step(args.order) * args.steps,
         }
+        if other_line:
+            line["other_order"] = other_line
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu:
@@ -288,11 +326,12 @@ def run_e2e(args, lb, edges, gmm, dev, world):
     n = args.samples
     steps = max(1, min(args.steps, 3))
     # host inputs: pinned fp32 vertex densities (evaluated once, outside the timed region)
-    g0 = lb.DensityGrid(edges, gmm, vectorizedpdf=True, dtype=np.float32, device=dev)
+    kw = dict(cell_records=False, guide_bits=16) if args.order == "cell" else dict(guide_bits=22)
+    g0 = lb.DensityGrid(edges, gmm, vectorizedpdf=True, dtype=np.float32, device=dev, **kw)
     v_host = torch.empty(g0._V.numel(), dtype=torch.float32, pin_memory=True)
     v_host.copy_(g0._V)
     out_host = torch.empty((n, DIM), dtype=torch.float32, pin_memory=True)
-    sampler = lb.LintSampler(g0, seed=SEED, dtype=np.float32)
+    sampler = lb.LintSampler(g0, seed=SEED, dtype=np.float32, order=args.order)
     torch.cuda.synchronize(dev)
 
     def one():
@@ -320,7 +359,7 @@ def run_e2e(args, lb, edges, gmm, dev, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--samples", type=int, default=N_SAMPLES, help="samples per GPU per step")
@@ -328,6 +367,7 @@ def main():
                     help="cell: rows grouped by cell (throughput mode); draw: u-driven per-sample search")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the 2-step run of the other row order")
     ap.add_argument("--guide-bits", type=int, default=None, help="tuning: log2 guide-table size")
     ap.add_argument("--no-records", action="store_true", help="tuning: gather corners from the vertex array")
     ap.add_argument("--grid-n", type=int, default=None, help="tuning: cells per dim (default 256)")

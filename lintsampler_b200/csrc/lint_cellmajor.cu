@@ -291,7 +291,7 @@ struct GroupUniforms {
     }
 };
 
-template <int K, typename T>
+template <int K, typename T, bool CELLS>
 __device__ __forceinline__ void emit_row(const CellCoefs<K, T> &coef, const T (&xlo)[K], const T (&xhi)[K],
                                          const T (&u)[K], uint32_t row, uint32_t cell,
                                          T *__restrict__ out, int64_t *__restrict__ cell_idx) {
@@ -300,7 +300,7 @@ __device__ __forceinline__ void emit_row(const CellCoefs<K, T> &coef, const T (&
 #pragma unroll
     for (int d = 0; d < K; ++d)
         store_stream(out + (size_t)row * K + d, affine(xlo[d], xhi[d], z[d]));   // sampling.py:126
-    if (cell_idx) __stcs(reinterpret_cast<long long *>(cell_idx) + row, (long long)cell);
+    if (CELLS) __stcs(reinterpret_cast<long long *>(cell_idx) + row, (long long)cell);
 }
 
 // Every warp works on its own chunks of EMIT_CHUNK consecutive rows and walks the
@@ -317,7 +317,7 @@ __device__ __forceinline__ void emit_row(const CellCoefs<K, T> &coef, const T (&
 //     (the cost of this path is bounded however small the cells are).
 constexpr int EMIT_WIN = 64;
 
-template <int K, typename T, typename Cells>
+template <int K, typename T, typename Cells, bool CELLS>
 __global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 && K <= 3 ? 4 : 1)
 emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
             const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ rows_p,
@@ -400,7 +400,7 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
                     for (int t = 0; t < EMIT_U; ++t) {
                         T u[K];
                         rnd.get(t, u);
-                        emit_row<K, T>(coef, xlo, xhi, u, first + 32u * t, cell, out, cell_idx);
+                        emit_row<K, T, CELLS>(coef, xlo, xhi, u, first + 32u * t, cell, out, cell_idx);
                     }
                     row += 32u * EMIT_U;
                 }
@@ -411,7 +411,7 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
                         rnd.fill(key, r, 1, offset);
                         T u[K];
                         rnd.get(0, u);
-                        emit_row<K, T>(coef, xlo, xhi, u, r, cell, out, cell_idx);
+                        emit_row<K, T, CELLS>(coef, xlo, xhi, u, r, cell, out, cell_idx);
                     }
                     row = min(row + 32u, seg_end);
                 }
@@ -435,7 +435,7 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
                     rnd.fill(key, r, 1, offset);
                     T u[K];
                     rnd.get(0, u);
-                    emit_row<K, T>(coef, xlo, xhi, u, r, cell, out, cell_idx);
+                    emit_row<K, T, CELLS>(coef, xlo, xhi, u, r, cell, out, cell_idx);
                 }
                 loaded = 0xffffffffu;
                 row = lim;
@@ -503,8 +503,12 @@ int launch_emit(const Cells &src, const Scratch &s, uint64_t N, uint2 key, uint6
                 int64_t *cell_idx, cudaStream_t st) {
     const uint32_t nchunks = (uint32_t)((N + EMIT_CHUNK - 1) / EMIT_CHUNK);
     const int blocks = (int)std::min<uint32_t>((nchunks + EMIT_THREADS / 32 - 1) / (EMIT_THREADS / 32), 148 * 8);
-    emit_kernel<K, T, Cells><<<blocks, EMIT_THREADS, src.smem_bytes(sizeof(T)), st>>>(
-        src, s.cid, s.coff, s.nnz, s.rows, s.chunk_start, (uint32_t)N, key, offset, (T *)out, cell_idx);
+    if (cell_idx)
+        emit_kernel<K, T, Cells, true><<<blocks, EMIT_THREADS, src.smem_bytes(sizeof(T)), st>>>(
+            src, s.cid, s.coff, s.nnz, s.rows, s.chunk_start, (uint32_t)N, key, offset, (T *)out, cell_idx);
+    else
+        emit_kernel<K, T, Cells, false><<<blocks, EMIT_THREADS, src.smem_bytes(sizeof(T)), st>>>(
+            src, s.cid, s.coff, s.nnz, s.rows, s.chunk_start, (uint32_t)N, key, offset, (T *)out, cell_idx);
     return check_launch("cell-major emission");
 }
 

@@ -139,10 +139,13 @@ class ShardedGrid:
         return out, counts
 
     # -- reporting -------------------------------------------------------------
-    def launches_per_step(self):
+    def launches_per_step(self, order="draw"):
         """Kernels of this library launched by enqueue_build + one sampling call:
-        masses 1, cell records 1, parallel CDF 4, guide 1, sampler 1."""
-        return 8 if self.grid._rec is not None else 7
+        masses 1, cell records 0/1, parallel CDF 4, guide 1; then the u-driven
+        sampler (1) or the grouped path (Poisson counts, scan+compact, chunk
+        starts, emit, top-up = 5)."""
+        build = 6 + (1 if self.grid._rec is not None else 0)
+        return build + (5 if order == "cell" else 1)
 
     def describe(self):
         if self.world == 1:

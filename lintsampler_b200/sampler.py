@@ -363,7 +363,10 @@ class LintSampler:
             n = min(chunk, N - done)
             buf = self._stage[i & 1]
             main.wait_event(self._stage_free[i & 1])            # previous copy out of this buffer
-            grid._sample_philox(n, self._philox_key, self._philox_offset, out=buf[:n])
+            if self.order == "cell":
+                grid._sample_cellmajor(n, self._philox_key, self._philox_offset, out=buf[:n])
+            else:
+                grid._sample_philox(n, self._philox_key, self._philox_offset, out=buf[:n])
             self._philox_offset += n
             ready = torch.cuda.Event()
             ready.record(main)
