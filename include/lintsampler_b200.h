@@ -250,6 +250,15 @@ int lint_cells_sample_cellmajor(const lint_cells_t *c, int64_t N, uint64_t seed,
                                 double u_lo, double u_hi, void *scratch_dev, size_t scratch_bytes, void *out_dev,
                                 int64_t *cell_idx_dev, lint_stream_t stream);
 
+/* ---- row order ------------------------------------------------------------------- */
+
+/* out[i] = in[pi(i)] for a pseudo-random bijection pi of [0, N) keyed by `seed`
+ * (8-round Feistel network + cycle walking): the device counterpart of the
+ * reference's final `rng.shuffle(X, axis=0)`  [lintsampler.py:309-311].  Rows
+ * are k values of `dtype`.  in and out must not overlap. */
+int lint_permute_rows(const void *in_dev, void *out_dev, int64_t N, int32_t k, int32_t dtype,
+                      uint64_t seed, lint_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,7 @@ PROTOTYPES = {
     "lint_grid_sample_sobol": (C.c_int, [C.POINTER(LintGrid), _I64, C.POINTER(LintSobol), _P, _P, _P]),
     "lint_cells_sample_sobol": (C.c_int, [C.POINTER(LintCells), _I64, C.POINTER(LintSobol), _P, _P, _P]),
     "lint_sobol_uniforms": (C.c_int, [C.c_int, _I64, C.POINTER(LintSobol), _P, _P]),
+    "lint_permute_rows": (C.c_int, [_P, _P, _I64, C.c_int32, C.c_int32, _U64, _P]),
     "lint_cellmajor_scratch_bytes": (C.c_size_t, [_I64, _I64]),
     "lint_grid_sample_cellmajor": (C.c_int, [C.POINTER(LintGrid), _I64, _U64, _U64, C.c_double, C.c_double,
                                              _P, C.c_size_t, _P, _P, _P]),

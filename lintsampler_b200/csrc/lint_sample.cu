@@ -407,3 +407,81 @@ int lint_sobol_uniforms(int dim, int64_t N, const lint_sobol_t *sobol, double *u
 }
 
 }  // extern "C"
+
+// ===========================================================================
+// row permutation: the device counterpart of `rng.shuffle(X, axis=0)`
+// [lintsampler.py:309-311]
+// ===========================================================================
+namespace lint {
+
+// Bijection of [0, 2^bits) : alternating unbalanced Feistel network whose round
+// function is a 32-bit integer mix; restricted to [0, N) by cycle walking
+// (expected < 2 evaluations since 2^bits < 2N).
+struct FeistelPerm {
+    uint32_t key[8];
+    uint32_t lb, rb;                  // bit widths of the two halves, lb + rb = bits, rb >= lb
+    uint64_t n;
+    __device__ __forceinline__ static uint32_t mix(uint32_t x, uint32_t k) {
+        x = x * 0x9E3779B1u + k;
+        x ^= x >> 15; x *= 0x85EBCA77u;
+        x ^= x >> 13; x *= 0xC2B2AE3Du;
+        x ^= x >> 16;
+        return x;
+    }
+    __device__ __forceinline__ uint64_t once(uint64_t x) const {
+        uint32_t wl = lb, wr = rb;
+        uint32_t l = (uint32_t)(x >> wr), r = (uint32_t)(x & ((1ull << wr) - 1));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t t = (l ^ mix(r, key[i])) & (uint32_t)((1ull << wl) - 1);
+            l = r;                    // widths swap every round; 8 rounds restore them
+            r = t;
+            const uint32_t w = wl; wl = wr; wr = w;
+        }
+        return ((uint64_t)l << wr) | r;
+    }
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const {
+        uint64_t x = once(i);
+        while (x >= n) x = once(x);
+        return x;
+    }
+};
+
+template <typename E>
+__global__ void __launch_bounds__(256)
+permute_rows_kernel(const E *__restrict__ in, E *__restrict__ out, uint64_t N, int k, FeistelPerm perm) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < N;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t j = perm(i);
+        for (int d = 0; d < k; ++d) __stcs(out + i * k + d, __ldg(in + j * k + d));
+    }
+}
+
+}  // namespace lint
+
+extern "C" int lint_permute_rows(const void *in_dev, void *out_dev, int64_t N, int32_t k, int32_t dtype,
+                                 uint64_t seed, lint_stream_t stream) {
+    using namespace lint;
+    if (N < 0 || k < 1 || k > LINT_MAX_DIM || (dtype != LINT_F32 && dtype != LINT_F64))
+        return fail(LINT_ERR_BAD_ARG, "lint_permute_rows: bad N / k / dtype");
+    if (N == 0) return LINT_OK;
+    if (!in_dev || !out_dev || in_dev == out_dev)
+        return fail(LINT_ERR_BAD_ARG, "lint_permute_rows: in/out must be distinct, non-NULL buffers");
+    FeistelPerm p;
+    uint32_t bits = 2;
+    while ((1ull << bits) < (uint64_t)N) ++bits;
+    p.lb = bits / 2;
+    p.rb = bits - p.lb;
+    p.n = (uint64_t)N;
+    uint4 a = philox4x32_10(make_uint4(0x50455231u, 0, 0, 0), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    uint4 b = philox4x32_10(make_uint4(0x50455232u, 0, 0, 0), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t ks[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    for (int i = 0; i < 8; ++i) p.key[i] = ks[i];
+    const int blocks = (int)std::min<int64_t>((N + 255) / 256, 148 * 32);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == LINT_F32)
+        permute_rows_kernel<float><<<blocks, 256, 0, st>>>((const float *)in_dev, (float *)out_dev, (uint64_t)N, k, p);
+    else
+        permute_rows_kernel<double><<<blocks, 256, 0, st>>>((const double *)in_dev, (double *)out_dev, (uint64_t)N, k, p);
+    return check_launch("lint_permute_rows");
+}

@@ -19,8 +19,15 @@ reference's observable behaviour:
     ``"draw"`` (default): rows in draw order, exchangeable like the reference's
     shuffled output.  ``"cell"``: the throughput mode — the same i.i.d. sample as a
     multiset (exact multinomial cell counts), but rows are emitted grouped by
-    cell; an order of magnitude faster on large grids.  Only for the device
-    Philox stream.
+    cell; several times faster on large grids.  Only for the device Philox stream.
+``shuffle``
+    the reference ends every multi-sample draw with ``rng.shuffle`` (lintsampler.py:
+    309-311).  ``"auto"`` (default) keeps that wherever it changes the distribution
+    of row order: replayed on the host with ``rng_backend="numpy"`` (bit parity),
+    done on the device (``lint_permute_rows``) for quasi-random rows and for rows
+    grouped by domain, skipped for i.i.d. device rows of a single domain (already
+    exchangeable) and for ``order="cell"`` (grouped by design).  ``True`` forces
+    the device permutation, ``False`` disables it.
 """
 import ctypes as C
 from warnings import warn
@@ -58,7 +65,7 @@ class LintSampler:
     def __init__(self, domain, pdf=None, vectorizedpdf=False, pdf_args=(), pdf_kwargs={},
                  seed=None, qmc=False, qmc_engine=None,
                  *, rng_backend="philox", dtype=np.float64, device=None, cdf_mode="parallel",
-                 return_tensor=False, order="draw"):
+                 return_tensor=False, order="draw", shuffle="auto"):
         if pdf:                                                 # truthiness, then callable
             if not callable(pdf):                               # [lintsampler.py:208-213]
                 raise TypeError("LintSampler.__init__: Given PDF is not callable.")
@@ -70,7 +77,10 @@ class LintSampler:
             raise ValueError("LintSampler: order must be 'draw' or 'cell'")
         if order == "cell" and (qmc or rng_backend != "philox"):
             raise ValueError("LintSampler: order='cell' needs the device Philox stream (no qmc)")
+        if shuffle not in ("auto", True, False):
+            raise ValueError("LintSampler: shuffle must be 'auto', True or False")
         self.order = order
+        self.shuffle = shuffle
         self.pdf = pdf
         self.vectorizedpdf = vectorizedpdf
         self.pdf_args = pdf_args
@@ -310,13 +320,15 @@ class LintSampler:
             X = self._sample_single(self.grids[0], n)
         else:
             X = self._sample_multi(n)
-        X = self._finalise_order(X, N)
+        mode = self._shuffle_mode() if N else None
+        if mode == "device":
+            X = self._permute_rows(X)
         if self.return_tensor:
             if not N:
                 return X[0, 0] if self.dim == 1 else X[0]
             return X.squeeze() if self.dim == 1 else X
         X = X.cpu().numpy()
-        if N and self._host_shuffle():
+        if mode == "host":
             self.rng.shuffle(X, axis=0)                         # [lintsampler.py:310-311]
         if not N and self.dim == 1:
             return X.item()
@@ -334,7 +346,7 @@ class LintSampler:
         domain's dtype; allocated (pinned) when omitted.  Returns the host tensor
         (``.numpy()`` gives a zero-copy NumPy view).  Only for a single native
         domain with the device Philox stream, whose rows are exchangeable, so no
-        shuffle pass is needed (see ``_host_shuffle``)."""
+        shuffle pass is needed (see ``_shuffle_mode``)."""
         import torch
         if not isinstance(N, int):
             raise TypeError(f"LintSampler.sample_to_host: Expected int N, got {type(N)}")
@@ -380,16 +392,24 @@ class LintSampler:
         return out
 
     # ------------------------------------------------------------------ row order
-    def _host_shuffle(self):
-        """The reference shuffles the rows of every multi-sample draw with
-        ``rng.shuffle`` (lintsampler.py:309-311).  With ``rng_backend="numpy"``
-        that exact call is replayed on the host.  With device-generated
-        independent Philox rows from a single domain the rows are already
-        exchangeable and the shuffle is skipped; quasi-random or domain-grouped
-        rows are permuted on the host with ``self.rng`` as in the reference."""
+    def _shuffle_mode(self):
+        """'host', 'device' or None — see the ``shuffle`` option in the module docstring."""
         if self.rng_backend == "numpy":
-            return True
-        return self.qmc or self.ngrids > 1
+            return "host" if self.shuffle in ("auto", True) else None
+        if self.shuffle is True:
+            return "device"
+        if self.shuffle is False:
+            return None
+        return "device" if (self.qmc or self.ngrids > 1) else None
 
-    def _finalise_order(self, X, N):
-        return X
+    def _permute_rows(self, X):
+        """Device row permutation keyed by the sampler's stream position."""
+        import torch
+        X = X.contiguous()
+        out = torch.empty_like(X)
+        n, k = X.shape
+        seed = (self._philox_key ^ (0x9E3779B97F4A7C15 * (self._philox_offset + n + 1))) & (2 ** 64 - 1)
+        _capi.call("lint_permute_rows", _device.ptr(X), _device.ptr(out), n, k,
+                   _device.lint_dtype(np.float32 if X.dtype == torch.float32 else np.float64),
+                   C.c_uint64(seed), _device.stream_ptr(X.device))
+        return out

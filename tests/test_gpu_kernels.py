@@ -451,3 +451,52 @@ def test_cellmajor_tree_leaves(lb, name):
     x_ref = O.cells_sample(g["leaf_x"], g["leaf_dx"], g["leaf_corners"], g["leaf_mass"], u)
     for d in range(x.shape[1]):
         assert stats.ks_2samp(x[:, d], x_ref[:, d]).pvalue > 1e-4
+
+
+# ----------------------------------------------------------------------------- device row permutation
+@pytest.mark.parametrize("N", [1, 2, 3, 31, 1000, 65536, 1_000_003])
+@pytest.mark.parametrize("k,dtype", [(1, np.float64), (3, np.float32), (6, np.float64)])
+def test_permute_rows_is_a_bijection(lb, N, k, dtype):
+    """lint_permute_rows == the reference's rng.shuffle as an operation: the same
+    rows, each exactly once, in a seed-determined pseudo-random order."""
+    import torch
+    from lintsampler_b200 import _capi, _device
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    x = torch.arange(N * k, dtype=tdt, device="cuda").reshape(N, k)
+    outs = []
+    for seed in (1, 1, 2):
+        out = torch.empty_like(x)
+        _capi.call("lint_permute_rows", _device.ptr(x), _device.ptr(out), N, k, _device.lint_dtype(dtype),
+                   C.c_uint64(seed), _device.stream_ptr(x.device))
+        outs.append(out.cpu().numpy())
+    a, b, c = outs
+    assert np.array_equal(a, b)                                   # deterministic in the seed
+    src = (a[:, 0] / k).astype(np.int64)
+    assert np.array_equal(np.sort(src), np.arange(N))             # every row exactly once
+    assert np.array_equal(a, x.cpu().numpy()[src])                # rows kept intact
+    if N >= 1000:
+        assert not np.array_equal(a, c)                           # another seed, another order
+        assert np.mean(src == np.arange(N)) < 0.01
+    if N >= 65536:
+        # positions look uniform: where the first tenth of the rows ends up
+        dest = np.flatnonzero(src < N // 10)
+        from scipy import stats
+        assert stats.kstest(dest / N, "uniform").pvalue > 1e-4
+        assert abs(np.corrcoef(src[:-1], src[1:])[0, 1]) < 0.02   # neighbours are unrelated (5 sigma)
+
+
+def test_cell_order_with_device_shuffle_is_exchangeable(lb):
+    from scipy import stats
+    g = load_golden("g3d_iso")
+    edges = golden_edges(g)
+    V = g["vertex_densities"]
+    grid = lb.DensityGrid(tuple(edges), lambda p: V.reshape(-1), vectorizedpdf=True, dtype=np.float32)
+    N = 400_000
+    grouped = lb.LintSampler(grid, seed=3, order="cell").sample(N)
+    mixed = lb.LintSampler(grid, seed=3, order="cell", shuffle=True).sample(N)
+    assert sorted(map(tuple, grouped[:2000])) != sorted(map(tuple, mixed[:2000]))
+    assert np.array_equal(np.sort(grouped[:, 0]), np.sort(mixed[:, 0]))          # same multiset
+    # grouped rows drift with the row index, shuffled rows do not
+    assert abs(stats.spearmanr(np.arange(N), grouped[:, 0])[0]) > 0.5
+    assert abs(stats.spearmanr(np.arange(N), mixed[:, 0])[0]) < 0.01
+    assert stats.ks_2samp(mixed[: N // 20, 0], mixed[N // 2:, 0]).pvalue > 1e-4  # any slice is representative
