@@ -97,9 +97,13 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU legs (oracle)
+_CPU_TABLES = None      # (edges, V, cdf): set before the pool forks, inherited copy-on-write
+
+
 def _cpu_worker(args):
-    seed, n, edges, V, cdf = args
+    seed, n = args
     from oracle import lint_oracle as O
+    edges, V, cdf = _CPU_TABLES
     u = np.random.default_rng(seed).random((n, DIM + 1))
     x = O.grid_sample(edges, V, u, cdf=cdf)
     return float(x[0, 0])
@@ -141,13 +145,15 @@ def run_reference_arm(args):
     V = O.gmm_pdf(mesh, w, means, sig[:, None, None] ** 2 * np.eye(DIM)[None])
     del mesh
     cdf = O.cdf_from_masses(O.cell_masses(edges, V))
+    global _CPU_TABLES
+    _CPU_TABLES = (edges, V, cdf)
     cores = min(len(os.sched_getaffinity(0)), 64)
-    per = 400_000
+    per = 1_000_000
     n_step = cores * per
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         def step(s):
-            pool.map(_cpu_worker, [(1000 * s + c, per, edges, V, cdf) for c in range(cores)])
+            pool.map(_cpu_worker, [(1000 * s + c, per) for c in range(cores)])
         for s in range(args.warmup):
             step(s)
         t0 = time.perf_counter()

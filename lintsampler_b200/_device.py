@@ -54,8 +54,12 @@ def check_dtype(dtype):
 
 
 def default_guide_bits(ncells):
-    """Guide-table size: the power of two >= ncells, within [2^4, 2^26]."""
-    bits = max(4, int(np.ceil(np.log2(max(int(ncells), 2)))))
+    """Guide-table size: about one bin per four cells, within [2^4, 2^26].  Bins that
+    lie inside one cell answer a query without touching the CDF; a finer table
+    answers more queries that way but is itself addressed uniformly at random, so
+    it competes with the hot cells for L2 (2^22 beat 2^24 and 2^20 at 256^3,
+    profiles/README.md)."""
+    bits = max(4, int(np.ceil(np.log2(max(int(ncells), 2)))) - 2)
     return min(bits, 26)
 
 

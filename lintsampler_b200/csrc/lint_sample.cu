@@ -114,21 +114,24 @@ sample_kernel(Source src, Uniforms unif, int64_t N, T *__restrict__ out,
     }
 }
 
-// First-row override for the next launch_sample on this thread (set by topup_*).
-struct RowWindow { const uint32_t *first_row_dev; int64_t max_rows; };
-static thread_local RowWindow g_window{nullptr, 0};
+// Rows [*first_row_dev, N) instead of [0, N), at most max_rows of them (the grid is
+// sized from max_rows because the first row is only known on the device).
+struct RowWindow {
+    const uint32_t *first_row_dev = nullptr;
+    int64_t max_rows = 0;
+};
 
 template <int K, typename T, typename Source, typename Uniforms>
 int launch_sample(const Source &src, const Uniforms &unif, int64_t N, void *out, int64_t *cell_idx,
-                  cudaStream_t st, const char *what) {
+                  cudaStream_t st, const char *what, const RowWindow &win) {
     if (N == 0) return LINT_OK;
-    const int64_t rows = g_window.first_row_dev ? std::min(N, g_window.max_rows) : N;
+    const int64_t rows = win.first_row_dev ? std::min(N, win.max_rows) : N;
     if (rows == 0) return LINT_OK;
     const int64_t tile = (int64_t)SAMPLE_THREADS * RowsPerThread<T>::value;
     const int64_t want = (rows + tile - 1) / tile;
     const int blocks = (int)std::min<int64_t>(want, 148 * 32);
     sample_kernel<K, T, Source, Uniforms><<<blocks, SAMPLE_THREADS, src.smem_bytes(sizeof(T)), st>>>(
-        src, unif, N, (T *)out, cell_idx, g_window.first_row_dev);
+        src, unif, N, (T *)out, cell_idx, win.first_row_dev);
     return check_launch(what);
 }
 
@@ -137,29 +140,29 @@ int launch_sample(const Source &src, const Uniforms &unif, int64_t N, void *out,
 // ---------------------------------------------------------------------------
 template <int K, typename UnifMaker>
 int grid_dispatch_k(const lint_grid_t *g, uint64_t ncells, int64_t N, void *out, int64_t *cell_idx,
-                    cudaStream_t st, const UnifMaker &mk, const char *what) {
+                    cudaStream_t st, const UnifMaker &mk, const char *what, const RowWindow &win) {
     if (g->dtype == LINT_F32) {
         GridSource<K, float> src{make_grid_view<K>(g, ncells, true)};
-        return launch_sample<K, float>(src, mk.template make<K>(), N, out, cell_idx, st, what);
+        return launch_sample<K, float>(src, mk.template make<K>(), N, out, cell_idx, st, what, win);
     }
     GridSource<K, double> src{make_grid_view<K>(g, ncells, true)};
-    return launch_sample<K, double>(src, mk.template make<K>(), N, out, cell_idx, st, what);
+    return launch_sample<K, double>(src, mk.template make<K>(), N, out, cell_idx, st, what, win);
 }
 
 template <typename UnifMaker>
 int grid_dispatch(const lint_grid_t *g, int64_t N, void *out, int64_t *cell_idx, lint_stream_t stream,
-                  const UnifMaker &mk, const char *what) {
+                  const UnifMaker &mk, const char *what, const RowWindow &win = RowWindow{}) {
     uint64_t nc, nv;
     if (int rc = validate_grid(g, true, &nc, &nv)) return rc;
     if (N < 0 || (N > 0 && !out)) return fail(LINT_ERR_BAD_ARG, "%s: bad N / out_dev", what);
     cudaStream_t st = (cudaStream_t)stream;
     switch (g->dim) {
-        case 1: return grid_dispatch_k<1>(g, nc, N, out, cell_idx, st, mk, what);
-        case 2: return grid_dispatch_k<2>(g, nc, N, out, cell_idx, st, mk, what);
-        case 3: return grid_dispatch_k<3>(g, nc, N, out, cell_idx, st, mk, what);
-        case 4: return grid_dispatch_k<4>(g, nc, N, out, cell_idx, st, mk, what);
-        case 5: return grid_dispatch_k<5>(g, nc, N, out, cell_idx, st, mk, what);
-        default: return grid_dispatch_k<6>(g, nc, N, out, cell_idx, st, mk, what);
+        case 1: return grid_dispatch_k<1>(g, nc, N, out, cell_idx, st, mk, what, win);
+        case 2: return grid_dispatch_k<2>(g, nc, N, out, cell_idx, st, mk, what, win);
+        case 3: return grid_dispatch_k<3>(g, nc, N, out, cell_idx, st, mk, what, win);
+        case 4: return grid_dispatch_k<4>(g, nc, N, out, cell_idx, st, mk, what, win);
+        case 5: return grid_dispatch_k<5>(g, nc, N, out, cell_idx, st, mk, what, win);
+        default: return grid_dispatch_k<6>(g, nc, N, out, cell_idx, st, mk, what, win);
     }
 }
 
@@ -192,28 +195,28 @@ static CellsView make_cells_view(const lint_cells_t *c) {
 
 template <int K, typename UnifMaker>
 int cells_dispatch_k(const lint_cells_t *c, int64_t N, void *out, int64_t *cell_idx, cudaStream_t st,
-                     const UnifMaker &mk, const char *what) {
+                     const UnifMaker &mk, const char *what, const RowWindow &win) {
     if (c->dtype == LINT_F32) {
         ListSource<K, float> src{make_cells_view(c)};
-        return launch_sample<K, float>(src, mk.template make<K>(), N, out, cell_idx, st, what);
+        return launch_sample<K, float>(src, mk.template make<K>(), N, out, cell_idx, st, what, win);
     }
     ListSource<K, double> src{make_cells_view(c)};
-    return launch_sample<K, double>(src, mk.template make<K>(), N, out, cell_idx, st, what);
+    return launch_sample<K, double>(src, mk.template make<K>(), N, out, cell_idx, st, what, win);
 }
 
 template <typename UnifMaker>
 int cells_dispatch(const lint_cells_t *c, int64_t N, void *out, int64_t *cell_idx, lint_stream_t stream,
-                   const UnifMaker &mk, const char *what) {
+                   const UnifMaker &mk, const char *what, const RowWindow &win = RowWindow{}) {
     if (int rc = validate_cells(c)) return rc;
     if (N < 0 || (N > 0 && !out)) return fail(LINT_ERR_BAD_ARG, "%s: bad N / out_dev", what);
     cudaStream_t st = (cudaStream_t)stream;
     switch (c->dim) {
-        case 1: return cells_dispatch_k<1>(c, N, out, cell_idx, st, mk, what);
-        case 2: return cells_dispatch_k<2>(c, N, out, cell_idx, st, mk, what);
-        case 3: return cells_dispatch_k<3>(c, N, out, cell_idx, st, mk, what);
-        case 4: return cells_dispatch_k<4>(c, N, out, cell_idx, st, mk, what);
-        case 5: return cells_dispatch_k<5>(c, N, out, cell_idx, st, mk, what);
-        default: return cells_dispatch_k<6>(c, N, out, cell_idx, st, mk, what);
+        case 1: return cells_dispatch_k<1>(c, N, out, cell_idx, st, mk, what, win);
+        case 2: return cells_dispatch_k<2>(c, N, out, cell_idx, st, mk, what, win);
+        case 3: return cells_dispatch_k<3>(c, N, out, cell_idx, st, mk, what, win);
+        case 4: return cells_dispatch_k<4>(c, N, out, cell_idx, st, mk, what, win);
+        case 5: return cells_dispatch_k<5>(c, N, out, cell_idx, st, mk, what, win);
+        default: return cells_dispatch_k<6>(c, N, out, cell_idx, st, mk, what, win);
     }
 }
 
@@ -315,21 +318,15 @@ int uniforms_dispatch(int dim, int dtype, int64_t N, const Maker &mk, double *ou
 int topup_grid(const lint_grid_t *g, int64_t N, const uint32_t *first_row_dev, int64_t max_rows,
                uint64_t seed, uint64_t offset, double u_lo, double u_hi, void *out, int64_t *cell_idx,
                cudaStream_t st) {
-    g_window = RowWindow{first_row_dev, max_rows};
-    const int rc = grid_dispatch(g, N, out, cell_idx, (lint_stream_t)st, PhiloxMaker{seed, offset, u_lo, u_hi},
-                                 "cell-major top-up");
-    g_window = RowWindow{nullptr, 0};
-    return rc;
+    return grid_dispatch(g, N, out, cell_idx, (lint_stream_t)st, PhiloxMaker{seed, offset, u_lo, u_hi},
+                         "cell-major top-up", RowWindow{first_row_dev, max_rows});
 }
 
 int topup_cells(const lint_cells_t *c, int64_t N, const uint32_t *first_row_dev, int64_t max_rows,
                 uint64_t seed, uint64_t offset, double u_lo, double u_hi, void *out, int64_t *cell_idx,
                 cudaStream_t st) {
-    g_window = RowWindow{first_row_dev, max_rows};
-    const int rc = cells_dispatch(c, N, out, cell_idx, (lint_stream_t)st, PhiloxMaker{seed, offset, u_lo, u_hi},
-                                  "cell-major top-up");
-    g_window = RowWindow{nullptr, 0};
-    return rc;
+    return cells_dispatch(c, N, out, cell_idx, (lint_stream_t)st, PhiloxMaker{seed, offset, u_lo, u_hi},
+                          "cell-major top-up", RowWindow{first_row_dev, max_rows});
 }
 
 }  // namespace lint

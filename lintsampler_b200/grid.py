@@ -128,14 +128,15 @@ class DensityGrid(DensityStructure):
     def vertex_densities(self):
         """(n0+1, ..., nk-1+1) NumPy array of vertex densities (fp64)."""
         if self._host_densities is None:
-            self._host_densities = self._V.cpu().numpy().astype(np.float64).reshape(self._edgeshape)
+            self._host_densities = (self._V.cpu().numpy().astype(np.float64)
+                                    / self._scale).reshape(self._edgeshape)
         return self._host_densities
 
     @property
     def masses(self):
         """Cell masses, shape ``self.shape`` (NumPy, fp64)  [grid.py:411]."""
         if self._masses_host is None:
-            self._masses_host = self._masses.cpu().numpy().reshape(self.shape)
+            self._masses_host = (self._masses.cpu().numpy() / self._scale).reshape(self.shape)
         return self._masses_host
 
     # ------------------------------------------------------------------ build
@@ -199,10 +200,25 @@ class DensityGrid(DensityStructure):
         ncells = int(self.ncells)
         self._edges_t = [torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=dev)
                          for a in self.edgearrays]
+        # fp32 storage: densities are kept times a power of two that brings the largest
+        # into [1, 2), so unnormalised pdfs in physical units (1e-40 .. 1e+40) neither
+        # flush to zero nor overflow.  Sampling only sees ratios; masses are unscaled
+        # again wherever they are reported.  (fp64: scale = 1.)
+        self._scale = 1.0
+        if self.dtype == np.float32:
+            if densities is not None:
+                peak = float(np.max(densities)) if densities.size else 0.0
+            elif dev_densities is not None:
+                peak = float(dev_densities.max().item())
+            else:
+                peak = float(np.exp(gmm._log_norm).sum())          # upper bound of the mixture
+            if np.isfinite(peak) and peak > 0.0:
+                self._scale = float(2.0 ** -np.floor(np.log2(peak)))
         if densities is not None:
-            self._V = torch.as_tensor(np.ascontiguousarray(densities).reshape(npts), device=dev).to(tdt)
+            self._V = torch.as_tensor(np.ascontiguousarray(densities).reshape(npts) * self._scale,
+                                      device=dev).to(tdt)
         elif dev_densities is not None:
-            self._V = dev_densities.to(tdt).contiguous()
+            self._V = (dev_densities * self._scale).to(tdt).contiguous()
         else:
             self._V = torch.empty(npts, dtype=tdt, device=dev)
         self._cdf = None
@@ -213,7 +229,7 @@ class DensityGrid(DensityStructure):
         self._gmm = gmm
         if gmm is not None:
             gs, keep = gmm._as_struct()
-            _capi.call("lint_grid_eval_gmm", C.byref(desc), C.byref(gs), 1.0, st)
+            _capi.call("lint_grid_eval_gmm", C.byref(desc), C.byref(gs), self._scale, st)
             del keep
         self._masses = torch.empty(ncells, dtype=torch.float64, device=dev)
         self._flags = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -264,6 +280,8 @@ class DensityGrid(DensityStructure):
             np.ascontiguousarray(densities))
         if t.numel() != npts:
             raise ValueError("DensityGrid.update_densities: wrong number of vertex densities")
+        if self._scale != 1.0:
+            t = t.to(self.device, non_blocking=True).to(torch.float64) * self._scale   # keeps the build's scale
         self._V.copy_(t.reshape(npts), non_blocking=True)       # H2D (+ cast) on the current stream
         self._host_densities = None
         self._enqueue_build()
@@ -276,7 +294,7 @@ class DensityGrid(DensityStructure):
             raise ValueError("DensityGrid: Densities can't be negative")
         if bad & _capi.LINT_FLAG_NONFINITE:                    # [grid.py:403-404]
             raise ValueError("DensityGrid: Detected non-finite density")
-        self._total_mass = float(self._total.item())
+        self._total_mass = float(self._total.item()) / self._scale
         if not (self._total_mass > 0.0) or not np.isfinite(self._total_mass):
             raise ValueError(
                 "DensityGrid: total mass of the grid is not positive and finite "

@@ -40,10 +40,6 @@ from .base import DensityStructure
 from .grid import DensityGrid, _is_flat_sequence
 
 
-def rng_backend_is_philox(sampler):
-    return sampler.rng_backend == "philox"
-
-
 def _boxes_overlap(a_lo, a_hi, b_lo, b_hi):
     """Axis-aligned boxes overlap unless separated along some axis [utils.py:156-176]."""
     return not np.any((a_hi <= b_lo) | (b_hi <= a_lo))
@@ -167,7 +163,7 @@ class LintSampler:
         # (lintsampler.py:72-77,458); None draws fresh entropy.
         if isinstance(seed, (int, np.integer)) and 0 <= int(seed) < 2 ** 64:
             self._philox_key = int(seed)
-        elif isinstance(seed, np.random.Generator) and rng_backend_is_philox(self):
+        elif isinstance(seed, np.random.Generator) and self.rng_backend == "philox":
             self._philox_key = int(seed.integers(0, 2 ** 64, dtype=np.uint64))
         else:
             ss = seed if isinstance(seed, np.random.SeedSequence) else np.random.SeedSequence(

@@ -407,7 +407,13 @@ class _CellTable:
         tdt = _device.torch_dtype(dtype)
         self._mins = torch.as_tensor(np.ascontiguousarray(mins), device=dev)
         self._widths = torch.as_tensor(np.ascontiguousarray(widths), device=dev)
-        self._corners = torch.as_tensor(np.ascontiguousarray(corners), device=dev).to(tdt).contiguous()
+        corners = np.ascontiguousarray(corners, dtype=np.float64)
+        if self.dtype == np.float32 and corners.size:
+            # only ratios of corner densities matter to the sampler: scale into fp32 range
+            peak = float(np.max(corners))
+            if np.isfinite(peak) and peak > 0.0:
+                corners = corners * 2.0 ** -np.floor(np.log2(peak))
+        self._corners = torch.as_tensor(corners, device=dev).to(tdt).contiguous()
         self._masses = torch.as_tensor(np.ascontiguousarray(masses), device=dev)
         self._cdf = None
         flags = torch.zeros(1, dtype=torch.int32, device=dev)

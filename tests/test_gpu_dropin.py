@@ -265,3 +265,25 @@ def test_device_tensor_return(lb):
 def _gm3():
     w, mu, cov = pdfs.gmm_params(3, seed=0)
     return w, mu, cov
+
+
+@pytest.mark.parametrize("factor", [1e-42, 1e-30, 1.0, 1e+30, 1e+42])
+def test_fp32_mode_is_scale_invariant(lb, factor):
+    """Unnormalised densities in physical units must not flush to zero or overflow in
+    fp32 storage: the same seed gives the same samples whatever the overall factor,
+    and masses/densities are reported unscaled."""
+    g = load_golden("g3d_iso")
+    edges = tuple(golden_edges(g))
+    V = g["vertex_densities"]
+    ref = lb.LintSampler(lb.DensityGrid(edges, lambda p: V.reshape(-1), vectorizedpdf=True,
+                                        dtype=np.float32), seed=4).sample(50_000)
+    grid = lb.DensityGrid(edges, lambda p: V.reshape(-1) * factor, vectorizedpdf=True, dtype=np.float32)
+    x = lb.LintSampler(grid, seed=4).sample(50_000)
+    assert np.allclose(x, ref, rtol=0, atol=1e-5)
+    assert grid.total_mass == pytest.approx(float(g["total_mass"]) * factor, rel=1e-6)
+    np.testing.assert_allclose(grid.vertex_densities, V * factor, rtol=1e-6, atol=1e-12 * V.max() * factor)
+    pdf, _ = PDFS["g3d_iso"]
+    w, mu, cov = pdfs.gmm_params(3, seed=0)
+    gm = lb.GaussianMixture(w * factor, mu, cov)
+    g2 = lb.DensityGrid(edges, gm, vectorizedpdf=True, dtype=np.float32)
+    assert g2.total_mass == pytest.approx(float(g["total_mass"]) * factor, rel=1e-5)
