@@ -65,6 +65,62 @@ def equal_mass_strata(world):
     return np.arange(world + 1, dtype=np.float64) / world
 
 
+def slab_bounds(n0, world):
+    """Cell-plane ranges along dim 0, one contiguous slab per rank:
+    rank g owns cell planes [b[g], b[g+1]) and vertex planes [b[g], b[g+1]]."""
+    return [(g * n0) // world for g in range(world + 1)]
+
+
+class SlabShardedGrid:
+    """The literal slab decomposition: rank g evaluates, reduces and scans ONLY its
+    own slab of dim-0 planes (one halo vertex plane, re-evaluated locally), the slab
+    masses are all-gathered (NCCL, 8 B per rank), N is split multinomially over
+    them with a shared seed and every rank samples its share from its own slab.
+
+    Work per rank is proportional to the slab's mass, so a peaked density leaves the
+    ranks that own its tails idle; ``ShardedGrid`` (equal-mass strata) is the
+    balanced alternative and what ``bench.py`` uses.  ``pdf`` must be evaluable on a
+    sub-grid (any callable or ``GaussianMixture``).
+    """
+
+    def __init__(self, edges, pdf, *, dtype=np.float64, device=None, rank=0, world=1, group=None,
+                 vectorizedpdf=True, cdf_mode="parallel", **grid_kw):
+        self.rank, self.world, self.group = int(rank), int(world), group
+        edges = [np.asarray(e) for e in (edges if isinstance(edges, tuple) else (edges,))]
+        n0 = len(edges[0]) - 1
+        if n0 < world:
+            raise ValueError("SlabShardedGrid: fewer cell planes along dim 0 than ranks")
+        b = slab_bounds(n0, world)
+        self.planes = (b[self.rank], b[self.rank + 1])
+        sub = [edges[0][b[self.rank]:b[self.rank + 1] + 1]] + edges[1:]
+        dom = tuple(sub) if len(sub) > 1 else sub[0]
+        self.grid = DensityGrid(dom, pdf, vectorizedpdf=vectorizedpdf, dtype=dtype, device=device,
+                                cdf_mode=cdf_mode, **grid_kw)
+        self.device = self.grid.device
+        self._gather_buf = None
+        self.shard_masses = self.exchange_masses()
+
+    def exchange_masses(self):
+        """NCCL all-gather of the slab masses (unscaled), as a NumPy array."""
+        mine = self.grid._total / self.grid._scale
+        self._gather_buf = all_gather_masses(mine, self.world, self.group, self._gather_buf)
+        return self._gather_buf.cpu().numpy().copy()
+
+    def sample(self, n_total, seed, offset=0, order="draw"):
+        """This rank's rows of an ``n_total``-row draw: (device tensor (N_g, k), counts)."""
+        import torch
+        counts = split_counts(n_total, self.shard_masses, seed)
+        n = int(counts[self.rank])
+        start = int(counts[:self.rank].sum())
+        out = torch.empty((n, self.grid.dim), dtype=_device.torch_dtype(self.grid.dtype), device=self.device)
+        if n:
+            if order == "cell":
+                self.grid._sample_cellmajor(n, seed, offset + start, out=out)
+            else:
+                self.grid._sample_philox(n, seed, offset + start, out=out)
+        return out, counts
+
+
 class ShardedGrid:
     """A ``DensityGrid`` whose sampling work is sharded over ``world`` ranks.
 

@@ -81,5 +81,7 @@ def test_split_and_routing_helpers():
     r, ul = lbd.route_rows(np.array([0.0, 0.24, 0.25, 0.5, 0.99]), b)
     assert list(r) == [0, 0, 1, 2, 3]
     assert np.allclose(ul, [0.0, 0.96, 0.0, 0.0, 0.96])
+    assert lbd.slab_bounds(256, 8) == [0, 32, 64, 96, 128, 160, 192, 224, 256]
+    assert lbd.slab_bounds(10, 3) == [0, 3, 6, 10]
     c = lbd.split_counts(10**9, [1.0, 3.0], seed=1)
     assert c.sum() == 10**9 and abs(c[1] / 10**9 - 0.75) < 1e-4
