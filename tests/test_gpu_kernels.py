@@ -500,3 +500,48 @@ def test_cell_order_with_device_shuffle_is_exchangeable(lb):
     assert abs(stats.spearmanr(np.arange(N), grouped[:, 0])[0]) > 0.5
     assert abs(stats.spearmanr(np.arange(N), mixed[:, 0])[0]) < 0.01
     assert stats.ks_2samp(mixed[: N // 20, 0], mixed[N // 2:, 0]).pvalue > 1e-4  # any slice is representative
+
+
+@pytest.mark.parametrize("N", [1, 2, 7, 33, 1000, 4097])
+def test_cellmajor_edge_cases(lb, N):
+    """Tiny draws (everything comes from the top-up), a single-cell grid, and a grid
+    whose whole mass sits in one cell."""
+    import torch
+    e = (np.linspace(0, 1, 5), np.linspace(0, 2, 4))
+    dens = np.zeros((5, 4))
+    dens[2:4, 1:3] = 1.0                       # only cell (2,1) has four non-zero corners... and neighbours partial
+    for grid in (lb.DensityGrid(e, lambda p: dens.reshape(-1), vectorizedpdf=True),
+                 lb.DensityGrid((np.array([0.0, 1.0]), np.array([0.0, 2.0])), lambda p: np.ones(4), vectorizedpdf=True),
+                 lb.DensityGrid(e, lambda p: dens.reshape(-1), vectorizedpdf=True, dtype=np.float32)):
+        x, cells = grid._sample_cellmajor(N, 9, 0, want_cells=True)
+        x, cells = x.cpu().numpy(), cells.cpu().numpy()
+        assert x.shape == (N, 2) and np.all(np.isfinite(x))
+        m = grid.masses.ravel()
+        assert np.all(m[cells] > 0)                                  # zero-mass cells never drawn
+        multi = np.unravel_index(cells, grid.shape)
+        for d in range(2):
+            ed = grid.edgearrays[d]
+            assert np.all(x[:, d] >= ed[multi[d]] - 1e-6) and np.all(x[:, d] <= ed[multi[d] + 1] + 1e-6)
+
+
+def test_sample_to_host_pipeline(lb):
+    import torch
+    g = load_golden("g3d_iso")
+    edges = tuple(golden_edges(g))
+    V = g["vertex_densities"]
+    for order in ("draw", "cell"):
+        grid = lb.DensityGrid(edges, lambda p: V.reshape(-1), vectorizedpdf=True, dtype=np.float32)
+        s = lb.LintSampler(grid, seed=2, order=order)
+        out = s.sample_to_host(300_000, chunk=70_000)                # 5 chunks, ragged tail
+        torch.cuda.synchronize()
+        assert out.shape == (300_000, 3) and out.is_pinned() and not out.is_cuda
+        a = out.numpy()
+        assert np.all(a >= -4) and np.all(a <= 4) and np.all(np.isfinite(a))
+        # same stream position as five successive device calls
+        s2 = lb.LintSampler(grid, seed=2, order=order, return_tensor=True)
+        parts = [s2.sample(n).cpu().numpy() for n in (70_000, 70_000, 70_000, 70_000, 20_000)]
+        assert np.array_equal(a, np.concatenate(parts))
+    with pytest.raises(TypeError):
+        s.sample_to_host(3.5)
+    with pytest.raises(ValueError):
+        s.sample_to_host(0)
