@@ -48,7 +48,8 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:                      # compile translation units in parallel
         obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("LINT_EXTRA_NVCC", "").split(), "-c",
+               os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))

@@ -261,7 +261,16 @@ struct ListCells {
     }
 };
 
-constexpr int EMIT_THREADS = 256, EMIT_CHUNK = 2048, EMIT_U = 4;
+#ifndef LINT_EMIT_U
+#define LINT_EMIT_U 4          // rows per lane in the straight-line fast path
+#endif
+#ifndef LINT_EMIT_MINB
+#define LINT_EMIT_MINB 4       // resident CTAs per SM the fp32 k<=3 emitter is compiled for
+#endif
+#ifndef LINT_EMIT_THREADS
+#define LINT_EMIT_THREADS 256
+#endif
+constexpr int EMIT_THREADS = LINT_EMIT_THREADS, EMIT_CHUNK = 2048, EMIT_U = LINT_EMIT_U;
 
 // In-cell uniforms of a group of R rows of one lane: R*K coordinates from
 // ceil(R*K*words/4) Philox blocks.  fp32 rows use one 32-bit word per coordinate
@@ -283,7 +292,8 @@ struct GroupUniforms {
     }
     __device__ __forceinline__ void get(int i, float (&u)[K]) const {
 #pragma unroll
-        for (int d = 0; d < K; ++d) u[d] = (float)(w[i * K + d] >> 8) * (1.0f / 16777216.0f);
+        // round-toward-zero conversion keeps the top 24 bits: u in [0, 1 - 2^-24]
+        for (int d = 0; d < K; ++d) u[d] = __uint2float_rz(w[i * K + d]) * (1.0f / 4294967296.0f);
     }
     __device__ __forceinline__ void get(int i, double (&u)[K]) const {
 #pragma unroll
@@ -318,7 +328,7 @@ __device__ __forceinline__ void emit_row(const CellCoefs<K, T> &coef, const T (&
 constexpr int EMIT_WIN = 64;
 
 template <int K, typename T, typename Cells, bool CELLS>
-__global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 && K <= 3 ? 4 : 1)
+__global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 && K <= 3 ? LINT_EMIT_MINB : 1)
 emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
             const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ rows_p,
             const uint32_t *__restrict__ chunk_start, uint32_t n_requested, uint2 key, uint64_t offset,

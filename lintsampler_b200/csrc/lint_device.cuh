@@ -153,9 +153,10 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 
 __device__ __forceinline__ float quantile_fast(float f0, float f1, float u) {
     const float rad = fmaf(u, fmaf(f1, f1, -f0 * f0), f0 * f0);
-    const float den = f0 + sqrt_approx(fmaxf(rad, 0.f));
-    // den == 0 only when both ends of the segment carry no density: uniform draw
-    return den > 0.f ? (f0 + f1) * u * rcp_approx(den) : u;
+    // den == 0 only where the segment carries no density at all (or f0 == 0 and u == 0):
+    // the numerator is 0 there too, so flooring den gives z = 0 instead of 0/0
+    const float den = fmaxf(f0 + sqrt_approx(fmaxf(rad, 0.f)), 1e-30f);
+    return (f0 + f1) * u * rcp_approx(den);
 }
 
 // ---------------------------------------------------------------------------
@@ -255,8 +256,8 @@ struct CellFast {
         for (int j = 0; j < H; ++j) { c[j] = corners[j]; dc[j] = corners[H + j] - corners[j]; }
     }
     __device__ __forceinline__ void draw(const float (&u)[K], float (&z)[K]) const {
-        const float den = g0 + sqrt_approx(fmaxf(fmaf(b0, u[0], a0), 0.f));
-        const float z0 = den > 0.f ? s0 * u[0] * rcp_approx(den) : u[0];
+        const float den = fmaxf(g0 + sqrt_approx(fmaxf(fmaf(b0, u[0], a0), 0.f)), 1e-30f);
+        const float z0 = s0 * u[0] * rcp_approx(den);
         z[0] = z0;
         if constexpr (K > 1) {
             float w[H];
