@@ -104,6 +104,12 @@ typedef struct lint_sobol {
     uint32_t sv[LINT_MAX_DIM + 1][32];    /* HOST: scrambled direction numbers           */
     uint32_t shift[LINT_MAX_DIM + 1];     /* HOST: digital shift                         */
     uint64_t first_index;                 /* index of the first point to emit            */
+    uint32_t sorted_bits;                 /* 0: rows are points first_index, first_index+1, ...
+                                             m: rows are the first 2^m points enumerated with the
+                                             cell-selecting coordinate increasing (needs N == 2^m,
+                                             first_index == 0 and sorted_ainv)             */
+    uint32_t sorted_ainv[32];             /* HOST: column r = A^-1 e_r over GF(2), A = top m x m
+                                             block of the cell coordinate's generator matrix */
 } lint_sobol_t;
 
 /* Gaussian mixture sum_j w_j N(x; mu_j, Sigma_j), passed as HOST arrays:

@@ -47,6 +47,8 @@ class LintSobol(C.Structure):
         ("sv", (C.c_uint32 * 32) * (LINT_MAX_DIM + 1)),
         ("shift", C.c_uint32 * (LINT_MAX_DIM + 1)),
         ("first_index", C.c_uint64),
+        ("sorted_bits", C.c_uint32),
+        ("sorted_ainv", C.c_uint32 * 32),
     ]
 
 

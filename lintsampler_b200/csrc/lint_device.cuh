@@ -411,8 +411,10 @@ __device__ __forceinline__ void cells_fetch(const CellsView &s, uint32_t idx, T 
 template <int K>
 struct UniformsFromArray {        // caller-supplied (N, K+1) fp64  [lintsampler.py:517]
     const double *u;
+    __host__ size_t smem_words() const { return 0; }
+    __device__ __forceinline__ const uint32_t *stage(uint32_t *) const { return nullptr; }
     template <typename T>
-    __device__ __forceinline__ void get(int64_t row, double &ucell, T (&uc)[K]) const {
+    __device__ __forceinline__ void get(int64_t row, double &ucell, T (&uc)[K], const uint32_t *) const {
         const double *p = u + row * (K + 1);
 #pragma unroll
         for (int d = 0; d < K; ++d) uc[d] = (T)__ldg(p + d);
@@ -425,11 +427,13 @@ struct UniformsPhilox {
     uint2 key;
     uint64_t offset;
     double u_lo, u_span;           // cell-uniform stratum [u_lo, u_lo + u_span); (0, 1) = whole domain
+    __host__ size_t smem_words() const { return 0; }
+    __device__ __forceinline__ const uint32_t *stage(uint32_t *) const { return nullptr; }
     __device__ __forceinline__ double stratum(double r) const {
         return __dadd_rn(u_lo, __dmul_rn(u_span, r));   // exact identity for (0, 1)
     }
     // fp64 rows: cell uniform from words (0,1), coordinate d from words (2+2d, 3+2d)
-    __device__ __forceinline__ void get(int64_t row, double &ucell, double (&uc)[K]) const {
+    __device__ __forceinline__ void get(int64_t row, double &ucell, double (&uc)[K], const uint32_t *) const {
         const uint64_t i = offset + (uint64_t)row;
         constexpr int NCALL = (K + 2) / 2;
         uint32_t w[4 * NCALL];
@@ -445,7 +449,7 @@ struct UniformsPhilox {
     // fp32 rows: cell uniform from words (0,1); 24-bit coordinates: d=0,1 from the
     // top bits of words 2,3; d=2 from the otherwise unused low bytes of words
     // 2, 3 and 0; d=3..5 from a second block.
-    __device__ __forceinline__ void get(int64_t row, double &ucell, float (&uc)[K]) const {
+    __device__ __forceinline__ void get(int64_t row, double &ucell, float (&uc)[K], const uint32_t *) const {
         const uint64_t i = offset + (uint64_t)row;
         const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0, 0), key);
         ucell = stratum(u53(r.x, r.y));
@@ -463,22 +467,59 @@ struct UniformsPhilox {
 };
 
 template <int K>
-struct UniformsSobol {            // scipy Sobol(d=K+1, bits=32), direct Gray-code index
-    uint32_t sv[K + 1][32];
-    uint32_t shift[K + 1];
-    uint64_t first;
+struct UniformsSobol {            // scipy Sobol(d=K+1, bits=32)
+    uint32_t sv[K + 1][32];       // scrambled direction numbers
+    uint32_t shift[K + 1];        // digital shift
+    uint32_t ainv[32];            // sorted mode: columns of the GF(2) inverse (see below)
+    uint64_t first;               // direct mode: index of the first point
+    uint32_t sorted_bits;         // 0 = direct Gray-code index; m = sorted enumeration of the first 2^m points
+
+    // tables are staged in shared memory: they are indexed by data-dependent bit
+    // positions, which serialises in the constant bank the parameters live in
+    static constexpr int TABLE_WORDS = (K + 1) * 33 + 32;
+    __host__ size_t smem_words() const { return TABLE_WORDS; }
+    __device__ __forceinline__ const uint32_t *stage(uint32_t *s) const {
+        for (int i = threadIdx.x; i < (K + 1) * 32; i += blockDim.x) s[i] = sv[i / 32][i % 32];
+        for (int i = threadIdx.x; i <= K; i += blockDim.x) s[(K + 1) * 32 + i] = shift[i];
+        for (int i = threadIdx.x; i < 32; i += blockDim.x) s[(K + 1) * 33 + i] = ainv[i];
+        __syncthreads();
+        return s;
+    }
+
+    // Direct mode: row i is point n = first + i, x_n[j] = shift[j] ^ XOR_{b in gray(n)} sv[j][b],
+    // bit-identical to scipy's recurrence.
+    // Sorted mode (N == 2^m, first == 0): row i is THE point of the first 2^m whose
+    // cell-selecting coordinate has top m bits == i.  The first 2^m points of one
+    // Sobol' coordinate visit every dyadic interval of width 2^-m exactly once (it is a
+    // (0,m,1)-net: the top m x m block A of its generator matrix is invertible over
+    // GF(2)), so gray(n) = A^-1 (i ^ top_m(shift)).  The same point set as scipy, but
+    // enumerated with the cell uniform increasing — consecutive rows land in the same
+    // or neighbouring cells, which turns the sampler's table accesses from random into
+    // streaming.  Row order is restored to random by the final row permutation that
+    // the reference applies to every draw anyway (lintsampler.py:309-311).
     template <typename T>
-    __device__ __forceinline__ void get(int64_t row, double &ucell, T (&uc)[K]) const {
-        const uint64_t n = first + (uint64_t)row;
-        uint32_t gray = (uint32_t)(n ^ (n >> 1));
+    __device__ __forceinline__ void get(int64_t row, double &ucell, T (&uc)[K], const uint32_t *tab) const {
+        uint32_t gray;
+        if (sorted_bits) {
+            uint32_t t = (uint32_t)row ^ (tab[(K + 1) * 32 + K] >> (32 - sorted_bits));
+            gray = 0;
+            while (t) {
+                const int r = __ffs(t) - 1;
+                t &= t - 1;
+                gray ^= tab[(K + 1) * 33 + r];
+            }
+        } else {
+            const uint64_t n = first + (uint64_t)row;
+            gray = (uint32_t)(n ^ (n >> 1));
+        }
         uint32_t x[K + 1];
 #pragma unroll
-        for (int j = 0; j <= K; ++j) x[j] = shift[j];
+        for (int j = 0; j <= K; ++j) x[j] = tab[(K + 1) * 32 + j];
         while (gray) {
             const int b = __ffs(gray) - 1;
             gray &= gray - 1;
 #pragma unroll
-            for (int j = 0; j <= K; ++j) x[j] ^= sv[j][b];
+            for (int j = 0; j <= K; ++j) x[j] ^= tab[j * 32 + b];
         }
         // scipy scales the 32-bit integers by 2^-32 in fp64
 #pragma unroll

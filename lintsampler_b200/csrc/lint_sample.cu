@@ -19,6 +19,7 @@ template <int K, typename DensT>
 struct GridSource {
     GridView<K> g;
     __host__ size_t smem_bytes(size_t elem) const { return (size_t)g.edge_total * elem; }
+    __device__ __forceinline__ size_t smem_bytes_dev(size_t elem) const { return (size_t)g.edge_total * elem; }
     template <typename T>
     __device__ __forceinline__ void prepare(T *smem) const { grid_stage_edges<K, T>(g, smem); }
     __device__ __forceinline__ void bracket(double u, uint32_t &lo, uint32_t &hi) const {
@@ -39,6 +40,7 @@ template <int K, typename DensT>
 struct ListSource {
     CellsView s;
     __host__ size_t smem_bytes(size_t) const { return 0; }
+    __device__ __forceinline__ size_t smem_bytes_dev(size_t) const { return 0; }
     template <typename T>
     __device__ __forceinline__ void prepare(T *) const {}
     __device__ __forceinline__ void bracket(double u, uint32_t &lo, uint32_t &hi) const {
@@ -75,7 +77,9 @@ sample_kernel(Source src, Uniforms unif, int64_t N, T *__restrict__ out,
     const int64_t first = first_row_dev ? (int64_t)*first_row_dev : 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *smem = reinterpret_cast<T *>(smem_raw);
-    src.prepare(smem);
+    src.prepare(smem);                                   // edge arrays
+    const uint32_t *utab = unif.stage(                   // uniform source's tables, after the edges
+        reinterpret_cast<uint32_t *>(smem_raw + ((src.smem_bytes_dev(sizeof(T)) + 15) & ~(size_t)15)));
     const int64_t tile = (int64_t)SAMPLE_THREADS * R;
     for (int64_t base = first + (int64_t)blockIdx.x * tile; base < N; base += (int64_t)gridDim.x * tile) {
         double ucell[R];
@@ -87,7 +91,7 @@ sample_kernel(Source src, Uniforms unif, int64_t N, T *__restrict__ out,
         for (int r = 0; r < R; ++r) {
             const int64_t row = base + (int64_t)r * SAMPLE_THREADS + threadIdx.x;
             live[r] = row < N;
-            unif.get(live[r] ? row : 0, ucell[r], u[r]);
+            unif.get(live[r] ? row : 0, ucell[r], u[r], utab);
             src.bracket(ucell[r], lo[r], hi[r]);           // grid.choose_cells(u[..., -1])
         }
         // stage 2: resolve the brackets that span more than one cell
@@ -130,7 +134,8 @@ int launch_sample(const Source &src, const Uniforms &unif, int64_t N, void *out,
     const int64_t tile = (int64_t)SAMPLE_THREADS * RowsPerThread<T>::value;
     const int64_t want = (rows + tile - 1) / tile;
     const int blocks = (int)std::min<int64_t>(want, 148 * 32);
-    sample_kernel<K, T, Source, Uniforms><<<blocks, SAMPLE_THREADS, src.smem_bytes(sizeof(T)), st>>>(
+    const size_t smem = ((src.smem_bytes(sizeof(T)) + 15) & ~(size_t)15) + unif.smem_words() * 4;
+    sample_kernel<K, T, Source, Uniforms><<<blocks, SAMPLE_THREADS, smem, st>>>(
         src, unif, N, (T *)out, cell_idx, win.first_row_dev);
     return check_launch(what);
 }
@@ -246,7 +251,9 @@ struct SobolMaker {
             for (int b = 0; b < 32; ++b) u.sv[j][b] = s->sv[j][b];
             u.shift[j] = s->shift[j];
         }
+        for (int b = 0; b < 32; ++b) u.ainv[b] = s->sorted_ainv[b];
         u.first = s->first_index;
+        u.sorted_bits = s->sorted_bits;
         return u;
     }
 };
@@ -275,11 +282,13 @@ incell_kernel(int64_t N, const double *mins, const double *maxs, const double *c
 template <int K, typename T, typename Uniforms>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 uniforms_kernel(Uniforms unif, int64_t N, double *out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t *utab = unif.stage(reinterpret_cast<uint32_t *>(smem_raw));
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < N; row += stride) {
         double ucell;
         T u[K];
-        unif.get(row, ucell, u);
+        unif.get(row, ucell, u, utab);
 #pragma unroll
         for (int d = 0; d < K; ++d) out[row * (K + 1) + d] = (double)u[d];
         out[row * (K + 1) + K] = ucell;
@@ -292,9 +301,9 @@ int uniforms_dispatch_k(int dtype, int64_t N, const Maker &mk, double *out, cuda
     const int blocks = (int)std::min<int64_t>((N + SAMPLE_THREADS - 1) / SAMPLE_THREADS, 148 * 32);
     auto u = mk.template make<K>();
     if (dtype == LINT_F32)
-        uniforms_kernel<K, float, decltype(u)><<<blocks, SAMPLE_THREADS, 0, st>>>(u, N, out);
+        uniforms_kernel<K, float, decltype(u)><<<blocks, SAMPLE_THREADS, u.smem_words() * 4, st>>>(u, N, out);
     else
-        uniforms_kernel<K, double, decltype(u)><<<blocks, SAMPLE_THREADS, 0, st>>>(u, N, out);
+        uniforms_kernel<K, double, decltype(u)><<<blocks, SAMPLE_THREADS, u.smem_words() * 4, st>>>(u, N, out);
     return check_launch("uniforms");
 }
 
@@ -385,21 +394,33 @@ int lint_philox_uniforms(int dim, int dtype, int64_t N, uint64_t seed, uint64_t 
     return uniforms_dispatch(dim, dtype, N, PhiloxMaker{seed, offset, 0.0, 1.0}, u_dev, stream);
 }
 
+static int check_sobol(const lint_sobol_t *sobol, int64_t N, const char *what) {
+    if (!sobol) return fail(LINT_ERR_BAD_ARG, "%s: sobol is NULL", what);
+    if (sobol->sorted_bits) {
+        if (sobol->sorted_bits > 32 || sobol->first_index != 0 || N != (1ll << sobol->sorted_bits))
+            return fail(LINT_ERR_BAD_ARG, "%s: sorted enumeration needs first_index == 0 and N == 2^sorted_bits",
+                        what);
+    } else if ((uint64_t)N + sobol->first_index > (1ull << 32)) {
+        return fail(LINT_ERR_BAD_ARG, "%s: a 32-bit Sobol sequence has 2^32 points", what);
+    }
+    return LINT_OK;
+}
+
 int lint_grid_sample_sobol(const lint_grid_t *g, int64_t N, const lint_sobol_t *sobol, void *out_dev,
                            int64_t *cell_idx_dev, lint_stream_t stream) {
-    if (!sobol) return fail(LINT_ERR_BAD_ARG, "lint_grid_sample_sobol: sobol is NULL");
+    if (int rc = check_sobol(sobol, N, "lint_grid_sample_sobol")) return rc;
     return grid_dispatch(g, N, out_dev, cell_idx_dev, stream, SobolMaker{sobol}, "lint_grid_sample_sobol");
 }
 
 int lint_cells_sample_sobol(const lint_cells_t *c, int64_t N, const lint_sobol_t *sobol, void *out_dev,
                             int64_t *cell_idx_dev, lint_stream_t stream) {
-    if (!sobol) return fail(LINT_ERR_BAD_ARG, "lint_cells_sample_sobol: sobol is NULL");
+    if (int rc = check_sobol(sobol, N, "lint_cells_sample_sobol")) return rc;
     return cells_dispatch(c, N, out_dev, cell_idx_dev, stream, SobolMaker{sobol}, "lint_cells_sample_sobol");
 }
 
 int lint_sobol_uniforms(int dim, int64_t N, const lint_sobol_t *sobol, double *u_dev,
                         lint_stream_t stream) {
-    if (!sobol) return fail(LINT_ERR_BAD_ARG, "lint_sobol_uniforms: sobol is NULL");
+    if (int rc = check_sobol(sobol, N, "lint_sobol_uniforms")) return rc;
     return uniforms_dispatch(dim, LINT_F64, N, SobolMaker{sobol}, u_dev, stream);
 }
 

@@ -40,6 +40,25 @@ from .base import DensityStructure
 from .grid import DensityGrid, _is_flat_sequence
 
 
+def sobol_sorted_inverse(sv_cell, m):
+    """Columns (as ints) of A^-1 over GF(2), A = top m x m block of the generator matrix
+    whose columns are the 32-bit direction numbers ``sv_cell``: with it,
+    ``gray(n) = XOR_{r in bits(y)} col[r]`` is the point of the first 2^m whose
+    coordinate has top m bits ``y ^ top_m(shift)``."""
+    a = [int(sv_cell[c]) >> (32 - m) for c in range(m)]
+    M = np.array([[(a[c] >> r) & 1 for c in range(m)] + [int(i == r) for i in range(m)]
+                  for r in range(m)], dtype=np.uint8)
+    for c in range(m):                                  # Gauss-Jordan elimination mod 2
+        p = next(r for r in range(c, m) if M[r, c])     # exists: the block is invertible
+        if p != c:
+            M[[c, p]] = M[[p, c]]
+        for r in range(m):
+            if r != c and M[r, c]:
+                M[r] ^= M[c]
+    inv = M[:, m:]
+    return [sum(int(inv[c, r]) << c for c in range(m)) for r in range(m)]
+
+
 def _boxes_overlap(a_lo, a_hi, b_lo, b_hi):
     """Axis-aligned boxes overlap unless separated along some axis [utils.py:156-176]."""
     return not np.any((a_hi <= b_lo) | (b_hi <= a_lo))
@@ -195,7 +214,11 @@ class LintSampler:
         if e.num_generated == 0 and n & (n - 1):
             warn("The balance properties of Sobol' points require n to be a power of 2.")
 
-    def _sobol_struct(self):
+    def _sobol_struct(self, sorted_n=None):
+        """Engine state for the C ABI.  ``sorted_n`` = 2^m asks for the first 2^m points
+        enumerated with the cell-selecting coordinate increasing (see
+        ``UniformsSobol`` in csrc/lint_device.cuh): needs the inverse over GF(2) of the
+        top m x m block of that coordinate's generator matrix."""
         e = self.qmc_engine
         s = _capi.LintSobol()
         for j in range(self.dim + 1):
@@ -203,7 +226,19 @@ class LintSampler:
                 s.sv[j][b] = int(e._sv[j, b])
             s.shift[j] = int(e._shift[j])
         s.first_index = int(e.num_generated)
+        s.sorted_bits = 0
+        if sorted_n:
+            m = int(sorted_n).bit_length() - 1
+            for r, col in enumerate(sobol_sorted_inverse(e._sv[self.dim], m)):
+                s.sorted_ainv[r] = col
+            s.sorted_bits = m
         return s
+
+    def _sobol_sorted_ok(self, n):
+        """Sorted enumeration applies to a fresh engine, N a power of two, and only when
+        the rows are permuted afterwards anyway (the reference's final shuffle)."""
+        return (self.qmc_engine.num_generated == 0 and n >= 2 and n & (n - 1) == 0
+                and n <= 2 ** 32 and self._shuffle_mode() == "device")
 
     def _host_uniforms(self, n):
         """[lintsampler.py:500-518] on the host, uploaded."""
@@ -270,7 +305,7 @@ class LintSampler:
             return self._sample_domain_u(grid, u)
         if self.qmc:
             self._sobol_precheck(n)
-            s = self._sobol_struct()
+            s = self._sobol_struct(sorted_n=n if self._sobol_sorted_ok(n) else None)
             x = grid._sample_sobol(n, s)
             self.qmc_engine.fast_forward(n)
             return x

@@ -84,12 +84,17 @@ def grid_case(name, edges, pdf, N, qmc=False):
                 warnings.simplefilter("ignore")
                 s = lb.LintSampler(grid, seed=1, qmc=True, return_tensor=True, shuffle=False)
                 st = s._sobol_struct()
+                st_sorted = s._sobol_struct(sorted_n=N)
             ms = timed(lambda: grid._sample_sobol(N, st), reps=3)
+            report(f"{name} [sobol, direct enumeration, no shuffle]", N, k, 4, ms, cells=int(grid.ncells))
+            ms = timed(lambda: s._permute_rows(grid._sample_sobol(N, st)), reps=3)
+            report(f"{name} [sobol, direct enumeration + device shuffle]", N, k, 4, ms, cells=int(grid.ncells))
+            ms = timed(lambda: s._permute_rows(grid._sample_sobol(N, st_sorted)), reps=3)
         elif order == "cell":
             ms = timed(lambda: grid._sample_cellmajor(N, 1, 0, out=out))
         else:
             ms = timed(lambda: grid._sample_philox(N, 1, 0, out=out))
-        report(f"{name} [{'sobol ' if qmc else ''}order={order}]", N, k, 4, ms,
+        report(f"{name} [{'sobol, sorted enumeration + device shuffle' if qmc else 'order=' + order}]", N, k, 4, ms,
                ms_build_kernels=ms_build, first_construct_s=t_build, cells=int(grid.ncells))
         del grid, out
         torch.cuda.empty_cache()

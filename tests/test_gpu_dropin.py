@@ -287,3 +287,24 @@ def test_fp32_mode_is_scale_invariant(lb, factor):
     gm = lb.GaussianMixture(w * factor, mu, cov)
     g2 = lb.DensityGrid(edges, gm, vectorizedpdf=True, dtype=np.float32)
     assert g2.total_mass == pytest.approx(float(g["total_mass"]) * factor, rel=1e-5)
+
+
+def test_sorted_sobol_draw_is_the_same_point_set(lb):
+    """With the default (device) shuffle a fresh power-of-two QMC draw uses the sorted
+    enumeration of the Sobol points; the samples are, as a set, exactly those of the
+    direct enumeration (= the reference's)."""
+    g = load_golden("g5d_sobol")
+    grid = lb.DensityGrid(_domain(g), PDFS["g5d_sobol"][0], vectorizedpdf=True, cdf_mode="sequential")
+    N = int(g["N"])
+    s = lb.LintSampler(grid, seed=int(g["seed"]), qmc=True)
+    assert s._sobol_sorted_ok(N)
+    x = s.sample(N)
+    assert s.qmc_engine.num_generated == N
+    ref = g["x_pre"]                                        # reference's pre-shuffle samples
+    assert np.array_equal(x[np.lexsort(x.T)], ref[np.lexsort(ref.T)])
+    assert not np.array_equal(x, ref)                       # but in permuted order
+    # a second call continues the sequence through the direct enumeration
+    x2 = s.sample(N)
+    assert x2.shape == ref.shape and s.qmc_engine.num_generated == 2 * N
+    direct = lb.LintSampler(grid, seed=int(g["seed"]), qmc=True, shuffle=False).sample(N)
+    assert np.array_equal(direct, ref)

@@ -275,3 +275,29 @@ def test_gaussian_mixture_host_call_matches_scipy(k, full):
     np.testing.assert_allclose(gm(x if k > 1 else x[:, 0]), ref, rtol=1e-11)
     with pytest.raises(ValueError):
         lb.GaussianMixture(w, mu)
+
+
+@pytest.mark.parametrize("d,m,seed", [(2, 5, 3), (4, 10, 1), (6, 12, 7)])
+def test_sobol_sorted_enumeration_construction(d, m, seed):
+    """The GF(2) inverse used by the sorted Sobol mode: enumerating y = 0..2^m-1 yields
+    exactly scipy's first 2^m points, in increasing order of the last coordinate."""
+    from lintsampler_b200.sampler import sobol_sorted_inverse
+    e = Sobol(d=d, bits=32, seed=seed)
+    sv, sh = e._sv.copy(), e._shift.copy()
+    U = e.random(2 ** m)
+    k = d - 1
+    ainv = sobol_sorted_inverse(sv[k], m)
+    top = int(sh[k]) >> (32 - m)
+    X = np.empty((2 ** m, d), dtype=np.uint64)
+    for y in range(2 ** m):
+        t, g = y ^ top, 0
+        for r in range(m):
+            if (t >> r) & 1:
+                g ^= ainv[r]
+        x = [int(v) for v in sh]
+        for c in range(m):
+            if (g >> c) & 1:
+                x = [x[j] ^ int(sv[j, c]) for j in range(d)]
+        assert x[k] >> (32 - m) == y
+        X[y] = x
+    assert np.array_equal(U[np.argsort(U[:, k])], X.astype(np.float64) * 2.0 ** -32)
