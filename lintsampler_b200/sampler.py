@@ -320,9 +320,25 @@ class LintSampler:
         """List of domains  [lintsampler.py:281-307]: domain chosen by the same
         uniform that then (rescaled) chooses the cell; rows grouped by domain."""
         import torch
-        u = self._host_uniforms(n) if self._uses_host_uniforms() else self._device_uniforms(n)
         masses = np.array([g.total_mass for g in self.grids])
         p = masses / masses.sum()
+        if (not self.qmc and self.rng_backend == "philox"
+                and all(hasattr(g, "_sample_philox") for g in self.grids)):
+            # i.i.d. device rows: choosing a domain per row with probability p (what `_choice`
+            # does row by row, lintsampler.py:290) is a Multinomial(n, p) split of the row
+            # count; each domain then draws its rows with one fused kernel, no uniforms
+            # are materialised or routed
+            split = np.random.Generator(np.random.Philox(key=self._philox_key,
+                                                         counter=self._philox_offset))
+            counts = split.multinomial(n, p)
+            parts = []
+            for grid, ni in zip(self.grids, counts):
+                if ni:
+                    fn = grid._sample_cellmajor if self.order == "cell" else grid._sample_philox
+                    parts.append(fn(int(ni), self._philox_key, self._philox_offset).to(torch.float64))
+                    self._philox_offset += int(ni)
+            return torch.cat(parts, dim=0)
+        u = self._host_uniforms(n) if self._uses_host_uniforms() else self._device_uniforms(n)
         c = p.cumsum()
         cdf_t = torch.as_tensor(c / c[-1], device=u.device)
         bounds = np.append(0, p.cumsum())

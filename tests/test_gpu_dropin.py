@@ -157,10 +157,14 @@ def test_two_component_mixture_on_disjoint_grids(lb):
     def pdf(x):
         return 0.3 * stats.norm.pdf(x, -5, 1.0) + 0.7 * stats.norm.pdf(x, 5, 0.5)
     doms = [np.linspace(-10, -1, 257), np.linspace(1, 10, 257)]
-    for qmc in (False, True):
-        x = lb.LintSampler(doms, pdf=pdf, vectorizedpdf=True, seed=7, qmc=qmc).sample(2 ** 17)
+    for qmc, order in ((False, "draw"), (True, "draw"), (False, "cell")):
+        s = lb.LintSampler(doms, pdf=pdf, vectorizedpdf=True, seed=7, qmc=qmc, order=order)
+        x = s.sample(2 ** 17)
         assert round((x < 0).mean(), 2) == 0.3
         assert round(x[x < 0].mean(), 1) == -5.0 and round(x[x > 0].std(), 1) == 0.5
+        if order == "draw":        # rows grouped by domain are permuted on the device (reference: rng.shuffle)
+            assert abs(np.mean(x[: 2 ** 12] < 0) - 0.3) < 0.05
+        assert not np.array_equal(x, s.sample(2 ** 17))
 
 
 # ----------------------------------------------------------------------------- shapes, determinism, state
