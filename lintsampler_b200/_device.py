@@ -103,3 +103,15 @@ def cellmajor_scratch(owner, ncells, N):
         buf = torch.empty(nbytes, dtype=torch.uint8, device=owner.device)
         owner._cm_scratch = buf
     return buf, nbytes
+
+
+CELLMAJOR_MAX_ROWS = 1 << 31     # lint_*_sample_cellmajor takes N < 2^32; larger draws are chunked
+
+
+def cellmajor_chunks(N):
+    """(start, rows) pieces of an N-row draw, each within the C ABI's per-call limit."""
+    start = 0
+    while start < N:
+        rows = min(N - start, CELLMAJOR_MAX_ROWS)
+        yield start, rows
+        start += rows

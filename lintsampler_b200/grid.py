@@ -344,11 +344,14 @@ class DensityGrid(DensityStructure):
         if out is None:
             out = torch.empty((N, self._dim), dtype=_device.torch_dtype(self.dtype), device=self.device)
         cells = torch.empty(N, dtype=torch.int64, device=self.device) if want_cells else None
-        scratch, nbytes = _device.cellmajor_scratch(self, int(self.ncells), N)
         desc = self._descriptor()
-        _capi.call("lint_grid_sample_cellmajor", C.byref(desc), N, C.c_uint64(seed), C.c_uint64(offset),
-                   C.c_double(stratum[0]), C.c_double(stratum[1]), _device.ptr(scratch), nbytes, _device.ptr(out), _device.ptr(cells),
-                   _device.stream_ptr(self.device))
+        for start, rows in _device.cellmajor_chunks(N):      # rows grouped by cell within each piece
+            scratch, nbytes = _device.cellmajor_scratch(self, int(self.ncells), rows)
+            _capi.call("lint_grid_sample_cellmajor", C.byref(desc), rows, C.c_uint64(seed),
+                       C.c_uint64(offset + start), C.c_double(stratum[0]), C.c_double(stratum[1]),
+                       _device.ptr(scratch), nbytes, _device.ptr(out[start:start + rows]),
+                       _device.ptr(cells[start:start + rows] if cells is not None else None),
+                       _device.stream_ptr(self.device))
         return (out, cells) if want_cells else out
 
     def _sample_sobol(self, N, sobol_struct, want_cells=False):

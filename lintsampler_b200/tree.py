@@ -466,11 +466,14 @@ class _CellTable:
     def sample_cellmajor(self, N, seed, offset, want_cells=False, out=None, stratum=(0.0, 1.0)):
         """Rows grouped by leaf (list order); ``lint_cells_sample_cellmajor``."""
         out, cells = self._alloc(N, want_cells, out)
-        scratch, nbytes = _device.cellmajor_scratch(self, self.ncells, N)
         desc = self.descriptor()
-        _capi.call("lint_cells_sample_cellmajor", C.byref(desc), N, C.c_uint64(seed), C.c_uint64(offset),
-                   C.c_double(stratum[0]), C.c_double(stratum[1]), _device.ptr(scratch), nbytes, _device.ptr(out), _device.ptr(cells),
-                   _device.stream_ptr(self.device))
+        for start, rows in _device.cellmajor_chunks(N):
+            scratch, nbytes = _device.cellmajor_scratch(self, self.ncells, rows)
+            _capi.call("lint_cells_sample_cellmajor", C.byref(desc), rows, C.c_uint64(seed),
+                       C.c_uint64(offset + start), C.c_double(stratum[0]), C.c_double(stratum[1]),
+                       _device.ptr(scratch), nbytes, _device.ptr(out[start:start + rows]),
+                       _device.ptr(cells[start:start + rows] if cells is not None else None),
+                       _device.stream_ptr(self.device))
         return (out, cells) if want_cells else out
 
     def sample_sobol(self, N, sobol_struct, want_cells=False):

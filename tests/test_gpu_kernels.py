@@ -545,3 +545,25 @@ def test_sample_to_host_pipeline(lb):
         s.sample_to_host(3.5)
     with pytest.raises(ValueError):
         s.sample_to_host(0)
+
+
+def test_cellmajor_draws_beyond_the_per_call_limit_are_chunked(lb, monkeypatch):
+    from scipy import stats
+    from lintsampler_b200 import _device
+    g = load_golden("g2d_fullcov")
+    edges = golden_edges(g)
+    V = g["vertex_densities"]
+    grid = lb.DensityGrid(tuple(edges), lambda p: V.reshape(-1), vectorizedpdf=True)
+    monkeypatch.setattr(_device, "CELLMAJOR_MAX_ROWS", 100_000)
+    N = 250_000
+    x, cells = grid._sample_cellmajor(N, 4, 0, want_cells=True)
+    cells = cells.cpu().numpy()
+    p = (g["masses"] / g["masses"].sum()).ravel()
+    counts = np.bincount(cells, minlength=p.size)
+    big = p * N >= 20
+    obs = np.append(counts[big], counts[~big].sum())
+    exp = np.append(p[big], p[~big].sum()) * N
+    assert counts.sum() == N and stats.chi2.sf(((obs - exp) ** 2 / exp).sum(), len(obs) - 1) > 1e-4
+    # three pieces, each grouped by cell on its own
+    assert np.sum(np.diff(cells[:99_000]) < 0) == 0 and np.sum(np.diff(cells[100_000:199_000]) < 0) == 0
+    assert cells[100_000] < cells[99_000]
