@@ -305,7 +305,7 @@ def run_b200(args):
             "roofline": {
                 "bound": "hbm",
                 "kernel": ("emit_kernel<3,float,GridCells<3,float>> incl. its row planning (poisson_counts, "
-                           "scan_compact, tile_start) and the sample_kernel top-up" if args.order == "cell"
+                           "scan_compact, chunk_start) and the sample_kernel top-up" if args.order == "cell"
                            else "sample_kernel<3,float,GridSource<3,float>,UniformsPhilox<3>>"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",

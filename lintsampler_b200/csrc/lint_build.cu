@@ -436,8 +436,8 @@ constexpr int PAR_THREADS = 256;
 constexpr int PAR_ITEMS = 8;
 constexpr int PAR_TILE = PAR_THREADS * PAR_ITEMS;
 
-// Inclusive prefix of one tile in registers; returns the tile's inclusive total
-// to thread 0 via *tile_total (shared).  x[] is replaced by E_warp(+)(E_lane(+)P_i).
+// Inclusive prefix of one tile in registers: x[] is replaced by
+// E_warp (+) (E_lane (+) P_i); returns the tile's inclusive total (all threads).
 __device__ __forceinline__ double tile_scan(double (&x)[PAR_ITEMS], double *warp_tot /*[8]*/) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -456,10 +456,9 @@ __device__ __forceinline__ double tile_scan(double (&x)[PAR_ITEMS], double *warp
     }
     if (lane == 31) warp_tot[warp] = x[PAR_ITEMS - 1];
     __syncthreads();
-    // chain across warps
+    // chain across warps: warp_tot[w] is warp w's own inclusive total
     double wex = 0.0;
     for (int w = 0; w < warp; ++w) wex = (w == 0) ? warp_tot[0] : __dadd_rn(wex, warp_tot[w]);
-    // note: warp_tot[w] for w>0 is that warp's *local* inclusive total; chain it
     double tile_total = 0.0;
     for (int w = 0; w < PAR_THREADS / 32; ++w)
         tile_total = (w == 0) ? warp_tot[0] : __dadd_rn(tile_total, warp_tot[w]);

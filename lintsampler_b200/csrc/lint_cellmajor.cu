@@ -30,8 +30,8 @@ namespace lint {
 int validate_grid(const lint_grid_t *g, bool need_cdf, uint64_t *ncells_out, uint64_t *nverts_out);
 template <int K> GridView<K> make_grid_view(const lint_grid_t *g, uint64_t ncells, bool stage_edges);
 
-// Philox counter word 1 tags (word 0 = node / row group, words 2-3 = call offset)
-constexpr uint32_t TAG_SPLIT = 0x53000000u;   // | attempt   (per-cell count draws)
+// Philox counter word 1 tags (word 0 = cell / first row of a group, words 2-3 = call offset)
+constexpr uint32_t TAG_COUNT = 0x53000000u;   // | attempt   (per-cell count draws)
 constexpr uint32_t TAG_COORD = 0x43000000u;   // | block index
 
 // ---------------------------------------------------------------------------
@@ -42,7 +42,7 @@ struct CellRng {
     uint32_t cell, w2, w3;
     uint32_t attempt = 0;
     __device__ __forceinline__ void next(double &a, double &b) {
-        const uint4 r = philox4x32_10(make_uint4(cell, TAG_SPLIT | attempt, w2, w3), key);
+        const uint4 r = philox4x32_10(make_uint4(cell, TAG_COUNT | attempt, w2, w3), key);
         ++attempt;
         a = u53(r.x, r.y);
         b = u53(r.z, r.w);
@@ -217,18 +217,18 @@ scan_compact_kernel(const uint32_t *counts, uint32_t ncells, unsigned long long 
 }
 
 // first segment of every output chunk: last j with coff[j] <= chunk * chunk_rows
-__global__ void tile_start_kernel(const uint32_t *coff, const uint32_t *nnz_p, const uint32_t *rows_p,
-                                  uint32_t tile_rows, uint32_t *tile_start) {
+__global__ void chunk_start_kernel(const uint32_t *coff, const uint32_t *nnz_p, const uint32_t *rows_p,
+                                  uint32_t chunk_rows, uint32_t *chunk_start) {
     const uint32_t nnz = *nnz_p;
-    const uint32_t ntiles = (*rows_p + tile_rows - 1) / tile_rows;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += gridDim.x * blockDim.x) {
-        const uint32_t r0 = t * tile_rows;
+    const uint32_t nchunks = (*rows_p + chunk_rows - 1) / chunk_rows;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nchunks; t += gridDim.x * blockDim.x) {
+        const uint32_t r0 = t * chunk_rows;
         uint32_t lo = 0, hi = nnz;                                 // coff[nnz] = N > r0
         while (lo < hi) {                                          // first j with coff[j] > r0
             const uint32_t mid = lo + ((hi - lo) >> 1);
             if (__ldg(coff + mid) > r0) hi = mid; else lo = mid + 1;
         }
-        tile_start[t] = lo - 1;
+        chunk_start[t] = lo - 1;
     }
 }
 
@@ -503,7 +503,7 @@ static int plan_rows(const double *cdf, uint64_t ncells, uint64_t N, uint2 key, 
     scan_compact_kernel<<<nscan, SCAN_THREADS, 0, st>>>(s.counts, (uint32_t)ncells, s.tile_state,
                                                        s.tile_counter, s.cid, s.coff, s.nnz, s.rows);
     const uint32_t nchunks = (uint32_t)((N + EMIT_CHUNK - 1) / EMIT_CHUNK);
-    tile_start_kernel<<<std::max(1u, std::min((nchunks + 255) / 256, 148u * 8)), 256, 0, st>>>(
+    chunk_start_kernel<<<std::max(1u, std::min((nchunks + 255) / 256, 148u * 8)), 256, 0, st>>>(
         s.coff, s.nnz, s.rows, EMIT_CHUNK, s.chunk_start);
     return check_launch("cell-major row planning");
 }
