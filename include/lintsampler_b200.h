@@ -96,6 +96,9 @@ typedef struct lint_cells {
     const uint32_t *guide_dev;
     int32_t guide_bits;
     int32_t reserved;
+    const void *cell_records_dev;         /* optional packed per-cell records built by
+                                             lint_cells_records (corners + box in one aligned
+                                             record); NULL = read the three arrays above     */
 } lint_cells_t;
 
 /* Scrambled Sobol state read from a host scipy.stats.qmc.Sobol(d=k+1, bits=32)
@@ -153,6 +156,13 @@ int lint_grid_masses(const lint_grid_t *g, double *masses_dev, uint32_t *flags_d
  * instead of 2^(k-1) scattered vertex pairs.  records_dev: prod(ncells)*2^k
  * values in g->dtype.  Optional: set g->cell_records_dev to use them. */
 int lint_grid_records(const lint_grid_t *g, void *records_dev, lint_stream_t stream);
+
+/* Packed per-cell records of a cell list: [2^k corners][k lower bounds][k upper bounds =
+ * fl(x + dx), tree.py:348] in c->dtype, each record padded to a multiple of 32 bytes
+ * (lint_cells_record_bytes) — the per-sample copies of tree.py:345-350 done once per
+ * build.  records_dev: ncells * lint_cells_record_bytes(dim, dtype) bytes. */
+size_t lint_cells_record_bytes(int dim, int dtype);
+int lint_cells_records(const lint_cells_t *c, void *records_dev, lint_stream_t stream);
 
 /* Same validity check for a cell list's corner densities [tree.py:598-605]. */
 int lint_cells_check(const lint_cells_t *c, uint32_t *flags_dev, lint_stream_t stream);

@@ -39,6 +39,7 @@ class LintCells(C.Structure):
         ("corners_dev", C.c_void_p), ("cdf_dev", C.c_void_p),
         ("guide_dev", C.c_void_p),
         ("guide_bits", C.c_int32), ("reserved", C.c_int32),
+        ("cell_records_dev", C.c_void_p),
     ]
 
 
@@ -72,6 +73,8 @@ PROTOTYPES = {
     "lint_grid_eval_gmm": (C.c_int, [C.POINTER(LintGrid), C.POINTER(LintGmm), C.c_double, _P]),
     "lint_grid_masses": (C.c_int, [C.POINTER(LintGrid), _P, _P, _P]),
     "lint_grid_records": (C.c_int, [C.POINTER(LintGrid), _P, _P]),
+    "lint_cells_record_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "lint_cells_records": (C.c_int, [C.POINTER(LintCells), _P, _P]),
     "lint_cells_check": (C.c_int, [C.POINTER(LintCells), _P, _P]),
     "lint_cdf_scratch_bytes": (C.c_size_t, [_I64]),
     "lint_sum_numpy_f64": (C.c_int, [_P, _I64, _P, _P, C.c_size_t, _P]),

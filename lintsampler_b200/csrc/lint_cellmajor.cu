@@ -560,6 +560,7 @@ int cells_cellmajor_k(const lint_cells_t *c, uint64_t N, uint2 key, uint64_t off
     v.mins = c->mins_dev;
     v.widths = c->widths_dev;
     v.corners = c->corners_dev;
+    v.rec = c->cell_records_dev;
     v.table.cdf = c->cdf_dev;
     v.table.guide = nullptr;
     v.table.guide_bits = 0;

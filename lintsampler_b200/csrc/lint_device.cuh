@@ -386,12 +386,35 @@ struct CellsView {
     const double *mins;
     const double *widths;
     const void *corners;
+    const void *rec;               // optional packed records (see cells_record_stride), or NULL
     CdfView table;
 };
+
+// Packed per-cell record, in the domain's element type: 2^K corner densities, K lower
+// bounds, K upper bounds (= fl(x + dx), tree.py:348), padded to a multiple of 32 bytes
+// so a record is read with aligned 256-bit loads.
+template <int K, typename DensT>
+__host__ __device__ constexpr int cells_record_stride() {
+    constexpr int per32 = 32 / (int)sizeof(DensT);
+    return (((1 << K) + 2 * K + per32 - 1) / per32) * per32;
+}
 
 template <int K, typename DensT, typename T>
 __device__ __forceinline__ void cells_fetch(const CellsView &s, uint32_t idx, T (&c)[1 << K],
                                             T (&lo)[K], T (&hi)[K]) {
+    if (s.rec) {
+        constexpr int RS = cells_record_stride<K, DensT>();
+        constexpr int PER = 32 / (int)sizeof(DensT);
+        const DensT *p = reinterpret_cast<const DensT *>(s.rec) + (size_t)idx * RS;
+        DensT v[RS];
+#pragma unroll
+        for (int q = 0; q < RS / PER; ++q) ldg256(p + q * PER, *reinterpret_cast<DensT(*)[PER]>(v + q * PER));
+#pragma unroll
+        for (int j = 0; j < (1 << K); ++j) c[j] = (T)v[j];
+#pragma unroll
+        for (int d = 0; d < K; ++d) { lo[d] = (T)v[(1 << K) + d]; hi[d] = (T)v[(1 << K) + K + d]; }
+        return;
+    }
 #pragma unroll
     for (int d = 0; d < K; ++d) {
         const double x = __ldg(s.mins + (size_t)idx * K + d);

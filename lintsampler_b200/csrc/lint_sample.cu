@@ -191,6 +191,7 @@ static CellsView make_cells_view(const lint_cells_t *c) {
     v.mins = c->mins_dev;
     v.widths = c->widths_dev;
     v.corners = c->corners_dev;
+    v.rec = c->cell_records_dev;
     v.table.cdf = c->cdf_dev;
     v.table.guide = c->guide_dev;
     v.table.guide_bits = c->guide_bits;
@@ -323,6 +324,39 @@ int uniforms_dispatch(int dim, int dtype, int64_t N, const Maker &mk, double *ou
     }
 }
 
+// packed leaf records (lint_cells_records)
+template <int K, typename DensT>
+__global__ void cells_records_kernel(CellsView s, uint32_t ncells, DensT *rec) {
+    constexpr int RS = cells_record_stride<K, DensT>();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ncells; i += gridDim.x * blockDim.x) {
+        DensT *dst = rec + (size_t)i * RS;
+        const DensT *C = reinterpret_cast<const DensT *>(s.corners) + (size_t)i * (1 << K);
+        for (int j = 0; j < (1 << K); ++j) dst[j] = C[j];
+        for (int d = 0; d < K; ++d) {
+            const double x = s.mins[(size_t)i * K + d], dx = s.widths[(size_t)i * K + d];
+            dst[(1 << K) + d] = (DensT)x;
+            dst[(1 << K) + K + d] = (DensT)__dadd_rn(x, dx);
+        }
+        for (int j = (1 << K) + 2 * K; j < RS; ++j) dst[j] = (DensT)0;
+    }
+}
+
+template <int K>
+int cells_records_k(const lint_cells_t *c, void *rec, cudaStream_t st) {
+    CellsView v = make_cells_view(c);
+    const int blocks = (int)std::min<int64_t>((c->ncells + 255) / 256, 148 * 16);
+    if (c->dtype == LINT_F32)
+        cells_records_kernel<K, float><<<blocks, 256, 0, st>>>(v, (uint32_t)c->ncells, (float *)rec);
+    else
+        cells_records_kernel<K, double><<<blocks, 256, 0, st>>>(v, (uint32_t)c->ncells, (double *)rec);
+    return check_launch("lint_cells_records");
+}
+
+template <int K> static size_t cells_record_bytes_k(int dtype) {
+    return dtype == LINT_F32 ? cells_record_stride<K, float>() * sizeof(float)
+                             : cells_record_stride<K, double>() * sizeof(double);
+}
+
 // u-driven top-up of rows [*first_row_dev, N) for the cell-major path
 int topup_grid(const lint_grid_t *g, int64_t N, const uint32_t *first_row_dev, int64_t max_rows,
                uint64_t seed, uint64_t offset, double u_lo, double u_hi, void *out, int64_t *cell_idx,
@@ -343,6 +377,34 @@ int topup_cells(const lint_cells_t *c, int64_t N, const uint32_t *first_row_dev,
 using namespace lint;
 
 extern "C" {
+
+size_t lint_cells_record_bytes(int dim, int dtype) {
+    switch (dim) {
+        case 1: return cells_record_bytes_k<1>(dtype);
+        case 2: return cells_record_bytes_k<2>(dtype);
+        case 3: return cells_record_bytes_k<3>(dtype);
+        case 4: return cells_record_bytes_k<4>(dtype);
+        case 5: return cells_record_bytes_k<5>(dtype);
+        case 6: return cells_record_bytes_k<6>(dtype);
+        default: return 0;
+    }
+}
+
+int lint_cells_records(const lint_cells_t *c, void *records_dev, lint_stream_t stream) {
+    if (!c || c->dim < 1 || c->dim > LINT_MAX_DIM || c->ncells < 1 || c->ncells >= (1ll << 31) ||
+        !c->mins_dev || !c->widths_dev || !c->corners_dev || !records_dev ||
+        (c->dtype != LINT_F32 && c->dtype != LINT_F64))
+        return fail(LINT_ERR_BAD_ARG, "lint_cells_records: bad cell-list descriptor or NULL records_dev");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (c->dim) {
+        case 1: return cells_records_k<1>(c, records_dev, st);
+        case 2: return cells_records_k<2>(c, records_dev, st);
+        case 3: return cells_records_k<3>(c, records_dev, st);
+        case 4: return cells_records_k<4>(c, records_dev, st);
+        case 5: return cells_records_k<5>(c, records_dev, st);
+        default: return cells_records_k<6>(c, records_dev, st);
+    }
+}
 
 int lint_grid_sample_u(const lint_grid_t *g, const double *u_dev, int64_t N, void *out_dev,
                        int64_t *cell_idx_dev, lint_stream_t stream) {

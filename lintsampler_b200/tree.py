@@ -426,8 +426,12 @@ class _CellTable:
             raise ValueError("Cell list: Detected non-finite density")
         self._cdf, self._guide, self._guide_bits, self.total_mass = _device.build_cdf(
             self._masses, cdf_mode, dev)
+        nbytes = int(_capi.load().lint_cells_record_bytes(self.dim, _device.lint_dtype(self.dtype)))
+        self._rec = torch.empty(self.ncells * nbytes, dtype=torch.uint8, device=dev)
+        _capi.call("lint_cells_records", C.byref(self.descriptor(need_cdf=False, records=False)),
+                   _device.ptr(self._rec), _device.stream_ptr(dev))
 
-    def descriptor(self, need_cdf=True):
+    def descriptor(self, need_cdf=True, records=True):
         d = _capi.LintCells()
         d.dim = self.dim
         d.dtype = _device.lint_dtype(self.dtype)
@@ -439,6 +443,8 @@ class _CellTable:
             d.cdf_dev = self._cdf.data_ptr()
             d.guide_dev = self._guide.data_ptr()
             d.guide_bits = self._guide_bits
+        rec = getattr(self, "_rec", None)
+        d.cell_records_dev = rec.data_ptr() if (records and rec is not None) else None
         return d
 
     def _alloc(self, N, want_cells, out=None):
