@@ -154,11 +154,15 @@ int lint_grid_masses(const lint_grid_t *g, double *masses_dev, uint32_t *flags_d
  * corner order — the gather of grid.py:440-467 done once per build instead of
  * once per sample, so a sample reads one record (one 32-byte sector at k=3 fp32)
  * instead of 2^(k-1) scattered vertex pairs.  records_dev: prod(ncells)*2^k
- * values in g->dtype.  Optional: set g->cell_records_dev to use them. */
+ * values in g->dtype.  LINT_F64 records hold the densities themselves; LINT_F32
+ * records hold them divided by the cell's largest corner (the in-cell draw depends
+ * on ratios only), which spares the sampler a per-sample normalisation.
+ * Optional: set g->cell_records_dev to use them. */
 int lint_grid_records(const lint_grid_t *g, void *records_dev, lint_stream_t stream);
 
 /* Packed per-cell records of a cell list: [2^k corners][k lower bounds][k upper bounds =
- * fl(x + dx), tree.py:348] in c->dtype, each record padded to a multiple of 32 bytes
+ * fl(x + dx), tree.py:348] in c->dtype (LINT_F32: corners divided by the cell's largest, as
+ * for lint_grid_records), each record padded to a multiple of 32 bytes
  * (lint_cells_record_bytes) — the per-sample copies of tree.py:345-350 done once per
  * build.  records_dev: ncells * lint_cells_record_bytes(dim, dtype) bytes. */
 size_t lint_cells_record_bytes(int dim, int dtype);

@@ -54,12 +54,14 @@ def check_dtype(dtype):
 
 
 def default_guide_bits(ncells):
-    """Guide-table size: about one bin per four cells, within [2^4, 2^26].  Bins that
-    lie inside one cell answer a query without touching the CDF; a finer table
-    answers more queries that way but is itself addressed uniformly at random, so
-    it competes with the hot cells for L2 (2^22 beat 2^24 and 2^20 at 256^3,
-    profiles/README.md)."""
-    bits = max(4, int(np.ceil(np.log2(max(int(ncells), 2)))) - 2)
+    """Guide-table size.  One bin per cell while the table stays small (<= 2^20 entries,
+    4 MB): bins that lie inside one cell answer a query without touching the CDF, so a
+    finer table means fewer probes.  Beyond that the table — addressed uniformly at
+    random — competes with the hot cells for L2, and one bin per four cells measured
+    best (2^22 beat 2^24 and 2^20 at 256^3; profiles/README.md)."""
+    bits = max(4, int(np.ceil(np.log2(max(int(ncells), 2)))))
+    if bits > 20:
+        bits = max(20, bits - 2)
     return min(bits, 26)
 
 

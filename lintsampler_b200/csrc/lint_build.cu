@@ -221,8 +221,8 @@ int masses_impl(const lint_grid_t *g, uint64_t ncells, double *masses, uint32_t 
 }
 
 // ---------------------------------------------------------------------------
-// per-cell corner records: the 2^K corner densities of every cell laid out
-// contiguously, so the sampler reads one record instead of 2^(K-1) scattered
+// per-cell corner records: the 2^K corner densities of every cell (fp32: divided by
+// the cell's largest, since a draw depends on their ratios only) laid out contiguously, so the sampler reads one record instead of 2^(K-1) scattered
 // vertex pairs  [layout for grid.py:440-467]
 // ---------------------------------------------------------------------------
 template <int K, typename DensT>
@@ -239,6 +239,14 @@ cell_records_kernel(GridView<K> g, uint32_t ncells, DensT *rec) {
         DensT v[1 << K];
 #pragma unroll
         for (int j = 0; j < (1 << K); ++j) v[j] = __ldg(V + base + g.corner_off[j]);
+        if (sizeof(DensT) == 4) {                 // fp32 records: corners / largest corner
+            float m = 0.f;
+#pragma unroll
+            for (int j = 0; j < (1 << K); ++j) m = fmaxf(m, (float)v[j]);
+            const float inv = m > 0.f ? 1.0f / m : 0.f;
+#pragma unroll
+            for (int j = 0; j < (1 << K); ++j) v[j] = (DensT)((float)v[j] * inv);
+        }
         DensT *dst = rec + (size_t)cell * (1 << K);
 #pragma unroll
         for (int j = 0; j < (1 << K); ++j) dst[j] = v[j];

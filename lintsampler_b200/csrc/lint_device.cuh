@@ -568,5 +568,13 @@ __device__ __forceinline__ void store_stream(double *p, double v) { __stcs(p, v)
 
 template <int K> __device__ __forceinline__ void incell(double (&c)[1 << K], const double (&u)[K], double (&z)[K]) { incell_exact<K>(c, u, z); }
 template <int K> __device__ __forceinline__ void incell(float (&c)[1 << K], const float (&u)[K], float (&z)[K]) { incell_fast<K>(c, u, z); }
+// `prenormalised`: the corners come from fp32 records, which are stored divided by the
+// cell's largest corner (the draw depends on ratios only), so the per-sample
+// normalisation is skipped.  fp64 records hold the raw densities.
+template <int K> __device__ __forceinline__ void incell(double (&c)[1 << K], const double (&u)[K], double (&z)[K], bool) { incell_exact<K>(c, u, z); }
+template <int K> __device__ __forceinline__ void incell(float (&c)[1 << K], const float (&u)[K], float (&z)[K], bool prenormalised) {
+    if (!prenormalised) normalise_corners<(1 << K)>(c);
+    incell_fast_core<K>(c, u, z);
+}
 
 }  // namespace lint

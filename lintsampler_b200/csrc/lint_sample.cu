@@ -22,6 +22,7 @@ struct GridSource {
     __device__ __forceinline__ size_t smem_bytes_dev(size_t elem) const { return (size_t)g.edge_total * elem; }
     template <typename T>
     __device__ __forceinline__ void prepare(T *smem) const { grid_stage_edges<K, T>(g, smem); }
+    __device__ __forceinline__ bool prenormalised() const { return g.rec != nullptr; }
     __device__ __forceinline__ void bracket(double u, uint32_t &lo, uint32_t &hi) const {
         if (g.table.n == 1) { lo = hi = 0; return; }             // grid.py:427-428 shortcut
         guide_bracket(g.table, u, lo, hi);
@@ -43,6 +44,7 @@ struct ListSource {
     __device__ __forceinline__ size_t smem_bytes_dev(size_t) const { return 0; }
     template <typename T>
     __device__ __forceinline__ void prepare(T *) const {}
+    __device__ __forceinline__ bool prenormalised() const { return s.rec != nullptr; }
     __device__ __forceinline__ void bracket(double u, uint32_t &lo, uint32_t &hi) const {
         guide_bracket(s.table, u, lo, hi);
     }
@@ -106,7 +108,7 @@ sample_kernel(Source src, Uniforms unif, int64_t N, T *__restrict__ out,
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             T z[K];
-            incell<K>(c[r], u[r], z);                      // _unitsample_kd(*corners, u=u[..., :-1])
+            incell<K>(c[r], u[r], z, src.prenormalised());  // _unitsample_kd(*corners, u=u[..., :-1])
             const int64_t row = base + (int64_t)r * SAMPLE_THREADS + threadIdx.x;
             if (live[r]) {
 #pragma unroll
@@ -331,7 +333,13 @@ __global__ void cells_records_kernel(CellsView s, uint32_t ncells, DensT *rec) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ncells; i += gridDim.x * blockDim.x) {
         DensT *dst = rec + (size_t)i * RS;
         const DensT *C = reinterpret_cast<const DensT *>(s.corners) + (size_t)i * (1 << K);
-        for (int j = 0; j < (1 << K); ++j) dst[j] = C[j];
+        double scale = 1.0;                       // fp32 records: corners / largest corner
+        if (sizeof(DensT) == 4) {
+            double m = 0.0;
+            for (int j = 0; j < (1 << K); ++j) m = fmax(m, (double)C[j]);
+            scale = m > 0.0 ? 1.0 / m : 0.0;
+        }
+        for (int j = 0; j < (1 << K); ++j) dst[j] = (DensT)((double)C[j] * scale);
         for (int d = 0; d < K; ++d) {
             const double x = s.mins[(size_t)i * K + d], dx = s.widths[(size_t)i * K + d];
             dst[(1 << K) + d] = (DensT)x;
