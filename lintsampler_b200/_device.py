@@ -6,6 +6,22 @@ import numpy as np
 from . import _capi
 
 
+def on_device(method):
+    """Run a method with the owner's CUDA device current: kernels launch on the current
+    device, which must be the one that holds the buffers (``self.device``)."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        dev = getattr(self, "device", None)
+        if dev is None:
+            return method(self, *args, **kwargs)
+        import torch
+        with torch.cuda.device(dev):
+            return method(self, *args, **kwargs)
+    return wrapper
+
+
 def require_cuda(device=None):
     """Return a torch CUDA device or raise: the product has no CPU path."""
     import torch

@@ -192,9 +192,13 @@ class DensityGrid(DensityStructure):
         self._build_device(pdf if fused else None, densities, dev_densities)
 
     def _build_device(self, gmm, densities, dev_densities):
+        self.device = _device.require_cuda(self._device_arg)
+        self._build_on_device(gmm, densities, dev_densities)
+
+    @_device.on_device
+    def _build_on_device(self, gmm, densities, dev_densities):
         import torch
-        dev = _device.require_cuda(self._device_arg)
-        self.device = dev
+        dev = self.device
         tdt = _device.torch_dtype(self.dtype)
         npts = int(np.prod(self._edgeshape))
         ncells = int(self.ncells)
@@ -246,6 +250,7 @@ class DensityGrid(DensityStructure):
         self._enqueue_build()
         self._check_build()
 
+    @_device.on_device
     def _enqueue_build(self):
         """Cell masses -> CDF -> guide table, enqueued on the current stream with no
         host synchronisation (grid.py:411-412, 431; utils.py:195-196)."""
@@ -268,6 +273,7 @@ class DensityGrid(DensityStructure):
         self._guide_bits = self._guide_bits_planned
         self._masses_host = None
 
+    @_device.on_device
     def update_densities(self, densities, check=True):
         """Replace the vertex densities (same edges) and rebuild masses, CDF and
         guide table on the current stream.  ``densities`` may be a NumPy array or
@@ -316,6 +322,7 @@ class DensityGrid(DensityStructure):
         return d
 
     # ------------------------------------------------------------------ sampling entry points
+    @_device.on_device
     def _sample_u(self, u_t, want_cells=False):
         """(N,k+1) fp64 device uniforms -> (N,k) device samples  [sampling.py:97-127]."""
         import torch
@@ -327,6 +334,7 @@ class DensityGrid(DensityStructure):
                    _device.ptr(cells), _device.stream_ptr(self.device))
         return (out, cells) if want_cells else out
 
+    @_device.on_device
     def _sample_philox(self, N, seed, offset, want_cells=False, out=None, stratum=(0.0, 1.0)):
         import torch
         if out is None:
@@ -337,6 +345,7 @@ class DensityGrid(DensityStructure):
                    C.c_double(stratum[0]), C.c_double(stratum[1]), _device.ptr(out), _device.ptr(cells), _device.stream_ptr(self.device))
         return (out, cells) if want_cells else out
 
+    @_device.on_device
     def _sample_cellmajor(self, N, seed, offset, want_cells=False, out=None, stratum=(0.0, 1.0)):
         """Throughput mode: rows grouped by cell (C order); exact multinomial cell
         counts, no per-sample search (``lint_grid_sample_cellmajor``)."""
@@ -354,6 +363,7 @@ class DensityGrid(DensityStructure):
                        _device.stream_ptr(self.device))
         return (out, cells) if want_cells else out
 
+    @_device.on_device
     def _sample_sobol(self, N, sobol_struct, want_cells=False):
         import torch
         out = torch.empty((N, self._dim), dtype=_device.torch_dtype(self.dtype), device=self.device)

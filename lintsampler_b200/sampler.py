@@ -250,6 +250,11 @@ class LintSampler:
         return torch.as_tensor(np.ascontiguousarray(u, dtype=np.float64), device=self._device())
 
     def _device_uniforms(self, n):
+        import torch
+        with torch.cuda.device(self._device()):
+            return self._device_uniforms_impl(n)
+
+    def _device_uniforms_impl(self, n):
         """The (n,k+1) matrix the fused device samplers would consume, materialised
         (needed only for lists of domains, where rows must be routed by value)."""
         import torch
@@ -278,6 +283,11 @@ class LintSampler:
 
     # ------------------------------------------------------------------ sampling
     def _sample_domain_u(self, grid, u_t):
+        import torch
+        with torch.cuda.device(self._device()):
+            return self._sample_domain_u_impl(grid, u_t)
+
+    def _sample_domain_u_impl(self, grid, u_t):
         """One domain, uniforms given on the device  [sampling.py:97-127]."""
         import torch
         if hasattr(grid, "_sample_u"):
@@ -450,6 +460,11 @@ class LintSampler:
         return "device" if (self.qmc or self.ngrids > 1) else None
 
     def _permute_rows(self, X):
+        import torch
+        with torch.cuda.device(self._device()):
+            return self._permute_rows_impl(X)
+
+    def _permute_rows_impl(self, X):
         """Device row permutation keyed by the sampler's stream position."""
         import torch
         X = X.contiguous()

@@ -398,9 +398,13 @@ class _CellTable:
     """Device copy of a flat cell list + its CDF/guide table (``lint_cells_t``)."""
 
     def __init__(self, mins, widths, corners, masses, dtype, device, cdf_mode):
+        self.device = _device.require_cuda(device)
+        self._build(mins, widths, corners, masses, dtype, cdf_mode)
+
+    @_device.on_device
+    def _build(self, mins, widths, corners, masses, dtype, cdf_mode):
         import torch
-        dev = _device.require_cuda(device)
-        self.device = dev
+        dev = self.device
         self.dtype = np.dtype(dtype)
         self.dim = mins.shape[1]
         self.ncells = mins.shape[0]
@@ -454,6 +458,7 @@ class _CellTable:
         cells = torch.empty(N, dtype=torch.int64, device=self.device) if want_cells else None
         return out, cells
 
+    @_device.on_device
     def sample_u(self, u_t, want_cells=False):
         N = u_t.shape[0]
         out, cells = self._alloc(N, want_cells)
@@ -462,6 +467,7 @@ class _CellTable:
                    _device.ptr(cells), _device.stream_ptr(self.device))
         return (out, cells) if want_cells else out
 
+    @_device.on_device
     def sample_philox(self, N, seed, offset, want_cells=False, out=None, stratum=(0.0, 1.0)):
         out, cells = self._alloc(N, want_cells, out)
         desc = self.descriptor()
@@ -469,6 +475,7 @@ class _CellTable:
                    C.c_double(stratum[0]), C.c_double(stratum[1]), _device.ptr(out), _device.ptr(cells), _device.stream_ptr(self.device))
         return (out, cells) if want_cells else out
 
+    @_device.on_device
     def sample_cellmajor(self, N, seed, offset, want_cells=False, out=None, stratum=(0.0, 1.0)):
         """Rows grouped by leaf (list order); ``lint_cells_sample_cellmajor``."""
         out, cells = self._alloc(N, want_cells, out)
@@ -482,6 +489,7 @@ class _CellTable:
                        _device.stream_ptr(self.device))
         return (out, cells) if want_cells else out
 
+    @_device.on_device
     def sample_sobol(self, N, sobol_struct, want_cells=False):
         out, cells = self._alloc(N, want_cells)
         desc = self.descriptor()

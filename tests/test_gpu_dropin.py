@@ -312,3 +312,34 @@ def test_sorted_sobol_draw_is_the_same_point_set(lb):
     assert x2.shape == ref.shape and s.qmc_engine.num_generated == 2 * N
     direct = lb.LintSampler(grid, seed=int(g["seed"]), qmc=True, shuffle=False).sample(N)
     assert np.array_equal(direct, ref)
+
+
+def test_device_resident_inputs_and_updates(lb):
+    """pdf_on_device (torch callable), from_densities (NumPy / pinned / device tensors) and
+    update_densities all reach the same tables as the host-evaluated construction."""
+    import torch
+    g = load_golden("g3d_iso")
+    edges = tuple(golden_edges(g))
+    V = g["vertex_densities"]
+    ref = lb.DensityGrid(edges, PDFS["g3d_iso"][0], vectorizedpdf=True, cdf_mode="sequential")
+    w, mu, cov = pdfs.gmm_params(3, seed=0)
+    sig2 = torch.tensor([c[0, 0] for c in cov], device="cuda")
+    wt, mut = torch.tensor(w, device="cuda"), torch.tensor(mu, device="cuda")
+
+    def torch_pdf(x):                                   # isotropic mixture on the device
+        d2 = ((x[:, None, :] - mut[None]) ** 2).sum(-1)
+        return (wt * torch.exp(-0.5 * d2 / sig2) / (2 * torch.pi * sig2) ** 1.5).sum(-1)
+
+    a = lb.DensityGrid(edges, torch_pdf, vectorizedpdf=True, pdf_on_device=True, cdf_mode="sequential")
+    np.testing.assert_allclose(a.vertex_densities, V, rtol=1e-10)
+    for dens in (V, torch.from_numpy(V.copy()).pin_memory(), torch.from_numpy(V.copy()).cuda()):
+        b = lb.DensityGrid.from_densities(edges, dens, cdf_mode="sequential")
+        assert np.array_equal(b.masses, ref.masses) and b.total_mass == ref.total_mass
+        assert torch.equal(b._cdf, ref._cdf)
+    b.update_densities(2.0 * V)                         # same shape of density, twice the mass
+    assert b.total_mass == pytest.approx(2 * ref.total_mass, rel=1e-14)
+    assert torch.equal(b._cdf, ref._cdf)
+    with pytest.raises(ValueError):
+        b.update_densities(-V)
+    with pytest.raises(ValueError):
+        lb.DensityGrid.from_densities(edges, V[:-1])
