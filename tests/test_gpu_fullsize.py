@@ -1,0 +1,120 @@
+"""Parity at BASELINE.json's full size (256^3 grid, N = 1e9): exact comparisons against the
+oracle where the oracle finishes in seconds (masses, total, NumPy-order CDF, a 2e6-row slice of
+u-driven samples), and size-independent properties of the full 1e9-row draws (bounds,
+determinism checksum, grouping, per-plane chi^2 against the exact plane masses)."""
+import numpy as np
+import pytest
+
+from oracle import lint_oracle as O
+
+pytestmark = pytest.mark.gpu
+N_CELLS = 256
+N_FULL = 1_000_000_000
+
+
+@pytest.fixture(scope="module")
+def lb():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs a large-memory GPU")
+    import lintsampler_b200
+    return lintsampler_b200
+
+
+def _c3():
+    rng = np.random.default_rng(0)
+    means = rng.uniform(-2, 2, size=(4, 3))
+    sig = rng.uniform(0.3, 0.8, size=4)
+    w = rng.dirichlet(np.ones(4))
+    edges = tuple(np.linspace(-4, 4, N_CELLS + 1) for _ in range(3))
+    return edges, w, means, sig
+
+
+def test_build_and_udriven_slice_bit_exact_at_256cubed(lb):
+    import torch
+    edges, w, means, sig = _c3()
+    grid = lb.DensityGrid(edges, lb.GaussianMixture(w, means, sigmas=sig), vectorizedpdf=True,
+                          cdf_mode="sequential")
+    V = grid.vertex_densities                                   # device-evaluated fp64 densities
+    masses = O.cell_masses(edges, V)
+    assert np.array_equal(grid.masses, masses)
+    assert grid.total_mass == O.total_mass(masses)
+    cdf = O.cdf_from_masses(masses)
+    assert np.array_equal(grid._cdf.cpu().numpy(), cdf)          # 16.8 M sequential fp64 adds, bit for bit
+    u, _ = O.reference_uniforms(1, 2_000_000, 3)
+    x_ref, flat_ref = O.grid_sample(edges, V, u, cdf=cdf, return_cells=True)
+    x, cells = grid._sample_u(torch.as_tensor(u, device="cuda"), want_cells=True)
+    assert np.array_equal(cells.cpu().numpy(), flat_ref)
+    assert np.array_equal(x.cpu().numpy(), x_ref)
+    # the throughput CDF differs from NumPy's only inside the rounding band of a boundary
+    fast = lb.DensityGrid.from_densities(edges, V)
+    cdf_fast = fast._cdf.cpu().numpy()
+    assert np.max(np.abs(cdf_fast - cdf)) < 1e-11 and np.all(np.diff(cdf_fast) >= 0) and cdf_fast[-1] == 1.0
+    _, cells_fast = fast._sample_u(torch.as_tensor(u, device="cuda"), want_cells=True)
+    cells_fast = cells_fast.cpu().numpy()
+    bad = np.flatnonzero(cells_fast != flat_ref)
+    assert len(bad) < 2e-4 * len(u)                             # ~1e-5 of the draws
+    for i in bad:
+        lo, hi = sorted((cells_fast[i], flat_ref[i]))
+        b = np.arange(lo, hi)
+        assert np.any((np.minimum(cdf_fast[b], cdf[b]) <= u[i, -1]) & (u[i, -1] < np.maximum(cdf_fast[b], cdf[b])))
+
+
+@pytest.mark.parametrize("order", ["cell", "draw"])
+def test_full_size_draw_properties(lb, order):
+    import torch
+    from scipy import stats
+    edges, w, means, sig = _c3()
+    kw = dict(cell_records=False, guide_bits=16) if order == "cell" else {}
+    grid = lb.DensityGrid(edges, lb.GaussianMixture(w, means, sigmas=sig), vectorizedpdf=True,
+                          dtype=np.float32, **kw)
+    out = torch.empty((N_FULL, 3), dtype=torch.float32, device="cuda")
+    draw = grid._sample_cellmajor if order == "cell" else grid._sample_philox
+
+    def digest():
+        cells = None
+        if order == "cell":
+            _, cells = draw(N_FULL, 1, 0, want_cells=True, out=out)
+        else:
+            draw(N_FULL, 1, 0, out=out)
+        plane = torch.zeros(N_CELLS, dtype=torch.float64, device="cuda")
+        acc = torch.zeros(3, dtype=torch.float64, device="cuda")
+        lo = torch.full((3,), float("inf"), device="cuda")
+        hi = torch.full((3,), float("-inf"), device="cuda")
+        sorted_ok = True
+        prev_last = -1
+        step = 1 << 26
+        for a in range(0, N_FULL, step):
+            x = out[a:a + step]
+            acc += x.sum(dim=0, dtype=torch.float64)
+            lo, hi = torch.minimum(lo, x.min(dim=0).values), torch.maximum(hi, x.max(dim=0).values)
+            ip = torch.clamp(((x[:, 0].double() + 4.0) * (N_CELLS / 8.0)).long(), 0, N_CELLS - 1)
+            plane += torch.bincount(ip, minlength=N_CELLS).double()
+            if order == "cell" and a + step <= N_FULL - (1 << 20):          # grouped part only
+                c = cells[a:a + step]
+                sorted_ok &= bool((c[1:] >= c[:-1]).all()) and int(c[0]) >= prev_last
+                prev_last = int(c[-1])
+        return plane.cpu().numpy(), acc.cpu().numpy(), lo.cpu().numpy(), hi.cpu().numpy(), sorted_ok
+
+    plane, acc, lo, hi, sorted_ok = digest()
+    assert plane.sum() == N_FULL
+    assert np.all(lo >= -4.0) and np.all(hi <= 4.0)              # every row inside the domain
+    assert sorted_ok                                            # order="cell": flat cell index never decreases
+    # per-plane counts against the exact plane masses (fp32-rounded densities)
+    V32 = grid.vertex_densities
+    p = O.cell_masses(edges, V32).sum(axis=(1, 2))
+    p /= p.sum()
+    big = p * N_FULL >= 50
+    obs = np.append(plane[big], plane[~big].sum())
+    exp = np.append(p[big], p[~big].sum()) * N_FULL
+    keep = exp > 0
+    chi2 = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum()
+    assert stats.chi2.sf(chi2, keep.sum() - 1) > 1e-5, chi2
+    # sample mean against the interpolant's mean along dim 0 (5 sigma of the Monte-Carlo error)
+    centers = 0.5 * (edges[0][1:] + edges[0][:-1])
+    assert abs(acc[0] / N_FULL - (p * centers).sum()) < 5 * 1.5 / np.sqrt(N_FULL) + 2e-4
+    # determinism: the same seed reproduces the same 12 GB
+    plane2, acc2, *_ = digest()
+    assert np.array_equal(plane, plane2) and np.array_equal(acc, acc2)
