@@ -326,6 +326,10 @@ __device__ __forceinline__ void emit_row(const CellCoefs<K, T> &coef, const T (&
 //   * 32 rows spanning several cells: each lane finds its own cell in the window
 //     (the cost of this path is bounded however small the cells are).
 constexpr int EMIT_WIN = 64;
+// A run of at least this many rows of one cell is emitted by the uniform path even if it
+// does not fill the warp (idle lanes are cheaper than the per-lane path); shorter runs go
+// through the per-lane path together with the cells that follow.
+constexpr uint32_t EMIT_MIN_UNIFORM = 8;
 
 template <int K, typename T, typename Cells, bool CELLS>
 __global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 && K <= 3 ? LINT_EMIT_MINB : 1)
@@ -393,7 +397,7 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
                 ++j;
             }
             const uint32_t seg_end = min(off(j + 1), r1);
-            if (seg_end - row >= 32u || seg_end == r1) {
+            if (seg_end - row >= EMIT_MIN_UNIFORM || seg_end == r1) {
                 // ---- rows [row, ...) of one cell, lanes = consecutive rows
                 if (loaded != j) {
                     T c0[1 << K];
@@ -414,7 +418,7 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
                     }
                     row += 32u * EMIT_U;
                 }
-                while (row < seg_end && (seg_end - row >= 32u || seg_end == r1)) {
+                while (row < seg_end && (seg_end - row >= EMIT_MIN_UNIFORM || seg_end == r1)) {
                     const uint32_t r = row + lane;
                     if (r < seg_end) {
                         GroupUniforms<K, T, 1> rnd;
@@ -431,8 +435,9 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
                 if (j + 33 - jbase >= EMIT_WIN) refill(j);
                 const uint32_t r = row + lane;
                 const uint32_t lim = min(row + 32u, r1);
+                uint32_t lo = j;
                 if (r < lim) {
-                    uint32_t lo = j, hi = min(j + lane, nnz - 1);
+                    uint32_t hi = min(j + lane, nnz - 1);
                     while (lo < hi) {
                         const uint32_t mid = lo + ((hi - lo + 1) >> 1);
                         if (s_off[mid - jbase] <= r) lo = mid; else hi = mid - 1;
@@ -448,6 +453,7 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
                     emit_row<K, T, CELLS>(coef, xlo, xhi, u, r, cell, out, cell_idx);
                 }
                 loaded = 0xffffffffu;
+                j = __shfl_sync(0xffffffffu, lo, (int)(lim - row) - 1);   // resume at the last row's segment
                 row = lim;
             }
         }
