@@ -329,7 +329,7 @@ constexpr int EMIT_WIN = 64;
 // A run of at least this many rows of one cell is emitted by the uniform path even if it
 // does not fill the warp (idle lanes are cheaper than the per-lane path); shorter runs go
 // through the per-lane path together with the cells that follow.
-constexpr uint32_t EMIT_MIN_UNIFORM = 8;
+constexpr uint32_t EMIT_MIN_UNIFORM = 16;
 
 template <int K, typename T, typename Cells, bool CELLS>
 __global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 && K <= 3 ? LINT_EMIT_MINB : 1)
