@@ -119,12 +119,6 @@ __device__ __forceinline__ void guide_bracket(const CdfView &t, double u, uint32
     }
 }
 
-__device__ __forceinline__ uint32_t search_right(const CdfView &t, double u) {
-    uint32_t lo, hi;
-    guide_bracket(t, u, lo, hi);
-    return lo < hi ? search_bracket(t, u, lo, hi) : lo;
-}
-
 // ---------------------------------------------------------------------------
 // 1-D inverse CDF of a linear density   [sampling.py:6-38]
 // ---------------------------------------------------------------------------
@@ -225,13 +219,6 @@ __device__ __forceinline__ void incell_fast_core(float *c, const float *u, float
 #pragma unroll
         for (int j = 0; j < half; ++j) c[j] = fmaf(zd, c[half + j] - c[j], c[j]);
     }
-}
-
-template <int K>
-__device__ __forceinline__ void incell_fast(float (&c)[1 << K], const float (&u)[K],
-                                            float (&z)[K]) {
-    normalise_corners<(1 << K)>(c);
-    incell_fast_core<K>(c, u, z);
 }
 
 // Per-cell constants of the fp32 draw, for callers that emit many rows per cell:
@@ -566,8 +553,6 @@ __device__ __forceinline__ float affine(float lo, float hi, float z) {
 __device__ __forceinline__ void store_stream(float *p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void store_stream(double *p, double v) { __stcs(p, v); }
 
-template <int K> __device__ __forceinline__ void incell(double (&c)[1 << K], const double (&u)[K], double (&z)[K]) { incell_exact<K>(c, u, z); }
-template <int K> __device__ __forceinline__ void incell(float (&c)[1 << K], const float (&u)[K], float (&z)[K]) { incell_fast<K>(c, u, z); }
 // `prenormalised`: the corners come from fp32 records, which are stored divided by the
 // cell's largest corner (the draw depends on ratios only), so the per-sample
 // normalisation is skipped.  fp64 records hold the raw densities.
