@@ -68,10 +68,13 @@ __device__ __forceinline__ double log_factorial(double k) {
 __device__ uint32_t poisson(double lam, CellRng &rng) {
     if (!(lam > 0.0)) return 0;
     if (lam < 10.0) {
+        double u, unused;
+        rng.next(u, unused);
+        // exp(-lam) >= 1 - lam: most cells of a fine grid hold lam << 1 and end here,
+        // without the exponential
+        if (u <= 1.0 - lam) return 0;
         const double p0 = exp(-lam);
         for (;;) {
-            double u, unused;
-            rng.next(u, unused);
             double p = p0;
             uint32_t x = 0;
             bool ok = true;
@@ -82,6 +85,7 @@ __device__ uint32_t poisson(double lam, CellRng &rng) {
                 p *= lam / (double)x;
             }
             if (ok) return x;
+            rng.next(u, unused);
         }
     }
     const double slam = sqrt(lam), loglam = log(lam);
@@ -246,6 +250,7 @@ struct GridCells {
                                           T (&hi)[K]) const {
         grid_fetch<K, DensT, T>(g, smem, idx, c, lo, hi);
     }
+    __device__ __forceinline__ bool prenormalised() const { return g.rec != nullptr; }
 };
 
 template <int K, typename DensT>
@@ -259,6 +264,7 @@ struct ListCells {
                                           T (&hi)[K]) const {
         cells_fetch<K, DensT, T>(s, idx, c, lo, hi);
     }
+    __device__ __forceinline__ bool prenormalised() const { return s.rec != nullptr; }
 };
 
 #ifndef LINT_EMIT_U
@@ -325,7 +331,13 @@ __device__ __forceinline__ void emit_row(const CellCoefs<K, T> &coef, const T (&
 //   * 32 rows inside one cell: the same with one row per lane;
 //   * 32 rows spanning several cells: each lane finds its own cell in the window
 //     (the cost of this path is bounded however small the cells are).
+// fp32, k <= 3: the per-cell constants (box, hoisted quantile coefficients) of 32
+// consecutive segments are computed at once, one segment per lane, and staged in
+// shared memory; entering a cell then costs a few broadcast loads instead of a
+// warp-redundant fetch + set.
 constexpr int EMIT_WIN = 64;
+constexpr uint32_t EMIT_PRE = 32;            // segments per staged block (= lanes)
+constexpr uint32_t EMIT_PRE_NONE = 0x80000000u;
 // A run of at least this many rows of one cell is emitted by the uniform path even if it
 // does not fill the warp (idle lanes are cheaper than the per-lane path); shorter runs go
 // through the per-lane path together with the cells that follow.
@@ -341,8 +353,15 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
     T *sedges = reinterpret_cast<T *>(smem_raw);
     __shared__ uint32_t s_off_all[EMIT_THREADS / 32][2][EMIT_WIN];
     __shared__ uint32_t s_cid_all[EMIT_THREADS / 32][2][EMIT_WIN];
+    // staged constants: CellCoefs words, then the box (lo[K], hi[K]); the slot stride is an
+    // odd number of 16-byte units so the per-lane 128-bit stores do not conflict
+    constexpr bool PRE = sizeof(T) == 4 && K <= 3;
+    constexpr int PRE_WORDS = CellCoefs<K, T>::WORDS + 2 * K;
+    constexpr int PRE_Q = ((PRE_WORDS + 3) / 4) | 1;
+    __shared__ float4 s_pre_all[PRE ? EMIT_THREADS / 32 : 1][PRE ? EMIT_PRE * PRE_Q : 1];
     src.prepare(sedges);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool pren = src.prenormalised();
     const uint32_t nnz = *nnz_p;
     const uint32_t N = min(*rows_p, n_requested);      // grouped rows T (T <= N but for an 8-sigma event)
     const uint32_t nchunks = (N + EMIT_CHUNK - 1) / EMIT_CHUNK;
@@ -390,6 +409,47 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
         T xlo[K], xhi[K];
         CellCoefs<K, T> coef;
         uint32_t cell = 0;
+        uint32_t cbase = EMIT_PRE_NONE;                  // staged block = segments [cbase, cbase + 32)
+        float4 *s_pre = s_pre_all[PRE ? warp : 0];
+        // stage the constants of segments [jb, jb + 32) that start inside this chunk;
+        // the window must hold entries jb .. jb + 32
+        auto stage = [&](uint32_t jb) {
+            __syncwarp();
+            const uint32_t js = jb + lane;
+            if (js < nnz && s_off[js - jbase] < r1) {
+                T c0[1 << K], lo[K], hi[K];
+                src.fetch(sedges, s_cid[js - jbase], c0, lo, hi);
+                CellCoefs<K, T> cf;
+                cf.set(c0, pren);
+                float w[4 * PRE_Q];
+                cf.pack(w);
+#pragma unroll
+                for (int d = 0; d < K; ++d) {
+                    w[CellCoefs<K, T>::WORDS + d] = (float)lo[d];
+                    w[CellCoefs<K, T>::WORDS + K + d] = (float)hi[d];
+                }
+#pragma unroll
+                for (int q = 0; q < (PRE_WORDS + 3) / 4; ++q)
+                    s_pre[lane * PRE_Q + q] = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+            }
+            cbase = jb;
+            __syncwarp();
+        };
+        auto unstage = [&](uint32_t seg) {               // seg in [cbase, cbase + 32) and in the window
+            float w[4 * PRE_Q];
+#pragma unroll
+            for (int q = 0; q < (PRE_WORDS + 3) / 4; ++q) {
+                const float4 v = s_pre[(seg - cbase) * PRE_Q + q];
+                w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+            }
+            coef.unpack(w);
+#pragma unroll
+            for (int d = 0; d < K; ++d) {
+                xlo[d] = (T)w[CellCoefs<K, T>::WORDS + d];
+                xhi[d] = (T)w[CellCoefs<K, T>::WORDS + K + d];
+            }
+            cell = s_cid[seg - jbase];
+        };
         while (row < r1) {
             for (;;) {                                   // segment containing `row`
                 if (j + 1 - jbase >= EMIT_WIN) refill(j);
@@ -400,10 +460,18 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
             if (seg_end - row >= EMIT_MIN_UNIFORM || seg_end == r1) {
                 // ---- rows [row, ...) of one cell, lanes = consecutive rows
                 if (loaded != j) {
-                    T c0[1 << K];
-                    cell = s_cid[j - jbase];
-                    src.fetch(sedges, cell, c0, xlo, xhi);
-                    coef.set(c0);
+                    if constexpr (PRE) {
+                        if (j - cbase >= EMIT_PRE) {
+                            if (j + EMIT_PRE + 1 - jbase >= EMIT_WIN) refill(j);
+                            stage(j);
+                        }
+                        unstage(j);
+                    } else {
+                        T c0[1 << K];
+                        cell = s_cid[j - jbase];
+                        src.fetch(sedges, cell, c0, xlo, xhi);
+                        coef.set(c0, pren);
+                    }
                     loaded = j;
                 }
                 while (seg_end - row >= 32u * EMIT_U) {
@@ -418,7 +486,9 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
                     }
                     row += 32u * EMIT_U;
                 }
-                while (row < seg_end && (seg_end - row >= EMIT_MIN_UNIFORM || seg_end == r1)) {
+                // the rest of the cell, however short: its constants are in registers already,
+                // which makes idle lanes cheaper than handing the tail to the per-lane path
+                while (row < seg_end) {
                     const uint32_t r = row + lane;
                     if (r < seg_end) {
                         GroupUniforms<K, T, 1> rnd;
@@ -442,10 +512,19 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
                         const uint32_t mid = lo + ((hi - lo + 1) >> 1);
                         if (s_off[mid - jbase] <= r) lo = mid; else hi = mid - 1;
                     }
-                    T c0[1 << K];
-                    cell = s_cid[lo - jbase];
-                    src.fetch(sedges, cell, c0, xlo, xhi);
-                    coef.set(c0);
+                    if constexpr (!PRE) {
+                        T c0[1 << K];
+                        cell = s_cid[lo - jbase];
+                        src.fetch(sedges, cell, c0, xlo, xhi);
+                        coef.set(c0, pren);
+                    }
+                }
+                const uint32_t last = __shfl_sync(0xffffffffu, lo, (int)(lim - row) - 1);   // the last row's segment
+                if constexpr (PRE) {
+                    if (j - cbase >= EMIT_PRE || last - cbase >= EMIT_PRE) stage(j);       // last <= j + 31
+                }
+                if (r < lim) {
+                    if constexpr (PRE) unstage(lo);
                     GroupUniforms<K, T, 1> rnd;
                     rnd.fill(key, r, 1, offset);
                     T u[K];
@@ -453,7 +532,7 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
                     emit_row<K, T, CELLS>(coef, xlo, xhi, u, r, cell, out, cell_idx);
                 }
                 loaded = 0xffffffffu;
-                j = __shfl_sync(0xffffffffu, lo, (int)(lim - row) - 1);   // resume at the last row's segment
+                j = last;                                // resume at the last row's segment
                 row = lim;
             }
         }

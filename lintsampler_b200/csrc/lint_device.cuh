@@ -146,10 +146,13 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 }
 
 __device__ __forceinline__ float quantile_fast(float f0, float f1, float u) {
-    const float rad = fmaf(u, fmaf(f1, f1, -f0 * f0), f0 * f0);
+    // rad >= 0 without a clamp: a = fl(f0^2) >= 0, b = fl(f1^2 - a) >= -a, 0 <= u <= 1, so
+    // a + b u >= 0 exactly and the single rounding of the fma keeps the sign
+    const float a = f0 * f0;
+    const float rad = fmaf(u, fmaf(f1, f1, -a), a);
     // den == 0 only where the segment carries no density at all (or f0 == 0 and u == 0):
     // the numerator is 0 there too, so flooring den gives z = 0 instead of 0/0
-    const float den = fmaxf(f0 + sqrt_approx(fmaxf(rad, 0.f)), 1e-30f);
+    const float den = fmaxf(f0 + sqrt_approx(rad), 1e-30f);
     return (f0 + f1) * u * rcp_approx(den);
 }
 
@@ -230,8 +233,8 @@ struct CellFast {
     static constexpr int H = 1 << (K - 1);
     float c[H], dc[H];             // corners with x0 = 0, and (x0 = 1) - (x0 = 0)
     float g0, a0, b0, s0;          // z0 = s0 u / (g0 + sqrt(a0 + b0 u))
-    __device__ __forceinline__ void set(float (&corners)[1 << K]) {
-        normalise_corners<(1 << K)>(corners);
+    __device__ __forceinline__ void set(float (&corners)[1 << K], bool prenormalised) {
+        if (!prenormalised) normalise_corners<(1 << K)>(corners);
         float g1 = corners[H];
         g0 = corners[0];
 #pragma unroll
@@ -242,8 +245,20 @@ struct CellFast {
 #pragma unroll
         for (int j = 0; j < H; ++j) { c[j] = corners[j]; dc[j] = corners[H + j] - corners[j]; }
     }
+    // flat image of the constants (for staging them in shared memory)
+    static constexpr int WORDS = 2 * H + 4;
+    __device__ __forceinline__ void pack(float *w) const {
+#pragma unroll
+        for (int j = 0; j < H; ++j) { w[j] = c[j]; w[H + j] = dc[j]; }
+        w[2 * H] = g0; w[2 * H + 1] = a0; w[2 * H + 2] = b0; w[2 * H + 3] = s0;
+    }
+    __device__ __forceinline__ void unpack(const float *w) {
+#pragma unroll
+        for (int j = 0; j < H; ++j) { c[j] = w[j]; dc[j] = w[H + j]; }
+        g0 = w[2 * H]; a0 = w[2 * H + 1]; b0 = w[2 * H + 2]; s0 = w[2 * H + 3];
+    }
     __device__ __forceinline__ void draw(const float (&u)[K], float (&z)[K]) const {
-        const float den = fmaxf(g0 + sqrt_approx(fmaxf(fmaf(b0, u[0], a0), 0.f)), 1e-30f);
+        const float den = fmaxf(g0 + sqrt_approx(fmaf(b0, u[0], a0)), 1e-30f);   // see quantile_fast
         const float z0 = s0 * u[0] * rcp_approx(den);
         z[0] = z0;
         if constexpr (K > 1) {
@@ -259,7 +274,10 @@ struct CellFast {
 template <int K>
 struct CellExact {
     double c[1 << K];
-    __device__ __forceinline__ void set(double (&corners)[1 << K]) {
+    static constexpr int WORDS = 0;                                  // never staged
+    __device__ __forceinline__ void pack(float *) const {}
+    __device__ __forceinline__ void unpack(const float *) {}
+    __device__ __forceinline__ void set(double (&corners)[1 << K], bool) {
 #pragma unroll
         for (int j = 0; j < (1 << K); ++j) c[j] = corners[j];
     }
