@@ -261,7 +261,7 @@ int lint_sobol_uniforms(int dim, int64_t N, const lint_sobol_t *sobol, double *u
  * [u_lo, u_hi) restricts the draw to a stratum of the cell CDF exactly as in
  * lint_grid_sample_philox ((0, 1) = whole domain; a cell straddling a stratum
  * boundary is shared in proportion to the overlap).
- * N < 2^32, fewer than 2^30 cells.  Scratch: lint_cellmajor_scratch_bytes. */
+ * N <= 2^32 - 2^16, fewer than 2^29 cells.  Scratch: lint_cellmajor_scratch_bytes. */
 size_t lint_cellmajor_scratch_bytes(int64_t ncells, int64_t N);
 int lint_grid_sample_cellmajor(const lint_grid_t *g, int64_t N, uint64_t seed, uint64_t offset,
                                double u_lo, double u_hi, void *scratch_dev, size_t scratch_bytes, void *out_dev,

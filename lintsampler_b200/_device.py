@@ -123,7 +123,7 @@ def cellmajor_scratch(owner, ncells, N):
     return buf, nbytes
 
 
-CELLMAJOR_MAX_ROWS = 1 << 31     # lint_*_sample_cellmajor takes N < 2^32; larger draws are chunked
+CELLMAJOR_MAX_ROWS = 1 << 31     # lint_*_sample_cellmajor takes N <= 2^32 - 2^16; larger draws are chunked
 
 
 def cellmajor_chunks(N):

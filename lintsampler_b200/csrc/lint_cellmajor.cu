@@ -17,11 +17,22 @@
 //   4. tops up the remaining N - T rows (~2.5e-4 N) with the u-driven kernel;
 //      Multinomial(T, p) + Multinomial(N - T, p) = Multinomial(N, p), so the N
 //      rows are an exact i.i.d. sample as a multiset.
+// Flat/residual split.  Inside a cell the interpolant is f = f_min + (f - f_min): a
+// constant plus a multilinear density that vanishes at one corner.  Rows of the
+// constant part are plain uniforms (z = u, no inverse CDF at all); only rows of the
+// residual need sampling.py:41-94.  Every cell therefore becomes two "virtual cells"
+// 2c (flat) and 2c + 1 (residual) with independent Poisson counts of means
+// lambda q and lambda (1 - q), q = f_min / mean(corners) — Poisson thinning, exact.
+// On a fine grid of a smooth pdf q is close to 1 (0.94 mass-weighted on the 256^3
+// benchmark grid), so most rows cost their uniforms, an fma and a store.  The split
+// doubles the segment table and adds a corner gather to the count pass, which only
+// pays with enough rows per cell: it is used when N >= SPLIT_MIN_ROWS_PER_CELL * cells.
 // Row ORDER is by cell (C order) for the first T rows, draw order for the
 // top-up tail.  Callers that need the reference's exchangeable row order
 // (lintsampler.py:309-311) apply the row permutation afterwards.
 #include <algorithm>
 #include <cmath>
+#include <type_traits>
 #include <cuda_pipeline.h>
 #include "lint_device.cuh"
 
@@ -51,13 +62,13 @@ struct CellRng {
 
 // log(k!) for integer-valued k >= 0: table below 16, Stirling series above
 // (truncation error < 2e-12 there)
+__constant__ double LOG_FACTORIAL_TAB[16] = {
+    0.0, 0.0, 0.6931471805599453, 1.791759469228055, 3.1780538303479458, 4.787491742782046,
+    6.579251212010101, 8.525161361065415, 10.604602902745251, 12.801827480081469,
+    15.104412573075516, 17.502307845873887, 19.987214495661885, 22.552163853123425,
+    25.19122118273868, 27.89927138384089};
 __device__ __forceinline__ double log_factorial(double k) {
-    const double tab[16] = {0.0, 0.0, 0.6931471805599453, 1.791759469228055, 3.1780538303479458,
-                            4.787491742782046, 6.579251212010101, 8.525161361065415,
-                            10.604602902745251, 12.801827480081469, 15.104412573075516,
-                            17.502307845873887, 19.987214495661885, 22.552163853123425,
-                            25.19122118273868, 27.89927138384089};
-    if (k < 16.0) return tab[(int)k];
+    if (k < 16.0) return LOG_FACTORIAL_TAB[(int)k];
     const double x = k + 1.0, r = 1.0 / x, r2 = r * r;
     return (x - 0.5) * log(x) - x + 0.9189385332046727 +
            r * (1.0 / 12.0 - r2 * (1.0 / 360.0 - r2 * (1.0 / 1260.0)));
@@ -65,7 +76,7 @@ __device__ __forceinline__ double log_factorial(double k) {
 
 // Poisson(lam): sequential inversion with one uniform below 10, Hörmann's
 // transformed rejection with squeeze (PTRS, 1993) above.
-__device__ uint32_t poisson(double lam, CellRng &rng) {
+__device__ __forceinline__ uint32_t poisson(double lam, CellRng &rng) {
     if (!(lam > 0.0)) return 0;
     if (lam < 10.0) {
         double u, unused;
@@ -82,16 +93,14 @@ __device__ uint32_t poisson(double lam, CellRng &rng) {
                 u -= p;
                 ++x;
                 if (x > 200) { ok = false; break; }     // fp dust past the far tail: redraw
-                p *= lam / (double)x;
+                p *= lam * __drcp_rn((double)x);
             }
             if (ok) return x;
             rng.next(u, unused);
         }
     }
-    const double slam = sqrt(lam), loglam = log(lam);
-    const double b = 0.931 + 2.53 * slam;
+    const double b = 0.931 + 2.53 * sqrt(lam);
     const double a = -0.059 + 0.02483 * b;
-    const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
     const double vr = 0.9277 - 3.6224 / (b - 2.0);
     for (;;) {
         double u, v;
@@ -99,9 +108,10 @@ __device__ uint32_t poisson(double lam, CellRng &rng) {
         u -= 0.5;
         const double us = 0.5 - fabs(u);
         const double k = floor((2.0 * a / us + b) * u + lam + 0.43);
-        if (us >= 0.07 && v <= vr) return (uint32_t)k;
+        if (us >= 0.07 && v <= vr) return (uint32_t)k;            // the squeeze accepts ~86 %
         if (k < 0.0 || (us < 0.013 && v > us)) continue;
-        if (log(v) + log(invalpha) - log(a / (us * us) + b) <= -lam + k * loglam - log_factorial(k))
+        const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
+        if (log(v * invalpha / (a / (us * us) + b)) <= -lam + k * log(lam) - log_factorial(k))
             return (uint32_t)k;
     }
 }
@@ -115,14 +125,54 @@ struct CdfSlice {
     double u_lo, u_hi;
 };
 
+// Below this mean a cell draws one count and thins it row by row (no corner gather for
+// the many cells that stay empty); above it, two independent Poisson draws.
+constexpr double SPLIT_BY_THINNING_BELOW = 4.0;
+
+template <typename Cells>
 __global__ void __launch_bounds__(256)
-poisson_counts_kernel(CdfSlice t, double lam_per_unit, uint2 key, uint64_t offset, uint32_t *counts) {
+poisson_counts_kernel(Cells src, CdfSlice t, double lam_per_unit, uint2 key, uint64_t offset, bool split,
+                      uint32_t *counts) {
+    const uint32_t w2 = (uint32_t)offset, w3 = (uint32_t)(offset >> 32);
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < t.ncells; c += gridDim.x * blockDim.x) {
         // mass of the cell inside the stratum: clamp both CDF values, then difference
         const double f0 = c == 0 ? 0.0 : __ldg(t.cdf + c - 1), f1 = __ldg(t.cdf + c);
         const double m = fmin(fmax(f1, t.u_lo), t.u_hi) - fmin(fmax(f0, t.u_lo), t.u_hi);
-        CellRng rng{key, c, (uint32_t)offset, (uint32_t)(offset >> 32)};
-        counts[c] = poisson(m * lam_per_unit, rng);
+        const double lam = m * lam_per_unit;
+        if (!split) {                                    // one count per cell
+            CellRng rng{key, c, w2, w3};
+            counts[c] = poisson(lam, rng);
+            continue;
+        }
+        uint32_t n[2] = {0, 0};                          // flat, residual
+        if (lam > 0.0) {
+            const bool thin = lam < SPLIT_BY_THINNING_BELOW;
+            double q = 0.0, mean[2] = {lam, 0.0};
+            if (!thin) {
+                q = src.flat_fraction(c);
+                mean[0] = lam * q;
+                mean[1] = lam - mean[0];
+            }
+#pragma unroll 1
+            for (int part = 0; part < 2; ++part) {       // one copy of the sampler's code
+                CellRng rng{key, 2 * c + part, w2, w3};
+                n[part] = poisson(mean[part], rng);
+            }
+            if (thin && n[0]) {                          // thin the few rows one by one
+                q = src.flat_fraction(c);
+                CellRng coin{key, 2 * c + 1, w2, w3};
+                const uint32_t total = n[0];
+                n[0] = 0;
+                for (uint32_t i = 0; i < total; i += 2) {
+                    double a, b;
+                    coin.next(a, b);
+                    n[0] += a < q;
+                    if (i + 1 < total) n[0] += b < q;
+                }
+                n[1] = total - n[0];
+            }
+        }
+        reinterpret_cast<uint2 *>(counts)[c] = make_uint2(n[0], n[1]);
     }
 }
 
@@ -239,6 +289,24 @@ __global__ void chunk_start_kernel(const uint32_t *coff, const uint32_t *nnz_p, 
 // ---------------------------------------------------------------------------
 // emission
 // ---------------------------------------------------------------------------
+template <int K, typename T>
+__device__ __forceinline__ double flat_fraction_of(const T (&c)[1 << K]) {
+    T lo = c[0], sum = c[0];
+#pragma unroll
+    for (int j = 1; j < (1 << K); ++j) { lo = c[j] < lo ? c[j] : lo; sum += c[j]; }
+    return sum > (T)0 ? fmin(fmax((double)lo * (double)(1 << K) / (double)sum, 0.0), 1.0) : 0.0;
+}
+
+// c <- c - min(c): the residual density of the flat/residual split
+template <int NC, typename T>
+__device__ __forceinline__ void subtract_min(T (&c)[NC]) {
+    T lo = c[0];
+#pragma unroll
+    for (int j = 1; j < NC; ++j) lo = c[j] < lo ? c[j] : lo;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) c[j] -= lo;
+}
+
 template <int K, typename DensT>
 struct GridCells {
     GridView<K> g;
@@ -251,6 +319,14 @@ struct GridCells {
         grid_fetch<K, DensT, T>(g, smem, idx, c, lo, hi);
     }
     __device__ __forceinline__ bool prenormalised() const { return g.rec != nullptr; }
+    // q = min(corners) / mean(corners): the share of the cell's mass under the constant f_min
+    __device__ __forceinline__ double flat_fraction(uint32_t idx) const {
+        uint32_t i[K];
+        grid_unravel<K>(g, idx, i);
+        DensT c[1 << K];
+        grid_corners<K, DensT, DensT>(g, idx, i, c);
+        return flat_fraction_of<K>(c);
+    }
 };
 
 template <int K, typename DensT>
@@ -265,6 +341,11 @@ struct ListCells {
         cells_fetch<K, DensT, T>(s, idx, c, lo, hi);
     }
     __device__ __forceinline__ bool prenormalised() const { return s.rec != nullptr; }
+    __device__ __forceinline__ double flat_fraction(uint32_t idx) const {
+        DensT c[1 << K];
+        cells_corners<K, DensT, DensT>(s, idx, c);
+        return flat_fraction_of<K>(c);
+    }
 };
 
 #ifndef LINT_EMIT_U
@@ -305,17 +386,40 @@ struct GroupUniforms {
 #pragma unroll
         for (int d = 0; d < K; ++d) u[d] = u53(w[2 * (i * K + d)], w[2 * (i * K + d) + 1]);
     }
+    // RAW: u / raw_scale — fp32 callers that only multiply u by a per-cell constant fold
+    // the 2^-32 into that constant
+    template <bool RAW>
+    __device__ __forceinline__ void get_as(int i, float (&u)[K]) const {
+        if constexpr (RAW) {
+#pragma unroll
+            for (int d = 0; d < K; ++d) u[d] = __uint2float_rz(w[i * K + d]);
+        } else {
+            get(i, u);
+        }
+    }
+    template <bool RAW>
+    __device__ __forceinline__ void get_as(int i, double (&u)[K]) const { get(i, u); }
 };
+template <typename T> __device__ __forceinline__ T raw_scale();
+template <> __device__ __forceinline__ float raw_scale<float>() { return 1.0f / 4294967296.0f; }
+template <> __device__ __forceinline__ double raw_scale<double>() { return 1.0; }
 
-template <int K, typename T, bool CELLS>
-__device__ __forceinline__ void emit_row(const CellCoefs<K, T> &coef, const T (&xlo)[K], const T (&xhi)[K],
+// FLAT: a row of the constant part of the density, z = u (the caller passes the raw
+// uniforms and a width that carries raw_scale)
+template <int K, typename T, bool CELLS, bool FLAT>
+__device__ __forceinline__ void emit_row(const CellCoefs<K, T> &coef, const T (&xlo)[K], const T (&xw)[K],
                                          const T (&u)[K], uint32_t row, uint32_t cell,
                                          T *__restrict__ out, int64_t *__restrict__ cell_idx) {
     T z[K];
-    coef.draw(u, z);                                               // sampling.py:41-94
+    if constexpr (FLAT) {
+#pragma unroll
+        for (int d = 0; d < K; ++d) z[d] = u[d];
+    } else {
+        coef.draw(u, z);                                           // sampling.py:41-94
+    }
 #pragma unroll
     for (int d = 0; d < K; ++d)
-        store_stream(out + (size_t)row * K + d, affine(xlo[d], xhi[d], z[d]));   // sampling.py:126
+        store_stream(out + (size_t)row * K + d, affine_w(xlo[d], xw[d], z[d]));   // sampling.py:126
     if (CELLS) __stcs(reinterpret_cast<long long *>(cell_idx) + row, (long long)cell);
 }
 
@@ -338,17 +442,13 @@ __device__ __forceinline__ void emit_row(const CellCoefs<K, T> &coef, const T (&
 constexpr int EMIT_WIN = 64;
 constexpr uint32_t EMIT_PRE = 32;            // segments per staged block (= lanes)
 constexpr uint32_t EMIT_PRE_NONE = 0x80000000u;
-// A run of at least this many rows of one cell is emitted by the uniform path even if it
-// does not fill the warp (idle lanes are cheaper than the per-lane path); shorter runs go
-// through the per-lane path together with the cells that follow.
-constexpr uint32_t EMIT_MIN_UNIFORM = 16;
 
 template <int K, typename T, typename Cells, bool CELLS>
 __global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 && K <= 3 ? LINT_EMIT_MINB : 1)
 emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
             const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ rows_p,
             const uint32_t *__restrict__ chunk_start, uint32_t n_requested, uint2 key, uint64_t offset,
-            T *__restrict__ out, int64_t *__restrict__ cell_idx) {
+            uint32_t split, T *__restrict__ out, int64_t *__restrict__ cell_idx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sedges = reinterpret_cast<T *>(smem_raw);
     __shared__ uint32_t s_off_all[EMIT_THREADS / 32][2][EMIT_WIN];
@@ -361,7 +461,6 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
     __shared__ float4 s_pre_all[PRE ? EMIT_THREADS / 32 : 1][PRE ? EMIT_PRE * PRE_Q : 1];
     src.prepare(sedges);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool pren = src.prenormalised();
     const uint32_t nnz = *nnz_p;
     const uint32_t N = min(*rows_p, n_requested);      // grouped rows T (T <= N but for an 8-sigma event)
     const uint32_t nchunks = (N + EMIT_CHUNK - 1) / EMIT_CHUNK;
@@ -405,28 +504,44 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
 
         uint32_t j = jbase;                              // warp-uniform segment cursor
         uint32_t row = r0;
-        uint32_t loaded = 0xffffffffu;                   // segment whose cell the registers hold
-        T xlo[K], xhi[K];
+        uint32_t loaded = 0xffffffffu;                   // segment whose constants the registers hold
+        T xlo[K], xw[K];                                 // box: lower corner, width (x raw_scale if flat)
         CellCoefs<K, T> coef;
         uint32_t cell = 0;
+        bool flat = false;                               // the segment is the flat part of its cell
         uint32_t cbase = EMIT_PRE_NONE;                  // staged block = segments [cbase, cbase + 32)
         float4 *s_pre = s_pre_all[PRE ? warp : 0];
+        // segment ids: the cell itself, or with the flat/residual split 2 cell + (residual ? 1 : 0)
+        auto is_flat = [&](uint32_t v) { return split && !(v & 1); };
+        // constants of one segment into the caller's registers
+        auto constants = [&](uint32_t v, CellCoefs<K, T> &cf, T (&lo)[K], T (&w)[K]) {
+            T c0[1 << K], hi[K];
+            src.fetch(sedges, v >> split, c0, lo, hi);
+#pragma unroll
+            for (int d = 0; d < K; ++d) w[d] = hi[d] - lo[d];              // maxs - mins, sampling.py:126
+            if (!is_flat(v)) {
+                if (split) subtract_min(c0);
+                cf.set(c0, !split && src.prenormalised());
+            } else {
+#pragma unroll
+                for (int d = 0; d < K; ++d) w[d] *= raw_scale<T>();
+            }
+        };
         // stage the constants of segments [jb, jb + 32) that start inside this chunk;
         // the window must hold entries jb .. jb + 32
         auto stage = [&](uint32_t jb) {
             __syncwarp();
             const uint32_t js = jb + lane;
             if (js < nnz && s_off[js - jbase] < r1) {
-                T c0[1 << K], lo[K], hi[K];
-                src.fetch(sedges, s_cid[js - jbase], c0, lo, hi);
+                T lo[K], wd[K];
                 CellCoefs<K, T> cf;
-                cf.set(c0, pren);
-                float w[4 * PRE_Q];
-                cf.pack(w);
+                float w[4 * PRE_Q] = {};
+                constants(s_cid[js - jbase], cf, lo, wd);
+                if (!is_flat(s_cid[js - jbase])) cf.pack(w);
 #pragma unroll
                 for (int d = 0; d < K; ++d) {
                     w[CellCoefs<K, T>::WORDS + d] = (float)lo[d];
-                    w[CellCoefs<K, T>::WORDS + K + d] = (float)hi[d];
+                    w[CellCoefs<K, T>::WORDS + K + d] = (float)wd[d];
                 }
 #pragma unroll
                 for (int q = 0; q < (PRE_WORDS + 3) / 4; ++q)
@@ -435,105 +550,110 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
             cbase = jb;
             __syncwarp();
         };
-        auto unstage = [&](uint32_t seg) {               // seg in [cbase, cbase + 32) and in the window
-            float w[4 * PRE_Q];
+        // registers <- constants of segment seg (in the window; PRE: also in the staged block)
+        auto enter = [&](uint32_t seg) {
+            const uint32_t v = s_cid[seg - jbase];
+            cell = v >> split;
+            flat = is_flat(v);
+            if constexpr (PRE) {
+                float w[4 * PRE_Q];
 #pragma unroll
-            for (int q = 0; q < (PRE_WORDS + 3) / 4; ++q) {
-                const float4 v = s_pre[(seg - cbase) * PRE_Q + q];
-                w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-            }
-            coef.unpack(w);
+                for (int q = 0; q < (PRE_WORDS + 3) / 4; ++q) {
+                    const float4 t4 = s_pre[(seg - cbase) * PRE_Q + q];
+                    w[4 * q] = t4.x; w[4 * q + 1] = t4.y; w[4 * q + 2] = t4.z; w[4 * q + 3] = t4.w;
+                }
+                coef.unpack(w);
 #pragma unroll
-            for (int d = 0; d < K; ++d) {
-                xlo[d] = (T)w[CellCoefs<K, T>::WORDS + d];
-                xhi[d] = (T)w[CellCoefs<K, T>::WORDS + K + d];
+                for (int d = 0; d < K; ++d) {
+                    xlo[d] = (T)w[CellCoefs<K, T>::WORDS + d];
+                    xw[d] = (T)w[CellCoefs<K, T>::WORDS + K + d];
+                }
+            } else {
+                constants(v, coef, xlo, xw);
             }
-            cell = s_cid[seg - jbase];
         };
+
+        // invariant: segment j holds `row` (segments are non-empty, so they tile the rows)
         while (row < r1) {
-            for (;;) {                                   // segment containing `row`
-                if (j + 1 - jbase >= EMIT_WIN) refill(j);
-                if (off(j + 1) > row) break;
-                ++j;
-            }
+            if (j + 2 - jbase >= EMIT_WIN) refill(j);
             const uint32_t seg_end = min(off(j + 1), r1);
-            if (seg_end - row >= EMIT_MIN_UNIFORM || seg_end == r1) {
-                // ---- rows [row, ...) of one cell, lanes = consecutive rows
+            // the per-lane path pays where the next 32 rows cover at least two whole segments
+            if (off(j + 2) > min(row + 32u, r1)) {
+                // ---- rows [row, seg_end) of one segment, lanes = consecutive rows
                 if (loaded != j) {
                     if constexpr (PRE) {
                         if (j - cbase >= EMIT_PRE) {
                             if (j + EMIT_PRE + 1 - jbase >= EMIT_WIN) refill(j);
                             stage(j);
                         }
-                        unstage(j);
-                    } else {
-                        T c0[1 << K];
-                        cell = s_cid[j - jbase];
-                        src.fetch(sedges, cell, c0, xlo, xhi);
-                        coef.set(c0, pren);
                     }
+                    enter(j);
                     loaded = j;
                 }
-                while (seg_end - row >= 32u * EMIT_U) {
-                    const uint32_t first = row + lane;
-                    GroupUniforms<K, T, EMIT_U> rnd;
-                    rnd.fill(key, first, 0, offset);
+                auto rows = [&](auto tag) {
+                    constexpr bool FLAT = decltype(tag)::value;
+                    // blocks of 32 * EMIT_U rows; a last partial block of more than half that
+                    // is still cheaper here (rows past the end masked) than one warp-row at a time
+                    while (seg_end - row > 16u * EMIT_U) {
+                        const uint32_t first = row + lane;
+                        GroupUniforms<K, T, EMIT_U> rnd;
+                        rnd.fill(key, first, 0, offset);
 #pragma unroll
-                    for (int t = 0; t < EMIT_U; ++t) {
-                        T u[K];
-                        rnd.get(t, u);
-                        emit_row<K, T, CELLS>(coef, xlo, xhi, u, first + 32u * t, cell, out, cell_idx);
+                        for (int t = 0; t < EMIT_U; ++t) {
+                            T u[K];
+                            rnd.template get_as<FLAT>(t, u);
+                            if (first + 32u * t < seg_end)
+                                emit_row<K, T, CELLS, FLAT>(coef, xlo, xw, u, first + 32u * t, cell, out, cell_idx);
+                        }
+                        row = min(row + 32u * EMIT_U, seg_end);
                     }
-                    row += 32u * EMIT_U;
-                }
-                // the rest of the cell, however short: its constants are in registers already,
-                // which makes idle lanes cheaper than handing the tail to the per-lane path
-                while (row < seg_end) {
-                    const uint32_t r = row + lane;
-                    if (r < seg_end) {
-                        GroupUniforms<K, T, 1> rnd;
-                        rnd.fill(key, r, 1, offset);
-                        T u[K];
-                        rnd.get(0, u);
-                        emit_row<K, T, CELLS>(coef, xlo, xhi, u, r, cell, out, cell_idx);
+                    // the rest of the segment, however short: its constants are in registers
+                    // already, which makes idle lanes cheaper than the per-lane path
+                    while (row < seg_end) {
+                        const uint32_t r = row + lane;
+                        if (r < seg_end) {
+                            GroupUniforms<K, T, 1> rnd;
+                            rnd.fill(key, r, 1, offset);
+                            T u[K];
+                            rnd.template get_as<FLAT>(0, u);
+                            emit_row<K, T, CELLS, FLAT>(coef, xlo, xw, u, r, cell, out, cell_idx);
+                        }
+                        row = min(row + 32u, seg_end);
                     }
-                    row = min(row + 32u, seg_end);
-                }
+                };
+                if (flat) rows(std::true_type{}); else rows(std::false_type{});
+                ++j;                                     // row == seg_end: the next segment, if row < r1
             } else {
-                // ---- the next 32 rows span several cells: one row per lane, own cell each.
+                // ---- the next 32 rows span several segments: one row per lane, own segment each.
                 // Segments hold >= 1 row, so lane l's segment is within [j, j + l].
                 if (j + 33 - jbase >= EMIT_WIN) refill(j);
                 const uint32_t r = row + lane;
                 const uint32_t lim = min(row + 32u, r1);
-                uint32_t lo = j;
-                if (r < lim) {
-                    uint32_t hi = min(j + lane, nnz - 1);
-                    while (lo < hi) {
-                        const uint32_t mid = lo + ((hi - lo + 1) >> 1);
-                        if (s_off[mid - jbase] <= r) lo = mid; else hi = mid - 1;
-                    }
-                    if constexpr (!PRE) {
-                        T c0[1 << K];
-                        cell = s_cid[lo - jbase];
-                        src.fetch(sedges, cell, c0, xlo, xhi);
-                        coef.set(c0, pren);
-                    }
-                }
+                // bit b of `starts`: a segment begins at row + b (lane i looks at segment j + 1 + i);
+                // a row's segment is j + the number of starts in (row, r]
+                const uint32_t o = off(j + 1 + lane) - row;                   // >= 1
+                const uint32_t starts = __reduce_or_sync(0xffffffffu, o < 32u ? 1u << o : 0u);
+                const uint32_t lo = j + __popc(starts & ((2u << lane) - 1u));
                 const uint32_t last = __shfl_sync(0xffffffffu, lo, (int)(lim - row) - 1);   // the last row's segment
                 if constexpr (PRE) {
                     if (j - cbase >= EMIT_PRE || last - cbase >= EMIT_PRE) stage(j);       // last <= j + 31
                 }
                 if (r < lim) {
-                    if constexpr (PRE) unstage(lo);
+                    enter(lo);
                     GroupUniforms<K, T, 1> rnd;
                     rnd.fill(key, r, 1, offset);
                     T u[K];
-                    rnd.get(0, u);
-                    emit_row<K, T, CELLS>(coef, xlo, xhi, u, r, cell, out, cell_idx);
+                    if (flat) {
+                        rnd.template get_as<true>(0, u);
+                        emit_row<K, T, CELLS, true>(coef, xlo, xw, u, r, cell, out, cell_idx);
+                    } else {
+                        rnd.template get_as<false>(0, u);
+                        emit_row<K, T, CELLS, false>(coef, xlo, xw, u, r, cell, out, cell_idx);
+                    }
                 }
                 loaded = 0xffffffffu;
-                j = last;                                // resume at the last row's segment
                 row = lim;
+                j = off(last + 1) <= row ? last + 1 : last;     // (window holds up to j + 32)
             }
         }
         __syncwarp();
@@ -549,7 +669,9 @@ struct Scratch {
     size_t bytes;
 };
 
-static Scratch carve(void *base, uint64_t ncells, uint64_t N) {
+// `ncells` real cells = 2 ncells virtual cells (flat, residual) in the count / segment tables
+static Scratch carve(void *base, uint64_t ncells_real, uint64_t N) {
+    const uint64_t ncells = 2 * ncells_real;
     const uint64_t nscan = (ncells + SCAN_TILE - 1) / SCAN_TILE;
     const uint64_t nchunks = (N + EMIT_CHUNK - 1) / EMIT_CHUNK;
     uintptr_t p = (uintptr_t)base;
@@ -576,16 +698,24 @@ static uint64_t topup_bound(uint64_t N) {
 }
 
 // counts -> offsets (+ compaction) -> chunk starts
-static int plan_rows(const double *cdf, uint64_t ncells, uint64_t N, uint2 key, uint64_t offset,
-                     double u_lo, double u_hi, const Scratch &s, cudaStream_t st) {
-    const CdfSlice t{cdf, (uint32_t)ncells, u_lo, u_hi};
-    const double lam_per_unit = grouped_mean(N) / (u_hi - u_lo);
+struct Stratum { double u_lo, u_hi; };
+
+constexpr uint64_t SPLIT_MIN_ROWS_PER_CELL = 32;
+static bool use_split(uint64_t ncells, uint64_t N) { return N >= SPLIT_MIN_ROWS_PER_CELL * ncells; }
+
+template <typename Cells>
+static int plan_rows(const Cells &src, const double *cdf, uint64_t ncells, uint64_t N, uint2 key,
+                     uint64_t offset, Stratum u, const Scratch &s, cudaStream_t st) {
+    const bool split = use_split(ncells, N);
+    const CdfSlice t{cdf, (uint32_t)ncells, u.u_lo, u.u_hi};
+    const double lam_per_unit = grouped_mean(N) / (u.u_hi - u.u_lo);
     const int cblocks = (int)std::min<uint64_t>((ncells + 255) / 256, 148 * 16);
-    poisson_counts_kernel<<<cblocks, 256, 0, st>>>(t, lam_per_unit, key, offset, s.counts);
-    const uint32_t nscan = (uint32_t)((ncells + SCAN_TILE - 1) / SCAN_TILE);
+    poisson_counts_kernel<<<cblocks, 256, 0, st>>>(src, t, lam_per_unit, key, offset, split, s.counts);
+    const uint32_t nvirt = (uint32_t)(split ? 2 * ncells : ncells);
+    const uint32_t nscan = (nvirt + SCAN_TILE - 1) / SCAN_TILE;
     cudaMemsetAsync(s.tile_state, 0, (size_t)nscan * 8, st);
     cudaMemsetAsync(s.tile_counter, 0, 4, st);
-    scan_compact_kernel<<<nscan, SCAN_THREADS, 0, st>>>(s.counts, (uint32_t)ncells, s.tile_state,
+    scan_compact_kernel<<<nscan, SCAN_THREADS, 0, st>>>(s.counts, nvirt, s.tile_state,
                                                        s.tile_counter, s.cid, s.coff, s.nnz, s.rows);
     const uint32_t nchunks = (uint32_t)((N + EMIT_CHUNK - 1) / EMIT_CHUNK);
     chunk_start_kernel<<<std::max(1u, std::min((nchunks + 255) / 256, 148u * 8)), 256, 0, st>>>(
@@ -594,16 +724,17 @@ static int plan_rows(const double *cdf, uint64_t ncells, uint64_t N, uint2 key, 
 }
 
 template <int K, typename T, typename Cells>
-int launch_emit(const Cells &src, const Scratch &s, uint64_t N, uint2 key, uint64_t offset, void *out,
-                int64_t *cell_idx, cudaStream_t st) {
+int launch_emit(const Cells &src, const Scratch &s, uint64_t ncells, uint64_t N, uint2 key, uint64_t offset,
+                void *out, int64_t *cell_idx, cudaStream_t st) {
+    const uint32_t split = use_split(ncells, N) ? 1u : 0u;
     const uint32_t nchunks = (uint32_t)((N + EMIT_CHUNK - 1) / EMIT_CHUNK);
     const int blocks = (int)std::min<uint32_t>((nchunks + EMIT_THREADS / 32 - 1) / (EMIT_THREADS / 32), 148 * 8);
     if (cell_idx)
         emit_kernel<K, T, Cells, true><<<blocks, EMIT_THREADS, src.smem_bytes(sizeof(T)), st>>>(
-            src, s.cid, s.coff, s.nnz, s.rows, s.chunk_start, (uint32_t)N, key, offset, (T *)out, cell_idx);
+            src, s.cid, s.coff, s.nnz, s.rows, s.chunk_start, (uint32_t)N, key, offset, split, (T *)out, cell_idx);
     else
         emit_kernel<K, T, Cells, false><<<blocks, EMIT_THREADS, src.smem_bytes(sizeof(T)), st>>>(
-            src, s.cid, s.coff, s.nnz, s.rows, s.chunk_start, (uint32_t)N, key, offset, (T *)out, cell_idx);
+            src, s.cid, s.coff, s.nnz, s.rows, s.chunk_start, (uint32_t)N, key, offset, split, (T *)out, cell_idx);
     return check_launch("cell-major emission");
 }
 
@@ -611,8 +742,10 @@ static int check_common(int64_t N, uint64_t ncells, double u_lo, double u_hi, vo
                         size_t scratch_bytes, const char *what) {
     if (!(u_lo >= 0.0) || !(u_hi <= 1.0) || !(u_lo < u_hi))
         return fail(LINT_ERR_BAD_ARG, "%s: stratum [%g, %g) is not inside [0, 1]", what, u_lo, u_hi);
-    if (N < 0 || N >= (1ll << 32)) return fail(LINT_ERR_BAD_ARG, "%s: N must be in [0, 2^32)", what);
-    if (ncells >= (1ull << 30)) return fail(LINT_ERR_UNSUPPORTED, "%s: needs < 2^30 cells", what);
+    // (row + 32 must not wrap in the emitter's 32-bit row arithmetic)
+    if (N < 0 || N > (1ll << 32) - (1ll << 16))
+        return fail(LINT_ERR_BAD_ARG, "%s: N must be in [0, 2^32 - 2^16]", what);
+    if (ncells >= (1ull << 29)) return fail(LINT_ERR_UNSUPPORTED, "%s: needs < 2^29 cells", what);
     if (N > 0 && !out) return fail(LINT_ERR_BAD_ARG, "%s: out_dev is NULL", what);
     if (!scratch || scratch_bytes < carve(nullptr, ncells, (uint64_t)N).bytes)
         return fail(LINT_ERR_BAD_ARG, "%s: scratch too small", what);
@@ -620,14 +753,16 @@ static int check_common(int64_t N, uint64_t ncells, double u_lo, double u_hi, vo
 }
 
 template <int K>
-int grid_cellmajor_k(const lint_grid_t *g, uint64_t nc, uint64_t N, uint2 key, uint64_t offset,
+int grid_cellmajor_k(const lint_grid_t *g, uint64_t nc, uint64_t N, uint2 key, uint64_t offset, Stratum u,
                      const Scratch &s, void *out, int64_t *cell_idx, cudaStream_t st) {
     if (g->dtype == LINT_F32) {
         GridCells<K, float> src{make_grid_view<K>(g, nc, true)};
-        return launch_emit<K, float>(src, s, N, key, offset, out, cell_idx, st);
+        if (int rc = plan_rows(src, g->cdf_dev, nc, N, key, offset, u, s, st)) return rc;
+        return launch_emit<K, float>(src, s, nc, N, key, offset, out, cell_idx, st);
     }
     GridCells<K, double> src{make_grid_view<K>(g, nc, true)};
-    return launch_emit<K, double>(src, s, N, key, offset, out, cell_idx, st);
+    if (int rc = plan_rows(src, g->cdf_dev, nc, N, key, offset, u, s, st)) return rc;
+    return launch_emit<K, double>(src, s, nc, N, key, offset, out, cell_idx, st);
 }
 
 // defined in lint_sample.cu: u-driven rows [*first_row_dev, N), at most max_rows of them
@@ -639,8 +774,8 @@ int topup_cells(const lint_cells_t *c, int64_t N, const uint32_t *first_row_dev,
                 cudaStream_t st);
 
 template <int K>
-int cells_cellmajor_k(const lint_cells_t *c, uint64_t N, uint2 key, uint64_t offset, const Scratch &s,
-                      void *out, int64_t *cell_idx, cudaStream_t st) {
+int cells_cellmajor_k(const lint_cells_t *c, uint64_t N, uint2 key, uint64_t offset, Stratum u,
+                      const Scratch &s, void *out, int64_t *cell_idx, cudaStream_t st) {
     CellsView v;
     v.mins = c->mins_dev;
     v.widths = c->widths_dev;
@@ -650,12 +785,15 @@ int cells_cellmajor_k(const lint_cells_t *c, uint64_t N, uint2 key, uint64_t off
     v.table.guide = nullptr;
     v.table.guide_bits = 0;
     v.table.n = (uint32_t)c->ncells;
+    const uint64_t nc = (uint64_t)c->ncells;
     if (c->dtype == LINT_F32) {
         ListCells<K, float> src{v};
-        return launch_emit<K, float>(src, s, N, key, offset, out, cell_idx, st);
+        if (int rc = plan_rows(src, c->cdf_dev, nc, N, key, offset, u, s, st)) return rc;
+        return launch_emit<K, float>(src, s, nc, N, key, offset, out, cell_idx, st);
     }
     ListCells<K, double> src{v};
-    return launch_emit<K, double>(src, s, N, key, offset, out, cell_idx, st);
+    if (int rc = plan_rows(src, c->cdf_dev, nc, N, key, offset, u, s, st)) return rc;
+    return launch_emit<K, double>(src, s, nc, N, key, offset, out, cell_idx, st);
 }
 
 }  // namespace lint
@@ -679,15 +817,15 @@ int lint_grid_sample_cellmajor(const lint_grid_t *g, int64_t N, uint64_t seed, u
     cudaStream_t st = (cudaStream_t)stream;
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     const Scratch s = carve(scratch_dev, nc, (uint64_t)N);
-    if (int rc = plan_rows(g->cdf_dev, nc, (uint64_t)N, key, offset, u_lo, u_hi, s, st)) return rc;
+    const Stratum u{u_lo, u_hi};
     int rc;
     switch (g->dim) {
-        case 1: rc = grid_cellmajor_k<1>(g, nc, N, key, offset, s, out_dev, cell_idx_dev, st); break;
-        case 2: rc = grid_cellmajor_k<2>(g, nc, N, key, offset, s, out_dev, cell_idx_dev, st); break;
-        case 3: rc = grid_cellmajor_k<3>(g, nc, N, key, offset, s, out_dev, cell_idx_dev, st); break;
-        case 4: rc = grid_cellmajor_k<4>(g, nc, N, key, offset, s, out_dev, cell_idx_dev, st); break;
-        case 5: rc = grid_cellmajor_k<5>(g, nc, N, key, offset, s, out_dev, cell_idx_dev, st); break;
-        default: rc = grid_cellmajor_k<6>(g, nc, N, key, offset, s, out_dev, cell_idx_dev, st); break;
+        case 1: rc = grid_cellmajor_k<1>(g, nc, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
+        case 2: rc = grid_cellmajor_k<2>(g, nc, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
+        case 3: rc = grid_cellmajor_k<3>(g, nc, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
+        case 4: rc = grid_cellmajor_k<4>(g, nc, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
+        case 5: rc = grid_cellmajor_k<5>(g, nc, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
+        default: rc = grid_cellmajor_k<6>(g, nc, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
     }
     if (rc) return rc;
     // rows [T, N): the u-driven sampler on the same stratum
@@ -707,15 +845,15 @@ int lint_cells_sample_cellmajor(const lint_cells_t *c, int64_t N, uint64_t seed,
     cudaStream_t st = (cudaStream_t)stream;
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     const Scratch s = carve(scratch_dev, nc, (uint64_t)N);
-    if (int rc = plan_rows(c->cdf_dev, nc, (uint64_t)N, key, offset, u_lo, u_hi, s, st)) return rc;
+    const Stratum u{u_lo, u_hi};
     int rc;
     switch (c->dim) {
-        case 1: rc = cells_cellmajor_k<1>(c, N, key, offset, s, out_dev, cell_idx_dev, st); break;
-        case 2: rc = cells_cellmajor_k<2>(c, N, key, offset, s, out_dev, cell_idx_dev, st); break;
-        case 3: rc = cells_cellmajor_k<3>(c, N, key, offset, s, out_dev, cell_idx_dev, st); break;
-        case 4: rc = cells_cellmajor_k<4>(c, N, key, offset, s, out_dev, cell_idx_dev, st); break;
-        case 5: rc = cells_cellmajor_k<5>(c, N, key, offset, s, out_dev, cell_idx_dev, st); break;
-        default: rc = cells_cellmajor_k<6>(c, N, key, offset, s, out_dev, cell_idx_dev, st); break;
+        case 1: rc = cells_cellmajor_k<1>(c, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
+        case 2: rc = cells_cellmajor_k<2>(c, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
+        case 3: rc = cells_cellmajor_k<3>(c, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
+        case 4: rc = cells_cellmajor_k<4>(c, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
+        case 5: rc = cells_cellmajor_k<5>(c, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
+        default: rc = cells_cellmajor_k<6>(c, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
     }
     if (rc) return rc;
     return topup_cells(c, N, s.rows, (int64_t)topup_bound((uint64_t)N), seed, offset, u_lo, u_hi, out_dev,

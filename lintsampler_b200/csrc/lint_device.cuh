@@ -132,6 +132,15 @@ __device__ __forceinline__ double quantile_exact(double f0, double f1, double u)
     return __ddiv_rn(__dadd_rn(-f0, __dsqrt_rn(rad)), __dsub_rn(f1, f0));
 }
 
+// fp64, cancellation-free: the conjugate form of the same root.  Used where rows are not
+// tied to a reference uniform stream (the cell-major emitter); the literal form collapses
+// z onto 0 when f0 and f1 differ by rounding noise only.
+__device__ __forceinline__ double quantile_conjugate(double f0, double f1, double u) {
+    const double a2 = f0 * f0;
+    const double den = f0 + sqrt(a2 + (f1 * f1 - a2) * u);
+    return den > 0.0 ? (f0 + f1) * u / den : u;
+}
+
 // fp32: algebraically equal conjugate form (no cancellation when f0 ~ f1,
 // SURVEY.md §7.3-3); inputs are pre-normalised so the squares cannot underflow.
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -161,7 +170,7 @@ __device__ __forceinline__ float quantile_fast(float f0, float f1, float u) {
 // ---------------------------------------------------------------------------
 // fp64 parity version: operation order identical to the oracle's
 // unit_cube_sample (= the order NumPy executes for the reference).
-template <int K>
+template <int K, bool LITERAL = true>
 __device__ __forceinline__ void incell_exact(const double (&c)[1 << K], const double (&u)[K],
                                              double (&z)[K]) {
 #pragma unroll
@@ -188,7 +197,7 @@ __device__ __forceinline__ void incell_exact(const double (&c)[1 << K], const do
             }
             g[b] = total;
         }
-        z[d] = quantile_exact(g[0], g[1], u[d]);
+        z[d] = LITERAL ? quantile_exact(g[0], g[1], u[d]) : quantile_conjugate(g[0], g[1], u[d]);
     }
 }
 
@@ -270,7 +279,8 @@ struct CellFast {
     }
 };
 
-// fp64: no hoisting — the reference's operation order is kept literally
+// fp64: no hoisting — the reference's order of the marginal sums, with the
+// cancellation-free quantile
 template <int K>
 struct CellExact {
     double c[1 << K];
@@ -282,7 +292,7 @@ struct CellExact {
         for (int j = 0; j < (1 << K); ++j) c[j] = corners[j];
     }
     __device__ __forceinline__ void draw(const double (&u)[K], double (&z)[K]) const {
-        incell_exact<K>(c, u, z);
+        incell_exact<K, false>(c, u, z);
     }
 };
 
@@ -322,6 +332,10 @@ __device__ __forceinline__ void grid_unravel(const GridView<K> &g, uint32_t flat
     i[0] = r;
 }
 
+template <int K, typename DensT, typename T>
+__device__ __forceinline__ void grid_corners(const GridView<K> &g, uint32_t flat, const uint32_t (&i)[K],
+                                             T (&c)[1 << K]);
+
 // Cell box + 2^K corner densities of cell `flat`.  `sedges` is the CTA's
 // shared-memory copy of the edge arrays in arithmetic type T (or unused when
 // g.edge_total == 0).
@@ -343,7 +357,14 @@ __device__ __forceinline__ void grid_fetch(const GridView<K> &g, const T *sedges
             hi[d] = (T)__ldg(g.edges[d] + i[d] + 1);
         }
     }
-    // 2^K corner densities, corner order = MSB-first bit pattern [grid.py:440-467]
+    grid_corners<K, DensT, T>(g, flat, i, c);
+}
+
+// 2^K corner densities of cell `flat` (= multi-index i), corner order = MSB-first bit
+// pattern [grid.py:440-467]
+template <int K, typename DensT, typename T>
+__device__ __forceinline__ void grid_corners(const GridView<K> &g, uint32_t flat, const uint32_t (&i)[K],
+                                             T (&c)[1 << K]) {
     if (g.rec) {
         // one contiguous record per cell: a single 32 B sector for K=3 fp32
         constexpr int NB = (1 << K) * (int)sizeof(DensT);
@@ -402,6 +423,15 @@ template <int K, typename DensT>
 __host__ __device__ constexpr int cells_record_stride() {
     constexpr int per32 = 32 / (int)sizeof(DensT);
     return (((1 << K) + 2 * K + per32 - 1) / per32) * per32;
+}
+
+// corner densities only
+template <int K, typename DensT, typename T>
+__device__ __forceinline__ void cells_corners(const CellsView &s, uint32_t idx, T (&c)[1 << K]) {
+    const DensT *C = s.rec ? reinterpret_cast<const DensT *>(s.rec) + (size_t)idx * cells_record_stride<K, DensT>()
+                           : reinterpret_cast<const DensT *>(s.corners) + (size_t)idx * (1 << K);
+#pragma unroll
+    for (int j = 0; j < (1 << K); ++j) c[j] = (T)__ldg(C + j);
 }
 
 template <int K, typename DensT, typename T>
@@ -565,6 +595,11 @@ __device__ __forceinline__ double affine(double lo, double hi, double z) {
 __device__ __forceinline__ float affine(float lo, float hi, float z) {
     return fmaf(hi - lo, z, lo);
 }
+// the same with the width w = hi - lo formed once per cell
+__device__ __forceinline__ double affine_w(double lo, double w, double z) {
+    return __dadd_rn(lo, __dmul_rn(w, z));
+}
+__device__ __forceinline__ float affine_w(float lo, float w, float z) { return fmaf(w, z, lo); }
 
 // streaming (evict-first) stores for the sample rows: 12 GB of output must not
 // evict the guide table and cell records from L2
