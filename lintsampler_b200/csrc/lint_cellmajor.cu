@@ -125,52 +125,44 @@ struct CdfSlice {
     double u_lo, u_hi;
 };
 
-// Below this mean a cell draws one count and thins it row by row (no corner gather for
-// the many cells that stay empty); above it, two independent Poisson draws.
-constexpr double SPLIT_BY_THINNING_BELOW = 4.0;
+// Expected number of grouped rows of cell c — evaluated identically by the count pass and
+// by the emitter (same operations on the same table).
+__device__ __forceinline__ double cell_lambda(const CdfSlice &t, uint32_t c, double lam_per_unit) {
+    // mass of the cell inside the stratum: clamp both CDF values, then difference
+    const double f0 = c == 0 ? 0.0 : __ldg(t.cdf + c - 1), f1 = __ldg(t.cdf + c);
+    const double m = fmin(fmax(f1, t.u_lo), t.u_hi) - fmin(fmax(f0, t.u_lo), t.u_hi);
+    return __dmul_rn(m, lam_per_unit);
+}
 
+// A cell is split into its flat and residual parts only where that pays: below this
+// many expected rows the residual part would be a handful of rows with a segment of
+// their own, dearer than drawing all of the cell's rows from the full interpolant.
+constexpr double SPLIT_MIN_LAMBDA = 64.0;
+
+// counts[c] (no split), or counts[2c] = flat rows, counts[2c + 1] = residual rows — or all
+// rows of a cell that is not split
 template <typename Cells>
 __global__ void __launch_bounds__(256)
 poisson_counts_kernel(Cells src, CdfSlice t, double lam_per_unit, uint2 key, uint64_t offset, bool split,
                       uint32_t *counts) {
     const uint32_t w2 = (uint32_t)offset, w3 = (uint32_t)(offset >> 32);
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < t.ncells; c += gridDim.x * blockDim.x) {
-        // mass of the cell inside the stratum: clamp both CDF values, then difference
-        const double f0 = c == 0 ? 0.0 : __ldg(t.cdf + c - 1), f1 = __ldg(t.cdf + c);
-        const double m = fmin(fmax(f1, t.u_lo), t.u_hi) - fmin(fmax(f0, t.u_lo), t.u_hi);
-        const double lam = m * lam_per_unit;
-        if (!split) {                                    // one count per cell
+        const double lam = cell_lambda(t, c, lam_per_unit);
+        if (!split) {
             CellRng rng{key, c, w2, w3};
             counts[c] = poisson(lam, rng);
             continue;
         }
-        uint32_t n[2] = {0, 0};                          // flat, residual
-        if (lam > 0.0) {
-            const bool thin = lam < SPLIT_BY_THINNING_BELOW;
-            double q = 0.0, mean[2] = {lam, 0.0};
-            if (!thin) {
-                q = src.flat_fraction(c);
-                mean[0] = lam * q;
-                mean[1] = lam - mean[0];
-            }
+        double mean[2] = {0.0, lam};
+        if (lam >= SPLIT_MIN_LAMBDA) {
+            mean[0] = lam * src.flat_fraction(c);
+            mean[1] = lam - mean[0];
+        }
+        uint32_t n[2];
 #pragma unroll 1
-            for (int part = 0; part < 2; ++part) {       // one copy of the sampler's code
-                CellRng rng{key, 2 * c + part, w2, w3};
-                n[part] = poisson(mean[part], rng);
-            }
-            if (thin && n[0]) {                          // thin the few rows one by one
-                q = src.flat_fraction(c);
-                CellRng coin{key, 2 * c + 1, w2, w3};
-                const uint32_t total = n[0];
-                n[0] = 0;
-                for (uint32_t i = 0; i < total; i += 2) {
-                    double a, b;
-                    coin.next(a, b);
-                    n[0] += a < q;
-                    if (i + 1 < total) n[0] += b < q;
-                }
-                n[1] = total - n[0];
-            }
+        for (int part = 0; part < 2; ++part) {           // one copy of the sampler's code
+            CellRng rng{key, 2 * c + part, w2, w3};
+            n[part] = poisson(mean[part], rng);
         }
         reinterpret_cast<uint2 *>(counts)[c] = make_uint2(n[0], n[1]);
     }
@@ -448,7 +440,8 @@ __global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 && K <= 3 ? LINT_
 emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
             const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ rows_p,
             const uint32_t *__restrict__ chunk_start, uint32_t n_requested, uint2 key, uint64_t offset,
-            uint32_t split, T *__restrict__ out, int64_t *__restrict__ cell_idx) {
+            uint32_t split, CdfSlice table, double lam_per_unit, T *__restrict__ out,
+            int64_t *__restrict__ cell_idx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sedges = reinterpret_cast<T *>(smem_raw);
     __shared__ uint32_t s_off_all[EMIT_THREADS / 32][2][EMIT_WIN];
@@ -520,8 +513,10 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
 #pragma unroll
             for (int d = 0; d < K; ++d) w[d] = hi[d] - lo[d];              // maxs - mins, sampling.py:126
             if (!is_flat(v)) {
-                if (split) subtract_min(c0);
-                cf.set(c0, !split && src.prenormalised());
+                // the residual of a split cell, or the whole of a cell that is not split
+                const bool residual = split && cell_lambda(table, v >> 1, lam_per_unit) >= SPLIT_MIN_LAMBDA;
+                if (residual) subtract_min(c0);
+                cf.set(c0, !residual && src.prenormalised());
             } else {
 #pragma unroll
                 for (int d = 0; d < K; ++d) w[d] *= raw_scale<T>();
@@ -592,9 +587,22 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
                 }
                 auto rows = [&](auto tag) {
                     constexpr bool FLAT = decltype(tag)::value;
-                    // blocks of 32 * EMIT_U rows; a last partial block of more than half that
-                    // is still cheaper here (rows past the end masked) than one warp-row at a time
-                    while (seg_end - row > 16u * EMIT_U) {
+                    // blocks of 32 * EMIT_U rows
+                    while (seg_end - row >= 32u * EMIT_U) {
+                        const uint32_t first = row + lane;
+                        GroupUniforms<K, T, EMIT_U> rnd;
+                        rnd.fill(key, first, 0, offset);
+#pragma unroll
+                        for (int t = 0; t < EMIT_U; ++t) {
+                            T u[K];
+                            rnd.template get_as<FLAT>(t, u);
+                            emit_row<K, T, CELLS, FLAT>(coef, xlo, xw, u, first + 32u * t, cell, out, cell_idx);
+                        }
+                        row += 32u * EMIT_U;
+                    }
+                    // a last partial block of more than half that is still cheaper in this form
+                    // (rows past the end masked) than one warp-row at a time
+                    if (seg_end - row > 16u * EMIT_U) {
                         const uint32_t first = row + lane;
                         GroupUniforms<K, T, EMIT_U> rnd;
                         rnd.fill(key, first, 0, offset);
@@ -605,7 +613,7 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
                             if (first + 32u * t < seg_end)
                                 emit_row<K, T, CELLS, FLAT>(coef, xlo, xw, u, first + 32u * t, cell, out, cell_idx);
                         }
-                        row = min(row + 32u * EMIT_U, seg_end);
+                        row = seg_end;
                     }
                     // the rest of the segment, however short: its constants are in registers
                     // already, which makes idle lanes cheaper than the per-lane path
@@ -724,17 +732,19 @@ static int plan_rows(const Cells &src, const double *cdf, uint64_t ncells, uint6
 }
 
 template <int K, typename T, typename Cells>
-int launch_emit(const Cells &src, const Scratch &s, uint64_t ncells, uint64_t N, uint2 key, uint64_t offset,
-                void *out, int64_t *cell_idx, cudaStream_t st) {
+int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t ncells, uint64_t N, uint2 key,
+                uint64_t offset, Stratum u, void *out, int64_t *cell_idx, cudaStream_t st) {
     const uint32_t split = use_split(ncells, N) ? 1u : 0u;
+    const CdfSlice t{cdf, (uint32_t)ncells, u.u_lo, u.u_hi};
+    const double lam_per_unit = grouped_mean(N) / (u.u_hi - u.u_lo);
     const uint32_t nchunks = (uint32_t)((N + EMIT_CHUNK - 1) / EMIT_CHUNK);
     const int blocks = (int)std::min<uint32_t>((nchunks + EMIT_THREADS / 32 - 1) / (EMIT_THREADS / 32), 148 * 8);
     if (cell_idx)
         emit_kernel<K, T, Cells, true><<<blocks, EMIT_THREADS, src.smem_bytes(sizeof(T)), st>>>(
-            src, s.cid, s.coff, s.nnz, s.rows, s.chunk_start, (uint32_t)N, key, offset, split, (T *)out, cell_idx);
+            src, s.cid, s.coff, s.nnz, s.rows, s.chunk_start, (uint32_t)N, key, offset, split, t, lam_per_unit, (T *)out, cell_idx);
     else
         emit_kernel<K, T, Cells, false><<<blocks, EMIT_THREADS, src.smem_bytes(sizeof(T)), st>>>(
-            src, s.cid, s.coff, s.nnz, s.rows, s.chunk_start, (uint32_t)N, key, offset, split, (T *)out, cell_idx);
+            src, s.cid, s.coff, s.nnz, s.rows, s.chunk_start, (uint32_t)N, key, offset, split, t, lam_per_unit, (T *)out, cell_idx);
     return check_launch("cell-major emission");
 }
 
@@ -758,11 +768,11 @@ int grid_cellmajor_k(const lint_grid_t *g, uint64_t nc, uint64_t N, uint2 key, u
     if (g->dtype == LINT_F32) {
         GridCells<K, float> src{make_grid_view<K>(g, nc, true)};
         if (int rc = plan_rows(src, g->cdf_dev, nc, N, key, offset, u, s, st)) return rc;
-        return launch_emit<K, float>(src, s, nc, N, key, offset, out, cell_idx, st);
+        return launch_emit<K, float>(src, g->cdf_dev, s, nc, N, key, offset, u, out, cell_idx, st);
     }
     GridCells<K, double> src{make_grid_view<K>(g, nc, true)};
     if (int rc = plan_rows(src, g->cdf_dev, nc, N, key, offset, u, s, st)) return rc;
-    return launch_emit<K, double>(src, s, nc, N, key, offset, out, cell_idx, st);
+    return launch_emit<K, double>(src, g->cdf_dev, s, nc, N, key, offset, u, out, cell_idx, st);
 }
 
 // defined in lint_sample.cu: u-driven rows [*first_row_dev, N), at most max_rows of them
@@ -789,11 +799,11 @@ int cells_cellmajor_k(const lint_cells_t *c, uint64_t N, uint2 key, uint64_t off
     if (c->dtype == LINT_F32) {
         ListCells<K, float> src{v};
         if (int rc = plan_rows(src, c->cdf_dev, nc, N, key, offset, u, s, st)) return rc;
-        return launch_emit<K, float>(src, s, nc, N, key, offset, out, cell_idx, st);
+        return launch_emit<K, float>(src, c->cdf_dev, s, nc, N, key, offset, u, out, cell_idx, st);
     }
     ListCells<K, double> src{v};
     if (int rc = plan_rows(src, c->cdf_dev, nc, N, key, offset, u, s, st)) return rc;
-    return launch_emit<K, double>(src, s, nc, N, key, offset, out, cell_idx, st);
+    return launch_emit<K, double>(src, c->cdf_dev, s, nc, N, key, offset, u, out, cell_idx, st);
 }
 
 }  // namespace lint

@@ -121,11 +121,21 @@ def c5():
 
 
 if __name__ == "__main__":
-    c1()
-    grid_case("C2 2-D 1024^2 full-cov GMM, N=1e8 fp32", tuple(np.linspace(-4, 4, 1025) for _ in range(2)),
-              gmm(2, 4, 0, 0, full=True), 100_000_000)
-    grid_case("C4 5-D 32^5 GMM, N=2^27 fp32", tuple(np.linspace(-4, 4, 33) for _ in range(5)),
-              gmm(5, 4, 0.5, 0.9), 1 << 27, qmc=True)
-    grid_case("C4' 5-D 32^5 GMM (pseudo-random), N=1e8 fp32", tuple(np.linspace(-4, 4, 33) for _ in range(5)),
-              gmm(5, 4, 0.5, 0.9), 100_000_000)
-    c5()
+    only = set(sys.argv[1:])            # e.g. `bench_configs.py c4p c5`; default: all
+
+    def want(tag):
+        return not only or tag in only
+
+    if want("c1"):
+        c1()
+    if want("c2"):
+        grid_case("C2 2-D 1024^2 full-cov GMM, N=1e8 fp32", tuple(np.linspace(-4, 4, 1025) for _ in range(2)),
+                  gmm(2, 4, 0, 0, full=True), 100_000_000)
+    if want("c4"):
+        grid_case("C4 5-D 32^5 GMM, N=2^27 fp32", tuple(np.linspace(-4, 4, 33) for _ in range(5)),
+                  gmm(5, 4, 0.5, 0.9), 1 << 27, qmc=True)
+    if want("c4p"):
+        grid_case("C4' 5-D 32^5 GMM (pseudo-random), N=1e8 fp32", tuple(np.linspace(-4, 4, 33) for _ in range(5)),
+                  gmm(5, 4, 0.5, 0.9), 100_000_000)
+    if want("c5"):
+        c5()
