@@ -311,9 +311,9 @@ def run_b200(args):
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
                 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch at
                 # N=1e9, from the ncu --set full captures summarised in profiles/README.md
-                "traffic": ((12.04e9 if args.order == "cell" else 59.7e9) * n_local / 1e9
+                "traffic": ((12.16e9 if args.order == "cell" else 59.7e9) * n_local / 1e9
                             if GRID_N == 256 else None),
-                "traffic_source": ("profiles/r1k_emit_kernel_metrics.txt" if args.order == "cell"
+                "traffic_source": ("profiles/r1o_emit_kernel_metrics.txt" if args.order == "cell"
                                    else "profiles/r1b_sample_kernel_metrics.txt"),
                 "ms_per_launch": ms_sample,
                 "step_frac_of_hbm_roofline": (b_mass + b_scan + b_sample) / (ms_step * 1e-3) / 1e9 / peak,

@@ -20,15 +20,18 @@
 // Flat/residual split.  Inside a cell the interpolant is f = f_min + (f - f_min): a
 // constant plus a multilinear density that vanishes at one corner.  Rows of the
 // constant part are plain uniforms (z = u, no inverse CDF at all); only rows of the
-// residual need sampling.py:41-94.  Every cell therefore becomes two "virtual cells"
-// 2c (flat) and 2c + 1 (residual) with independent Poisson counts of means
-// lambda q and lambda (1 - q), q = f_min / mean(corners) — Poisson thinning, exact.
-// On a fine grid of a smooth pdf q is close to 1 (0.94 mass-weighted on the 256^3
-// benchmark grid), so most rows cost their uniforms, an fma and a store.  The split
-// doubles the segment table and adds a corner gather to the count pass, which only
-// pays with enough rows per cell: it is used when N >= SPLIT_MIN_ROWS_PER_CELL * cells.
-// Row ORDER is by cell (C order) for the first T rows, draw order for the
-// top-up tail.  Callers that need the reference's exchangeable row order
+// residual need sampling.py:41-94.  A split cell c becomes two segments, 2c (flat)
+// and 2c + 1 (residual), with independent Poisson counts of means lambda q and
+// lambda (1 - q), q = f_min / mean(corners) — Poisson thinning, exact.  On a fine
+// grid of a smooth pdf q is close to 1 (0.94 mass-weighted on the 256^3 benchmark
+// grid), so most rows cost their uniforms, an fma and a store.  The split doubles
+// the segment table and adds a corner gather to the count pass, so it is used only
+// when N >= SPLIT_MIN_ROWS_PER_CELL * cells, and within such a draw only for cells
+// expecting >= SPLIT_MIN_LAMBDA rows (the others keep all rows in segment 2c + 1,
+// drawn from the full interpolant; the emitter re-derives the decision from the
+// same CDF entries).
+// Row ORDER is by cell (C order; a split cell's flat rows, then its residual rows)
+// for the first T rows, draw order for the top-up tail.  Callers that need the reference's exchangeable row order
 // (lintsampler.py:309-311) apply the row permutation afterwards.
 #include <algorithm>
 #include <cmath>
@@ -137,7 +140,10 @@ __device__ __forceinline__ double cell_lambda(const CdfSlice &t, uint32_t c, dou
 // A cell is split into its flat and residual parts only where that pays: below this
 // many expected rows the residual part would be a handful of rows with a segment of
 // their own, dearer than drawing all of the cell's rows from the full interpolant.
-constexpr double SPLIT_MIN_LAMBDA = 64.0;
+#ifndef LINT_SPLIT_MIN_LAMBDA
+#define LINT_SPLIT_MIN_LAMBDA 128.0
+#endif
+constexpr double SPLIT_MIN_LAMBDA = LINT_SPLIT_MIN_LAMBDA;
 
 // counts[c] (no split), or counts[2c] = flat rows, counts[2c + 1] = residual rows — or all
 // rows of a cell that is not split
@@ -436,7 +442,7 @@ constexpr uint32_t EMIT_PRE = 32;            // segments per staged block (= lan
 constexpr uint32_t EMIT_PRE_NONE = 0x80000000u;
 
 template <int K, typename T, typename Cells, bool CELLS>
-__global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 && K <= 3 ? LINT_EMIT_MINB : 1)
+__global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 ? (K <= 3 ? LINT_EMIT_MINB : 2) : 1)
 emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
             const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ rows_p,
             const uint32_t *__restrict__ chunk_start, uint32_t n_requested, uint2 key, uint64_t offset,

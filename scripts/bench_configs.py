@@ -69,15 +69,17 @@ def c1():
                           N=10000, ms=dt * 1e3, samples_per_s=10000 / dt, mean=float(x.mean()))), flush=True)
 
 
-def grid_case(name, edges, pdf, N, qmc=False):
+def grid_case(name, edges, pdf, N, qmc=False, dtype=np.float32):
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    isz = 4 if dtype == np.float32 else 8
     for order in (("draw",) if qmc else ("cell", "draw")):
         kw = dict(cell_records=False, guide_bits=16) if order == "cell" else {}
         t0 = time.perf_counter()
-        grid = lb.DensityGrid(edges, pdf, vectorizedpdf=True, dtype=np.float32, **kw)
+        grid = lb.DensityGrid(edges, pdf, vectorizedpdf=True, dtype=dtype, **kw)
         torch.cuda.synchronize()
         t_build = time.perf_counter() - t0
         k = grid.dim
-        out = torch.empty((N, k), dtype=torch.float32, device="cuda")
+        out = torch.empty((N, k), dtype=tdt, device="cuda")
         ms_build = timed(grid._enqueue_build)
         if qmc:
             with warnings.catch_warnings():
@@ -94,7 +96,7 @@ def grid_case(name, edges, pdf, N, qmc=False):
             ms = timed(lambda: grid._sample_cellmajor(N, 1, 0, out=out))
         else:
             ms = timed(lambda: grid._sample_philox(N, 1, 0, out=out))
-        report(f"{name} [{'sobol, sorted enumeration + device shuffle' if qmc else 'order=' + order}]", N, k, 4, ms,
+        report(f"{name} [{'sobol, sorted enumeration + device shuffle' if qmc else 'order=' + order}]", N, k, isz, ms,
                ms_build_kernels=ms_build, first_construct_s=t_build, cells=int(grid.ncells))
         del grid, out
         torch.cuda.empty_cache()
@@ -131,6 +133,14 @@ if __name__ == "__main__":
     if want("c2"):
         grid_case("C2 2-D 1024^2 full-cov GMM, N=1e8 fp32", tuple(np.linspace(-4, 4, 1025) for _ in range(2)),
                   gmm(2, 4, 0, 0, full=True), 100_000_000)
+    if want("c3d"):
+        # the headline grid (bench.py's generator) with fp64 densities and samples
+        rng = np.random.default_rng(0)
+        means = rng.uniform(-2, 2, size=(4, 3))
+        sig = rng.uniform(0.3, 0.8, size=4)
+        w = rng.dirichlet(np.ones(4))
+        grid_case("C3 3-D 256^3 isotropic GMM, N=1e9 fp64", tuple(np.linspace(-4, 4, 257) for _ in range(3)),
+                  lb.GaussianMixture(w, means, sigmas=sig), 1_000_000_000, dtype=np.float64)
     if want("c4"):
         grid_case("C4 5-D 32^5 GMM, N=2^27 fp32", tuple(np.linspace(-4, 4, 33) for _ in range(5)),
                   gmm(5, 4, 0.5, 0.9), 1 << 27, qmc=True)
