@@ -129,6 +129,22 @@ typedef struct lint_gmm {
 } lint_gmm_t;
 #define LINT_GMM_MAX_COMP 16
 
+/* Sum of spherical double-power-law profiles (the NFW family of the reference's
+ * docs/source/example_notebooks/3_dark_matter.ipynb, cells 11 and 16), HOST arrays:
+ *   rho(x) = sum_h rho0[h] / ((q + eps)^gamma * (1 + q^alpha)^((beta - gamma)/alpha)),
+ *   q = |x - centre[h]| / r_s[h];   a halo contributes 0 where q > q_cut (q_cut <= 0: never).
+ * NFW as in the notebook: alpha 1, beta 3, gamma 1, eps 0.1, q_cut 10. */
+typedef struct lint_halos {
+    int32_t dim;
+    int32_t ncomp;                        /* 1..LINT_GMM_MAX_COMP                        */
+    const double *rho0;                   /* [ncomp]                                     */
+    const double *centre;                 /* [ncomp * dim]                               */
+    const double *r_s;                    /* [ncomp], > 0                                */
+    double alpha, beta, gamma;
+    double eps;
+    double q_cut;
+} lint_halos_t;
+
 /* ---- library ---------------------------------------------------------------- */
 int lint_abi_version(void);
 const char *lint_last_error(void);
@@ -141,6 +157,9 @@ const char *lint_last_error(void);
  * (cast away const) in g->dtype; densities are multiplied by `scale` first. */
 int lint_grid_eval_gmm(const lint_grid_t *g, const lint_gmm_t *gmm, double scale,
                        lint_stream_t stream);
+/* The same for a sum of double-power-law halos (3_dark_matter.ipynb cells 11, 16). */
+int lint_grid_eval_halos(const lint_grid_t *g, const lint_halos_t *halos, double scale,
+                         lint_stream_t stream);
 
 /* Trapezoid cell masses: mean of the 2^k corner densities (summed in corner
  * order from zero, one division by 2^k) times the cell volume ((w0*w1)*w2...)

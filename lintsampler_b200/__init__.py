@@ -9,8 +9,9 @@ streams.  There is no CPU fallback.
 from .base import DensityStructure
 from .grid import DensityGrid
 from .tree import DensityTree
-from .pdfs import GaussianMixture
+from .pdfs import DoublePowerLaw, GaussianMixture
 from .sampler import LintSampler
 
 __version__ = "0.1.0"
-__all__ = ["LintSampler", "DensityGrid", "DensityTree", "DensityStructure", "GaussianMixture"]
+__all__ = ["LintSampler", "DensityGrid", "DensityTree", "DensityStructure", "GaussianMixture",
+           "DoublePowerLaw"]

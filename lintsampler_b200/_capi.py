@@ -53,6 +53,17 @@ class LintSobol(C.Structure):
     ]
 
 
+class LintHalos(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32), ("ncomp", C.c_int32),
+        ("rho0", C.POINTER(C.c_double)),
+        ("centre", C.POINTER(C.c_double)),
+        ("r_s", C.POINTER(C.c_double)),
+        ("alpha", C.c_double), ("beta", C.c_double), ("gamma", C.c_double),
+        ("eps", C.c_double), ("q_cut", C.c_double),
+    ]
+
+
 class LintGmm(C.Structure):
     _fields_ = [
         ("dim", C.c_int32), ("ncomp", C.c_int32),
@@ -71,6 +82,7 @@ PROTOTYPES = {
     "lint_abi_version": (C.c_int, []),
     "lint_last_error": (C.c_char_p, []),
     "lint_grid_eval_gmm": (C.c_int, [C.POINTER(LintGrid), C.POINTER(LintGmm), C.c_double, _P]),
+    "lint_grid_eval_halos": (C.c_int, [C.POINTER(LintGrid), C.POINTER(LintHalos), C.c_double, _P]),
     "lint_grid_masses": (C.c_int, [C.POINTER(LintGrid), _P, _P, _P]),
     "lint_grid_records": (C.c_int, [C.POINTER(LintGrid), _P, _P]),
     "lint_cells_record_bytes": (C.c_size_t, [C.c_int, C.c_int]),

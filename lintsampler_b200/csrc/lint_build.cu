@@ -179,6 +179,73 @@ int eval_gmm_impl(const lint_grid_t *g, const lint_gmm_t *gmm, double scale, uin
 }
 
 // ---------------------------------------------------------------------------
+// fused double-power-law halo evaluation   [3_dark_matter.ipynb cells 11, 16 through grid.py:384-398]
+// ---------------------------------------------------------------------------
+template <int K>
+struct HaloParams {
+    int ncomp;
+    double rho0[LINT_GMM_MAX_COMP], inv_rs[LINT_GMM_MAX_COMP], centre[LINT_GMM_MAX_COMP][K];
+    double alpha, outer, gamma, eps, q_cut;      // outer = (beta - gamma) / alpha
+    bool nfw;                                    // alpha 1, beta 3, gamma 1: no pow()
+};
+
+template <int K, typename DensT>
+__global__ void __launch_bounds__(256)
+halo_eval_kernel(GridView<K> g, HaloParams<K> p, double scale, uint32_t nverts, DensT *out) {
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nverts; v += gridDim.x * blockDim.x) {
+        double x[K];
+        uint32_t r = v;
+#pragma unroll
+        for (int d = K - 1; d >= 0; --d) {
+            const uint32_t nd = g.n[d] + 1;
+            uint32_t i;
+            if (d == 0) { i = r; } else { const uint32_t q = r / nd; i = r - q * nd; r = q; }
+            x[d] = __ldg(g.edges[d] + i);
+        }
+        double f = 0.0;
+        for (int j = 0; j < p.ncomp; ++j) {
+            double r2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < K; ++d) { const double y = x[d] - p.centre[j][d]; r2 = fma(y, y, r2); }
+            const double q = sqrt(r2) * p.inv_rs[j];
+            if (p.q_cut > 0.0 && q > p.q_cut) continue;
+            const double den = p.nfw ? (q + p.eps) * (1.0 + q) * (1.0 + q)
+                                     : pow(q + p.eps, p.gamma) * pow(1.0 + pow(q, p.alpha), p.outer);
+            f += p.rho0[j] / den;
+        }
+        out[v] = (DensT)(f * scale);
+    }
+}
+
+template <int K>
+int eval_halos_impl(const lint_grid_t *g, const lint_halos_t *h, double scale, uint64_t nverts,
+                    cudaStream_t st) {
+    HaloParams<K> p;
+    p.ncomp = h->ncomp;
+    for (int j = 0; j < h->ncomp; ++j) {
+        p.rho0[j] = h->rho0[j];
+        p.inv_rs[j] = 1.0 / h->r_s[j];
+        for (int d = 0; d < K; ++d) p.centre[j][d] = h->centre[j * K + d];
+    }
+    p.alpha = h->alpha;
+    p.outer = (h->beta - h->gamma) / h->alpha;
+    p.gamma = h->gamma;
+    p.eps = h->eps;
+    p.q_cut = h->q_cut;
+    p.nfw = h->alpha == 1.0 && h->beta == 3.0 && h->gamma == 1.0;
+    GridView<K> v = make_grid_view<K>(g, 1, false);
+    const int threads = 256;
+    const int blocks = (int)std::min<uint64_t>((nverts + threads - 1) / threads, 148 * 32);
+    if (g->dtype == LINT_F32)
+        halo_eval_kernel<K, float><<<blocks, threads, 0, st>>>(v, p, scale, (uint32_t)nverts,
+                                                              (float *)g->vertex_densities_dev);
+    else
+        halo_eval_kernel<K, double><<<blocks, threads, 0, st>>>(v, p, scale, (uint32_t)nverts,
+                                                               (double *)g->vertex_densities_dev);
+    return check_launch("lint_grid_eval_halos");
+}
+
+// ---------------------------------------------------------------------------
 // trapezoid cell masses + density validity check   [grid.py:469-518, 411, 401-404]
 // ---------------------------------------------------------------------------
 template <int K, typename DensT>
@@ -610,6 +677,30 @@ int lint_grid_eval_gmm(const lint_grid_t *g, const lint_gmm_t *gmm, double scale
         case 4: return eval_gmm_impl<4>(g, gmm, scale, nv, st);
         case 5: return eval_gmm_impl<5>(g, gmm, scale, nv, st);
         default: return eval_gmm_impl<6>(g, gmm, scale, nv, st);
+    }
+}
+
+int lint_grid_eval_halos(const lint_grid_t *g, const lint_halos_t *h, double scale,
+                         lint_stream_t stream) {
+    uint64_t nc, nv;
+    if (int rc = validate_grid(g, false, &nc, &nv)) return rc;
+    if (!h || h->dim != g->dim) return fail(LINT_ERR_BAD_ARG, "halo dim does not match grid dim");
+    if (h->ncomp < 1 || h->ncomp > LINT_GMM_MAX_COMP)
+        return fail(LINT_ERR_BAD_ARG, "halo ncomp %d outside 1..%d", h->ncomp, LINT_GMM_MAX_COMP);
+    if (!h->rho0 || !h->centre || !h->r_s)
+        return fail(LINT_ERR_BAD_ARG, "halo parameter arrays must not be NULL");
+    if (!(h->alpha > 0.0) || !(h->eps >= 0.0))
+        return fail(LINT_ERR_BAD_ARG, "halo profile needs alpha > 0 and eps >= 0");
+    for (int j = 0; j < h->ncomp; ++j)
+        if (!(h->r_s[j] > 0.0)) return fail(LINT_ERR_BAD_ARG, "halo scale radius %d is not positive", j);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (g->dim) {
+        case 1: return eval_halos_impl<1>(g, h, scale, nv, st);
+        case 2: return eval_halos_impl<2>(g, h, scale, nv, st);
+        case 3: return eval_halos_impl<3>(g, h, scale, nv, st);
+        case 4: return eval_halos_impl<4>(g, h, scale, nv, st);
+        case 5: return eval_halos_impl<5>(g, h, scale, nv, st);
+        default: return eval_halos_impl<6>(g, h, scale, nv, st);
     }
 }
 

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _capi, _device
 from .base import DensityStructure
-from .pdfs import GaussianMixture
+from .pdfs import FUSED_PDFS
 
 
 def _is_flat_sequence(obj):
@@ -37,7 +37,7 @@ class DensityGrid(DensityStructure):
     ----------
     edges : 1-D sequence (k = 1) or tuple of k 1-D sequences of cell edges.
     pdf : callable returning the (unnormalised) density; a
-        ``lintsampler_b200.GaussianMixture`` is evaluated by a fused kernel.
+        ``lintsampler_b200.GaussianMixture`` or ``DoublePowerLaw`` is evaluated by a fused kernel.
     vectorizedpdf, pdf_args, pdf_kwargs : as the reference.
 
     Keyword-only extensions (defaults reproduce the reference)
@@ -143,13 +143,13 @@ class DensityGrid(DensityStructure):
     def _evaluate_pdf(self, pdf, vectorizedpdf, pdf_args, pdf_kwargs, pdf_on_device):
         """Vertex evaluation [grid.py:358-404] then the device build."""
         npts = int(np.prod(self._edgeshape))
-        fused = isinstance(pdf, GaussianMixture) and not pdf_args and not pdf_kwargs
+        fused = isinstance(pdf, FUSED_PDFS) and not pdf_args and not pdf_kwargs
         if fused and pdf.dim != self._dim:
-            raise ValueError("DensityGrid: GaussianMixture dimensionality does not match the grid")
+            raise ValueError(f"DensityGrid: {type(pdf).__name__} dimensionality does not match the grid")
         densities = None
         dev_densities = None
         if fused:
-            pass                                    # evaluated by lint_grid_eval_gmm below
+            pass                                    # evaluated by its fused kernel below
         elif isinstance(pdf, _TensorDensities):
             import torch
             dev = _device.require_cuda(self._device_arg)
@@ -215,7 +215,7 @@ class DensityGrid(DensityStructure):
             elif dev_densities is not None:
                 peak = float(dev_densities.max().item())
             else:
-                peak = float(np.exp(gmm._log_norm).sum())          # upper bound of the mixture
+                peak = gmm._peak_bound(self.edgearrays)            # upper bound of a fused pdf
             if np.isfinite(peak) and peak > 0.0:
                 self._scale = float(2.0 ** -np.floor(np.log2(peak)))
         if densities is not None:
@@ -232,9 +232,7 @@ class DensityGrid(DensityStructure):
         desc = self._descriptor()
         self._gmm = gmm
         if gmm is not None:
-            gs, keep = gmm._as_struct()
-            _capi.call("lint_grid_eval_gmm", C.byref(desc), C.byref(gs), self._scale, st)
-            del keep
+            gmm._eval_on_grid(desc, self._scale, st)
         self._masses = torch.empty(ncells, dtype=torch.float64, device=dev)
         self._flags = torch.zeros(1, dtype=torch.int32, device=dev)
         self._cdf = torch.empty(ncells, dtype=torch.float64, device=dev)

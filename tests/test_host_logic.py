@@ -277,6 +277,37 @@ def test_gaussian_mixture_host_call_matches_scipy(k, full):
         lb.GaussianMixture(w, mu)
 
 
+def test_double_power_law_host_call_matches_the_notebook_nfw():
+    """DoublePowerLaw.nfw == the two-halo pdf of the reference's dark-matter example
+    (docs/source/example_notebooks/3_dark_matter.ipynb, cells 11 and 16), restated here."""
+    def nfw_density_vectorized(X, rho_0, r_s):
+        r = np.linalg.norm(X, axis=-1)
+        q = r / r_s
+        rho = rho_0 / ((q + 1e-1) * (1 + q) ** 2)
+        rho[q > 10] = 0
+        return rho
+    centres = [np.array([0.5, -2.5, 3.0]), np.array([-2.5, -2.0, -5.5])]
+    rho_0s, scale_radii = [1.0, 2.0], [0.5, 0.5]
+    X = np.random.default_rng(0).uniform(-8, 8, size=(4000, 3))
+    ref = np.sum([nfw_density_vectorized(X - centres[h], rho_0s[h], scale_radii[h]) for h in range(2)], axis=0)
+    dpl = lb.DoublePowerLaw.nfw(rho_0s, centres, scale_radii)
+    np.testing.assert_allclose(dpl(X), ref, rtol=1e-13)
+    assert (ref == 0).any() and np.array_equal(dpl(X) == 0, ref == 0)          # the q > 10 truncation
+    # general exponents (Hernquist: alpha 1, beta 4, gamma 1) and the 1-D calling convention
+    h = lb.DoublePowerLaw(2.0, [0.25], 0.5, alpha=1, beta=4, gamma=1, eps=0.01)
+    x = np.linspace(-3, 3, 41)
+    q = np.abs(x - 0.25) / 0.5
+    np.testing.assert_allclose(h(x), 2.0 / ((q + 0.01) * (1 + q) ** 3), rtol=1e-13)
+    # the bound used for the fp32 storage scale really bounds the vertex values
+    edges = (np.linspace(-6, 6, 30), np.linspace(-6, 6, 31), np.linspace(-7, 7, 32))
+    mesh = np.stack(np.meshgrid(*edges, indexing="ij"), axis=-1)
+    assert dpl(mesh).max() <= dpl._peak_bound(edges) * (1 + 1e-12)
+    with pytest.raises(ValueError):
+        lb.DoublePowerLaw([1.0, 2.0], centres, [0.5, -0.5])
+    with pytest.raises(ValueError):
+        lb.DoublePowerLaw([1.0], centres, 0.5)
+
+
 @pytest.mark.parametrize("d,m,seed", [(2, 5, 3), (4, 10, 1), (6, 12, 7)])
 def test_sobol_sorted_enumeration_construction(d, m, seed):
     """The GF(2) inverse used by the sorted Sobol mode: enumerating y = 0..2^m-1 yields
