@@ -114,8 +114,22 @@ __device__ __forceinline__ uint32_t poisson(double lam, CellRng &rng) {
         if (us >= 0.07 && v <= vr) return (uint32_t)k;            // the squeeze accepts ~86 %
         if (k < 0.0 || (us < 0.013 && v > us)) continue;
         const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
-        if (log(v * invalpha / (a / (us * us) + b)) <= -lam + k * log(lam) - log_factorial(k))
-            return (uint32_t)k;
+        const double lhs_arg = v * invalpha / (a / (us * us) + b);
+        // Acceptance test log(lhs_arg) <= -lam + k log(lam) - log(k!).  ~14 % of the draws get
+        // here, i.e. nearly every warp, so it is first decided in fp32 wherever the margin
+        // exceeds a generous bound on the fp32 error; the fp64 test below settles the rest
+        // (a few per thousand).  With k1 = k + 1, d = k1 - lam, x = d / k1 and Stirling's
+        // series the right-hand side is  k log1p(-x) + d - log(k1)/2 - log(2 pi)/2 - s(k1).
+        if (k >= 4.0 && lam < 1.0e5) {
+            const float d = (float)(k + 1.0 - lam), k1 = (float)k + 1.0f, x = d / k1;
+            const float series = (1.0f / 12.0f - (1.0f / 360.0f) / (k1 * k1)) / k1;
+            const float rhs = ((float)k * log1pf(-x) + d) - 0.5f * __logf(k1) - 0.9189385f - series;
+            const float t = __logf((float)lhs_arg) - rhs;
+            const float tol = 2e-3f + 4e-6f * fabsf(d);
+            if (t < -tol) return (uint32_t)k;
+            if (t > tol) continue;
+        }
+        if (log(lhs_arg) <= -lam + k * log(lam) - log_factorial(k)) return (uint32_t)k;
     }
 }
 
