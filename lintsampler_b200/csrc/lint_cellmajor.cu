@@ -436,17 +436,20 @@ __device__ __forceinline__ void emit_row(const CellCoefs<K, T> &coef, const T (&
 }
 
 // Every warp works on its own chunks of EMIT_CHUNK consecutive rows and walks the
-// segments (= non-empty cells) that intersect the chunk in order, through a small
-// private shared-memory window of the segment table (EMIT_WIN entries, refilled
-// as the walk advances; the next chunk's first window is prefetched with cp.async
-// while the current chunk is computed).  No CTA-wide barrier.  Lanes map to
+// segments (a non-empty cell, or the non-empty flat / residual part of a split cell)
+// that intersect the chunk in order, through a small private shared-memory window of
+// the segment table (EMIT_WIN entries, refilled as the walk advances; the next chunk's
+// first window is prefetched with cp.async while the current chunk is computed).  No
+// CTA-wide barrier.  Segments tile the rows, so the walk never searches.  Lanes map to
 // consecutive rows:
-//   * 32*EMIT_U rows inside one cell: the cell's box and corners are loaded once
-//     (all lanes the same address) and every lane draws EMIT_U rows from
-//     straight-line code — no per-row bookkeeping, coalesced stores;
-//   * 32 rows inside one cell: the same with one row per lane;
-//   * 32 rows spanning several cells: each lane finds its own cell in the window
-//     (the cost of this path is bounded however small the cells are).
+//   * blocks of 32*EMIT_U rows inside one segment: the segment's constants are in
+//     registers and every lane draws EMIT_U rows from straight-line code (a last block
+//     of more than half that size runs in the same form with the rows past the end
+//     masked);
+//   * the rest of the segment 32 rows at a time, one row per lane;
+//   * where the next 32 rows cover two or more whole segments: one row per lane, each
+//     lane with the constants of its own segment (found from one warp-wide OR of the
+//     segment starts), so the cost stays bounded however small the cells are.
 // fp32, k <= 3: the per-cell constants (box, hoisted quantile coefficients) of 32
 // consecutive segments are computed at once, one segment per lane, and staged in
 // shared memory; entering a cell then costs a few broadcast loads instead of a

@@ -410,6 +410,47 @@ def test_cellmajor_structure_and_distribution(lb, name, dtype, monkeypatch):
         assert stats.ks_2samp(x[:, d], x_ref[:, d]).pvalue > 1e-4
 
 
+@pytest.mark.parametrize("k,dtype", [(1, np.float64), (2, np.float32), (3, np.float32), (3, np.float64),
+                                     (4, np.float32)])
+def test_cellmajor_flat_residual_split_keeps_the_incell_distribution(lb, k, dtype):
+    """Few cells, a million rows each: every cell is split into its flat part (plain uniforms)
+    and its residual (inverse CDF on corners - min).  The mixture must be the cell's
+    interpolant: joint 2-D histograms inside each cell against the exact bilinear masses
+    (chi^2), and per-coordinate KS against oracle samples."""
+    from scipy import stats
+    rng = np.random.default_rng(k)
+    shape = (2,) * k
+    edges = [np.array([0.0, 0.7, 2.0]) + d for d in range(k)]
+    V = rng.uniform(0.2, 1.0, size=tuple(n + 1 for n in shape))
+    V[(0,) * k] = 3.0                                  # one steep cell, the others nearly flat
+    dom = tuple(edges) if k > 1 else edges[0]
+    grid = lb.DensityGrid(dom, lambda p: V.reshape(-1), vectorizedpdf=True, dtype=dtype)
+    N = 2_000_000
+    x, cells = grid._sample_cellmajor(N, 3, 0, want_cells=True)
+    x, cells = x.cpu().numpy().astype(np.float64).reshape(N, k), cells.cpu().numpy()
+    u = np.random.default_rng(9).random((N, k + 1))
+    x_ref = O.grid_sample(edges, V, u).reshape(N, k)
+    for d in range(k):
+        assert stats.ks_2samp(x[:, d], x_ref[:, d]).pvalue > 1e-4
+    if k < 2:
+        return
+    # joint distribution of (z0, z_last) in the steep cell: 8 x 8 bins against the oracle's draws
+    # of the same cell (a product of correct marginals would pass the KS tests above)
+    ref_cells = np.ravel_multi_index(tuple(np.searchsorted(edges[d], x_ref[:, d], side="right") - 1
+                                           for d in range(k)), shape)
+    for c in (0, int(np.prod(shape)) - 1):
+        m, mr = cells == c, ref_cells == c
+        idx = np.unravel_index(c, shape)
+        def bins(pts):
+            z0 = (pts[:, 0] - edges[0][idx[0]]) / np.diff(edges[0])[idx[0]]
+            z1 = (pts[:, -1] - edges[-1][idx[-1]]) / np.diff(edges[-1])[idx[-1]]
+            return np.histogram2d(z0, z1, bins=8, range=[[0, 1], [0, 1]])[0].ravel()
+        a, b = bins(x[m]), bins(x_ref[mr])
+        assert a.sum() > 20000 and b.sum() > 20000
+        _, p, _, _ = stats.chi2_contingency(np.stack([a, b]))
+        assert p > 1e-4
+
+
 def test_cellmajor_counts_are_exactly_multinomial(lb):
     """Dispersion test of the per-cell counts (Poisson counts conditioned by the
     u-driven top-up to total N) in both Poisson regimes (inversion for small means,
