@@ -369,7 +369,11 @@ struct ListCells {
 #ifndef LINT_EMIT_THREADS
 #define LINT_EMIT_THREADS 256
 #endif
-constexpr int EMIT_THREADS = LINT_EMIT_THREADS, EMIT_CHUNK = 2048, EMIT_U = LINT_EMIT_U;
+constexpr int EMIT_THREADS = LINT_EMIT_THREADS, EMIT_U = LINT_EMIT_U;
+// Rows per warp work item ("chunk"): 4096 amortises the per-chunk set-up best (4.64 against
+// 4.73 ms per 1e9 rows with 2048), but a draw needs enough chunks to balance ~9500 resident warps.
+constexpr uint32_t EMIT_CHUNK_MIN = 2048, EMIT_CHUNK_MAX = 4096;
+static uint32_t emit_chunk_rows(uint64_t N) { return N >= (1ull << 28) ? EMIT_CHUNK_MAX : EMIT_CHUNK_MIN; }
 
 // In-cell uniforms of a group of R rows of one lane: R*K coordinates from
 // ceil(R*K*words/4) Philox blocks.  fp32 rows use one 32-bit word per coordinate
@@ -435,7 +439,7 @@ __device__ __forceinline__ void emit_row(const CellCoefs<K, T> &coef, const T (&
     if (CELLS) __stcs(reinterpret_cast<long long *>(cell_idx) + row, (long long)cell);
 }
 
-// Every warp works on its own chunks of EMIT_CHUNK consecutive rows and walks the
+// Every warp works on its own chunks of `chunk_rows` consecutive rows and walks the
 // segments (a non-empty cell, or the non-empty flat / residual part of a split cell)
 // that intersect the chunk in order, through a small private shared-memory window of
 // the segment table (EMIT_WIN entries, refilled as the walk advances; the next chunk's
@@ -462,8 +466,8 @@ template <int K, typename T, typename Cells, bool CELLS>
 __global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 ? (K <= 3 ? LINT_EMIT_MINB : 2) : 1)
 emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
             const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ rows_p,
-            const uint32_t *__restrict__ chunk_start, uint32_t n_requested, uint2 key, uint64_t offset,
-            uint32_t split, CdfSlice table, double lam_per_unit, T *__restrict__ out,
+            const uint32_t *__restrict__ chunk_start, uint32_t n_requested, uint32_t chunk_rows, uint2 key,
+            uint64_t offset, uint32_t split, CdfSlice table, double lam_per_unit, T *__restrict__ out,
             int64_t *__restrict__ cell_idx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sedges = reinterpret_cast<T *>(smem_raw);
@@ -479,7 +483,7 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nnz = *nnz_p;
     const uint32_t N = min(*rows_p, n_requested);      // grouped rows T (T <= N but for an 8-sigma event)
-    const uint32_t nchunks = (N + EMIT_CHUNK - 1) / EMIT_CHUNK;
+    const uint32_t nchunks = (N + chunk_rows - 1) / chunk_rows;
     const uint32_t nwarps = gridDim.x * (EMIT_THREADS / 32);
     // window entry i of buffer b <- segment jb + i (offsets exist for 0..nnz, cells for 0..nnz-1)
     auto prefetch = [&](uint32_t jb, int b) {
@@ -496,7 +500,7 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
     uint32_t j0_next = chunk + nwarps < nchunks ? __ldg(chunk_start + chunk + nwarps) : 0;
     if (chunk < nchunks) prefetch(j0, 0);
     for (; chunk < nchunks; chunk += nwarps, buf ^= 1) {
-        const uint32_t r0 = chunk * EMIT_CHUNK, r1 = min(r0 + EMIT_CHUNK, N);
+        const uint32_t r0 = chunk * chunk_rows, r1 = min(r0 + chunk_rows, N);
         const bool more = chunk + nwarps < nchunks;
         if (more) prefetch(j0_next, buf ^ 1);
         uint32_t jbase = j0;                             // segment held in window slot 0
@@ -704,7 +708,7 @@ struct Scratch {
 static Scratch carve(void *base, uint64_t ncells_real, uint64_t N) {
     const uint64_t ncells = 2 * ncells_real;
     const uint64_t nscan = (ncells + SCAN_TILE - 1) / SCAN_TILE;
-    const uint64_t nchunks = (N + EMIT_CHUNK - 1) / EMIT_CHUNK;
+    const uint64_t nchunks = (N + EMIT_CHUNK_MIN - 1) / EMIT_CHUNK_MIN;      // the most any draw uses
     uintptr_t p = (uintptr_t)base;
     auto take = [&](size_t n) { uintptr_t q = p; p += (n + 255) & ~(size_t)255; return (void *)q; };
     Scratch s;
@@ -748,9 +752,10 @@ static int plan_rows(const Cells &src, const double *cdf, uint64_t ncells, uint6
     cudaMemsetAsync(s.tile_counter, 0, 4, st);
     scan_compact_kernel<<<nscan, SCAN_THREADS, 0, st>>>(s.counts, nvirt, s.tile_state,
                                                        s.tile_counter, s.cid, s.coff, s.nnz, s.rows);
-    const uint32_t nchunks = (uint32_t)((N + EMIT_CHUNK - 1) / EMIT_CHUNK);
+    const uint32_t chunk_rows = emit_chunk_rows(N);
+    const uint32_t nchunks = (uint32_t)((N + chunk_rows - 1) / chunk_rows);
     chunk_start_kernel<<<std::max(1u, std::min((nchunks + 255) / 256, 148u * 8)), 256, 0, st>>>(
-        s.coff, s.nnz, s.rows, EMIT_CHUNK, s.chunk_start);
+        s.coff, s.nnz, s.rows, chunk_rows, s.chunk_start);
     return check_launch("cell-major row planning");
 }
 
@@ -760,14 +765,15 @@ int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t 
     const uint32_t split = use_split(ncells, N) ? 1u : 0u;
     const CdfSlice t{cdf, (uint32_t)ncells, u.u_lo, u.u_hi};
     const double lam_per_unit = grouped_mean(N) / (u.u_hi - u.u_lo);
-    const uint32_t nchunks = (uint32_t)((N + EMIT_CHUNK - 1) / EMIT_CHUNK);
+    const uint32_t chunk_rows = emit_chunk_rows(N);
+    const uint32_t nchunks = (uint32_t)((N + chunk_rows - 1) / chunk_rows);
     const int blocks = (int)std::min<uint32_t>((nchunks + EMIT_THREADS / 32 - 1) / (EMIT_THREADS / 32), 148 * 8);
     if (cell_idx)
         emit_kernel<K, T, Cells, true><<<blocks, EMIT_THREADS, src.smem_bytes(sizeof(T)), st>>>(
-            src, s.cid, s.coff, s.nnz, s.rows, s.chunk_start, (uint32_t)N, key, offset, split, t, lam_per_unit, (T *)out, cell_idx);
+            src, s.cid, s.coff, s.nnz, s.rows, s.chunk_start, (uint32_t)N, chunk_rows, key, offset, split, t, lam_per_unit, (T *)out, cell_idx);
     else
         emit_kernel<K, T, Cells, false><<<blocks, EMIT_THREADS, src.smem_bytes(sizeof(T)), st>>>(
-            src, s.cid, s.coff, s.nnz, s.rows, s.chunk_start, (uint32_t)N, key, offset, split, t, lam_per_unit, (T *)out, cell_idx);
+            src, s.cid, s.coff, s.nnz, s.rows, s.chunk_start, (uint32_t)N, chunk_rows, key, offset, split, t, lam_per_unit, (T *)out, cell_idx);
     return check_launch("cell-major emission");
 }
 
