@@ -1,0 +1,1100 @@
+// Cell-major ("grouped") sampling: the throughput path.
+//
+// The u-driven sampler of lint_sample.cu spends its time on per-sample random
+// access (guide, CDF, cell record) — work the reference also does per sample
+// (utils.py:197, grid.py:440-467).  N i.i.d. draws of a cell are however fully
+// described by the per-cell counts (n_c) ~ Multinomial(N, p_c), so this path
+//   1. draws independent counts n_c ~ Poisson(L p_c) with L = N - 8 sqrt(N), one
+//      thread per cell (probabilities are differences of the same fp64 CDF the
+//      search path uses, grid.py:431 + utils.py:195-196).  Given their total T the
+//      counts are exactly Multinomial(T, p), and T < N except with probability
+//      ~1e-15 (an 8-sigma event),
+//   2. turns them into row offsets with a single-pass decoupled look-back scan
+//      (integer sums, hence deterministic) that also compacts away empty cells,
+//   3. emits each cell's rows contiguously: the cell's box and corners are
+//      loaded once per cell, every row costs only its k in-cell uniforms and the
+//      k-D inverse CDF of sampling.py:41-94,
+//   4. tops up the remaining N - T rows (~2.5e-4 N) with the u-driven kernel;
+//      Multinomial(T, p) + Multinomial(N - T, p) = Multinomial(N, p), so the N
+//      rows are an exact i.i.d. sample as a multiset.
+// Flat/residual split.  Inside a cell the interpolant is f = f_min + (f - f_min): a
+// constant plus a multilinear density that vanishes at one corner.  Rows of the
+// constant part are plain uniforms (z = u, no inverse CDF at all); only rows of the
+// residual need sampling.py:41-94.  A split cell c becomes two segments, 2c (flat)
+// and 2c + 1 (residual), with independent Poisson counts of means lambda q and
+// lambda (1 - q), q = f_min / mean(corners) — Poisson thinning, exact.  On a fine
+// grid of a smooth pdf q is close to 1 (0.94 mass-weighted on the 256^3 benchmark
+// grid), so most rows cost their uniforms, an fma and a store.  The split doubles
+// the segment table and adds a corner gather to the count pass, so it is used only
+// when N >= SPLIT_MIN_ROWS_PER_CELL * cells, and within such a draw only for cells
+// expecting >= SPLIT_MIN_LAMBDA rows (the others keep all rows in segment 2c + 1,
+// drawn from the full interpolant; the emitter re-derives the decision from the
+// same CDF entries).
+// Row ORDER: three runs.  Rows [0, T_f) are the flat parts of the split cells, grouped by
+// cell in C order; rows [T_f, T) are everything else drawn by count — the residual parts of
+// the split cells and all rows of the cells that are not split — again grouped by cell in C
+// order; rows [T, N) are the top-up tail in draw order.  Keeping the flat rows apart lets a
+// lean kernel of their own write them (no quantile, no per-cell coefficients, 16-byte
+// coalesced stores) while the general emitter works on the rest.  Callers that need the
+// reference's exchangeable row order (lintsampler.py:309-311) apply the row permutation
+// afterwards.
+#include <algorithm>
+#include <cmath>
+#include <type_traits>
+#include <cuda_pipeline.h>
+#pragma once
+#include "lint_device.cuh"
+#include "lint_cellmajor_plan.h"
+
+namespace lint {
+
+int validate_grid(const lint_grid_t *g, bool need_cdf, uint64_t *ncells_out, uint64_t *nverts_out);
+template <int K> GridView<K> make_grid_view(const lint_grid_t *g, uint64_t ncells, bool stage_edges);
+
+// Philox counter word 1 tags (word 0 = cell / first row of a group, words 2-3 = call offset)
+constexpr uint32_t TAG_COUNT = 0x53000000u;   // | attempt   (per-cell count draws)
+constexpr uint32_t TAG_COORD = 0x43000000u;   // | block index
+
+// ---------------------------------------------------------------------------
+// Poisson counts
+// ---------------------------------------------------------------------------
+struct CellRng {
+    uint2 key;
+    uint32_t cell, w2, w3;
+    uint32_t attempt = 0;
+    __device__ __forceinline__ void next(double &a, double &b) {
+        const uint4 r = philox4x32_10(make_uint4(cell, TAG_COUNT | attempt, w2, w3), key);
+        ++attempt;
+        a = u53(r.x, r.y);
+        b = u53(r.z, r.w);
+    }
+};
+
+// log(k!) for integer-valued k >= 0: table below 16, Stirling series above
+// (truncation error < 2e-12 there)
+static __constant__ double LOG_FACTORIAL_TAB[16] = {
+    0.0, 0.0, 0.6931471805599453, 1.791759469228055, 3.1780538303479458, 4.787491742782046,
+    6.579251212010101, 8.525161361065415, 10.604602902745251, 12.801827480081469,
+    15.104412573075516, 17.502307845873887, 19.987214495661885, 22.552163853123425,
+    25.19122118273868, 27.89927138384089};
+__device__ __forceinline__ double log_factorial(double k) {
+    if (k < 16.0) return LOG_FACTORIAL_TAB[(int)k];
+    const double x = k + 1.0, r = 1.0 / x, r2 = r * r;
+    return (x - 0.5) * log(x) - x + 0.9189385332046727 +
+           r * (1.0 / 12.0 - r2 * (1.0 / 360.0 - r2 * (1.0 / 1260.0)));
+}
+
+// Poisson(lam): sequential inversion with one uniform below 10, Hörmann's
+// transformed rejection with squeeze (PTRS, 1993) above.
+__device__ __forceinline__ uint32_t poisson(double lam, CellRng &rng) {
+    if (!(lam > 0.0)) return 0;
+    if (lam < 10.0) {
+        double u, unused;
+        rng.next(u, unused);
+        // exp(-lam) >= 1 - lam: most cells of a fine grid hold lam << 1 and end here,
+        // without the exponential
+        if (u <= 1.0 - lam) return 0;
+        const double p0 = exp(-lam);
+        for (;;) {
+            double p = p0;
+            uint32_t x = 0;
+            bool ok = true;
+            while (u > p) {
+                u -= p;
+                ++x;
+                if (x > 200) { ok = false; break; }     // fp dust past the far tail: redraw
+                p *= lam * __drcp_rn((double)x);
+            }
+            if (ok) return x;
+            rng.next(u, unused);
+        }
+    }
+    const double b = 0.931 + 2.53 * sqrt(lam);
+    const double a = -0.059 + 0.02483 * b;
+    const double vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (;;) {
+        double u, v;
+        rng.next(u, v);
+        u -= 0.5;
+        const double us = 0.5 - fabs(u);
+        const double k = floor((2.0 * a / us + b) * u + lam + 0.43);
+        if (us >= 0.07 && v <= vr) return (uint32_t)k;            // the squeeze accepts ~86 %
+        if (k < 0.0 || (us < 0.013 && v > us)) continue;
+        const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
+        const double lhs_arg = v * invalpha / (a / (us * us) + b);
+        // Acceptance test log(lhs_arg) <= -lam + k log(lam) - log(k!).  ~14 % of the draws get
+        // here, i.e. nearly every warp, so it is first decided in fp32 wherever the margin
+        // exceeds a generous bound on the fp32 error; the fp64 test below settles the rest
+        // (a few per thousand).  With k1 = k + 1, d = k1 - lam, x = d / k1 and Stirling's
+        // series the right-hand side is  k log1p(-x) + d - log(k1)/2 - log(2 pi)/2 - s(k1).
+        if (k >= 4.0 && lam < 1.0e5) {
+            const float d = (float)(k + 1.0 - lam), k1 = (float)k + 1.0f, x = d / k1;
+            const float series = (1.0f / 12.0f - (1.0f / 360.0f) / (k1 * k1)) / k1;
+            const float rhs = ((float)k * log1pf(-x) + d) - 0.5f * __logf(k1) - 0.9189385f - series;
+            const float t = __logf((float)lhs_arg) - rhs;
+            const float tol = 2e-3f + 4e-6f * fabsf(d);
+            if (t < -tol) return (uint32_t)k;
+            if (t > tol) continue;
+        }
+        if (log(lhs_arg) <= -lam + k * log(lam) - log_factorial(k)) return (uint32_t)k;
+    }
+}
+
+// The table the counts are read from: the normalised CDF restricted to the stratum
+// [u_lo, u_hi) of the cell-selecting uniform ((0, 1) = the whole domain; a rank of
+// a sharded run passes its own slice).
+struct CdfSlice {
+    const double *cdf;
+    uint32_t ncells;
+    double u_lo, u_hi;
+};
+
+// Expected number of grouped rows of cell c — evaluated identically by the count pass and
+// by the emitter (same operations on the same table).
+__device__ __forceinline__ double cell_lambda(const CdfSlice &t, uint32_t c, double lam_per_unit) {
+    // mass of the cell inside the stratum: clamp both CDF values, then difference
+    const double f0 = c == 0 ? 0.0 : __ldg(t.cdf + c - 1), f1 = __ldg(t.cdf + c);
+    const double m = fmin(fmax(f1, t.u_lo), t.u_hi) - fmin(fmax(f0, t.u_lo), t.u_hi);
+    return __dmul_rn(m, lam_per_unit);
+}
+
+// A cell is split into its flat and residual parts only where that pays: below this
+// many expected rows the residual part would be a handful of rows with a segment of
+// their own, dearer than drawing all of the cell's rows from the full interpolant.
+#ifndef LINT_SPLIT_MIN_LAMBDA
+#define LINT_SPLIT_MIN_LAMBDA 128.0
+#endif
+constexpr double SPLIT_MIN_LAMBDA = LINT_SPLIT_MIN_LAMBDA;
+
+// counts_rest[c] = rows of cell c drawn from its full interpolant (no split), or with the
+// split: counts_flat[c] = flat rows, counts_rest[c] = residual rows — or all rows of a cell
+// that is not split
+template <typename Cells>
+__global__ void __launch_bounds__(256)
+poisson_counts_kernel(Cells src, CdfSlice t, double lam_per_unit, uint2 key, uint64_t offset, bool split,
+                      uint32_t *__restrict__ counts_flat, uint32_t *__restrict__ counts_rest) {
+    const uint32_t w2 = (uint32_t)offset, w3 = (uint32_t)(offset >> 32);
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < t.ncells; c += gridDim.x * blockDim.x) {
+        const double lam = cell_lambda(t, c, lam_per_unit);
+        if (!split) {
+            CellRng rng{key, c, w2, w3};
+            counts_rest[c] = poisson(lam, rng);
+            continue;
+        }
+        double mean[2] = {0.0, lam};
+        if (lam >= SPLIT_MIN_LAMBDA) {
+            mean[0] = lam * src.flat_fraction(c);
+            mean[1] = lam - mean[0];
+        }
+        uint32_t n[2];
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {           // one copy of the sampler's code
+            CellRng rng{key, 2 * c + part, w2, w3};
+            n[part] = poisson(mean[part], rng);
+        }
+        counts_flat[c] = n[0];
+        counts_rest[c] = n[1];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// decoupled look-back scan of (count, non-empty) pairs + compaction
+// ---------------------------------------------------------------------------
+// A tile publishes its aggregate, then its inclusive prefix, in one 64-bit word:
+// bits 63-62 status, bits 61-32 non-empty cells, bits 31-0 rows.  Integer sums
+// are associative, so the look-back's variable association is harmless here.
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = 3ull << 62;
+
+__device__ __forceinline__ unsigned long long pack(uint32_t rows, uint32_t cells) {
+    return ((unsigned long long)cells << 32) | rows;
+}
+
+static __global__ void __launch_bounds__(SCAN_THREADS)
+scan_compact_kernel(const uint32_t *counts, uint32_t ncells, uint32_t id_mul, uint32_t id_add,
+                    unsigned long long *tile_state, uint32_t *tile_counter, uint32_t *cid, uint32_t *coff,
+                    uint32_t *nnz_out, uint32_t *rows_out) {
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
+    __shared__ unsigned long long s_excl;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);   // tiles start in index order
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t c[SCAN_ITEMS];
+    unsigned long long run = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        c[i] = base + i < ncells ? __ldg(counts + base + i) : 0;
+        run += pack(c[i], c[i] != 0);
+    }
+    // block-wide inclusive scan of the per-thread totals
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    unsigned long long wex = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        if (w < warp) wex += s_warp[w];
+        tile_total += s_warp[w];
+    }
+    // look-back (warp 0)
+    if (warp == 0) {
+        if (lane == 0) {
+            const unsigned long long st = tile == 0 ? (ST_INC | tile_total) : (ST_AGG | tile_total);
+            atomicExch(tile_state + tile, st);
+        }
+        unsigned long long excl = 0;
+        if (tile > 0) {
+            int look = (int)tile - 1;
+            for (;;) {
+                const int idx = look - lane;
+                unsigned long long v = ST_INC;                      // virtual tile -1: empty inclusive
+                if (idx >= 0) {
+                    do { v = atomicAdd(tile_state + idx, 0ull); } while ((v & ST_MASK) == 0);
+                }
+                const uint32_t inc_mask = __ballot_sync(0xffffffffu, (v & ST_MASK) == ST_INC);
+                const int first_inc = inc_mask ? __ffs(inc_mask) - 1 : 32;
+                unsigned long long contrib = lane <= first_inc ? (v & ~ST_MASK) : 0ull;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+                excl += contrib;
+                if (inc_mask) break;
+                look -= 32;
+            }
+            if (lane == 0) atomicExch(tile_state + tile, ST_INC | (excl + tile_total));
+        }
+        if (lane == 0) s_excl = excl;
+    }
+    __syncthreads();
+    unsigned long long pre = s_excl + wex + (inc - run);           // exclusive prefix of this thread
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (c[i] != 0) {
+            const uint32_t slot = (uint32_t)(pre >> 32);
+            cid[slot] = (base + i) * id_mul + id_add;
+            coff[slot] = (uint32_t)pre;
+        }
+        pre += pack(c[i], c[i] != 0);
+    }
+    if (base <= ncells - 1 && ncells - 1 < base + SCAN_ITEMS) {    // owner of the last cell
+        const uint32_t nnz = (uint32_t)(pre >> 32);
+        *nnz_out = nnz;
+        *rows_out = (uint32_t)pre;                                 // T = total grouped rows
+        coff[nnz] = (uint32_t)pre;                                 // sentinel
+    }
+}
+
+// Row budget of the two grouped runs.  T_f + T_r <= N but for an 8-sigma event of the Poisson
+// total; clamping keeps every writer inside the output whatever happened.  Also resets the
+// flat emitter's chunk counter.  plan[0] = T_f, plan[1] = T_r, plan[2] = T_f + T_r.
+static __global__ void plan_totals_kernel(const uint32_t *rows_flat, const uint32_t *rows_rest, uint32_t n_requested,
+                                   uint32_t *plan, uint32_t *chunk_counter) {
+    const uint32_t tf = rows_flat ? min(*rows_flat, n_requested) : 0u;
+    const uint32_t tr = min(*rows_rest, n_requested - tf);
+    plan[0] = tf;
+    plan[1] = tr;
+    plan[2] = tf + tr;
+    *chunk_counter = 0;
+}
+
+// first segment of every output chunk: last j with coff[j] <= chunk * chunk_rows
+static __global__ void chunk_start_kernel(const uint32_t *coff, const uint32_t *nnz_p, const uint32_t *rows_p,
+                                  uint32_t chunk_rows, uint32_t *chunk_start) {
+    const uint32_t nnz = *nnz_p;
+    const uint32_t nchunks = (*rows_p + chunk_rows - 1) / chunk_rows;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nchunks; t += gridDim.x * blockDim.x) {
+        const uint32_t r0 = t * chunk_rows;
+        uint32_t lo = 0, hi = nnz;                                 // coff[nnz] = N > r0
+        while (lo < hi) {                                          // first j with coff[j] > r0
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (__ldg(coff + mid) > r0) hi = mid; else lo = mid + 1;
+        }
+        chunk_start[t] = lo - 1;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// emission
+// ---------------------------------------------------------------------------
+template <int K, typename T>
+__device__ __forceinline__ double flat_fraction_of(const T (&c)[1 << K]) {
+    T lo = c[0], sum = c[0];
+#pragma unroll
+    for (int j = 1; j < (1 << K); ++j) { lo = c[j] < lo ? c[j] : lo; sum += c[j]; }
+    return sum > (T)0 ? fmin(fmax((double)lo * (double)(1 << K) / (double)sum, 0.0), 1.0) : 0.0;
+}
+
+// c <- c - min(c): the residual density of the flat/residual split
+template <int NC, typename T>
+__device__ __forceinline__ void subtract_min(T (&c)[NC]) {
+    T lo = c[0];
+#pragma unroll
+    for (int j = 1; j < NC; ++j) lo = c[j] < lo ? c[j] : lo;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) c[j] -= lo;
+}
+
+template <int K, typename DensT>
+struct GridCells {
+    GridView<K> g;
+    __host__ size_t smem_bytes(size_t elem) const { return (size_t)g.edge_total * elem; }
+    template <typename T>
+    __device__ __forceinline__ void prepare(T *smem) const { grid_stage_edges<K, T>(g, smem); }
+    template <typename T>
+    __device__ __forceinline__ void fetch(const T *smem, uint32_t idx, T (&c)[1 << K], T (&lo)[K],
+                                          T (&hi)[K]) const {
+        grid_fetch<K, DensT, T>(g, smem, idx, c, lo, hi);
+    }
+    __device__ __forceinline__ bool prenormalised() const { return g.rec != nullptr; }
+    // q = min(corners) / mean(corners): the share of the cell's mass under the constant f_min
+    __device__ __forceinline__ double flat_fraction(uint32_t idx) const {
+        uint32_t i[K];
+        grid_unravel<K>(g, idx, i);
+        DensT c[1 << K];
+        grid_corners<K, DensT, DensT>(g, idx, i, c);
+        return flat_fraction_of<K>(c);
+    }
+    // the cell's box only: lower corner and widths (maxs - mins, sampling.py:126) in T
+    template <typename T>
+    __device__ __forceinline__ void box(const T *smem, uint32_t idx, T (&lo)[K], T (&w)[K]) const {
+        uint32_t i[K];
+        grid_unravel<K>(g, idx, i);
+#pragma unroll
+        for (int d = 0; d < K; ++d) {
+            T hi;
+            if (g.edge_total) {
+                lo[d] = smem[g.edge_off[d] + i[d]];
+                hi = smem[g.edge_off[d] + i[d] + 1];
+            } else {
+                lo[d] = (T)__ldg(g.edges[d] + i[d]);
+                hi = (T)__ldg(g.edges[d] + i[d] + 1);
+            }
+            w[d] = hi - lo[d];
+        }
+    }
+};
+
+template <int K, typename DensT>
+struct ListCells {
+    CellsView s;
+    __host__ size_t smem_bytes(size_t) const { return 0; }
+    template <typename T>
+    __device__ __forceinline__ void prepare(T *) const {}
+    template <typename T>
+    __device__ __forceinline__ void fetch(const T *, uint32_t idx, T (&c)[1 << K], T (&lo)[K],
+                                          T (&hi)[K]) const {
+        cells_fetch<K, DensT, T>(s, idx, c, lo, hi);
+    }
+    __device__ __forceinline__ bool prenormalised() const { return s.rec != nullptr; }
+    __device__ __forceinline__ double flat_fraction(uint32_t idx) const {
+        DensT c[1 << K];
+        cells_corners<K, DensT, DensT>(s, idx, c);
+        return flat_fraction_of<K>(c);
+    }
+    template <typename T>
+    __device__ __forceinline__ void box(const T *, uint32_t idx, T (&lo)[K], T (&w)[K]) const {
+#pragma unroll
+        for (int d = 0; d < K; ++d) {
+            const double x = __ldg(s.mins + (size_t)idx * K + d);
+            const double dx = __ldg(s.widths + (size_t)idx * K + d);
+            lo[d] = (T)x;
+            w[d] = (T)__dadd_rn(x, dx) - lo[d];       // maxs = leaf.x + leaf.dx [tree.py:348]
+        }
+    }
+};
+
+#ifndef LINT_EMIT_U
+#define LINT_EMIT_U 4          // rows per lane in the straight-line fast path
+#endif
+#ifndef LINT_EMIT_MINB
+#define LINT_EMIT_MINB 4       // resident CTAs per SM the fp32 k<=3 emitter is compiled for
+#endif
+#ifndef LINT_EMIT_THREADS
+#define LINT_EMIT_THREADS 256
+#endif
+constexpr int EMIT_THREADS = LINT_EMIT_THREADS, EMIT_U = LINT_EMIT_U;
+
+// In-cell uniforms of a group of R rows of one lane: R*K coordinates from
+// ceil(R*K*words/4) Philox blocks.  fp32 rows use one 32-bit word per coordinate
+// (top 24 bits); fp64 rows two words (53 bits).  The counter names the group's
+// first row, `sub` separates the multi-row groups (0) from single rows (1).
+template <int K, typename T, int R>
+struct GroupUniforms {
+    static constexpr int WORDS = K * R * (sizeof(T) == 8 ? 2 : 1);
+    static constexpr int CALLS = (WORDS + 3) / 4;
+    uint32_t w[4 * CALLS];
+    __device__ __forceinline__ void fill(uint2 key, uint32_t first_row, uint32_t sub, uint64_t offset) {
+#pragma unroll
+        for (int q = 0; q < CALLS; ++q) {
+            const uint4 r = philox4x32_10(
+                make_uint4(first_row, TAG_COORD | (sub << 16) | q, (uint32_t)offset, (uint32_t)(offset >> 32)),
+                key);
+            w[4 * q] = r.x; w[4 * q + 1] = r.y; w[4 * q + 2] = r.z; w[4 * q + 3] = r.w;
+        }
+    }
+    __device__ __forceinline__ void get(int i, float (&u)[K]) const {
+#pragma unroll
+        // round-toward-zero conversion keeps the top 24 bits: u in [0, 1 - 2^-24]
+        for (int d = 0; d < K; ++d) u[d] = __uint2float_rz(w[i * K + d]) * (1.0f / 4294967296.0f);
+    }
+    __device__ __forceinline__ void get(int i, double (&u)[K]) const {
+#pragma unroll
+        for (int d = 0; d < K; ++d) u[d] = u53(w[2 * (i * K + d)], w[2 * (i * K + d) + 1]);
+    }
+};
+
+template <int K, typename T, bool CELLS>
+__device__ __forceinline__ void emit_row(const CellCoefs<K, T> &coef, const T (&xlo)[K], const T (&xw)[K],
+                                         const T (&u)[K], uint32_t row, uint32_t cell,
+                                         T *__restrict__ out, int64_t *__restrict__ cell_idx) {
+    T z[K];
+    coef.draw(u, z);                                               // sampling.py:41-94
+#pragma unroll
+    for (int d = 0; d < K; ++d)
+        store_stream(out + (size_t)row * K + d, affine_w(xlo[d], xw[d], z[d]));   // sampling.py:126
+    if (CELLS) __stcs(reinterpret_cast<long long *>(cell_idx) + row, (long long)cell);
+}
+
+// ---------------------------------------------------------------------------
+// general emitter: rows [T_f, T_f + T_r), every segment drawn from an interpolant
+// ---------------------------------------------------------------------------
+// Every warp works on its own chunks of `chunk_rows` consecutive rows and walks the
+// segments (a non-empty cell that is not split, or the non-empty residual part of a split
+// cell) that intersect the chunk in order, through a small private shared-memory window of
+// the segment table (EMIT_WIN entries, refilled as the walk advances; the next chunk's
+// first window is prefetched with cp.async while the current chunk is computed).  No
+// CTA-wide barrier.  Segments tile the rows, so the walk never searches.  Lanes map to
+// consecutive rows:
+//   * blocks of 32*EMIT_U rows inside one segment: the segment's constants are in
+//     registers and every lane draws EMIT_U rows from straight-line code (a last block
+//     of more than half that size runs in the same form with the rows past the end
+//     masked);
+//   * the rest of the segment 32 rows at a time, one row per lane;
+//   * where the next 32 rows cover two or more whole segments: one row per lane, each
+//     lane with the constants of its own segment (found from one warp-wide OR of the
+//     segment starts), so the cost stays bounded however small the cells are.
+// fp32, k <= 3: the per-cell constants (box, hoisted quantile coefficients) of 32
+// consecutive segments are computed at once, one segment per lane, and staged in
+// shared memory; entering a cell then costs a few broadcast loads instead of a
+// warp-redundant fetch + set.
+// Rows are local to the run: row r is output row plan[0] + r.
+constexpr int EMIT_WIN = 64;
+constexpr uint32_t EMIT_PRE = 32;            // segments per staged block (= lanes)
+constexpr uint32_t EMIT_PRE_NONE = 0x80000000u;
+
+template <int K, typename T, typename Cells, bool CELLS>
+__global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 ? (K <= 3 ? LINT_EMIT_MINB : 2) : 1)
+emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
+            const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ plan,
+            const uint32_t *__restrict__ chunk_start, uint32_t chunk_rows, uint2 key,
+            uint64_t offset, uint32_t split, CdfSlice table, double lam_per_unit, T *__restrict__ out,
+            int64_t *__restrict__ cell_idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sedges = reinterpret_cast<T *>(smem_raw);
+    __shared__ uint32_t s_off_all[EMIT_THREADS / 32][2][EMIT_WIN];
+    __shared__ uint32_t s_cid_all[EMIT_THREADS / 32][2][EMIT_WIN];
+    // staged constants: CellCoefs words, then the box (lo[K], hi[K]); the slot stride is an
+    // odd number of 16-byte units so the per-lane 128-bit stores do not conflict
+    constexpr bool PRE = sizeof(T) == 4 && K <= 3;
+    constexpr int PRE_WORDS = CellCoefs<K, T>::WORDS + 2 * K;
+    constexpr int PRE_Q = ((PRE_WORDS + 3) / 4) | 1;
+    __shared__ float4 s_pre_all[PRE ? EMIT_THREADS / 32 : 1][PRE ? EMIT_PRE * PRE_Q : 1];
+    src.prepare(sedges);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nnz = *nnz_p;
+    const uint32_t N = plan[1];                        // rows of this run
+    out += (size_t)plan[0] * K;                        // ... which starts after the flat run
+    if (CELLS) cell_idx += plan[0];
+    const uint32_t nchunks = (N + chunk_rows - 1) / chunk_rows;
+    const uint32_t nwarps = gridDim.x * (EMIT_THREADS / 32);
+    // window entry i of buffer b <- segment jb + i (offsets exist for 0..nnz, cells for 0..nnz-1)
+    auto prefetch = [&](uint32_t jb, int b) {
+#pragma unroll
+        for (uint32_t i = lane; i < EMIT_WIN; i += 32) {
+            if (jb + i <= nnz) __pipeline_memcpy_async(&s_off_all[warp][b][i], coff + jb + i, 4);
+            if (jb + i < nnz) __pipeline_memcpy_async(&s_cid_all[warp][b][i], cid + jb + i, 4);
+        }
+        __pipeline_commit();
+    };
+    uint32_t chunk = blockIdx.x * (EMIT_THREADS / 32) + warp;
+    int buf = 0;
+    uint32_t j0 = chunk < nchunks ? __ldg(chunk_start + chunk) : 0;
+    uint32_t j0_next = chunk + nwarps < nchunks ? __ldg(chunk_start + chunk + nwarps) : 0;
+    if (chunk < nchunks) prefetch(j0, 0);
+    for (; chunk < nchunks; chunk += nwarps, buf ^= 1) {
+        const uint32_t r0 = chunk * chunk_rows, r1 = min(r0 + chunk_rows, N);
+        const bool more = chunk + nwarps < nchunks;
+        if (more) prefetch(j0_next, buf ^ 1);
+        uint32_t jbase = j0;                             // segment held in window slot 0
+        j0 = j0_next;
+        if (chunk + 2 * (uint64_t)nwarps < nchunks) j0_next = __ldg(chunk_start + chunk + 2 * nwarps);
+        if (more) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
+        __syncwarp();
+        uint32_t *s_off = s_off_all[warp][buf], *s_cid = s_cid_all[warp][buf];
+        // offset of segment j (j > nnz: +inf); callers keep j - jbase < EMIT_WIN
+        auto off = [&](uint32_t j) { return j <= nnz ? s_off[j - jbase] : 0xffffffffu; };
+        auto refill = [&](uint32_t jb) {                 // slide the window so that slot 0 = segment jb
+            __syncwarp();
+#pragma unroll
+            for (uint32_t i = lane; i < EMIT_WIN; i += 32) {
+                if (jb + i <= nnz) s_off[i] = __ldg(coff + jb + i);
+                if (jb + i < nnz) s_cid[i] = __ldg(cid + jb + i);
+            }
+            jbase = jb;
+            __syncwarp();
+        };
+
+        uint32_t j = jbase;                              // warp-uniform segment cursor
+        uint32_t row = r0;
+        uint32_t loaded = 0xffffffffu;                   // segment whose constants the registers hold
+        T xlo[K], xw[K];                                 // box: lower corner, width
+        CellCoefs<K, T> coef;
+        uint32_t cell = 0;
+        uint32_t cbase = EMIT_PRE_NONE;                  // staged block = segments [cbase, cbase + 32)
+        float4 *s_pre = s_pre_all[PRE ? warp : 0];
+        // segment ids: the cell itself, or with the flat/residual split 2 cell + 1
+        // constants of one segment into the caller's registers
+        auto constants = [&](uint32_t v, CellCoefs<K, T> &cf, T (&lo)[K], T (&w)[K]) {
+            T c0[1 << K], hi[K];
+            src.fetch(sedges, v >> split, c0, lo, hi);
+#pragma unroll
+            for (int d = 0; d < K; ++d) w[d] = hi[d] - lo[d];              // maxs - mins, sampling.py:126
+            // the residual of a split cell, or the whole of a cell that is not split
+            const bool residual = split && cell_lambda(table, v >> 1, lam_per_unit) >= SPLIT_MIN_LAMBDA;
+            if (residual) subtract_min(c0);
+            cf.set(c0, !residual && src.prenormalised());
+        };
+        // stage the constants of segments [jb, jb + 32) that start inside this chunk;
+        // the window must hold entries jb .. jb + 32
+        auto stage = [&](uint32_t jb) {
+            __syncwarp();
+            const uint32_t js = jb + lane;
+            if (js < nnz && s_off[js - jbase] < r1) {
+                T lo[K], wd[K];
+                CellCoefs<K, T> cf;
+                float w[4 * PRE_Q] = {};
+                constants(s_cid[js - jbase], cf, lo, wd);
+                cf.pack(w);
+#pragma unroll
+                for (int d = 0; d < K; ++d) {
+                    w[CellCoefs<K, T>::WORDS + d] = (float)lo[d];
+                    w[CellCoefs<K, T>::WORDS + K + d] = (float)wd[d];
+                }
+#pragma unroll
+                for (int q = 0; q < (PRE_WORDS + 3) / 4; ++q)
+                    s_pre[lane * PRE_Q + q] = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+            }
+            cbase = jb;
+            __syncwarp();
+        };
+        // registers <- constants of segment seg (in the window; PRE: also in the staged block)
+        auto enter = [&](uint32_t seg) {
+            const uint32_t v = s_cid[seg - jbase];
+            cell = v >> split;
+            if constexpr (PRE) {
+                float w[4 * PRE_Q];
+#pragma unroll
+                for (int q = 0; q < (PRE_WORDS + 3) / 4; ++q) {
+                    const float4 t4 = s_pre[(seg - cbase) * PRE_Q + q];
+                    w[4 * q] = t4.x; w[4 * q + 1] = t4.y; w[4 * q + 2] = t4.z; w[4 * q + 3] = t4.w;
+                }
+                coef.unpack(w);
+#pragma unroll
+                for (int d = 0; d < K; ++d) {
+                    xlo[d] = (T)w[CellCoefs<K, T>::WORDS + d];
+                    xw[d] = (T)w[CellCoefs<K, T>::WORDS + K + d];
+                }
+            } else {
+                constants(v, coef, xlo, xw);
+            }
+        };
+
+        // invariant: segment j holds `row` (segments are non-empty, so they tile the rows)
+        while (row < r1) {
+            if (j + 2 - jbase >= EMIT_WIN) refill(j);
+            const uint32_t seg_end = min(off(j + 1), r1);
+            // the per-lane path pays where the next 32 rows cover at least two whole segments
+            if (off(j + 2) > min(row + 32u, r1)) {
+                // ---- rows [row, seg_end) of one segment, lanes = consecutive rows
+                if (loaded != j) {
+                    if constexpr (PRE) {
+                        if (j - cbase >= EMIT_PRE) {
+                            if (j + EMIT_PRE + 1 - jbase >= EMIT_WIN) refill(j);
+                            stage(j);
+                        }
+                    }
+                    enter(j);
+                    loaded = j;
+                }
+                // blocks of 32 * EMIT_U rows
+                while (seg_end - row >= 32u * EMIT_U) {
+                    const uint32_t first = row + lane;
+                    GroupUniforms<K, T, EMIT_U> rnd;
+                    rnd.fill(key, first, 0, offset);
+#pragma unroll
+                    for (int t = 0; t < EMIT_U; ++t) {
+                        T u[K];
+                        rnd.get(t, u);
+                        emit_row<K, T, CELLS>(coef, xlo, xw, u, first + 32u * t, cell, out, cell_idx);
+                    }
+                    row += 32u * EMIT_U;
+                }
+                // a last partial block of more than half that is still cheaper in this form
+                // (rows past the end masked) than one warp-row at a time
+                if (seg_end - row > 16u * EMIT_U) {
+                    const uint32_t first = row + lane;
+                    GroupUniforms<K, T, EMIT_U> rnd;
+                    rnd.fill(key, first, 0, offset);
+#pragma unroll
+                    for (int t = 0; t < EMIT_U; ++t) {
+                        T u[K];
+                        rnd.get(t, u);
+                        if (first + 32u * t < seg_end)
+                            emit_row<K, T, CELLS>(coef, xlo, xw, u, first + 32u * t, cell, out, cell_idx);
+                    }
+                    row = seg_end;
+                }
+                // the rest of the segment, however short: its constants are in registers
+                // already, which makes idle lanes cheaper than the per-lane path
+                while (row < seg_end) {
+                    const uint32_t r = row + lane;
+                    if (r < seg_end) {
+                        GroupUniforms<K, T, 1> rnd;
+                        rnd.fill(key, r, 1, offset);
+                        T u[K];
+                        rnd.get(0, u);
+                        emit_row<K, T, CELLS>(coef, xlo, xw, u, r, cell, out, cell_idx);
+                    }
+                    row = min(row + 32u, seg_end);
+                }
+                ++j;                                     // row == seg_end: the next segment, if row < r1
+            } else {
+                // ---- the next 32 rows span several segments: one row per lane, own segment each.
+                // Segments hold >= 1 row, so lane l's segment is within [j, j + l].
+                if (j + 33 - jbase >= EMIT_WIN) refill(j);
+                const uint32_t r = row + lane;
+                const uint32_t lim = min(row + 32u, r1);
+                // bit b of `starts`: a segment begins at row + b (lane i looks at segment j + 1 + i);
+                // a row's segment is j + the number of starts in (row, r]
+                const uint32_t o = off(j + 1 + lane) - row;                   // >= 1
+                const uint32_t starts = __reduce_or_sync(0xffffffffu, o < 32u ? 1u << o : 0u);
+                const uint32_t lo = j + __popc(starts & ((2u << lane) - 1u));
+                const uint32_t last = __shfl_sync(0xffffffffu, lo, (int)(lim - row) - 1);   // the last row's segment
+                if constexpr (PRE) {
+                    if (j - cbase >= EMIT_PRE || last - cbase >= EMIT_PRE) stage(j);       // last <= j + 31
+                }
+                if (r < lim) {
+                    enter(lo);
+                    GroupUniforms<K, T, 1> rnd;
+                    rnd.fill(key, r, 1, offset);
+                    T u[K];
+                    rnd.get(0, u);
+                    emit_row<K, T, CELLS>(coef, xlo, xw, u, r, cell, out, cell_idx);
+                }
+                loaded = 0xffffffffu;
+                row = lim;
+                j = off(last + 1) <= row ? last + 1 : last;     // (window holds up to j + 32)
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// flat emitter: rows [0, T_f), every segment the constant part of a split cell
+// ---------------------------------------------------------------------------
+// A flat row is K independent uniforms mapped into the cell's box, x_d = lo_d + w_d u
+// (sampling.py:126 with z = u), so the run is a stream of independent ELEMENTS: element e
+// of the row-major output belongs to row e / K, dimension e % K, and needs nothing but the
+// box of that row's segment and a fresh uniform.  The kernel therefore works on 16-byte
+// output vectors instead of rows: in a step, lane l writes vectors v + l, v + 32 + l, ...
+// of the segment — each store instruction covers 512 contiguous bytes of the output — and a
+// vector's elements simply use the box constants of their own dimensions (a per-lane
+// rotation of (lo, w), fixed for the whole segment because a step spans a multiple of K
+// elements).  No row is ever assembled, nothing is shuffled, nothing is staged.
+// Uniforms: fp32 elements take 21-bit fields, six to a Philox4x32-10 block (the in-cell
+// position is resolved to 2^-21 of the cell width, finer than an fp32 ulp of any
+// coordinate with |x| >= 4 cell widths), built as the mantissa of a float in [1, 2);
+// fp64 elements take 53 bits, two to a block.  Counters name the lane's first vector of
+// the step, so the value of every element depends on (seed, offset, N, position) only.
+// A vector that straddles two segments (or the end of the run) is written element by
+// element by its first lanes, each with its own segment's box.
+constexpr uint32_t TAG_FLAT = 0x46000000u;   // | bits 32.. of the vector index << 8 | block
+constexpr uint32_t TAG_EDGE = 0x45000000u;   // | bits 32.. of the element index << 8
+#ifndef LINT_FLAT_THREADS
+#define LINT_FLAT_THREADS 256
+#endif
+#ifndef LINT_FLAT_MINB
+#define LINT_FLAT_MINB 5
+#endif
+constexpr int FLAT_THREADS = LINT_FLAT_THREADS;
+
+template <typename T> struct FlatTraits;
+template <> struct FlatTraits<float> {
+    static constexpr int VEC = 4, FIELDS = 6;
+    // field f of a block: bits [21 f, 21 f + 21) of the 128-bit word, centred, in [2^-22, 1 - 2^-22]
+    template <int F>
+    static __device__ __forceinline__ float uniform(const uint4 &r) {
+        uint32_t s;
+        if (F == 0) s = r.x << 2;
+        else if (F == 1) s = __funnelshift_r(r.x, r.y, 19);
+        else if (F == 2) s = __funnelshift_r(r.y, r.z, 8);
+        else if (F == 3) s = __funnelshift_r(r.y, r.z, 29);
+        else if (F == 4) s = __funnelshift_r(r.z, r.w, 18);
+        else s = r.w >> 7;
+        return __uint_as_float((s & 0x007ffffcu) | 0x3f800002u) - 1.0f;
+    }
+    static __device__ __forceinline__ void store(float *p, const float (&v)[4]) {
+        __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
+    }
+};
+template <> struct FlatTraits<double> {
+    static constexpr int VEC = 2, FIELDS = 2;
+    template <int F>
+    static __device__ __forceinline__ double uniform(const uint4 &r) {
+        return F == 0 ? u53(r.x, r.y) : u53(r.z, r.w);
+    }
+    static __device__ __forceinline__ void store(double *p, const double (&v)[2]) {
+        __stcs(reinterpret_cast<double2 *>(p), make_double2(v[0], v[1]));
+    }
+};
+
+// vectors per lane per step: the smallest J >= 3 such that a step (32 J vectors) spans a
+// multiple of K elements, which keeps a lane's rotation fixed from step to step
+template <int K, int VEC>
+__host__ __device__ constexpr int flat_vectors_per_lane() {
+    int base = 1;
+    while ((32 * VEC * base) % K) ++base;
+    int J = base;
+    while (J < 3) J += base;
+    return J;
+}
+
+template <int F, int NF, typename T>
+struct FlatFieldOf {                       // uniform #F of a lane's step: block F / NF, field F % NF
+    static __device__ __forceinline__ T get(const uint4 *r) {
+        return FlatTraits<T>::template uniform<F % NF>(r[F / NF]);
+    }
+};
+
+template <int K, typename T, typename Cells, bool CELLS>
+__global__ void __launch_bounds__(FLAT_THREADS, LINT_FLAT_MINB)
+emit_flat_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
+                 const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ plan,
+                 const uint32_t *__restrict__ chunk_start, uint32_t chunk_rows, uint32_t *chunk_counter,
+                 uint2 key, uint64_t offset, T *__restrict__ out, int64_t *__restrict__ cell_idx) {
+    using FT = FlatTraits<T>;
+    constexpr int VEC = FT::VEC, NF = FT::FIELDS;
+    constexpr int J = flat_vectors_per_lane<K, VEC>();
+    constexpr int NB = (VEC * J + NF - 1) / NF;        // Philox blocks per lane per step
+    constexpr bool ROT = (VEC % K) != 0;               // do a lane's elements start at varying dimensions?
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sedges = reinterpret_cast<T *>(smem_raw);
+    __shared__ T s_box[FLAT_THREADS / 32][2 * K];
+    src.prepare(sedges);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nnz = *nnz_p;
+    const uint32_t N = plan[0];                        // rows of the flat run
+    const uint32_t nchunks = (N + chunk_rows - 1) / chunk_rows;
+    const uint32_t olo = (uint32_t)offset, ohi = (uint32_t)(offset >> 32);
+    constexpr uint32_t FULL = 0xffffffffu;
+
+    for (;;) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(chunk_counter, 1u);
+        chunk = __shfl_sync(FULL, chunk, 0);
+        if (chunk >= nchunks) break;
+        const uint32_t r0 = chunk * chunk_rows, r1 = min(r0 + chunk_rows, N);
+        uint64_t v = (uint64_t)r0 * K / VEC;                               // chunk_rows * K is a multiple of VEC
+        const uint64_t e_end = (uint64_t)r1 * K;
+        const uint64_t vend = (e_end + VEC - 1) / VEC;
+        uint32_t j = __ldg(chunk_start + chunk);                           // segment that holds row r0
+        // 32-entry register window of the segment table: lane i holds segment jbase + i
+        uint32_t jbase = j, w_off = 0xffffffffu, w_cid = 0;
+        auto reload = [&](uint32_t jb) {
+            jbase = jb;
+            w_off = jb + lane <= nnz ? __ldg(coff + jb + lane) : 0xffffffffu;
+            w_cid = jb + lane < nnz ? __ldg(cid + jb + lane) : 0u;
+        };
+        reload(j);
+        auto off = [&](uint32_t jj) { return __shfl_sync(FULL, w_off, (int)(jj - jbase)); };
+
+        while (v < vend) {
+            // invariant: segment j holds element VEC * v
+            if (j + VEC + 2 - jbase >= 32u) reload(j);
+            const uint32_t seg_end = min(off(j + 1), r1);
+            const uint64_t eb = (uint64_t)seg_end * K;                     // end element of the segment
+            const uint64_t v1 = eb / VEC;                                  // vectors [v, v1) lie inside it
+            if (v1 > v) {
+                const uint32_t cell = __shfl_sync(FULL, w_cid, (int)(j - jbase));
+                T lo[K], w[K], rlo[K], rw[K];
+                src.box(sedges, cell, lo, w);
+                if constexpr (ROT) {
+                    // rlo[t] = lo[(phi + t) % K], phi = dimension of the lane's first element
+                    __syncwarp();
+                    if (lane == 0) {
+#pragma unroll
+                        for (int d = 0; d < K; ++d) { s_box[warp][d] = lo[d]; s_box[warp][K + d] = w[d]; }
+                    }
+                    __syncwarp();
+                    const uint32_t phi = (uint32_t)(((v + lane) * VEC) % K);
+#pragma unroll
+                    for (int t = 0; t < K; ++t) {
+                        uint32_t d = phi + t;
+                        d = d >= K ? d - K : d;
+                        rlo[t] = s_box[warp][d];
+                        rw[t] = s_box[warp][K + d];
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < K; ++t) { rlo[t] = lo[t]; rw[t] = w[t]; }
+                }
+                // a step: J vectors per lane, vectors vl + 32 jj; rows past v1 masked if MASKED
+                auto step = [&](auto masked) {
+                    constexpr bool MASKED = decltype(masked)::value;
+                    const uint64_t vl = v + lane;
+                    uint4 r[NB];
+#pragma unroll
+                    for (int q = 0; q < NB; ++q)
+                        r[q] = philox4x32_10(make_uint4((uint32_t)vl, TAG_FLAT | ((uint32_t)(vl >> 32) << 8) | q,
+                                                        olo, ohi), key);
+                    T *p = out + vl * VEC;
+                    auto vec = [&](auto jj_tag) {
+                        constexpr int jj = decltype(jj_tag)::value;
+                        T x[VEC];
+                        auto el = [&](auto i_tag) {
+                            constexpr int i = decltype(i_tag)::value;
+                            constexpr int t = (32 * VEC * jj + i) % K;
+                            x[i] = affine_w(rlo[t], rw[t], FlatFieldOf<jj * VEC + i, NF, T>::get(r));
+                        };
+                        el(std::integral_constant<int, 0>{});
+                        el(std::integral_constant<int, 1>{});
+                        if constexpr (VEC == 4) {
+                            el(std::integral_constant<int, 2>{});
+                            el(std::integral_constant<int, 3>{});
+                        }
+                        if (!MASKED || vl + 32u * jj < v1) FT::store(p + (size_t)32 * VEC * jj, x);
+                    };
+                    vec(std::integral_constant<int, 0>{});
+                    vec(std::integral_constant<int, 1>{});
+                    vec(std::integral_constant<int, 2>{});
+                    if constexpr (J > 3) vec(std::integral_constant<int, 3>{});
+                    if constexpr (J > 4) vec(std::integral_constant<int, 4>{});
+                    static_assert(J <= 5, "flat step holds at most five vectors per lane");
+                };
+                while (v + 32u * J <= v1) {
+                    step(std::false_type{});
+                    v += 32u * J;
+                }
+                if (v1 - v > 32u) {
+                    step(std::true_type{});
+                    v = v1;
+                } else if (v < v1) {
+                    // at most one vector per lane left: one Philox block
+                    const uint64_t vl = v + lane;
+                    if (vl < v1) {
+                        const uint4 r1b = philox4x32_10(
+                            make_uint4((uint32_t)vl, TAG_FLAT | ((uint32_t)(vl >> 32) << 8) | 15u, olo, ohi), key);
+                        T x[VEC];
+                        auto el = [&](auto i_tag) {
+                            constexpr int i = decltype(i_tag)::value;
+                            x[i] = affine_w(rlo[i % K], rw[i % K], FlatFieldOf<i, NF, T>::get(&r1b));
+                        };
+                        el(std::integral_constant<int, 0>{});
+                        el(std::integral_constant<int, 1>{});
+                        if constexpr (VEC == 4) {
+                            el(std::integral_constant<int, 2>{});
+                            el(std::integral_constant<int, 3>{});
+                        }
+                        FT::store(out + vl * VEC, x);
+                    }
+                    v = v1;
+                }
+            }
+            if (v < vend && v * VEC < eb) {
+                // vector v holds the last elements of segment j and the first of the next one(s),
+                // or runs past the end of the flat rows: lane i writes element VEC v + i by itself
+                const uint64_t e = v * VEC + (lane < VEC ? lane : 0);
+                uint32_t js = j;
+#pragma unroll
+                for (int it = 0; it < VEC; ++it) {
+                    const uint32_t o = __shfl_sync(FULL, w_off, (int)min(js + 1 - jbase, 31u));
+                    if (e >= (uint64_t)o * K) ++js;
+                }
+                const uint32_t cell = __shfl_sync(FULL, w_cid, (int)min(js - jbase, 31u));
+                if (lane < VEC && e < e_end) {
+                    T lo[K], w[K];
+                    src.box(sedges, cell, lo, w);
+                    const uint32_t d = (uint32_t)(e % K);
+                    T lo_d = lo[0], w_d = w[0];
+#pragma unroll
+                    for (int dd = 1; dd < K; ++dd)
+                        if (d == dd) { lo_d = lo[dd]; w_d = w[dd]; }
+                    const uint4 rb = philox4x32_10(
+                        make_uint4((uint32_t)e, TAG_EDGE | ((uint32_t)(e >> 32) << 8), olo, ohi), key);
+                    store_stream(out + e, affine_w(lo_d, w_d, FT::template uniform<0>(rb)));
+                }
+                ++v;
+            }
+            // the segment that holds element VEC * v
+            while (j < nnz && (uint64_t)off(j + 1) * K <= v * VEC) ++j;
+        }
+        if (CELLS) {
+            // cell index of the chunk's rows: a second walk over its segments
+            uint32_t jj = __ldg(chunk_start + chunk);
+            uint32_t row = r0;
+            while (row < r1) {
+                const uint32_t end = min(__ldg(coff + jj + 1), r1);
+                const long long c = (long long)__ldg(cid + jj);
+                for (uint32_t r = row + lane; r < end; r += 32)
+                    __stcs(reinterpret_cast<long long *>(cell_idx) + r, c);
+                row = end;
+                ++jj;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------
+static void scan_list(const uint32_t *counts, uint32_t n, uint32_t id_mul, uint32_t id_add, const SegList &l,
+                      cudaStream_t st) {
+    const uint32_t nscan = (n + SCAN_TILE - 1) / SCAN_TILE;
+    scan_compact_kernel<<<nscan, SCAN_THREADS, 0, st>>>(counts, n, id_mul, id_add, l.tile_state, l.tile_counter,
+                                                       l.cid, l.coff, l.nnz, l.rows);
+}
+
+// counts -> offsets (+ compaction) -> row budget -> chunk starts, for both runs
+template <typename Cells>
+static int plan_rows(const Cells &src, const double *cdf, uint64_t ncells, uint64_t N, uint2 key,
+                     uint64_t offset, Stratum u, const Scratch &s, cudaStream_t st) {
+    const bool split = use_split(ncells, N);
+    const CdfSlice t{cdf, (uint32_t)ncells, u.u_lo, u.u_hi};
+    const double lam_per_unit = grouped_mean(N) / (u.u_hi - u.u_lo);
+    const int cblocks = (int)std::min<uint64_t>((ncells + 255) / 256, 148 * 16);
+    cudaMemsetAsync(s.zero_begin, 0, s.zero_bytes, st);
+    poisson_counts_kernel<<<cblocks, 256, 0, st>>>(src, t, lam_per_unit, key, offset, split, s.counts_flat,
+                                                   s.counts_rest);
+    if (split) scan_list(s.counts_flat, (uint32_t)ncells, 1, 0, s.flat, st);
+    scan_list(s.counts_rest, (uint32_t)ncells, split ? 2 : 1, split ? 1 : 0, s.rest, st);
+    plan_totals_kernel<<<1, 1, 0, st>>>(split ? s.flat.rows : nullptr, s.rest.rows, (uint32_t)N, s.plan,
+                                        s.chunk_counter);
+    const uint32_t chunk_rows = emit_chunk_rows(N);
+    const uint32_t nchunks = (uint32_t)((N + chunk_rows - 1) / chunk_rows);
+    const int sblocks = (int)std::max(1u, std::min((nchunks + 255) / 256, 148u * 8));
+    if (split)
+        chunk_start_kernel<<<sblocks, 256, 0, st>>>(s.flat.coff, s.flat.nnz, s.plan + 0, chunk_rows,
+                                                    s.flat.chunk_start);
+    chunk_start_kernel<<<sblocks, 256, 0, st>>>(s.rest.coff, s.rest.nnz, s.plan + 1, chunk_rows,
+                                                s.rest.chunk_start);
+    return check_launch("cell-major row planning");
+}
+
+#ifndef LINT_REST_BLOCKS_PER_SM
+#define LINT_REST_BLOCKS_PER_SM 2      // general emitter's share of an SM while the flat emitter runs
+#endif
+#ifndef LINT_FLAT_BLOCKS_PER_SM
+#define LINT_FLAT_BLOCKS_PER_SM 3
+#endif
+
+template <int K, typename T, typename Cells>
+int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t ncells, uint64_t N, uint2 key,
+                uint64_t offset, Stratum u, void *out, int64_t *cell_idx, cudaStream_t st) {
+    const bool split = use_split(ncells, N);
+    const CdfSlice t{cdf, (uint32_t)ncells, u.u_lo, u.u_hi};
+    const double lam_per_unit = grouped_mean(N) / (u.u_hi - u.u_lo);
+    const uint32_t chunk_rows = emit_chunk_rows(N);
+    const uint32_t nchunks = (uint32_t)((N + chunk_rows - 1) / chunk_rows);
+    const uint32_t per_cta = EMIT_THREADS / 32;
+    const size_t smem = src.smem_bytes(sizeof(T));
+    // with the split the general emitter leaves room on every SM for the flat one
+    SideStream *side = split ? side_stream() : nullptr;
+    cudaStream_t st_rest = st;
+    if (side) {
+        cudaEventRecord(side->fork, st);
+        cudaStreamWaitEvent(side->stream, side->fork, 0);
+        st_rest = side->stream;
+    }
+    const uint32_t rest_cap = split ? 148u * LINT_REST_BLOCKS_PER_SM : 148u * 8;
+    const int blocks = (int)std::min<uint32_t>((nchunks + per_cta - 1) / per_cta, rest_cap);
+    if (cell_idx)
+        emit_kernel<K, T, Cells, true><<<blocks, EMIT_THREADS, smem, st_rest>>>(
+            src, s.rest.cid, s.rest.coff, s.rest.nnz, s.plan, s.rest.chunk_start, chunk_rows, key, offset,
+            split ? 1u : 0u, t, lam_per_unit, (T *)out, cell_idx);
+    else
+        emit_kernel<K, T, Cells, false><<<blocks, EMIT_THREADS, smem, st_rest>>>(
+            src, s.rest.cid, s.rest.coff, s.rest.nnz, s.plan, s.rest.chunk_start, chunk_rows, key, offset,
+            split ? 1u : 0u, t, lam_per_unit, (T *)out, cell_idx);
+    if (int rc = check_launch("cell-major emission")) return rc;
+    if (split) {
+        const uint32_t fper = FLAT_THREADS / 32;
+        const int fblocks = (int)std::min<uint32_t>((nchunks + fper - 1) / fper, 148u * LINT_FLAT_BLOCKS_PER_SM);
+        if (cell_idx)
+            emit_flat_kernel<K, T, Cells, true><<<fblocks, FLAT_THREADS, smem, st>>>(
+                src, s.flat.cid, s.flat.coff, s.flat.nnz, s.plan, s.flat.chunk_start, chunk_rows, s.chunk_counter,
+                key, offset, (T *)out, cell_idx);
+        else
+            emit_flat_kernel<K, T, Cells, false><<<fblocks, FLAT_THREADS, smem, st>>>(
+                src, s.flat.cid, s.flat.coff, s.flat.nnz, s.plan, s.flat.chunk_start, chunk_rows, s.chunk_counter,
+                key, offset, (T *)out, cell_idx);
+        if (int rc = check_launch("cell-major flat emission")) return rc;
+    }
+    if (side) {
+        cudaEventRecord(side->join, side->stream);
+        cudaStreamWaitEvent(st, side->join, 0);
+    }
+    return LINT_OK;
+}
+
+template <int K>
+int grid_cellmajor_k(const lint_grid_t *g, uint64_t nc, uint64_t N, uint2 key, uint64_t offset, Stratum u,
+                     const Scratch &s, void *out, int64_t *cell_idx, cudaStream_t st) {
+    if (g->dtype == LINT_F32) {
+        GridCells<K, float> src{make_grid_view<K>(g, nc, true)};
+        if (int rc = plan_rows(src, g->cdf_dev, nc, N, key, offset, u, s, st)) return rc;
+        return launch_emit<K, float>(src, g->cdf_dev, s, nc, N, key, offset, u, out, cell_idx, st);
+    }
+    GridCells<K, double> src{make_grid_view<K>(g, nc, true)};
+    if (int rc = plan_rows(src, g->cdf_dev, nc, N, key, offset, u, s, st)) return rc;
+    return launch_emit<K, double>(src, g->cdf_dev, s, nc, N, key, offset, u, out, cell_idx, st);
+}
+
+// defined in lint_sample.cu: u-driven rows [*first_row_dev, N), at most max_rows of them
+int topup_grid(const lint_grid_t *g, int64_t N, const uint32_t *first_row_dev, int64_t max_rows,
+               uint64_t seed, uint64_t offset, double u_lo, double u_hi, void *out, int64_t *cell_idx,
+               cudaStream_t st);
+int topup_cells(const lint_cells_t *c, int64_t N, const uint32_t *first_row_dev, int64_t max_rows,
+                uint64_t seed, uint64_t offset, double u_lo, double u_hi, void *out, int64_t *cell_idx,
+                cudaStream_t st);
+
+template <int K>
+int cells_cellmajor_k(const lint_cells_t *c, uint64_t N, uint2 key, uint64_t offset, Stratum u,
+                      const Scratch &s, void *out, int64_t *cell_idx, cudaStream_t st) {
+    CellsView v;
+    v.mins = c->mins_dev;
+    v.widths = c->widths_dev;
+    v.corners = c->corners_dev;
+    v.rec = c->cell_records_dev;
+    v.table.cdf = c->cdf_dev;
+    v.table.guide = nullptr;
+    v.table.guide_bits = 0;
+    v.table.n = (uint32_t)c->ncells;
+    const uint64_t nc = (uint64_t)c->ncells;
+    if (c->dtype == LINT_F32) {
+        ListCells<K, float> src{v};
+        if (int rc = plan_rows(src, c->cdf_dev, nc, N, key, offset, u, s, st)) return rc;
+        return launch_emit<K, float>(src, c->cdf_dev, s, nc, N, key, offset, u, out, cell_idx, st);
+    }
+    ListCells<K, double> src{v};
+    if (int rc = plan_rows(src, c->cdf_dev, nc, N, key, offset, u, s, st)) return rc;
+    return launch_emit<K, double>(src, c->cdf_dev, s, nc, N, key, offset, u, out, cell_idx, st);
+}
+
+}  // namespace lint

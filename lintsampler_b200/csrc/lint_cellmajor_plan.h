@@ -1,0 +1,92 @@
+// Host-side plan of a cell-major draw: scratch layout and row-budget helpers shared by the
+// C-ABI file (lint_cellmajor.cu) and the per-dimension kernel translation units
+// (lint_cellmajor_inst.cu, compiled once per LINT_K so that the build runs in parallel).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/lintsampler_b200.h"
+
+namespace lint {
+
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+// Rows per warp work item ("chunk"): 4096 amortises the per-chunk set-up best (4.64 against
+// 4.73 ms per 1e9 rows with 2048), but a draw needs enough chunks to balance ~9500 resident warps.
+constexpr uint32_t EMIT_CHUNK_MIN = 2048, EMIT_CHUNK_MAX = 4096;
+inline uint32_t emit_chunk_rows(uint64_t N) { return N >= (1ull << 28) ? EMIT_CHUNK_MAX : EMIT_CHUNK_MIN; }
+
+// One segment list per run: the flat parts (cid = cell) and the rest (cid = 2 cell + 1 with
+// the split, the cell itself without).
+struct SegList {
+    uint32_t *cid, *coff, *chunk_start, *nnz, *rows, *tile_counter;
+    unsigned long long *tile_state;
+};
+struct Scratch {
+    uint32_t *counts_flat, *counts_rest;
+    SegList flat, rest;
+    uint32_t *plan;              // [0] T_f, [1] T_r, [2] T = first top-up row
+    uint32_t *chunk_counter;     // the flat emitter's work counter
+    void *zero_begin;            // [zero_begin, zero_begin + zero_bytes): cleared before every draw
+    size_t zero_bytes;
+    size_t bytes;
+};
+
+inline Scratch carve(void *base, uint64_t ncells, uint64_t N) {
+    const uint64_t nscan = (ncells + SCAN_TILE - 1) / SCAN_TILE;
+    const uint64_t nchunks = (N + EMIT_CHUNK_MIN - 1) / EMIT_CHUNK_MIN;      // the most any draw uses
+    uintptr_t p = (uintptr_t)base;
+    auto take = [&](size_t n) { uintptr_t q = p; p += (n + 255) & ~(size_t)255; return (void *)q; };
+    Scratch s;
+    s.counts_flat = (uint32_t *)take(ncells * 4);
+    s.counts_rest = (uint32_t *)take(ncells * 4);
+    for (SegList *l : {&s.flat, &s.rest}) {
+        l->cid = (uint32_t *)take((ncells + 1) * 4);
+        l->coff = (uint32_t *)take((ncells + 1) * 4);
+        l->chunk_start = (uint32_t *)take(std::max<uint64_t>(nchunks, 1) * 4);
+    }
+    s.plan = (uint32_t *)take(16);
+    s.chunk_counter = (uint32_t *)take(4);
+    s.zero_begin = (void *)p;
+    for (SegList *l : {&s.flat, &s.rest}) {
+        l->tile_state = (unsigned long long *)take(nscan * 8);
+        l->nnz = (uint32_t *)take(4);
+        l->rows = (uint32_t *)take(4);
+        l->tile_counter = (uint32_t *)take(4);
+    }
+    s.zero_bytes = (size_t)(p - (uintptr_t)s.zero_begin);
+    s.bytes = (size_t)(p - (uintptr_t)base);
+    return s;
+}
+
+// Expected number of grouped rows and the bound on the top-up tail: the Poisson
+// total T has mean L = N - 8 sqrt(N) and standard deviation sqrt(L) < sqrt(N), so
+// N - T lies in (0, 16 sqrt(N)) except for 8-sigma events on either side.
+inline double grouped_mean(uint64_t N) { return std::max(0.0, (double)N - 8.0 * std::sqrt((double)N)); }
+inline uint64_t topup_bound(uint64_t N) {
+    return std::min<uint64_t>(N, (uint64_t)(16.0 * std::sqrt((double)N)) + 64);
+}
+
+struct Stratum { double u_lo, u_hi; };
+
+constexpr uint64_t SPLIT_MIN_ROWS_PER_CELL = 32;
+inline bool use_split(uint64_t ncells, uint64_t N) { return N >= SPLIT_MIN_ROWS_PER_CELL * ncells; }
+
+
+// A second stream per device so that the two emitters of a draw run side by side (defined
+// in lint_cellmajor.cu).
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream *side_stream();
+
+// per-dimension entry points, instantiated in lint_cellmajor_inst.cu
+template <int K>
+int grid_cellmajor_k(const lint_grid_t *g, uint64_t nc, uint64_t N, uint2 key, uint64_t offset, Stratum u,
+                     const Scratch &s, void *out, int64_t *cell_idx, cudaStream_t st);
+template <int K>
+int cells_cellmajor_k(const lint_cells_t *c, uint64_t N, uint2 key, uint64_t offset, Stratum u,
+                      const Scratch &s, void *out, int64_t *cell_idx, cudaStream_t st);
+
+}  // namespace lint

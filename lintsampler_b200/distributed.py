@@ -198,10 +198,10 @@ class ShardedGrid:
     def launches_per_step(self, order="draw"):
         """Kernels of this library launched by enqueue_build + one sampling call:
         masses 1, cell records 0/1, parallel CDF 4, guide 1; then the u-driven
-        sampler (1) or the grouped path (Poisson counts, scan+compact, chunk
-        starts, emit, top-up = 5)."""
+        sampler (1) or the grouped path (Poisson counts, 2 x scan+compact, row budget,
+        2 x chunk starts, general emitter, flat emitter, top-up = 9)."""
         build = 6 + (1 if self.grid._rec is not None else 0)
-        return build + (5 if order == "cell" else 1)
+        return build + (9 if order == "cell" else 1)
 
     def describe(self):
         if self.world == 1:

@@ -122,6 +122,8 @@ class DensityGrid(DensityStructure):
 
     @property
     def total_mass(self):
+        if self._total_stale:                 # an unchecked update_densities left it behind
+            self._check_build()
         return self._total_mass
 
     @property
@@ -270,6 +272,7 @@ class DensityGrid(DensityStructure):
                    _device.ptr(self._guide), st)
         self._guide_bits = self._guide_bits_planned
         self._masses_host = None
+        self._total_stale = True
 
     @_device.on_device
     def update_densities(self, densities, check=True):
@@ -299,6 +302,7 @@ class DensityGrid(DensityStructure):
         if bad & _capi.LINT_FLAG_NONFINITE:                    # [grid.py:403-404]
             raise ValueError("DensityGrid: Detected non-finite density")
         self._total_mass = float(self._total.item()) / self._scale
+        self._total_stale = False
         if not (self._total_mass > 0.0) or not np.isfinite(self._total_mass):
             raise ValueError(
                 "DensityGrid: total mass of the grid is not positive and finite "

@@ -192,6 +192,13 @@ class LintSampler:
 
     # ------------------------------------------------------------------ uniform sources
     def _device(self):
+        """The device every buffer of a draw lives on: the (first) domain's own device when it
+        has one, else the `device=` argument / the current CUDA device."""
+        if self._device_arg is None:
+            for g in getattr(self, "grids", ()):
+                dev = getattr(g, "device", None)
+                if dev is not None:
+                    return dev
         return _device.require_cuda(self._device_arg)
 
     def _sobol_on_device(self):
@@ -383,6 +390,14 @@ class LintSampler:
         if self.return_tensor:
             if not N:
                 return X[0, 0] if self.dim == 1 else X[0]
+            if mode == "host":
+                # rng.shuffle(X, axis=0) [lintsampler.py:310-311] replayed on the device rows:
+                # shuffling arange(N) consumes the generator exactly as shuffling X would and
+                # yields the source row of every output row
+                import torch
+                perm = np.arange(n)
+                self.rng.shuffle(perm)
+                X = X[torch.as_tensor(perm, device=X.device)]
             return X.squeeze() if self.dim == 1 else X
         X = X.cpu().numpy()
         if mode == "host":
@@ -421,7 +436,8 @@ class LintSampler:
                              "in the domain's dtype")
         chunk = min(int(chunk), N)
         if getattr(self, "_stage", None) is None or self._stage[0].shape[0] < chunk \
-                or self._stage[0].dtype != tdt:
+                or self._stage[0].dtype != tdt or self._stage[0].shape[1] != self.dim \
+                or self._stage[0].device != dev:
             self._stage = [torch.empty((chunk, self.dim), dtype=tdt, device=dev) for _ in range(2)]
             self._copy_stream = torch.cuda.Stream(device=dev)
             self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
@@ -446,6 +462,7 @@ class LintSampler:
             done += n
             i += 1
         main.wait_stream(self._copy_stream)
+        self._copy_stream.synchronize()         # the caller may read `out` as soon as this returns
         return out
 
     # ------------------------------------------------------------------ row order
@@ -470,7 +487,11 @@ class LintSampler:
         X = X.contiguous()
         out = torch.empty_like(X)
         n, k = X.shape
-        seed = (self._philox_key ^ (0x9E3779B97F4A7C15 * (self._philox_offset + n + 1))) & (2 ** 64 - 1)
+        # every call gets its own permutation: QMC draws do not advance the Philox offset, so
+        # a per-sampler call counter is mixed in as well
+        self._permute_calls = getattr(self, "_permute_calls", 0) + 1
+        seed = (self._philox_key ^ (0x9E3779B97F4A7C15 * (self._philox_offset + n + 1))
+                ^ (0xD1B54A32D192ED03 * self._permute_calls)) & (2 ** 64 - 1)
         _capi.call("lint_permute_rows", _device.ptr(X), _device.ptr(out), n, k,
                    _device.lint_dtype(np.float32 if X.dtype == torch.float32 else np.float64),
                    C.c_uint64(seed), _device.stream_ptr(X.device))

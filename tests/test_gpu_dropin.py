@@ -79,6 +79,17 @@ def test_tree_sample_reproduces_reference_exactly(lb, name, pdf, kw, ref):
         tree.refine(**ref)
     x = lb.LintSampler(tree, seed=int(g["seed"]), rng_backend="numpy").sample(int(g["N"]))
     assert np.array_equal(np.atleast_1d(x).reshape(g["x_final"].shape), g["x_final"])
+    # the choose_cells return contract [tree.py:314-355] against the reference's leaf table:
+    # (leaf.x, leaf.x + leaf.dx, leaf.corner_densities) of the leaf the oracle's search picks
+    u = np.random.default_rng(11).random(3000)
+    u[:3] = [0.0, 0.5, 1.0 - 2.0 ** -53]
+    tmins, tmaxs, tcorners = tree.choose_cells(u)
+    idx = O.choose_index(O.cdf_from_masses(g["leaf_mass"]), u)
+    assert np.array_equal(tmins, g["leaf_x"][idx])
+    assert np.array_equal(tmaxs, g["leaf_x"][idx] + g["leaf_dx"][idx])
+    assert len(tcorners) == g["leaf_corners"].shape[1]
+    for j, c in enumerate(tcorners):
+        assert np.array_equal(c, g["leaf_corners"][idx, j])
 
 
 @pytest.mark.parametrize("name,qmc", [("m2d_quadrants", False), ("m1d_halves", False),

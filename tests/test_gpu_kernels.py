@@ -346,7 +346,38 @@ def test_sobol_stream_and_sampler_bit_exact(lb, name):
     assert np.array_equal(x2.cpu().numpy(), g["x_pre"][1500:])
 
 
+@pytest.mark.parametrize("name", ["g2d_fullcov", "g3d_holes"])
+def test_grid_choose_cells_contract_equals_oracle(lb, name):
+    """DensityGrid.choose_cells returns the reference's triple (mins, maxs, corners)
+    [grid.py:325-356] — compared with the oracle's restatement element for element."""
+    g = load_golden(name)
+    edges = golden_edges(g)
+    grid = _grid_from_golden(lb, g, cdf_mode="sequential")
+    u = np.random.default_rng(3).random(5000)
+    u[:3] = [0.0, 0.5, 1.0 - 2.0 ** -53]
+    mins, maxs, corners = grid.choose_cells(u)
+    _, rmins, rmaxs, rcorners = O.grid_choose_cells(edges, g["vertex_densities"], u)
+    assert np.array_equal(mins, rmins) and np.array_equal(maxs, rmaxs)
+    assert len(corners) == len(rcorners) == 2 ** len(edges)
+    for a, b in zip(corners, rcorners):
+        assert a.shape == b.shape and np.array_equal(a, b)
+
+
 # ----------------------------------------------------------------------------- cell-major throughput mode
+def grouped_runs(cells, N):
+    """Row layout of a cell-major draw: rows [0, T_f) flat parts grouped by cell, rows [T_f, T)
+    the rest grouped by cell, rows [T, N) the u-driven top-up in draw order (at most
+    16 sqrt(N) + 64 rows).  Returns (descents inside the grouped part, T)."""
+    tail = int(16 * np.sqrt(N)) + 64
+    down = np.flatnonzero(np.diff(cells) < 0)
+    early = down[down < N - tail - 1]            # a descent this early is the flat -> rest boundary
+    assert len(early) <= 1, early[:5]
+    rest = down[len(early):]
+    T = int(rest[0]) + 1 if len(rest) else N     # the grouped part ends at the next descent
+    assert N - tail <= T <= N
+    return len(early), T
+
+
 @pytest.mark.parametrize("name,dtype", [
     ("g1d_nonuniform", np.float64), ("g2d_fullcov", np.float64), ("g3d_iso", np.float64),
     ("g3d_holes", np.float64), ("g4d_iso", np.float64), ("g6d_iso", np.float64),
@@ -354,7 +385,7 @@ def test_sobol_stream_and_sampler_bit_exact(lb, name):
     ("g3d_holes", np.float32), ("g4d_iso", np.float32), ("g6d_iso", np.float32),
 ])
 def test_cellmajor_structure_and_distribution(lb, name, dtype, monkeypatch):
-    """Rows grouped by cell in C order, every row inside its cell, counts sum to N and
+    """Rows grouped by cell in C order (two runs: the flat parts, then the rest), every row inside its cell, counts sum to N and
     follow Multinomial(N, p) (chi^2), zero-mass cells never drawn, per-coordinate KS
     against oracle samples, determinism."""
     from scipy import stats
@@ -372,8 +403,8 @@ def test_cellmajor_structure_and_distribution(lb, name, dtype, monkeypatch):
     x3 = grid._sample_cellmajor(N, 11, N)
     assert not torch.equal(x, x3)                                            # offset decorrelates calls
     x, cells = x.cpu().numpy().astype(np.float64), cells.cpu().numpy()
-    tail = int(16 * np.sqrt(N)) + 64          # rows past the grouped part come from the u-driven top-up
-    assert x.shape == (N, k) and np.all(np.diff(cells[:N - tail]) >= 0)      # grouped, C order
+    assert x.shape == (N, k)
+    _, T = grouped_runs(cells, N)                                            # grouped, C order, two runs
     shape = tuple(len(e) - 1 for e in edges)
     multi = np.unravel_index(cells, shape)
     tol = 1e-6 if dtype == np.float32 else 0.0
@@ -401,10 +432,8 @@ def test_cellmajor_structure_and_distribution(lb, name, dtype, monkeypatch):
             den = f0 + np.sqrt(f0 * f0 + (f1 * f1 - f0 * f0) * uu)
             return np.where(den > 0, (f0 + f1) * uu / np.where(den > 0, den, 1.0), uu)
         monkeypatch.setattr(O, "quantile_1d", conjugate_quantile)
-        # the fp64 top-up rows are the u-driven kernel's (literal formula): drop them — the
-        # grouped part ends where the cell index first decreases
-        x = x[:int(np.argmax(np.diff(cells) < 0)) + 1]
-        assert N - tail <= len(x) < N
+        # the fp64 top-up rows are the u-driven kernel's (literal formula): drop them
+        x = x[:T]
     x_ref = O.grid_sample(edges, V, u)
     for d in range(k):
         assert stats.ks_2samp(x[:, d], x_ref[:, d]).pvalue > 1e-4
@@ -480,6 +509,45 @@ def test_cellmajor_counts_are_exactly_multinomial(lb):
         assert abs(rho - expect) < 0.25, (rho, expect)
 
 
+@pytest.mark.parametrize("lam", [12, 60, 130, 1000, 10_000, 90_000])
+@pytest.mark.parametrize("zigzag", [False, True])
+def test_cellmajor_poisson_counts_in_every_regime(lb, lam, zigzag):
+    """4096 equal-mass cells, N = lam * 4096 rows: the per-cell counts of ONE draw are 4096
+    (weakly dependent) Binomial(N, 1/4096) variates.  lam = 12 is the inversion branch of the
+    Poisson sampler, 60 PTRS on cells that are not split, 130 ... 9e4 PTRS on split cells (fp32
+    screen active below 1e5 — exactly where the 256^3 / 1e9 benchmark lives).  `zigzag`: vertex
+    densities 1, 3, 1, 3, ...: the same masses, but half of every cell's mass is residual (q = 1/2),
+    so the flat and the residual counts are drawn with means lam / 2 each; flat density: q = 1."""
+    import torch
+    from scipy import stats
+    C_ = 4096
+    e = np.linspace(0.0, 1.0, C_ + 1)
+    dens = np.where(np.arange(C_ + 1) % 2 == 0, 1.0, 3.0) if zigzag else np.ones(C_ + 1)
+    grid = lb.DensityGrid(e, lambda p: dens, vectorizedpdf=True, dtype=np.float32)
+    N = lam * C_
+    _, cells = grid._sample_cellmajor(N, 17, 0, want_cells=True)
+    counts = torch.bincount(cells, minlength=C_).cpu().numpy().astype(np.float64)
+    del cells
+    assert counts.sum() == N
+    p = 1.0 / C_
+    var = N * p * (1 - p)
+    # mean is exact by construction; dispersion: sum of squared z-scores ~ chi^2(C - 1)
+    z2 = ((counts - lam) ** 2 / var).sum()
+    assert stats.chi2.cdf(z2, C_ - 1) > 1e-5 and stats.chi2.sf(z2, C_ - 1) > 1e-5, z2 / (C_ - 1)
+    # shape: 32 equiprobable bins of the Binomial(N, p) pmf
+    edges_q = stats.binom.ppf(np.linspace(0, 1, 33)[1:-1], N, p)
+    edges_q = np.unique(edges_q)
+    cdf = np.concatenate([[0.0], stats.binom.cdf(edges_q, N, p), [1.0]])
+    expected = np.diff(cdf) * C_
+    observed = np.histogram(counts, bins=np.concatenate([[-0.5], edges_q + 0.5, [N + 0.5]]))[0]
+    keep = expected > 5
+    chi2 = ((observed[keep] - expected[keep]) ** 2 / expected[keep]).sum()
+    assert stats.chi2.sf(chi2, keep.sum() - 1) > 1e-5, (chi2, keep.sum())
+    # third moment (skewness of a binomial ~ 1/sqrt(lam)): 5 sigma of its sampling error
+    skew = (((counts - lam) / np.sqrt(var)) ** 3).mean()
+    assert abs(skew - (1 - 2 * p) / np.sqrt(var)) < 5 * np.sqrt(6.0 / C_)
+
+
 @pytest.mark.parametrize("name", ["t3d_refined", "t2d_refined", "t1d_refined"])
 def test_cellmajor_tree_leaves(lb, name):
     from scipy import stats
@@ -490,7 +558,7 @@ def test_cellmajor_tree_leaves(lb, name):
     N = 200_000
     x, cells = table.sample_cellmajor(N, 5, 0, want_cells=True)
     x, cells = x.cpu().numpy(), cells.cpu().numpy()
-    assert np.all(np.diff(cells[:N - int(16 * np.sqrt(N)) - 64]) >= 0)
+    grouped_runs(cells, N)
     assert np.all(x >= g["leaf_x"][cells]) and np.all(x <= g["leaf_x"][cells] + g["leaf_dx"][cells])
     p = g["leaf_mass"] / g["leaf_mass"].sum()
     counts = np.bincount(cells, minlength=p.size)
@@ -618,5 +686,5 @@ def test_cellmajor_draws_beyond_the_per_call_limit_are_chunked(lb, monkeypatch):
     assert counts.sum() == N and stats.chi2.sf(((obs - exp) ** 2 / exp).sum(), len(obs) - 1) > 1e-4
     # three pieces, each grouped by cell on its own (the last ~16 sqrt(n) rows of a piece are
     # its u-driven top-up, in draw order)
-    assert np.sum(np.diff(cells[:94_000]) < 0) == 0 and np.sum(np.diff(cells[100_000:194_000]) < 0) == 0
-    assert cells[100_000] < cells[90_000]
+    assert np.sum(np.diff(cells[:94_000]) < 0) <= 1 and np.sum(np.diff(cells[100_000:194_000]) < 0) <= 1
+    assert cells[100_000] < cells[99_000 - int(16 * np.sqrt(100_000))]

@@ -332,3 +332,21 @@ def test_sobol_sorted_enumeration_construction(d, m, seed):
         assert x[k] >> (32 - m) == y
         X[y] = x
     assert np.array_equal(U[np.argsort(U[:, k])], X.astype(np.float64) * 2.0 ** -32)
+
+
+def test_ptrs_fp32_screen_never_decides_wrongly():
+    """The Poisson count sampler settles most PTRS acceptance tests in fp32 (csrc/lint_cellmajor.cuh);
+    scripts/ptrs_fp32_screen_check.py replays that screen in float32 with the worst-case error of the
+    device intrinsics added: its error must stay well inside the tolerance band, for every lambda
+    regime the kernel uses it in (10 <= lambda < 1e5)."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts",
+                        "ptrs_fp32_screen_check.py")
+    spec = importlib.util.spec_from_file_location("ptrs_fp32_screen_check", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    res = mod.check(40_000, seed=1)
+    assert res["proposals"] > 100_000
+    assert res["wrong_decisions"] == 0
+    assert res["max_err_over_tol"] < 0.5
