@@ -14,8 +14,9 @@ LINT_F32, LINT_F64 = 0, 1
 LINT_CDF_PARALLEL, LINT_CDF_SEQUENTIAL = 0, 1
 LINT_FLAG_NEGATIVE, LINT_FLAG_NONFINITE = 1, 2
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib",
-                        "liblintsampler_b200.so")
+# LINTSAMPLER_B200_LIB: load another build of the same library (kernel experiments)
+LIB_PATH = os.environ.get("LINTSAMPLER_B200_LIB") or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), "_lib", "liblintsampler_b200.so")
 
 
 class LintGrid(C.Structure):

@@ -7,24 +7,6 @@ namespace lint {
 
 int validate_grid(const lint_grid_t *g, bool need_cdf, uint64_t *ncells_out, uint64_t *nverts_out);
 
-// A second stream so that the two emitters run side by side: the flat emitter is bound by
-// the output bandwidth, the general one by instruction issue.  One pair of events and one
-// stream per device, created on first use; the fork and the join are event waits, so the
-// caller's stream semantics are unchanged (the call is still asynchronous and complete, in
-// stream order, on `st`).
-SideStream *side_stream() {
-    static SideStream table[64];
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    SideStream &s = table[dev];
-    if (!s.stream) {
-        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
-    }
-    return &s;
-}
-
 static int check_common(int64_t N, uint64_t ncells, double u_lo, double u_hi, void *out, void *scratch,
                         size_t scratch_bytes, const char *what) {
     if (!(u_lo >= 0.0) || !(u_hi <= 1.0) || !(u_lo < u_hi))

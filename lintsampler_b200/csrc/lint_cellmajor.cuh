@@ -40,6 +40,7 @@
 // afterwards.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <type_traits>
 #include <cuda_pipeline.h>
 #pragma once
@@ -158,13 +159,6 @@ __device__ __forceinline__ double cell_lambda(const CdfSlice &t, uint32_t c, dou
     return __dmul_rn(m, lam_per_unit);
 }
 
-// A cell is split into its flat and residual parts only where that pays: below this
-// many expected rows the residual part would be a handful of rows with a segment of
-// their own, dearer than drawing all of the cell's rows from the full interpolant.
-#ifndef LINT_SPLIT_MIN_LAMBDA
-#define LINT_SPLIT_MIN_LAMBDA 128.0
-#endif
-constexpr double SPLIT_MIN_LAMBDA = LINT_SPLIT_MIN_LAMBDA;
 
 // counts_rest[c] = rows of cell c drawn from its full interpolant (no split), or with the
 // split: counts_flat[c] = flat rows, counts_rest[c] = residual rows — or all rows of a cell
@@ -368,7 +362,7 @@ struct GridCells {
 #pragma unroll
         for (int d = 0; d < K; ++d) {
             T hi;
-            if (g.edge_total) {
+            if (g.edge_total && smem) {
                 lo[d] = smem[g.edge_off[d] + i[d]];
                 hi = smem[g.edge_off[d] + i[d] + 1];
             } else {
@@ -713,34 +707,40 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
 // (sampling.py:126 with z = u), so the run is a stream of independent ELEMENTS: element e
 // of the row-major output belongs to row e / K, dimension e % K, and needs nothing but the
 // box of that row's segment and a fresh uniform.  The kernel therefore works on 16-byte
-// output vectors instead of rows: in a step, lane l writes vectors v + l, v + 32 + l, ...
-// of the segment — each store instruction covers 512 contiguous bytes of the output — and a
-// vector's elements simply use the box constants of their own dimensions (a per-lane
-// rotation of (lo, w), fixed for the whole segment because a step spans a multiple of K
-// elements).  No row is ever assembled, nothing is shuffled, nothing is staged.
+// output vectors, not rows, in STEPS laid over the output itself: step s of a chunk covers
+// vectors [v, v + 32 J) — a whole number of rows — and lane l writes vectors v + l,
+// v + 32 + l, ...: every store instruction covers 512 contiguous bytes.  Because steps
+// start at multiples of K elements, the dimension of a lane's i-th element is the same in
+// every step: a lane keeps the box constants rotated once and for all (dsel below).  No row
+// is ever assembled, nothing is shuffled.
+//   * A step that lies inside one segment (the common case: flat segments are hundreds of
+//     rows long) runs straight-line code with that segment's constants in registers.
+//   * A step that holds a segment boundary (or the end of the run) stages the boxes of the
+//     segments it touches in shared memory, one segment per lane, and every element picks
+//     its own segment's constants; vectors are still written whole.
 // Uniforms: fp32 elements take 21-bit fields, six to a Philox4x32-10 block (the in-cell
 // position is resolved to 2^-21 of the cell width, finer than an fp32 ulp of any
 // coordinate with |x| >= 4 cell widths), built as the mantissa of a float in [1, 2);
 // fp64 elements take 53 bits, two to a block.  Counters name the lane's first vector of
-// the step, so the value of every element depends on (seed, offset, N, position) only.
-// A vector that straddles two segments (or the end of the run) is written element by
-// element by its first lanes, each with its own segment's box.
+// the step, so the value of every element depends on (seed, offset, N, position) only —
+// not on which path or which warp produced it.
 constexpr uint32_t TAG_FLAT = 0x46000000u;   // | bits 32.. of the vector index << 8 | block
-constexpr uint32_t TAG_EDGE = 0x45000000u;   // | bits 32.. of the element index << 8
 #ifndef LINT_FLAT_THREADS
 #define LINT_FLAT_THREADS 256
 #endif
 #ifndef LINT_FLAT_MINB
-#define LINT_FLAT_MINB 5
+#define LINT_FLAT_MINB 3
 #endif
 constexpr int FLAT_THREADS = LINT_FLAT_THREADS;
 
 template <typename T> struct FlatTraits;
 template <> struct FlatTraits<float> {
     static constexpr int VEC = 4, FIELDS = 6;
-    // field f of a block: bits [21 f, 21 f + 21) of the 128-bit word, centred, in [2^-22, 1 - 2^-22]
+    // field f of a block: bits [21 f, 21 f + 21) of the 128-bit word, centred, in [2^-22, 1 - 2^-22].
+    // (m, o) = (0x007ffffc, 0x3f800002) held in registers by the caller, so that mask and
+    // exponent are one three-input logic instruction.
     template <int F>
-    static __device__ __forceinline__ float uniform(const uint4 &r) {
+    static __device__ __forceinline__ float uniform(const uint4 &r, uint32_t m, uint32_t o) {
         uint32_t s;
         if (F == 0) s = r.x << 2;
         else if (F == 1) s = __funnelshift_r(r.x, r.y, 19);
@@ -748,16 +748,23 @@ template <> struct FlatTraits<float> {
         else if (F == 3) s = __funnelshift_r(r.y, r.z, 29);
         else if (F == 4) s = __funnelshift_r(r.z, r.w, 18);
         else s = r.w >> 7;
-        return __uint_as_float((s & 0x007ffffcu) | 0x3f800002u) - 1.0f;
+        return __uint_as_float((s & m) | o) - 1.0f;
     }
     static __device__ __forceinline__ void store(float *p, const float (&v)[4]) {
+#if defined(LINT_FLAT_NOSTORE)
+        if (v[0] == 12345.678f && v[1] == v[2] && v[3] == 1.0f)          // experiment: never true
+#endif
+#if defined(LINT_FLAT_PLAINSTORE)
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+#else
         __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
+#endif
     }
 };
 template <> struct FlatTraits<double> {
     static constexpr int VEC = 2, FIELDS = 2;
     template <int F>
-    static __device__ __forceinline__ double uniform(const uint4 &r) {
+    static __device__ __forceinline__ double uniform(const uint4 &r, uint32_t, uint32_t) {
         return F == 0 ? u53(r.x, r.y) : u53(r.z, r.w);
     }
     static __device__ __forceinline__ void store(double *p, const double (&v)[2]) {
@@ -765,45 +772,82 @@ template <> struct FlatTraits<double> {
     }
 };
 
-// vectors per lane per step: the smallest J >= 3 such that a step (32 J vectors) spans a
-// multiple of K elements, which keeps a lane's rotation fixed from step to step
+// Vectors per lane per step: a step (32 J vectors) must span a whole number of rows and
+// divide a chunk; J = 3 or 5 where K has that factor, 4 otherwise.
 template <int K, int VEC>
 __host__ __device__ constexpr int flat_vectors_per_lane() {
     int base = 1;
     while ((32 * VEC * base) % K) ++base;
-    int J = base;
-    while (J < 3) J += base;
-    return J;
+    return base == 1 ? 4 : base;
 }
 
 template <int F, int NF, typename T>
 struct FlatFieldOf {                       // uniform #F of a lane's step: block F / NF, field F % NF
-    static __device__ __forceinline__ T get(const uint4 *r) {
-        return FlatTraits<T>::template uniform<F % NF>(r[F / NF]);
+    static __device__ __forceinline__ T get(const uint4 *r, uint32_t m, uint32_t o) {
+        return FlatTraits<T>::template uniform<F % NF>(r[F / NF], m, o);
     }
 };
 
-template <int K, typename T, typename Cells, bool CELLS>
+// f(integral_constant<int, 0>) ... f(integral_constant<int, N - 1>)
+template <int I, int N, typename Fn>
+__device__ __forceinline__ void static_for(Fn &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+// Box of every flat segment, once per draw: boxes[j] = (lo[K], w[K]) of segment j's cell in the
+// output type (w = maxs - mins, sampling.py:126).  The emitter reads a segment's constants from
+// this table (a few coalesced loads) instead of unravelling the cell index and gathering its
+// edges; the table is a fraction of a percent of the output and stays in L2.
+template <int K, typename T, typename Cells>
+__global__ void __launch_bounds__(256)
+flat_boxes_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ nnz_p,
+                  T *__restrict__ boxes) {
+    const uint32_t nnz = *nnz_p;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += gridDim.x * blockDim.x) {
+        T lo[K], w[K];
+        src.box((const T *)nullptr, __ldg(cid + j), lo, w);
+#pragma unroll
+        for (int d = 0; d < K; ++d) {
+            boxes[(size_t)j * (2 * K) + d] = lo[d];
+            boxes[(size_t)j * (2 * K) + K + d] = w[d];
+        }
+    }
+}
+
+template <int K, typename T, bool CELLS>
 __global__ void __launch_bounds__(FLAT_THREADS, LINT_FLAT_MINB)
-emit_flat_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
+emit_flat_kernel(const T *__restrict__ boxes, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
                  const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ plan,
                  const uint32_t *__restrict__ chunk_start, uint32_t chunk_rows, uint32_t *chunk_counter,
-                 uint2 key, uint64_t offset, T *__restrict__ out, int64_t *__restrict__ cell_idx) {
+                 const __grid_constant__ PhiloxKeys key, uint64_t offset, T *__restrict__ out,
+                 int64_t *__restrict__ cell_idx) {
     using FT = FlatTraits<T>;
+    const uint32_t fm = key.field_mask, fo = key.field_one;      // see FlatTraits<float>::uniform
     constexpr int VEC = FT::VEC, NF = FT::FIELDS;
     constexpr int J = flat_vectors_per_lane<K, VEC>();
     constexpr int NB = (VEC * J + NF - 1) / NF;        // Philox blocks per lane per step
-    constexpr bool ROT = (VEC % K) != 0;               // do a lane's elements start at varying dimensions?
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *sedges = reinterpret_cast<T *>(smem_raw);
-    __shared__ T s_box[FLAT_THREADS / 32][2 * K];
-    src.prepare(sedges);
+    constexpr uint32_t STEP_ELEMS = 32u * VEC * J, STEP_ROWS = STEP_ELEMS / K;
+    static_assert(STEP_ELEMS % K == 0 && EMIT_CHUNK_MIN % STEP_ROWS == 0, "steps tile rows and chunks");
+    constexpr int WARPS = FLAT_THREADS / 32;
+    constexpr int SLOT = 2 * K + 1;                    // staged box: lo[K], w[K]; odd stride
+    __shared__ T s_box_all[WARPS][32 * SLOT];
+    __shared__ uint32_t s_end_all[WARPS][32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T *s_box = s_box_all[warp];
+    uint32_t *s_end = s_end_all[warp];
     const uint32_t nnz = *nnz_p;
     const uint32_t N = plan[0];                        // rows of the flat run
     const uint32_t nchunks = (N + chunk_rows - 1) / chunk_rows;
     const uint32_t olo = (uint32_t)offset, ohi = (uint32_t)(offset >> 32);
     constexpr uint32_t FULL = 0xffffffffu;
+    // dimension of the lane's elements: element i of vector jj has dimension
+    // (VEC * lane + 32 * VEC * jj + i) % K = dsel[(32 * VEC * jj + i) % K]
+    uint32_t dsel[K];
+#pragma unroll
+    for (int t = 0; t < K; ++t) dsel[t] = (VEC * lane + t) % K;
 
     for (;;) {
         uint32_t chunk = 0;
@@ -811,139 +855,172 @@ emit_flat_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__
         chunk = __shfl_sync(FULL, chunk, 0);
         if (chunk >= nchunks) break;
         const uint32_t r0 = chunk * chunk_rows, r1 = min(r0 + chunk_rows, N);
-        uint64_t v = (uint64_t)r0 * K / VEC;                               // chunk_rows * K is a multiple of VEC
-        const uint64_t e_end = (uint64_t)r1 * K;
-        const uint64_t vend = (e_end + VEC - 1) / VEC;
         uint32_t j = __ldg(chunk_start + chunk);                           // segment that holds row r0
         // 32-entry register window of the segment table: lane i holds segment jbase + i
-        uint32_t jbase = j, w_off = 0xffffffffu, w_cid = 0;
+        uint32_t jbase = j, w_off = 0xffffffffu;
         auto reload = [&](uint32_t jb) {
             jbase = jb;
             w_off = jb + lane <= nnz ? __ldg(coff + jb + lane) : 0xffffffffu;
-            w_cid = jb + lane < nnz ? __ldg(cid + jb + lane) : 0u;
         };
         reload(j);
-        auto off = [&](uint32_t jj) { return __shfl_sync(FULL, w_off, (int)(jj - jbase)); };
+        // Stage the boxes of the segments from jb on that start at or before row `upto`, as far as
+        // the window reaches: window entry b (= segment jbase + b, one per lane) goes to slot b;
+        // s_end[b] = the segment's end as an element index relative to row `rel` (saturated),
+        // s_box[b] = (lo, w).  Returns the number staged (>= 1: segment jb) and the first slot.
+        auto stage = [&](uint32_t jb, uint32_t upto, uint32_t rel, uint32_t &first) {
+            if (jb - jbase >= 24u) reload(jb);
+            first = jb - jbase;
+            const uint32_t end = __shfl_down_sync(FULL, w_off, 1);         // lane 31: unused
+            const bool valid = lane >= first && lane < 31 && jbase + lane < nnz && w_off <= upto;
+            __syncwarp();
+            if (valid) {
+                const T *b = boxes + (size_t)(jbase + lane) * (2 * K);
+#pragma unroll
+                for (int d = 0; d < 2 * K; ++d) s_box[lane * SLOT + d] = __ldg(b + d);
+                const uint64_t e = (uint64_t)(min(end, N) - rel) * K;      // end > rel: the segment reaches row rel
+                s_end[lane] = (uint32_t)min(e, (uint64_t)0xfffffff0u);
+            }
+            __syncwarp();
+            return (uint32_t)__popc(__ballot_sync(FULL, valid));
+        };
+        T rlo[K], rw[K];                               // constants of segment `held`, rotated for this lane
+        uint32_t held = 0xffffffffu;
+        auto take = [&](uint32_t slot) {               // registers <- staged slot
+#pragma unroll
+            for (int t = 0; t < K; ++t) {
+                rlo[t] = s_box[slot * SLOT + dsel[t]];
+                rw[t] = s_box[slot * SLOT + K + dsel[t]];
+            }
+        };
 
-        while (v < vend) {
-            // invariant: segment j holds element VEC * v
-            if (j + VEC + 2 - jbase >= 32u) reload(j);
-            const uint32_t seg_end = min(off(j + 1), r1);
-            const uint64_t eb = (uint64_t)seg_end * K;                     // end element of the segment
-            const uint64_t v1 = eb / VEC;                                  // vectors [v, v1) lie inside it
-            if (v1 > v) {
-                const uint32_t cell = __shfl_sync(FULL, w_cid, (int)(j - jbase));
-                T lo[K], w[K], rlo[K], rw[K];
-                src.box(sedges, cell, lo, w);
-                if constexpr (ROT) {
-                    // rlo[t] = lo[(phi + t) % K], phi = dimension of the lane's first element
-                    __syncwarp();
-                    if (lane == 0) {
+        for (uint32_t R = r0; R < r1; R += STEP_ROWS) {
+            // invariant: segment j holds row R
+            const uint64_t vl = (uint64_t)R * K / VEC + lane;              // the lane's first vector
+            uint4 r[NB];
 #pragma unroll
-                        for (int d = 0; d < K; ++d) { s_box[warp][d] = lo[d]; s_box[warp][K + d] = w[d]; }
-                    }
-                    __syncwarp();
-                    const uint32_t phi = (uint32_t)(((v + lane) * VEC) % K);
+            for (int q = 0; q < NB; ++q)
+#if defined(LINT_FLAT_NOPHILOX)
+                r[q] = make_uint4((uint32_t)vl * 0x9E3779B9u, q ^ olo, ohi, (uint32_t)vl + key.k0[3]);   // experiment
+#else
+                r[q] = philox4x32_10(make_uint4((uint32_t)vl, TAG_FLAT | ((uint32_t)(vl >> 32) << 8) | q, olo, ohi),
+                                     key);
+#endif
+            T u[J][VEC];                                                   // the lane's uniforms of this step
+            static_for<0, J * VEC>([&](auto f_tag) {
+                constexpr int f = decltype(f_tag)::value;
+                u[f / VEC][f % VEC] = FlatFieldOf<f, NF, T>::get(r, fm, fo);
+            });
+            T *p = out + vl * VEC;
+            if (j + 3 - jbase >= 32u) reload(j);
+            const uint32_t seg_end = __shfl_sync(FULL, w_off, (int)(j + 1 - jbase));
+            const bool whole = R + STEP_ROWS <= N;                         // the step ends inside the run
+            // constants of segment sg, rotated for this lane, from the box table
+            auto load = [&](uint32_t sg, T (&lo)[K], T (&w)[K]) {
+                const T *b = boxes + (size_t)sg * (2 * K);
 #pragma unroll
-                    for (int t = 0; t < K; ++t) {
-                        uint32_t d = phi + t;
-                        d = d >= K ? d - K : d;
-                        rlo[t] = s_box[warp][d];
-                        rw[t] = s_box[warp][K + d];
-                    }
-                } else {
-#pragma unroll
-                    for (int t = 0; t < K; ++t) { rlo[t] = lo[t]; rw[t] = w[t]; }
+                for (int t = 0; t < K; ++t) { lo[t] = __ldg(b + dsel[t]); w[t] = __ldg(b + K + dsel[t]); }
+            };
+            if (whole && seg_end >= R + STEP_ROWS) {
+                // ---- the whole step lies in segment j
+                if (held != j) {
+                    load(j, rlo, rw);
+                    held = j;
                 }
-                // a step: J vectors per lane, vectors vl + 32 jj; rows past v1 masked if MASKED
-                auto step = [&](auto masked) {
-                    constexpr bool MASKED = decltype(masked)::value;
-                    const uint64_t vl = v + lane;
-                    uint4 r[NB];
 #pragma unroll
-                    for (int q = 0; q < NB; ++q)
-                        r[q] = philox4x32_10(make_uint4((uint32_t)vl, TAG_FLAT | ((uint32_t)(vl >> 32) << 8) | q,
-                                                        olo, ohi), key);
-                    T *p = out + vl * VEC;
-                    auto vec = [&](auto jj_tag) {
-                        constexpr int jj = decltype(jj_tag)::value;
-                        T x[VEC];
-                        auto el = [&](auto i_tag) {
-                            constexpr int i = decltype(i_tag)::value;
-                            constexpr int t = (32 * VEC * jj + i) % K;
-                            x[i] = affine_w(rlo[t], rw[t], FlatFieldOf<jj * VEC + i, NF, T>::get(r));
-                        };
-                        el(std::integral_constant<int, 0>{});
-                        el(std::integral_constant<int, 1>{});
-                        if constexpr (VEC == 4) {
-                            el(std::integral_constant<int, 2>{});
-                            el(std::integral_constant<int, 3>{});
-                        }
-                        if (!MASKED || vl + 32u * jj < v1) FT::store(p + (size_t)32 * VEC * jj, x);
-                    };
-                    vec(std::integral_constant<int, 0>{});
-                    vec(std::integral_constant<int, 1>{});
-                    vec(std::integral_constant<int, 2>{});
-                    if constexpr (J > 3) vec(std::integral_constant<int, 3>{});
-                    if constexpr (J > 4) vec(std::integral_constant<int, 4>{});
-                    static_assert(J <= 5, "flat step holds at most five vectors per lane");
-                };
-                while (v + 32u * J <= v1) {
-                    step(std::false_type{});
-                    v += 32u * J;
-                }
-                if (v1 - v > 32u) {
-                    step(std::true_type{});
-                    v = v1;
-                } else if (v < v1) {
-                    // at most one vector per lane left: one Philox block
-                    const uint64_t vl = v + lane;
-                    if (vl < v1) {
-                        const uint4 r1b = philox4x32_10(
-                            make_uint4((uint32_t)vl, TAG_FLAT | ((uint32_t)(vl >> 32) << 8) | 15u, olo, ohi), key);
-                        T x[VEC];
-                        auto el = [&](auto i_tag) {
-                            constexpr int i = decltype(i_tag)::value;
-                            x[i] = affine_w(rlo[i % K], rw[i % K], FlatFieldOf<i, NF, T>::get(&r1b));
-                        };
-                        el(std::integral_constant<int, 0>{});
-                        el(std::integral_constant<int, 1>{});
-                        if constexpr (VEC == 4) {
-                            el(std::integral_constant<int, 2>{});
-                            el(std::integral_constant<int, 3>{});
-                        }
-                        FT::store(out + vl * VEC, x);
+                for (int jj = 0; jj < J; ++jj) {
+                    T x[VEC];
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        const int t = (32 * VEC * jj + i) % K;
+                        x[i] = affine_w(rlo[t], rw[t], u[jj][i]);
                     }
-                    v = v1;
+                    FT::store(p + (size_t)32 * VEC * jj, x);
+                }
+                if (seg_end == R + STEP_ROWS) ++j;
+            } else if (whole && __shfl_sync(FULL, w_off, (int)(j + 2 - jbase)) >= R + STEP_ROWS) {
+                // ---- one boundary inside the step: elements below it belong to segment j, the
+                // others to segment j + 1; both boxes in registers, every element picks its own
+                if (held != j) load(j, rlo, rw);
+                T blo[K], bw[K];
+                load(j + 1, blo, bw);
+                const uint32_t eb = (seg_end - R) * K;                     // first element of segment j + 1
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) {
+                    T x[VEC];
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        const int t = (32 * VEC * jj + i) % K;
+                        const T xa = affine_w(rlo[t], rw[t], u[jj][i]), xb = affine_w(blo[t], bw[t], u[jj][i]);
+                        x[i] = VEC * (lane + 32u * jj) + i >= eb ? xb : xa;
+                    }
+                    FT::store(p + (size_t)32 * VEC * jj, x);
+                }
+#pragma unroll
+                for (int t = 0; t < K; ++t) { rlo[t] = blo[t]; rw[t] = bw[t]; }
+                held = j + 1;
+                j += __shfl_sync(FULL, w_off, (int)(j + 2 - jbase)) == R + STEP_ROWS ? 2 : 1;
+            } else {
+                // ---- segment boundaries (or the end of the run) inside the step: every element
+                // takes the box of its own segment.  At most 31 segments are staged at a time;
+                // elements past the last staged one wait for the next pass.
+                const uint32_t step_end = min(R + STEP_ROWS, N);           // rows
+                const uint32_t lim = (step_end - R) * K;                   // elements of the step that exist
+                uint32_t done = 0;                                         // elements [0, done) are settled
+                uint32_t jp = j;
+                for (;;) {
+                    uint32_t first;
+                    const uint32_t ns = stage(jp, step_end, R, first);
+                    // elements below `upto` belong to the staged segments
+                    const uint32_t last_end = s_end[first + ns - 1];
+                    const uint32_t upto = min(last_end, lim);
+                    // slot of every element: first + the number of staged segments that end at or
+                    // before it; the element's uniform is replaced by its coordinate in place
+#pragma unroll
+                    for (int jj = 0; jj < J; ++jj) {
+                        uint32_t sidx[VEC];
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) sidx[i] = first;
+                        for (uint32_t b = first; b + 1 < first + ns; ++b) {
+                            const uint32_t eb = s_end[b];
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) sidx[i] += VEC * (lane + 32u * jj) + i >= eb ? 1u : 0u;
+                        }
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) {
+                            const int t = (32 * VEC * jj + i) % K;
+                            const uint32_t e = VEC * (lane + 32u * jj) + i;
+                            if (e >= done && e < upto)
+                                u[jj][i] = affine_w(s_box[sidx[i] * SLOT + dsel[t]], s_box[sidx[i] * SLOT + K + dsel[t]],
+                                                    u[jj][i]);
+                        }
+                    }
+                    done = upto;
+                    if (done >= lim) {
+                        // the segment that holds row step_end: the first staged one that ends after it
+                        uint32_t adv = 0;
+                        for (uint32_t b = first; b < first + ns; ++b) adv += s_end[b] <= lim ? 1u : 0u;
+                        j = jp + adv;
+                        held = 0xffffffffu;
+                        if (adv < ns) {                                    // ... and it is staged: keep its constants
+                            take(first + adv);
+                            held = j;
+                        }
+                        break;
+                    }
+                    jp += ns;                                              // all staged segments ended before `lim`
+                }
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) {
+                    const uint32_t e0 = VEC * (lane + 32u * jj);
+                    if (e0 + VEC <= lim) {
+                        FT::store(p + (size_t)32 * VEC * jj, u[jj]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i)
+                            if (e0 + i < lim) store_stream(p + (size_t)32 * VEC * jj + i, u[jj][i]);
+                    }
                 }
             }
-            if (v < vend && v * VEC < eb) {
-                // vector v holds the last elements of segment j and the first of the next one(s),
-                // or runs past the end of the flat rows: lane i writes element VEC v + i by itself
-                const uint64_t e = v * VEC + (lane < VEC ? lane : 0);
-                uint32_t js = j;
-#pragma unroll
-                for (int it = 0; it < VEC; ++it) {
-                    const uint32_t o = __shfl_sync(FULL, w_off, (int)min(js + 1 - jbase, 31u));
-                    if (e >= (uint64_t)o * K) ++js;
-                }
-                const uint32_t cell = __shfl_sync(FULL, w_cid, (int)min(js - jbase, 31u));
-                if (lane < VEC && e < e_end) {
-                    T lo[K], w[K];
-                    src.box(sedges, cell, lo, w);
-                    const uint32_t d = (uint32_t)(e % K);
-                    T lo_d = lo[0], w_d = w[0];
-#pragma unroll
-                    for (int dd = 1; dd < K; ++dd)
-                        if (d == dd) { lo_d = lo[dd]; w_d = w[dd]; }
-                    const uint4 rb = philox4x32_10(
-                        make_uint4((uint32_t)e, TAG_EDGE | ((uint32_t)(e >> 32) << 8), olo, ohi), key);
-                    store_stream(out + e, affine_w(lo_d, w_d, FT::template uniform<0>(rb)));
-                }
-                ++v;
-            }
-            // the segment that holds element VEC * v
-            while (j < nnz && (uint64_t)off(j + 1) * K <= v * VEC) ++j;
         }
         if (CELLS) {
             // cell index of the chunk's rows: a second walk over its segments
@@ -952,8 +1029,8 @@ emit_flat_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__
             while (row < r1) {
                 const uint32_t end = min(__ldg(coff + jj + 1), r1);
                 const long long c = (long long)__ldg(cid + jj);
-                for (uint32_t r = row + lane; r < end; r += 32)
-                    __stcs(reinterpret_cast<long long *>(cell_idx) + r, c);
+                for (uint32_t rr = row + lane; rr < end; rr += 32)
+                    __stcs(reinterpret_cast<long long *>(cell_idx) + rr, c);
                 row = end;
                 ++jj;
             }
@@ -997,13 +1074,15 @@ static int plan_rows(const Cells &src, const double *cdf, uint64_t ncells, uint6
     return check_launch("cell-major row planning");
 }
 
-#ifndef LINT_REST_BLOCKS_PER_SM
-#define LINT_REST_BLOCKS_PER_SM 2      // general emitter's share of an SM while the flat emitter runs
-#endif
-#ifndef LINT_FLAT_BLOCKS_PER_SM
-#define LINT_FLAT_BLOCKS_PER_SM 3
-#endif
+// tuning overrides read from the environment at every call (profiling sweeps only)
+inline int env_int(const char *name, int fallback) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : fallback;
+}
 
+// The two emitters run back to back on the caller's stream.  (Both are bound by integer
+// instruction issue — Philox's wide multiplies and XORs — so running them side by side on two
+// streams gains nothing: measured, profiles/README.md r2b.)
 template <int K, typename T, typename Cells>
 int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t ncells, uint64_t N, uint2 key,
                 uint64_t offset, Stratum u, void *out, int64_t *cell_idx, cudaStream_t st) {
@@ -1012,45 +1091,36 @@ int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t 
     const double lam_per_unit = grouped_mean(N) / (u.u_hi - u.u_lo);
     const uint32_t chunk_rows = emit_chunk_rows(N);
     const uint32_t nchunks = (uint32_t)((N + chunk_rows - 1) / chunk_rows);
-    const uint32_t per_cta = EMIT_THREADS / 32;
     const size_t smem = src.smem_bytes(sizeof(T));
-    // with the split the general emitter leaves room on every SM for the flat one
-    SideStream *side = split ? side_stream() : nullptr;
-    cudaStream_t st_rest = st;
-    if (side) {
-        cudaEventRecord(side->fork, st);
-        cudaStreamWaitEvent(side->stream, side->fork, 0);
-        st_rest = side->stream;
+    if (split) {
+        const uint32_t fper = FLAT_THREADS / 32;
+        const int fblocks = (int)std::min<uint32_t>((nchunks + fper - 1) / fper,
+                                                     148u * env_int("LINT_FLAT_BPS", LINT_FLAT_MINB));
+        T *boxes = (T *)s.boxes;
+        flat_boxes_kernel<K, T, Cells><<<(int)std::min<uint64_t>((ncells + 255) / 256, 148 * 8), 256, 0, st>>>(
+            src, s.flat.cid, s.flat.nnz, boxes);
+        if (cell_idx)
+            emit_flat_kernel<K, T, true><<<fblocks, FLAT_THREADS, 0, st>>>(
+                boxes, s.flat.cid, s.flat.coff, s.flat.nnz, s.plan, s.flat.chunk_start, chunk_rows, s.chunk_counter,
+                philox_round_keys(key), offset, (T *)out, cell_idx);
+        else
+            emit_flat_kernel<K, T, false><<<fblocks, FLAT_THREADS, 0, st>>>(
+                boxes, s.flat.cid, s.flat.coff, s.flat.nnz, s.plan, s.flat.chunk_start, chunk_rows, s.chunk_counter,
+                philox_round_keys(key), offset, (T *)out, cell_idx);
+        if (int rc = check_launch("cell-major flat emission")) return rc;
     }
-    const uint32_t rest_cap = split ? 148u * LINT_REST_BLOCKS_PER_SM : 148u * 8;
-    const int blocks = (int)std::min<uint32_t>((nchunks + per_cta - 1) / per_cta, rest_cap);
+    const uint32_t per_cta = EMIT_THREADS / 32;
+    const int blocks = (int)std::min<uint32_t>((nchunks + per_cta - 1) / per_cta,
+                                                148u * env_int("LINT_REST_BPS", 8));
     if (cell_idx)
-        emit_kernel<K, T, Cells, true><<<blocks, EMIT_THREADS, smem, st_rest>>>(
+        emit_kernel<K, T, Cells, true><<<blocks, EMIT_THREADS, smem, st>>>(
             src, s.rest.cid, s.rest.coff, s.rest.nnz, s.plan, s.rest.chunk_start, chunk_rows, key, offset,
             split ? 1u : 0u, t, lam_per_unit, (T *)out, cell_idx);
     else
-        emit_kernel<K, T, Cells, false><<<blocks, EMIT_THREADS, smem, st_rest>>>(
+        emit_kernel<K, T, Cells, false><<<blocks, EMIT_THREADS, smem, st>>>(
             src, s.rest.cid, s.rest.coff, s.rest.nnz, s.plan, s.rest.chunk_start, chunk_rows, key, offset,
             split ? 1u : 0u, t, lam_per_unit, (T *)out, cell_idx);
-    if (int rc = check_launch("cell-major emission")) return rc;
-    if (split) {
-        const uint32_t fper = FLAT_THREADS / 32;
-        const int fblocks = (int)std::min<uint32_t>((nchunks + fper - 1) / fper, 148u * LINT_FLAT_BLOCKS_PER_SM);
-        if (cell_idx)
-            emit_flat_kernel<K, T, Cells, true><<<fblocks, FLAT_THREADS, smem, st>>>(
-                src, s.flat.cid, s.flat.coff, s.flat.nnz, s.plan, s.flat.chunk_start, chunk_rows, s.chunk_counter,
-                key, offset, (T *)out, cell_idx);
-        else
-            emit_flat_kernel<K, T, Cells, false><<<fblocks, FLAT_THREADS, smem, st>>>(
-                src, s.flat.cid, s.flat.coff, s.flat.nnz, s.plan, s.flat.chunk_start, chunk_rows, s.chunk_counter,
-                key, offset, (T *)out, cell_idx);
-        if (int rc = check_launch("cell-major flat emission")) return rc;
-    }
-    if (side) {
-        cudaEventRecord(side->join, side->stream);
-        cudaStreamWaitEvent(st, side->join, 0);
-    }
-    return LINT_OK;
+    return check_launch("cell-major emission");
 }
 
 template <int K>

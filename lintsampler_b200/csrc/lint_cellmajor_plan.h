@@ -25,6 +25,7 @@ struct SegList {
 struct Scratch {
     uint32_t *counts_flat, *counts_rest;
     SegList flat, rest;
+    void *boxes;                 // (lo, w) of every flat segment, 2 * LINT_MAX_DIM doubles at most
     uint32_t *plan;              // [0] T_f, [1] T_r, [2] T = first top-up row
     uint32_t *chunk_counter;     // the flat emitter's work counter
     void *zero_begin;            // [zero_begin, zero_begin + zero_bytes): cleared before every draw
@@ -32,7 +33,19 @@ struct Scratch {
     size_t bytes;
 };
 
-inline Scratch carve(void *base, uint64_t ncells, uint64_t N) {
+// A cell is split into its flat and residual parts only where that pays: below this
+// many expected rows the residual part would be a handful of rows with a segment of
+// their own, dearer than drawing all of the cell's rows from the full interpolant.
+#ifndef LINT_SPLIT_MIN_LAMBDA
+#define LINT_SPLIT_MIN_LAMBDA 128.0
+#endif
+constexpr double SPLIT_MIN_LAMBDA = LINT_SPLIT_MIN_LAMBDA;
+
+// `box_bytes`: bytes of one flat segment's box (2 * dim values of the output type; the default is
+// the largest).  Only split cells have a flat segment: a draw splits cells at all when
+// N >= SPLIT_MIN_ROWS_PER_CELL * ncells, and then those expecting >= SPLIT_MIN_LAMBDA rows, of
+// which there are at most N / SPLIT_MIN_LAMBDA.
+inline Scratch carve(void *base, uint64_t ncells, uint64_t N, size_t box_bytes = 2 * LINT_MAX_DIM * 8) {
     const uint64_t nscan = (ncells + SCAN_TILE - 1) / SCAN_TILE;
     const uint64_t nchunks = (N + EMIT_CHUNK_MIN - 1) / EMIT_CHUNK_MIN;      // the most any draw uses
     uintptr_t p = (uintptr_t)base;
@@ -45,6 +58,8 @@ inline Scratch carve(void *base, uint64_t ncells, uint64_t N) {
         l->coff = (uint32_t *)take((ncells + 1) * 4);
         l->chunk_start = (uint32_t *)take(std::max<uint64_t>(nchunks, 1) * 4);
     }
+    const uint64_t nbox = N >= 32 * ncells ? std::min<uint64_t>(ncells, (uint64_t)((double)N / SPLIT_MIN_LAMBDA) + 1) : 0;
+    s.boxes = take(nbox * box_bytes);
     s.plan = (uint32_t *)take(16);
     s.chunk_counter = (uint32_t *)take(4);
     s.zero_begin = (void *)p;
@@ -72,14 +87,6 @@ struct Stratum { double u_lo, u_hi; };
 constexpr uint64_t SPLIT_MIN_ROWS_PER_CELL = 32;
 inline bool use_split(uint64_t ncells, uint64_t N) { return N >= SPLIT_MIN_ROWS_PER_CELL * ncells; }
 
-
-// A second stream per device so that the two emitters of a draw run side by side (defined
-// in lint_cellmajor.cu).
-struct SideStream {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-};
-SideStream *side_stream();
 
 // per-dimension entry points, instantiated in lint_cellmajor_inst.cu
 template <int K>

@@ -42,6 +42,37 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     return ctr;
 }
 
+// The same block function with the ten round keys formed beforehand (on the host, passed as a
+// kernel parameter): inside a kernel every key is then a constant-bank operand of the round's
+// XOR instead of two additions per round.
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+    // mantissa mask and exponent bits of the 21-bit uniform fields (see FlatTraits<float>): kept
+    // beside the keys so that the compiler sees run-time values and fuses mask and OR into one
+    // three-input logic instruction instead of two with an immediate each
+    uint32_t field_mask, field_one;
+};
+inline PhiloxKeys philox_round_keys(uint2 key) {
+    PhiloxKeys s;
+    s.field_mask = 0x007ffffcu;
+    s.field_one = 0x3f800002u;
+    for (int r = 0; r < 10; ++r) {
+        s.k0[r] = key.x + (uint32_t)r * 0x9E3779B9u;
+        s.k1[r] = key.y + (uint32_t)r * 0xBB67AE85u;
+    }
+    return s;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, const PhiloxKeys &k) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ k.k0[r], lo1, hi0 ^ ctr.w ^ k.k1[r], lo0);
+    }
+    return ctr;
+}
+
 __host__ __device__ __forceinline__ double u53(uint32_t lo, uint32_t hi) {
     // same construction as NumPy's Generator.random: top 53 bits * 2^-53
     const uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;
