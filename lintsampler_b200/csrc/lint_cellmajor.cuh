@@ -297,13 +297,16 @@ static __global__ void plan_totals_kernel(const uint32_t *rows_flat, const uint3
     *chunk_counter = 0;
 }
 
-// first segment of every output chunk: last j with coff[j] <= chunk * chunk_rows
+// First segment of every output chunk: last j with coff[j] <= first row of the chunk.  Chunk t
+// holds the rows r with t * chunk_rows <= r + shift < (t + 1) * chunk_rows, shift = *shift_p & 1
+// (the general emitter lays its chunks over even global rows, see emit_kernel) or 0.
 static __global__ void chunk_start_kernel(const uint32_t *coff, const uint32_t *nnz_p, const uint32_t *rows_p,
-                                  uint32_t chunk_rows, uint32_t *chunk_start) {
+                                          const uint32_t *shift_p, uint32_t chunk_rows, uint32_t *chunk_start) {
     const uint32_t nnz = *nnz_p;
-    const uint32_t nchunks = (*rows_p + chunk_rows - 1) / chunk_rows;
+    const uint32_t shift = shift_p ? (*shift_p & 1u) : 0u;
+    const uint32_t nchunks = (*rows_p + shift + chunk_rows - 1) / chunk_rows;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nchunks; t += gridDim.x * blockDim.x) {
-        const uint32_t r0 = t * chunk_rows;
+        const uint32_t r0 = max(t * chunk_rows, shift) - shift;
         uint32_t lo = 0, hi = nnz;                                 // coff[nnz] = N > r0
         while (lo < hi) {                                          // first j with coff[j] > r0
             const uint32_t mid = lo + ((hi - lo) >> 1);
@@ -402,303 +405,6 @@ struct ListCells {
         }
     }
 };
-
-#ifndef LINT_EMIT_U
-#define LINT_EMIT_U 4          // rows per lane in the straight-line fast path
-#endif
-#ifndef LINT_EMIT_MINB
-#define LINT_EMIT_MINB 4       // resident CTAs per SM the fp32 k<=3 emitter is compiled for
-#endif
-#ifndef LINT_EMIT_THREADS
-#define LINT_EMIT_THREADS 256
-#endif
-constexpr int EMIT_THREADS = LINT_EMIT_THREADS, EMIT_U = LINT_EMIT_U;
-
-// In-cell uniforms of a group of R rows of one lane: R*K coordinates from
-// ceil(R*K*words/4) Philox blocks.  fp32 rows use one 32-bit word per coordinate
-// (top 24 bits); fp64 rows two words (53 bits).  The counter names the group's
-// first row, `sub` separates the multi-row groups (0) from single rows (1).
-template <int K, typename T, int R>
-struct GroupUniforms {
-    static constexpr int WORDS = K * R * (sizeof(T) == 8 ? 2 : 1);
-    static constexpr int CALLS = (WORDS + 3) / 4;
-    uint32_t w[4 * CALLS];
-    __device__ __forceinline__ void fill(uint2 key, uint32_t first_row, uint32_t sub, uint64_t offset) {
-#pragma unroll
-        for (int q = 0; q < CALLS; ++q) {
-            const uint4 r = philox4x32_10(
-                make_uint4(first_row, TAG_COORD | (sub << 16) | q, (uint32_t)offset, (uint32_t)(offset >> 32)),
-                key);
-            w[4 * q] = r.x; w[4 * q + 1] = r.y; w[4 * q + 2] = r.z; w[4 * q + 3] = r.w;
-        }
-    }
-    __device__ __forceinline__ void get(int i, float (&u)[K]) const {
-#pragma unroll
-        // round-toward-zero conversion keeps the top 24 bits: u in [0, 1 - 2^-24]
-        for (int d = 0; d < K; ++d) u[d] = __uint2float_rz(w[i * K + d]) * (1.0f / 4294967296.0f);
-    }
-    __device__ __forceinline__ void get(int i, double (&u)[K]) const {
-#pragma unroll
-        for (int d = 0; d < K; ++d) u[d] = u53(w[2 * (i * K + d)], w[2 * (i * K + d) + 1]);
-    }
-};
-
-template <int K, typename T, bool CELLS>
-__device__ __forceinline__ void emit_row(const CellCoefs<K, T> &coef, const T (&xlo)[K], const T (&xw)[K],
-                                         const T (&u)[K], uint32_t row, uint32_t cell,
-                                         T *__restrict__ out, int64_t *__restrict__ cell_idx) {
-    T z[K];
-    coef.draw(u, z);                                               // sampling.py:41-94
-#pragma unroll
-    for (int d = 0; d < K; ++d)
-        store_stream(out + (size_t)row * K + d, affine_w(xlo[d], xw[d], z[d]));   // sampling.py:126
-    if (CELLS) __stcs(reinterpret_cast<long long *>(cell_idx) + row, (long long)cell);
-}
-
-// ---------------------------------------------------------------------------
-// general emitter: rows [T_f, T_f + T_r), every segment drawn from an interpolant
-// ---------------------------------------------------------------------------
-// Every warp works on its own chunks of `chunk_rows` consecutive rows and walks the
-// segments (a non-empty cell that is not split, or the non-empty residual part of a split
-// cell) that intersect the chunk in order, through a small private shared-memory window of
-// the segment table (EMIT_WIN entries, refilled as the walk advances; the next chunk's
-// first window is prefetched with cp.async while the current chunk is computed).  No
-// CTA-wide barrier.  Segments tile the rows, so the walk never searches.  Lanes map to
-// consecutive rows:
-//   * blocks of 32*EMIT_U rows inside one segment: the segment's constants are in
-//     registers and every lane draws EMIT_U rows from straight-line code (a last block
-//     of more than half that size runs in the same form with the rows past the end
-//     masked);
-//   * the rest of the segment 32 rows at a time, one row per lane;
-//   * where the next 32 rows cover two or more whole segments: one row per lane, each
-//     lane with the constants of its own segment (found from one warp-wide OR of the
-//     segment starts), so the cost stays bounded however small the cells are.
-// fp32, k <= 3: the per-cell constants (box, hoisted quantile coefficients) of 32
-// consecutive segments are computed at once, one segment per lane, and staged in
-// shared memory; entering a cell then costs a few broadcast loads instead of a
-// warp-redundant fetch + set.
-// Rows are local to the run: row r is output row plan[0] + r.
-constexpr int EMIT_WIN = 64;
-constexpr uint32_t EMIT_PRE = 32;            // segments per staged block (= lanes)
-constexpr uint32_t EMIT_PRE_NONE = 0x80000000u;
-
-template <int K, typename T, typename Cells, bool CELLS>
-__global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 ? (K <= 3 ? LINT_EMIT_MINB : 2) : 1)
-emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
-            const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ plan,
-            const uint32_t *__restrict__ chunk_start, uint32_t chunk_rows, uint2 key,
-            uint64_t offset, uint32_t split, CdfSlice table, double lam_per_unit, T *__restrict__ out,
-            int64_t *__restrict__ cell_idx) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *sedges = reinterpret_cast<T *>(smem_raw);
-    __shared__ uint32_t s_off_all[EMIT_THREADS / 32][2][EMIT_WIN];
-    __shared__ uint32_t s_cid_all[EMIT_THREADS / 32][2][EMIT_WIN];
-    // staged constants: CellCoefs words, then the box (lo[K], hi[K]); the slot stride is an
-    // odd number of 16-byte units so the per-lane 128-bit stores do not conflict
-    constexpr bool PRE = sizeof(T) == 4 && K <= 3;
-    constexpr int PRE_WORDS = CellCoefs<K, T>::WORDS + 2 * K;
-    constexpr int PRE_Q = ((PRE_WORDS + 3) / 4) | 1;
-    __shared__ float4 s_pre_all[PRE ? EMIT_THREADS / 32 : 1][PRE ? EMIT_PRE * PRE_Q : 1];
-    src.prepare(sedges);
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t nnz = *nnz_p;
-    const uint32_t N = plan[1];                        // rows of this run
-    out += (size_t)plan[0] * K;                        // ... which starts after the flat run
-    if (CELLS) cell_idx += plan[0];
-    const uint32_t nchunks = (N + chunk_rows - 1) / chunk_rows;
-    const uint32_t nwarps = gridDim.x * (EMIT_THREADS / 32);
-    // window entry i of buffer b <- segment jb + i (offsets exist for 0..nnz, cells for 0..nnz-1)
-    auto prefetch = [&](uint32_t jb, int b) {
-#pragma unroll
-        for (uint32_t i = lane; i < EMIT_WIN; i += 32) {
-            if (jb + i <= nnz) __pipeline_memcpy_async(&s_off_all[warp][b][i], coff + jb + i, 4);
-            if (jb + i < nnz) __pipeline_memcpy_async(&s_cid_all[warp][b][i], cid + jb + i, 4);
-        }
-        __pipeline_commit();
-    };
-    uint32_t chunk = blockIdx.x * (EMIT_THREADS / 32) + warp;
-    int buf = 0;
-    uint32_t j0 = chunk < nchunks ? __ldg(chunk_start + chunk) : 0;
-    uint32_t j0_next = chunk + nwarps < nchunks ? __ldg(chunk_start + chunk + nwarps) : 0;
-    if (chunk < nchunks) prefetch(j0, 0);
-    for (; chunk < nchunks; chunk += nwarps, buf ^= 1) {
-        const uint32_t r0 = chunk * chunk_rows, r1 = min(r0 + chunk_rows, N);
-        const bool more = chunk + nwarps < nchunks;
-        if (more) prefetch(j0_next, buf ^ 1);
-        uint32_t jbase = j0;                             // segment held in window slot 0
-        j0 = j0_next;
-        if (chunk + 2 * (uint64_t)nwarps < nchunks) j0_next = __ldg(chunk_start + chunk + 2 * nwarps);
-        if (more) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
-        __syncwarp();
-        uint32_t *s_off = s_off_all[warp][buf], *s_cid = s_cid_all[warp][buf];
-        // offset of segment j (j > nnz: +inf); callers keep j - jbase < EMIT_WIN
-        auto off = [&](uint32_t j) { return j <= nnz ? s_off[j - jbase] : 0xffffffffu; };
-        auto refill = [&](uint32_t jb) {                 // slide the window so that slot 0 = segment jb
-            __syncwarp();
-#pragma unroll
-            for (uint32_t i = lane; i < EMIT_WIN; i += 32) {
-                if (jb + i <= nnz) s_off[i] = __ldg(coff + jb + i);
-                if (jb + i < nnz) s_cid[i] = __ldg(cid + jb + i);
-            }
-            jbase = jb;
-            __syncwarp();
-        };
-
-        uint32_t j = jbase;                              // warp-uniform segment cursor
-        uint32_t row = r0;
-        uint32_t loaded = 0xffffffffu;                   // segment whose constants the registers hold
-        T xlo[K], xw[K];                                 // box: lower corner, width
-        CellCoefs<K, T> coef;
-        uint32_t cell = 0;
-        uint32_t cbase = EMIT_PRE_NONE;                  // staged block = segments [cbase, cbase + 32)
-        float4 *s_pre = s_pre_all[PRE ? warp : 0];
-        // segment ids: the cell itself, or with the flat/residual split 2 cell + 1
-        // constants of one segment into the caller's registers
-        auto constants = [&](uint32_t v, CellCoefs<K, T> &cf, T (&lo)[K], T (&w)[K]) {
-            T c0[1 << K], hi[K];
-            src.fetch(sedges, v >> split, c0, lo, hi);
-#pragma unroll
-            for (int d = 0; d < K; ++d) w[d] = hi[d] - lo[d];              // maxs - mins, sampling.py:126
-            // the residual of a split cell, or the whole of a cell that is not split
-            const bool residual = split && cell_lambda(table, v >> 1, lam_per_unit) >= SPLIT_MIN_LAMBDA;
-            if (residual) subtract_min(c0);
-            cf.set(c0, !residual && src.prenormalised());
-        };
-        // stage the constants of segments [jb, jb + 32) that start inside this chunk;
-        // the window must hold entries jb .. jb + 32
-        auto stage = [&](uint32_t jb) {
-            __syncwarp();
-            const uint32_t js = jb + lane;
-            if (js < nnz && s_off[js - jbase] < r1) {
-                T lo[K], wd[K];
-                CellCoefs<K, T> cf;
-                float w[4 * PRE_Q] = {};
-                constants(s_cid[js - jbase], cf, lo, wd);
-                cf.pack(w);
-#pragma unroll
-                for (int d = 0; d < K; ++d) {
-                    w[CellCoefs<K, T>::WORDS + d] = (float)lo[d];
-                    w[CellCoefs<K, T>::WORDS + K + d] = (float)wd[d];
-                }
-#pragma unroll
-                for (int q = 0; q < (PRE_WORDS + 3) / 4; ++q)
-                    s_pre[lane * PRE_Q + q] = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-            }
-            cbase = jb;
-            __syncwarp();
-        };
-        // registers <- constants of segment seg (in the window; PRE: also in the staged block)
-        auto enter = [&](uint32_t seg) {
-            const uint32_t v = s_cid[seg - jbase];
-            cell = v >> split;
-            if constexpr (PRE) {
-                float w[4 * PRE_Q];
-#pragma unroll
-                for (int q = 0; q < (PRE_WORDS + 3) / 4; ++q) {
-                    const float4 t4 = s_pre[(seg - cbase) * PRE_Q + q];
-                    w[4 * q] = t4.x; w[4 * q + 1] = t4.y; w[4 * q + 2] = t4.z; w[4 * q + 3] = t4.w;
-                }
-                coef.unpack(w);
-#pragma unroll
-                for (int d = 0; d < K; ++d) {
-                    xlo[d] = (T)w[CellCoefs<K, T>::WORDS + d];
-                    xw[d] = (T)w[CellCoefs<K, T>::WORDS + K + d];
-                }
-            } else {
-                constants(v, coef, xlo, xw);
-            }
-        };
-
-        // invariant: segment j holds `row` (segments are non-empty, so they tile the rows)
-        while (row < r1) {
-            if (j + 2 - jbase >= EMIT_WIN) refill(j);
-            const uint32_t seg_end = min(off(j + 1), r1);
-            // the per-lane path pays where the next 32 rows cover at least two whole segments
-            if (off(j + 2) > min(row + 32u, r1)) {
-                // ---- rows [row, seg_end) of one segment, lanes = consecutive rows
-                if (loaded != j) {
-                    if constexpr (PRE) {
-                        if (j - cbase >= EMIT_PRE) {
-                            if (j + EMIT_PRE + 1 - jbase >= EMIT_WIN) refill(j);
-                            stage(j);
-                        }
-                    }
-                    enter(j);
-                    loaded = j;
-                }
-                // blocks of 32 * EMIT_U rows
-                while (seg_end - row >= 32u * EMIT_U) {
-                    const uint32_t first = row + lane;
-                    GroupUniforms<K, T, EMIT_U> rnd;
-                    rnd.fill(key, first, 0, offset);
-#pragma unroll
-                    for (int t = 0; t < EMIT_U; ++t) {
-                        T u[K];
-                        rnd.get(t, u);
-                        emit_row<K, T, CELLS>(coef, xlo, xw, u, first + 32u * t, cell, out, cell_idx);
-                    }
-                    row += 32u * EMIT_U;
-                }
-                // a last partial block of more than half that is still cheaper in this form
-                // (rows past the end masked) than one warp-row at a time
-                if (seg_end - row > 16u * EMIT_U) {
-                    const uint32_t first = row + lane;
-                    GroupUniforms<K, T, EMIT_U> rnd;
-                    rnd.fill(key, first, 0, offset);
-#pragma unroll
-                    for (int t = 0; t < EMIT_U; ++t) {
-                        T u[K];
-                        rnd.get(t, u);
-                        if (first + 32u * t < seg_end)
-                            emit_row<K, T, CELLS>(coef, xlo, xw, u, first + 32u * t, cell, out, cell_idx);
-                    }
-                    row = seg_end;
-                }
-                // the rest of the segment, however short: its constants are in registers
-                // already, which makes idle lanes cheaper than the per-lane path
-                while (row < seg_end) {
-                    const uint32_t r = row + lane;
-                    if (r < seg_end) {
-                        GroupUniforms<K, T, 1> rnd;
-                        rnd.fill(key, r, 1, offset);
-                        T u[K];
-                        rnd.get(0, u);
-                        emit_row<K, T, CELLS>(coef, xlo, xw, u, r, cell, out, cell_idx);
-                    }
-                    row = min(row + 32u, seg_end);
-                }
-                ++j;                                     // row == seg_end: the next segment, if row < r1
-            } else {
-                // ---- the next 32 rows span several segments: one row per lane, own segment each.
-                // Segments hold >= 1 row, so lane l's segment is within [j, j + l].
-                if (j + 33 - jbase >= EMIT_WIN) refill(j);
-                const uint32_t r = row + lane;
-                const uint32_t lim = min(row + 32u, r1);
-                // bit b of `starts`: a segment begins at row + b (lane i looks at segment j + 1 + i);
-                // a row's segment is j + the number of starts in (row, r]
-                const uint32_t o = off(j + 1 + lane) - row;                   // >= 1
-                const uint32_t starts = __reduce_or_sync(0xffffffffu, o < 32u ? 1u << o : 0u);
-                const uint32_t lo = j + __popc(starts & ((2u << lane) - 1u));
-                const uint32_t last = __shfl_sync(0xffffffffu, lo, (int)(lim - row) - 1);   // the last row's segment
-                if constexpr (PRE) {
-                    if (j - cbase >= EMIT_PRE || last - cbase >= EMIT_PRE) stage(j);       // last <= j + 31
-                }
-                if (r < lim) {
-                    enter(lo);
-                    GroupUniforms<K, T, 1> rnd;
-                    rnd.fill(key, r, 1, offset);
-                    T u[K];
-                    rnd.get(0, u);
-                    emit_row<K, T, CELLS>(coef, xlo, xw, u, r, cell, out, cell_idx);
-                }
-                loaded = 0xffffffffu;
-                row = lim;
-                j = off(last + 1) <= row ? last + 1 : last;     // (window holds up to j + 32)
-            }
-        }
-        __syncwarp();
-    }
-}
 
 // ---------------------------------------------------------------------------
 // flat emitter: rows [0, T_f), every segment the constant part of a split cell
@@ -1039,6 +745,237 @@ emit_flat_kernel(const T *__restrict__ boxes, const uint32_t *__restrict__ cid, 
 }
 
 // ---------------------------------------------------------------------------
+// general emitter: rows [T_f, T_f + T_r), every segment drawn from an interpolant
+// ---------------------------------------------------------------------------
+// Segments here are short (a few dozen rows: the residual parts of the split cells and the
+// cells too small to split), so the kernel never specialises on segment length: a warp step
+// covers 64 consecutive rows, lane l owns the two rows 2 l and 2 l + 1 of the step, and each
+// row finds its own segment from one warp-wide OR of the segment starts inside the step.
+//   * One Philox block yields the in-cell uniforms of a lane's two rows (fp32, k <= 3: six
+//     21-bit fields, see FlatTraits).
+//   * fp32, k <= 3: the per-cell constants (box, hoisted quantile coefficients) of 64
+//     consecutive segments are computed one segment per lane and staged in shared memory;
+//     a row then costs a few 128-bit loads instead of a fetch + normalisation.
+//   * Steps are laid over EVEN global rows (the run starts at the arbitrary row T_f), so a lane's
+//     two rows are 2 k contiguous, 8- or 16-byte aligned values and leave as k vector stores.
+// Every warp works on its own chunks of `chunk_rows` rows and walks the chunk's segments
+// through a private shared-memory window of the segment table (the next chunk's first window
+// is prefetched with cp.async).  No CTA-wide barrier.
+#ifndef LINT_EMIT_MINB
+#define LINT_EMIT_MINB 4       // resident CTAs per SM the fp32 k<=3 emitter is compiled for
+#endif
+#ifndef LINT_EMIT_THREADS
+#define LINT_EMIT_THREADS 256
+#endif
+constexpr int EMIT_THREADS = LINT_EMIT_THREADS;
+constexpr int EMIT_WIN = 96;                 // window entries (>= 66: a step looks at 65 segment starts)
+constexpr uint32_t EMIT_STEP = 64;           // rows per warp step
+constexpr uint32_t EMIT_PRE = 32;            // staged segments (= lanes); a step that draws from more
+                                             // (segments of less than two rows on average) fetches per row
+constexpr uint32_t EMIT_PRE_NONE = 0x80000000u;
+
+template <int K, typename T, typename Cells, bool CELLS>
+__global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 ? (K <= 3 ? LINT_EMIT_MINB : 2) : 1)
+emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
+            const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ plan,
+            const uint32_t *__restrict__ chunk_start, uint32_t chunk_rows, const __grid_constant__ PhiloxKeys key,
+            uint64_t offset, uint32_t split, CdfSlice table, double lam_per_unit, T *__restrict__ out,
+            int64_t *__restrict__ cell_idx) {
+    using FT = FlatTraits<T>;
+    constexpr int NF = FT::FIELDS, NB = (2 * K + NF - 1) / NF;       // Philox blocks per pair of rows
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sedges = reinterpret_cast<T *>(smem_raw);
+    __shared__ uint32_t s_off_all[EMIT_THREADS / 32][2][EMIT_WIN];
+    __shared__ uint32_t s_cid_all[EMIT_THREADS / 32][2][EMIT_WIN];
+    // staged constants: CellCoefs words, then the box (lo[K], w[K]); the slot stride is an
+    // odd number of 16-byte units so the per-lane 128-bit stores do not conflict
+    constexpr bool PRE = sizeof(T) == 4 && K <= 3;
+    constexpr int PRE_WORDS = CellCoefs<K, T>::WORDS + 2 * K;
+    constexpr int PRE_Q = ((PRE_WORDS + 3) / 4) | 1;
+    __shared__ float4 s_pre_all[PRE ? EMIT_THREADS / 32 : 1][PRE ? EMIT_PRE * PRE_Q : 1];
+    src.prepare(sedges);
+    const uint32_t fm = key.field_mask, fo = key.field_one;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nnz = *nnz_p;
+    // Rows are counted from the even global row at or before the start of the run: row r of this
+    // frame is global row (T_f - shift) + r and belongs to the run when shift <= r < end.
+    const uint32_t shift = plan[0] & 1u, end = plan[1] + shift;
+    out += (size_t)(plan[0] - shift) * K;
+    if (CELLS) cell_idx += plan[0] - shift;
+    const uint32_t pair0 = (plan[0] - shift) >> 1;     // global index of the frame's first pair of rows
+    const uint32_t nchunks = (end + chunk_rows - 1) / chunk_rows;
+    const uint32_t nwarps = gridDim.x * (EMIT_THREADS / 32);
+    const uint32_t olo = (uint32_t)offset, ohi = (uint32_t)(offset >> 32);
+    constexpr uint32_t FULL = 0xffffffffu;
+    // window entry i of buffer b <- segment jb + i (offsets exist for 0..nnz, cells for 0..nnz-1)
+    auto prefetch = [&](uint32_t jb, int b) {
+#pragma unroll
+        for (uint32_t i = lane; i < EMIT_WIN; i += 32) {
+            if (jb + i <= nnz) __pipeline_memcpy_async(&s_off_all[warp][b][i], coff + jb + i, 4);
+            if (jb + i < nnz) __pipeline_memcpy_async(&s_cid_all[warp][b][i], cid + jb + i, 4);
+        }
+        __pipeline_commit();
+    };
+    uint32_t chunk = blockIdx.x * (EMIT_THREADS / 32) + warp;
+    int buf = 0;
+    uint32_t j0 = chunk < nchunks ? __ldg(chunk_start + chunk) : 0;
+    uint32_t j0_next = chunk + nwarps < nchunks ? __ldg(chunk_start + chunk + nwarps) : 0;
+    if (chunk < nchunks) prefetch(j0, 0);
+    for (; chunk < nchunks; chunk += nwarps, buf ^= 1) {
+        const uint32_t r0 = chunk * chunk_rows, r1 = min(r0 + chunk_rows, end);
+        const bool more = chunk + nwarps < nchunks;
+        if (more) prefetch(j0_next, buf ^ 1);
+        uint32_t jbase = j0;                             // segment held in window slot 0
+        j0 = j0_next;
+        if (chunk + 2 * (uint64_t)nwarps < nchunks) j0_next = __ldg(chunk_start + chunk + 2 * nwarps);
+        if (more) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
+        __syncwarp();
+        uint32_t *s_off = s_off_all[warp][buf], *s_cid = s_cid_all[warp][buf];
+        // first row (in the frame) of segment sg (sg > nnz: +inf); callers keep sg - jbase < EMIT_WIN
+        auto off = [&](uint32_t sg) { return sg <= nnz ? s_off[sg - jbase] + shift : 0xffffffffu; };
+        auto refill = [&](uint32_t jb) {                 // slide the window so that slot 0 = segment jb
+            __syncwarp();
+#pragma unroll
+            for (uint32_t i = lane; i < EMIT_WIN; i += 32) {
+                if (jb + i <= nnz) s_off[i] = __ldg(coff + jb + i);
+                if (jb + i < nnz) s_cid[i] = __ldg(cid + jb + i);
+            }
+            jbase = jb;
+            __syncwarp();
+        };
+        uint32_t cbase = EMIT_PRE_NONE;                  // staged block = segments [cbase, cbase + EMIT_PRE)
+        float4 *s_pre = s_pre_all[PRE ? warp : 0];
+        // segment ids: the cell itself, or with the flat/residual split 2 cell + 1
+        // constants of one segment into the caller's registers
+        auto constants = [&](uint32_t v, CellCoefs<K, T> &cf, T (&lo)[K], T (&w)[K]) {
+            T c0[1 << K], hi[K];
+            src.fetch(sedges, v >> split, c0, lo, hi);
+#pragma unroll
+            for (int d = 0; d < K; ++d) w[d] = hi[d] - lo[d];              // maxs - mins, sampling.py:126
+            // the residual of a split cell, or the whole of a cell that is not split
+            const bool residual = split && cell_lambda(table, v >> 1, lam_per_unit) >= SPLIT_MIN_LAMBDA;
+            if (residual) subtract_min(c0);
+            cf.set(c0, !residual && src.prenormalised());
+        };
+        // stage the constants of segments [jb, jb + EMIT_PRE) that start inside this chunk;
+        // the window must hold entries jb .. jb + EMIT_PRE - 1
+        auto stage = [&](uint32_t jb) {
+            __syncwarp();
+            {
+                constexpr uint32_t h = 0;
+                const uint32_t js = jb + lane;
+                if (js < nnz && off(js) < r1) {
+                    T lo[K], wd[K];
+                    CellCoefs<K, T> cf;
+                    float w[4 * PRE_Q] = {};
+                    constants(s_cid[js - jbase], cf, lo, wd);
+                    cf.pack(w);
+#pragma unroll
+                    for (int d = 0; d < K; ++d) {
+                        w[CellCoefs<K, T>::WORDS + d] = (float)lo[d];
+                        w[CellCoefs<K, T>::WORDS + K + d] = (float)wd[d];
+                    }
+#pragma unroll
+                    for (int q = 0; q < (PRE_WORDS + 3) / 4; ++q)
+                        s_pre[(32 * h + lane) * PRE_Q + q] =
+                            make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+                }
+            }
+            cbase = jb;
+            __syncwarp();
+        };
+        // one row of segment sg: constants (staged, or fetched), in-cell draw, affine map
+        auto draw_row = [&](uint32_t sg, bool staged, const T (&u)[K], T (&x)[K], uint32_t &cell) {
+            const uint32_t v = s_cid[sg - jbase];
+            cell = v >> split;
+            T xlo[K], xw[K], z[K];
+            CellCoefs<K, T> coef;
+            if (PRE && staged) {
+                float w[4 * PRE_Q];
+#pragma unroll
+                for (int q = 0; q < (PRE_WORDS + 3) / 4; ++q) {
+                    const float4 t4 = s_pre[(sg - cbase) * PRE_Q + q];
+                    w[4 * q] = t4.x; w[4 * q + 1] = t4.y; w[4 * q + 2] = t4.z; w[4 * q + 3] = t4.w;
+                }
+                coef.unpack(w);
+#pragma unroll
+                for (int d = 0; d < K; ++d) {
+                    xlo[d] = (T)w[CellCoefs<K, T>::WORDS + d];
+                    xw[d] = (T)w[CellCoefs<K, T>::WORDS + K + d];
+                }
+            } else {
+                constants(v, coef, xlo, xw);
+            }
+            coef.draw(u, z);                                               // sampling.py:41-94
+#pragma unroll
+            for (int d = 0; d < K; ++d) x[d] = affine_w(xlo[d], xw[d], z[d]);   // sampling.py:126
+        };
+
+        uint32_t j = jbase;        // warp-uniform: the segment that holds row R (or ends exactly there)
+        for (uint32_t R = r0; R < r1; R += EMIT_STEP) {
+            if (j + EMIT_STEP + 2 - jbase >= (uint32_t)EMIT_WIN) refill(j);
+            // bit b of (lo_m, hi_m): a segment starts at row R + b, 0 <= b < 64 (lane i looks at
+            // segments j + 1 + i and j + 33 + i; segments hold >= 1 row, so no other can)
+            const uint32_t o1 = off(j + 1 + lane) - R, o2 = off(j + 33 + lane) - R;
+            uint32_t lo_m = (o1 < 32u ? 1u << o1 : 0u) | (o2 < 32u ? 1u << o2 : 0u);
+            uint32_t hi_m = (o1 - 32u < 32u ? 1u << (o1 - 32u) : 0u) | (o2 - 32u < 32u ? 1u << (o2 - 32u) : 0u);
+            lo_m = __reduce_or_sync(FULL, lo_m);
+            hi_m = __reduce_or_sync(FULL, hi_m);
+            const uint32_t nstart = __popc(lo_m) + __popc(hi_m);
+            // segments this step draws from: j (unless it ends at R: bit 0) .. j + nstart, at most 64
+            const uint32_t first = j + (lo_m & 1u);
+            const bool staged = PRE && j + nstart - first < EMIT_PRE;
+            if (staged && (first - cbase >= EMIT_PRE || j + nstart - cbase >= EMIT_PRE)) stage(first);
+            // the lane's rows: R + 2 lane and the next one; a row's segment is j + the number of
+            // starts in (R, row]
+            const uint32_t x0 = 2u * lane, ra = R + x0;
+            uint32_t sa;
+            if (x0 < 32u) sa = j + __popc(lo_m & ((2u << x0) - 1u));
+            else sa = j + __popc(lo_m) + __popc(hi_m & ((2u << (x0 - 32u)) - 1u));
+            const uint32_t bit_b = x0 + 1u < 32u ? (lo_m >> (x0 + 1u)) & 1u : (hi_m >> (x0 - 31u)) & 1u;
+            const uint32_t sb = sa + bit_b;
+            const bool va = ra >= shift && ra < end, vb = ra + 1u >= shift && ra + 1u < end;
+            if (va || vb) {
+                const uint32_t pair = pair0 + (ra >> 1);
+                uint4 r[NB];
+#pragma unroll
+                for (int q = 0; q < NB; ++q)
+                    r[q] = philox4x32_10(make_uint4(pair, TAG_COORD | q, olo, ohi), key);
+                T ua[K], ub[K], xa[K], xb[K];
+                static_for<0, K>([&](auto d_tag) {
+                    constexpr int d = decltype(d_tag)::value;
+                    ua[d] = FlatFieldOf<d, NF, T>::get(r, fm, fo);
+                    ub[d] = FlatFieldOf<K + d, NF, T>::get(r, fm, fo);
+                });
+                uint32_t ca = 0, cb = 0;
+                draw_row(va ? sa : sb, staged, ua, xa, ca);
+                draw_row(vb ? sb : sa, staged, ub, xb, cb);
+                T *p = out + (size_t)ra * K;
+                if (va && vb) {
+                    T e[2 * K];
+#pragma unroll
+                    for (int d = 0; d < K; ++d) { e[d] = xa[d]; e[K + d] = xb[d]; }
+#pragma unroll
+                    for (int m = 0; m < K; ++m) store_stream2(p + 2 * m, e[2 * m], e[2 * m + 1]);
+                } else {
+#pragma unroll
+                    for (int d = 0; d < K; ++d) {
+                        if (va) store_stream(p + d, xa[d]);
+                        if (vb) store_stream(p + K + d, xb[d]);
+                    }
+                }
+                if (CELLS) {
+                    if (va) __stcs(reinterpret_cast<long long *>(cell_idx) + ra, (long long)ca);
+                    if (vb) __stcs(reinterpret_cast<long long *>(cell_idx) + ra + 1, (long long)cb);
+                }
+            }
+            j += nstart;                                 // the segment that holds row R + 64
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------
 static void scan_list(const uint32_t *counts, uint32_t n, uint32_t id_mul, uint32_t id_add, const SegList &l,
@@ -1067,9 +1004,9 @@ static int plan_rows(const Cells &src, const double *cdf, uint64_t ncells, uint6
     const uint32_t nchunks = (uint32_t)((N + chunk_rows - 1) / chunk_rows);
     const int sblocks = (int)std::max(1u, std::min((nchunks + 255) / 256, 148u * 8));
     if (split)
-        chunk_start_kernel<<<sblocks, 256, 0, st>>>(s.flat.coff, s.flat.nnz, s.plan + 0, chunk_rows,
+        chunk_start_kernel<<<sblocks, 256, 0, st>>>(s.flat.coff, s.flat.nnz, s.plan + 0, nullptr, chunk_rows,
                                                     s.flat.chunk_start);
-    chunk_start_kernel<<<sblocks, 256, 0, st>>>(s.rest.coff, s.rest.nnz, s.plan + 1, chunk_rows,
+    chunk_start_kernel<<<sblocks, 256, 0, st>>>(s.rest.coff, s.rest.nnz, s.plan + 1, s.plan + 0, chunk_rows,
                                                 s.rest.chunk_start);
     return check_launch("cell-major row planning");
 }
@@ -1090,7 +1027,7 @@ int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t 
     const CdfSlice t{cdf, (uint32_t)ncells, u.u_lo, u.u_hi};
     const double lam_per_unit = grouped_mean(N) / (u.u_hi - u.u_lo);
     const uint32_t chunk_rows = emit_chunk_rows(N);
-    const uint32_t nchunks = (uint32_t)((N + chunk_rows - 1) / chunk_rows);
+    const uint32_t nchunks = (uint32_t)((N + 1 + chunk_rows - 1) / chunk_rows);     // (+1: the general emitter's frame)
     const size_t smem = src.smem_bytes(sizeof(T));
     if (split) {
         const uint32_t fper = FLAT_THREADS / 32;
@@ -1114,12 +1051,12 @@ int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t 
                                                 148u * env_int("LINT_REST_BPS", 8));
     if (cell_idx)
         emit_kernel<K, T, Cells, true><<<blocks, EMIT_THREADS, smem, st>>>(
-            src, s.rest.cid, s.rest.coff, s.rest.nnz, s.plan, s.rest.chunk_start, chunk_rows, key, offset,
-            split ? 1u : 0u, t, lam_per_unit, (T *)out, cell_idx);
+            src, s.rest.cid, s.rest.coff, s.rest.nnz, s.plan, s.rest.chunk_start, chunk_rows,
+            philox_round_keys(key), offset, split ? 1u : 0u, t, lam_per_unit, (T *)out, cell_idx);
     else
         emit_kernel<K, T, Cells, false><<<blocks, EMIT_THREADS, smem, st>>>(
-            src, s.rest.cid, s.rest.coff, s.rest.nnz, s.plan, s.rest.chunk_start, chunk_rows, key, offset,
-            split ? 1u : 0u, t, lam_per_unit, (T *)out, cell_idx);
+            src, s.rest.cid, s.rest.coff, s.rest.nnz, s.plan, s.rest.chunk_start, chunk_rows,
+            philox_round_keys(key), offset, split ? 1u : 0u, t, lam_per_unit, (T *)out, cell_idx);
     return check_launch("cell-major emission");
 }
 

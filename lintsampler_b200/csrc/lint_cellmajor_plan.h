@@ -47,7 +47,7 @@ constexpr double SPLIT_MIN_LAMBDA = LINT_SPLIT_MIN_LAMBDA;
 // which there are at most N / SPLIT_MIN_LAMBDA.
 inline Scratch carve(void *base, uint64_t ncells, uint64_t N, size_t box_bytes = 2 * LINT_MAX_DIM * 8) {
     const uint64_t nscan = (ncells + SCAN_TILE - 1) / SCAN_TILE;
-    const uint64_t nchunks = (N + EMIT_CHUNK_MIN - 1) / EMIT_CHUNK_MIN;      // the most any draw uses
+    const uint64_t nchunks = (N + 1 + EMIT_CHUNK_MIN - 1) / EMIT_CHUNK_MIN;  // the most any draw uses
     uintptr_t p = (uintptr_t)base;
     auto take = [&](size_t n) { uintptr_t q = p; p += (n + 255) & ~(size_t)255; return (void *)q; };
     Scratch s;

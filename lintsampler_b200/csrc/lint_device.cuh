@@ -636,6 +636,13 @@ __device__ __forceinline__ float affine_w(float lo, float w, float z) { return f
 // evict the guide table and cell records from L2
 __device__ __forceinline__ void store_stream(float *p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void store_stream(double *p, double v) { __stcs(p, v); }
+// two consecutive values, p aligned to twice the element size
+__device__ __forceinline__ void store_stream2(float *p, float a, float b) {
+    __stcs(reinterpret_cast<float2 *>(p), make_float2(a, b));
+}
+__device__ __forceinline__ void store_stream2(double *p, double a, double b) {
+    __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b));
+}
 
 // `prenormalised`: the corners come from fp32 records, which are stored divided by the
 // cell's largest corner (the draw depends on ratios only), so the per-sample
