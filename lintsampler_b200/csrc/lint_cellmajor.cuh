@@ -304,7 +304,7 @@ static __global__ void chunk_start_kernel(const uint32_t *coff, const uint32_t *
                                           const uint32_t *shift_p, uint32_t chunk_rows, uint32_t *chunk_start) {
     const uint32_t nnz = *nnz_p;
     const uint32_t shift = shift_p ? (*shift_p & 1u) : 0u;
-    const uint32_t nchunks = (*rows_p + shift + chunk_rows - 1) / chunk_rows;
+    const uint32_t nchunks = *rows_p ? (*rows_p + shift + chunk_rows - 1) / chunk_rows : 0u;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nchunks; t += gridDim.x * blockDim.x) {
         const uint32_t r0 = max(t * chunk_rows, shift) - shift;
         uint32_t lo = 0, hi = nnz;                                 // coff[nnz] = N > r0
@@ -803,7 +803,7 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
     out += (size_t)(plan[0] - shift) * K;
     if (CELLS) cell_idx += plan[0] - shift;
     const uint32_t pair0 = (plan[0] - shift) >> 1;     // global index of the frame's first pair of rows
-    const uint32_t nchunks = (end + chunk_rows - 1) / chunk_rows;
+    const uint32_t nchunks = plan[1] ? (end + chunk_rows - 1) / chunk_rows : 0u;      // (an empty run has no chunk)
     const uint32_t nwarps = gridDim.x * (EMIT_THREADS / 32);
     const uint32_t olo = (uint32_t)offset, ohi = (uint32_t)(offset >> 32);
     constexpr uint32_t FULL = 0xffffffffu;
