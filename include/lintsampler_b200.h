@@ -36,7 +36,7 @@ extern "C" {
 #endif
 
 #define LINT_MAX_DIM 6          /* reference advises <= 6 dims (paper/paper.md:84) */
-#define LINT_ABI_VERSION 1
+#define LINT_ABI_VERSION 2
 
 typedef void *lint_stream_t;    /* cudaStream_t */
 
@@ -205,6 +205,23 @@ int lint_cdf_build(const double *masses_dev, int64_t n, int mode, double *cdf_de
                    double *total_dev, void *scratch_dev, size_t scratch_bytes,
                    lint_stream_t stream);
 
+/* Fused parallel build for a grid: cell masses [grid.py:469-518, 411] -> normalised inclusive
+ * CDF [grid.py:431 + utils.py:195-196] -> guide table, with the masses computed on the fly from
+ * the vertex densities in both scan passes and never stored (masses_dev == NULL) — the values are
+ * bit-identical to lint_grid_masses + lint_cdf_build(LINT_CDF_PARALLEL) + lint_guide_build.
+ * [u_lo, u_hi) is the stratum of the cell-selecting uniform the caller will draw from ((0, 1) =
+ * whole domain): every rank of a sharded run reduces the whole vertex table to tile totals (which
+ * yields the total mass and every tile's offset without communication) but scans, and writes
+ * cdf_dev / masses_dev / guide_dev for, only the slab of cells its stratum can touch, plus a
+ * margin.  range_dev (4 words, device) receives that slab: [0] first cell, [1] end cell, [2], [3]
+ * the same in tiles of 2048 cells; hand it to lint_grid_sample_cellmajor.  Outside the slab the
+ * three tables are left untouched.  Validity flags as lint_grid_masses (every vertex is checked).
+ * total_dev receives the total mass. */
+size_t lint_grid_build_scratch_bytes(int64_t ncells);
+int lint_grid_build(const lint_grid_t *g, double u_lo, double u_hi, double *cdf_dev, double *total_dev,
+                    uint32_t *guide_dev, int guide_bits, double *masses_dev, uint32_t *flags_dev,
+                    uint32_t *range_dev, void *scratch_dev, size_t scratch_bytes, lint_stream_t stream);
+
 /* Guide (index) table that shortens the searchsorted of utils.py:197 without
  * changing its result: guide[j] & 0x7fffffff = first i with cdf[i] > j / 2^guide_bits
  * for j = 0..2^guide_bits (inclusive; last entry n-1); bit 31 is set when
@@ -280,11 +297,16 @@ int lint_sobol_uniforms(int dim, int64_t N, const lint_sobol_t *sobol, double *u
  * [u_lo, u_hi) restricts the draw to a stratum of the cell CDF exactly as in
  * lint_grid_sample_philox ((0, 1) = whole domain; a cell straddling a stratum
  * boundary is shared in proportion to the overlap).
- * N <= 2^32 - 2^16, fewer than 2^29 cells.  Scratch: lint_cellmajor_scratch_bytes. */
+ * cell_range_dev (grid only): NULL, or the slab written by lint_grid_build for this stratum — the
+ * count and scan passes then visit those cells only.
+ * Row order: the flat parts of the split cells grouped by cell, then all other counted rows
+ * grouped by cell, then the top-up rows in draw order (see csrc/lint_cellmajor.cuh).
+ * N <= 2^32 - 2^16, fewer than 2^29 cells, out_dev 16-byte aligned.
+ * Scratch: lint_cellmajor_scratch_bytes. */
 size_t lint_cellmajor_scratch_bytes(int64_t ncells, int64_t N);
 int lint_grid_sample_cellmajor(const lint_grid_t *g, int64_t N, uint64_t seed, uint64_t offset,
-                               double u_lo, double u_hi, void *scratch_dev, size_t scratch_bytes, void *out_dev,
-                               int64_t *cell_idx_dev, lint_stream_t stream);
+                               double u_lo, double u_hi, const uint32_t *cell_range_dev, void *scratch_dev,
+                               size_t scratch_bytes, void *out_dev, int64_t *cell_idx_dev, lint_stream_t stream);
 int lint_cells_sample_cellmajor(const lint_cells_t *c, int64_t N, uint64_t seed, uint64_t offset,
                                 double u_lo, double u_hi, void *scratch_dev, size_t scratch_bytes, void *out_dev,
                                 int64_t *cell_idx_dev, lint_stream_t stream);

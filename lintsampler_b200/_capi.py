@@ -93,6 +93,9 @@ PROTOTYPES = {
     "lint_sum_numpy_f64": (C.c_int, [_P, _I64, _P, _P, C.c_size_t, _P]),
     "lint_cdf_build": (C.c_int, [_P, _I64, C.c_int, _P, _P, _P, C.c_size_t, _P]),
     "lint_guide_build": (C.c_int, [_P, _I64, C.c_int, _P, _P]),
+    "lint_grid_build_scratch_bytes": (C.c_size_t, [_I64]),
+    "lint_grid_build": (C.c_int, [C.POINTER(LintGrid), C.c_double, C.c_double, _P, _P, _P, C.c_int, _P, _P, _P,
+                                  _P, C.c_size_t, _P]),
     "lint_grid_sample_u": (C.c_int, [C.POINTER(LintGrid), _P, _I64, _P, _P, _P]),
     "lint_cells_sample_u": (C.c_int, [C.POINTER(LintCells), _P, _I64, _P, _P, _P]),
     "lint_incell_sample_u": (C.c_int, [C.c_int, _I64, _P, _P, _P, _P, _P, _P]),
@@ -107,7 +110,7 @@ PROTOTYPES = {
     "lint_permute_rows": (C.c_int, [_P, _P, _I64, C.c_int32, C.c_int32, _U64, _P]),
     "lint_cellmajor_scratch_bytes": (C.c_size_t, [_I64, _I64]),
     "lint_grid_sample_cellmajor": (C.c_int, [C.POINTER(LintGrid), _I64, _U64, _U64, C.c_double, C.c_double,
-                                             _P, C.c_size_t, _P, _P, _P]),
+                                             _P, _P, C.c_size_t, _P, _P, _P]),
     "lint_cells_sample_cellmajor": (C.c_int, [C.POINTER(LintCells), _I64, _U64, _U64, C.c_double,
                                               C.c_double, _P, C.c_size_t, _P, _P, _P]),
 }
@@ -135,7 +138,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.lint_abi_version() != 1:
+    if lib.lint_abi_version() != 2:
         raise ImportError("lintsampler_b200: ABI version mismatch; rebuild the library")
     _lib = lib
     return lib

@@ -248,27 +248,34 @@ int eval_halos_impl(const lint_grid_t *g, const lint_halos_t *h, double scale, u
 // ---------------------------------------------------------------------------
 // trapezoid cell masses + density validity check   [grid.py:469-518, 411, 401-404]
 // ---------------------------------------------------------------------------
+// mass of one cell and the validity bits of its corners: the sum starts from 0 and adds the
+// corners in corner order (`sum = np.zeros(shape)` then += per corner, grid.py:489-497), one
+// multiplication by 1/2^k, volume ((w0*w1)*w2)... (np.outer chain, grid.py:516-517)
+template <int K, typename DensT>
+__device__ __forceinline__ double cell_mass_one(const GridView<K> &g, uint32_t cell, uint32_t &bad) {
+    double c[1 << K], lo[K], hi[K];
+    grid_fetch<K, DensT, double>(g, (const double *)nullptr, cell, c, lo, hi);
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < (1 << K); ++j) {
+        acc = __dadd_rn(acc, c[j]);
+        if (c[j] < 0.0) bad |= LINT_FLAG_NEGATIVE;
+        if (!isfinite(c[j])) bad |= LINT_FLAG_NONFINITE;
+    }
+    const double mean = __dmul_rn(acc, 1.0 / (1 << K));     // exact /2^K
+    double vol = __dsub_rn(hi[0], lo[0]);                   // np.diff, then outer products
+#pragma unroll
+    for (int d = 1; d < K; ++d) vol = __dmul_rn(vol, __dsub_rn(hi[d], lo[d]));
+    return __dmul_rn(mean, vol);
+}
+
 template <int K, typename DensT>
 __global__ void __launch_bounds__(256)
 cell_mass_kernel(GridView<K> g, uint32_t ncells, double *masses, uint32_t *flags) {
     uint32_t bad = 0;
     for (uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x; cell < ncells;
-         cell += gridDim.x * blockDim.x) {
-        double c[1 << K], lo[K], hi[K];
-        grid_fetch<K, DensT, double>(g, (const double *)nullptr, cell, c, lo, hi);
-        double acc = 0.0;                      // `sum = np.zeros(shape)` then += per corner
-#pragma unroll
-        for (int j = 0; j < (1 << K); ++j) {
-            acc = __dadd_rn(acc, c[j]);
-            if (c[j] < 0.0) bad |= LINT_FLAG_NEGATIVE;
-            if (!isfinite(c[j])) bad |= LINT_FLAG_NONFINITE;
-        }
-        const double mean = __dmul_rn(acc, 1.0 / (1 << K));     // exact /2^K
-        double vol = __dsub_rn(hi[0], lo[0]);                   // np.diff, then outer products
-#pragma unroll
-        for (int d = 1; d < K; ++d) vol = __dmul_rn(vol, __dsub_rn(hi[d], lo[d]));
-        masses[cell] = __dmul_rn(mean, vol);
-    }
+         cell += gridDim.x * blockDim.x)
+        masses[cell] = cell_mass_one<K, DensT>(g, cell, bad);
     bad = __reduce_or_sync(0xffffffffu, bad);
     if (bad && (threadIdx.x & 31) == 0) atomicOr(flags, bad);
 }
@@ -620,15 +627,17 @@ scan_apply_kernel(const double *m, uint64_t n, const double *tile_off, const dou
 // One warp walks 32 consecutive cells; short runs are written by the owning
 // lane, long runs cooperatively.
 __global__ void __launch_bounds__(256)
-guide_build_kernel(const double *cdf, uint32_t n, int bits, uint32_t *guide) {
+guide_build_kernel(const double *cdf, uint32_t n, int bits, uint32_t *guide, const uint32_t *range) {
     const double G = (double)(1u << bits);
     const uint32_t Gi = 1u << bits;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; (uint64_t)w * 32 < n; w += warps) {
+    // cells [c0, c1) only (range: a multiple of 32 at the low end); the others own bins nobody asks for
+    const uint32_t c0 = range ? range[0] : 0u, c1 = range ? range[1] : n;
+    for (uint32_t w = (c0 >> 5) + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); (uint64_t)w * 32 < c1; w += warps) {
         const uint32_t i = w * 32 + lane;
         uint32_t j0 = 0, j1 = 0;
-        if (i < n) {
+        if (i < c1) {
             const double lo = i == 0 ? 0.0 : cdf[i - 1];
             j0 = (uint32_t)min(ceil(lo * G), G);
             j1 = i == n - 1 ? Gi + 1 : (uint32_t)min(ceil(cdf[i] * G), G);   // last cell also owns j = G
@@ -646,6 +655,215 @@ guide_build_kernel(const double *cdf, uint32_t n, int bits, uint32_t *guide) {
             for (uint32_t j = a + lane; j < b; j += 32) guide[j] = j + 1 < b ? (ci | GUIDE_SAME) : ci;
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// fused parallel build: cell masses -> CDF without ever storing the masses
+// ---------------------------------------------------------------------------
+// The parallel CDF above reads the masses twice (tile totals, then apply).  Here both passes
+// compute the masses from the vertex densities on the fly — the same arithmetic as
+// cell_mass_one, so the CDF is bit-identical to lint_grid_masses + lint_cdf_build(PARALLEL) —
+// and the second pass runs only over the tiles that a stratum [u_lo, u_hi) of the cell-selecting
+// uniform can touch: a rank of a sharded run reduces the whole (small, L2-resident) vertex
+// table to tile totals, which gives it the total mass and the offset of every tile, and then
+// scans only its own slab of cells.  No communication is needed for that: every rank derives the
+// same totals from the same vertices.
+//
+// Eight consecutive cells per thread.  Where the last dimension holds a multiple of 8 cells
+// the eight share their multi-index but for the last entry: the 2^(K-1) vertex rows they touch
+// are read once (9 values each) instead of 16 values per cell pair.
+template <int K, typename DensT>
+__device__ __forceinline__ void cell_masses8(const GridView<K> &g, uint32_t base, uint32_t ncells, bool row8,
+                                             double (&m)[PAR_ITEMS], uint32_t &bad) {
+    static_assert(PAR_ITEMS == 8, "eight cells per thread");
+    if (base >= ncells) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) m[q] = 0.0;
+        return;
+    }
+    if (!row8) {
+#pragma unroll 1
+        for (int q = 0; q < 8; ++q) m[q] = base + q < ncells ? cell_mass_one<K, DensT>(g, base + q, bad) : 0.0;
+        return;
+    }
+    uint32_t i[K];
+    grid_unravel<K>(g, base, i);
+    uint32_t vbase = 0;
+#pragma unroll
+    for (int d = 0; d < K; ++d) vbase += i[d] * g.vstride[d];
+    const DensT *V = reinterpret_cast<const DensT *>(g.V) + vbase;
+    double acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+#pragma unroll
+    for (int h = 0; h < (1 << (K - 1)); ++h) {                 // corner order: (h, 0), (h, 1), h ascending
+        const DensT *row = V + g.corner_off[2 * h];
+        double r[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            r[q] = (double)__ldg(row + q);
+            if (r[q] < 0.0) bad |= LINT_FLAG_NEGATIVE;
+            if (!isfinite(r[q])) bad |= LINT_FLAG_NONFINITE;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = __dadd_rn(__dadd_rn(acc[q], r[q]), r[q + 1]);
+    }
+    double pv = 1.0;                                           // (w0 * w1) * ... over the leading dims
+#pragma unroll
+    for (int d = 0; d + 1 < K; ++d) {
+        const double w = __dsub_rn(__ldg(g.edges[d] + i[d] + 1), __ldg(g.edges[d] + i[d]));
+        pv = d == 0 ? w : __dmul_rn(pv, w);
+    }
+    const double *el = g.edges[K - 1] + i[K - 1];
+    double e[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) e[q] = __ldg(el + q);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const double w = __dsub_rn(e[q + 1], e[q]);
+        const double vol = K == 1 ? w : __dmul_rn(pv, w);
+        m[q] = __dmul_rn(__dmul_rn(acc[q], 1.0 / (1 << K)), vol);
+    }
+}
+
+// range_out: [0] first cell, [1] end cell, [2] first tile, [3] end tile of the slab
+struct BuildPlan {
+    double u_lo, u_hi;
+    uint32_t ntiles, ngroups;
+};
+
+template <int K, typename DensT>
+__global__ void __launch_bounds__(PAR_THREADS)
+fused_tile_totals_kernel(GridView<K> g, uint32_t ncells, bool row8, BuildPlan plan, double *tile_tot,
+                         double *group_off, double *total, uint32_t *flags, uint32_t *done_counter,
+                         uint32_t *range_out) {
+    __shared__ double warp_tot[PAR_THREADS / 32];
+    __shared__ bool s_last;
+    uint32_t bad = 0;
+    for (uint32_t t = blockIdx.x; t < plan.ntiles; t += gridDim.x) {
+        double x[PAR_ITEMS];
+        cell_masses8<K, DensT>(g, t * PAR_TILE + threadIdx.x * PAR_ITEMS, ncells, row8, x, bad);
+        const double tot = tile_scan(x, warp_tot);
+        if (threadIdx.x == 0) tile_tot[t] = tot;
+    }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if (bad && (threadIdx.x & 31) == 0) atomicOr(flags, bad);
+    // the block that finishes last chains the tile totals (same nesting as scan_group_kernel /
+    // scan_group_chain_kernel) and finds the slab of the stratum
+    __threadfence();
+    if (threadIdx.x == 0) s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    volatile double *vt = tile_tot;
+    for (uint32_t gi = threadIdx.x; gi < plan.ngroups; gi += blockDim.x) {
+        const uint32_t lo = gi * PAR_GROUP, hi = min(lo + PAR_GROUP, plan.ntiles);
+        double run = 0.0;
+        for (uint32_t t = lo; t < hi; ++t) {
+            const double mine = vt[t];
+            vt[t] = run;
+            run = __dadd_rn(run, mine);
+        }
+        group_off[gi] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double run = 0.0;
+        for (uint32_t gi = 0; gi < plan.ngroups; ++gi) {
+            const double mine = group_off[gi];
+            group_off[gi] = run;
+            run = __dadd_rn(run, mine);
+        }
+        *total = run;
+        *done_counter = 0;                                     // ready for the next build
+        // B(t) = CDF value just before tile t = (G (+) T) / total, exactly the value the apply
+        // pass gives the cell before the tile.  Cells before the last tile with B <= u_lo end at
+        // or below u_lo; cells from the first tile with B >= u_hi start at or above u_hi.
+        auto before = [&](uint32_t t) { return __ddiv_rn(__dadd_rn(group_off[t / PAR_GROUP], vt[t]), run); };
+        uint32_t lo = 0, hi = plan.ntiles;                     // last t with B(t) <= u_lo  (B(0) = 0)
+        while (hi - lo > 1) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (before(mid) <= plan.u_lo) lo = mid; else hi = mid;
+        }
+        uint32_t t_lo = lo > 0 ? lo - 1 : 0;                   // one tile of margin on either side
+        uint32_t a = 0, b = plan.ntiles;                       // first t with B(t) >= u_hi
+        while (a < b) {
+            const uint32_t mid = a + ((b - a) >> 1);
+            if (before(mid) >= plan.u_hi) b = mid; else a = mid + 1;
+        }
+        uint32_t t_hi = min(a + 1, plan.ntiles);
+        if (plan.u_lo <= 0.0) t_lo = 0;                        // a stratum that starts / ends with the domain
+        if (plan.u_hi >= 1.0) t_hi = plan.ntiles;              // covers its zero-mass head / tail too
+        range_out[0] = t_lo * PAR_TILE;
+        range_out[1] = min(t_hi * (uint32_t)PAR_TILE, ncells);
+        range_out[2] = t_lo;
+        range_out[3] = t_hi;
+    }
+}
+
+template <int K, typename DensT>
+__global__ void __launch_bounds__(PAR_THREADS)
+fused_apply_kernel(GridView<K> g, uint32_t ncells, bool row8, const double *tile_off, const double *group_off,
+                   const double *total, const uint32_t *range, double *cdf, double *masses) {
+    __shared__ double warp_tot[PAR_THREADS / 32];
+    const double tot = *total;
+    const uint32_t t_lo = range[2], t_hi = range[3];
+    uint32_t bad = 0;
+    for (uint32_t t = t_lo + blockIdx.x; t < t_hi; t += gridDim.x) {
+        double x[PAR_ITEMS];
+        const uint32_t base = t * PAR_TILE + threadIdx.x * PAR_ITEMS;
+        cell_masses8<K, DensT>(g, base, ncells, row8, x, bad);
+        if (masses) {
+#pragma unroll
+            for (int j = 0; j < PAR_ITEMS; ++j)
+                if (base + j < ncells) masses[base + j] = x[j];
+        }
+        tile_scan(x, warp_tot);
+        const double toff = tile_off[t], goff = group_off[t / PAR_GROUP];
+#pragma unroll
+        for (int j = 0; j < PAR_ITEMS; ++j) {
+            if (base + j < ncells) {
+                const double s = __dadd_rn(goff, __dadd_rn(toff, x[j]));
+                cdf[base + j] = __ddiv_rn(s, tot);
+            }
+        }
+        // the entry just before the slab: readers difference cdf[c] - cdf[c - 1]
+        if (t == t_lo && t > 0 && threadIdx.x == 0) cdf[t * PAR_TILE - 1] = __ddiv_rn(__dadd_rn(goff, toff), tot);
+    }
+}
+
+template <int K>
+int fused_build_impl(const lint_grid_t *g, uint64_t ncells, double u_lo, double u_hi, double *cdf, double *total,
+                     uint32_t *guide, int guide_bits, double *masses, uint32_t *flags, uint32_t *range,
+                     void *scratch, cudaStream_t st) {
+    GridView<K> v = make_grid_view<K>(g, ncells, false);
+    v.rec = nullptr;
+    const uint32_t ntiles = (uint32_t)((ncells + PAR_TILE - 1) / PAR_TILE);
+    const uint32_t ngroups = (ntiles + PAR_GROUP - 1) / PAR_GROUP;
+    double *tile_tot = (double *)scratch;
+    double *group_off = tile_tot + ntiles;
+    uint32_t *done = (uint32_t *)(group_off + ngroups);
+    const bool row8 = g->ncells[K - 1] % 8 == 0;
+    const BuildPlan plan{u_lo, u_hi, ntiles, ngroups};
+    const int blocks = (int)std::min<uint32_t>(ntiles, 148 * 8);
+    cudaMemsetAsync(done, 0, sizeof(uint32_t), st);
+    if (g->dtype == LINT_F32) {
+        fused_tile_totals_kernel<K, float><<<blocks, PAR_THREADS, 0, st>>>(v, (uint32_t)ncells, row8, plan, tile_tot,
+                                                                          group_off, total, flags, done, range);
+        fused_apply_kernel<K, float><<<blocks, PAR_THREADS, 0, st>>>(v, (uint32_t)ncells, row8, tile_tot, group_off,
+                                                                    total, range, cdf, masses);
+    } else {
+        fused_tile_totals_kernel<K, double><<<blocks, PAR_THREADS, 0, st>>>(v, (uint32_t)ncells, row8, plan, tile_tot,
+                                                                           group_off, total, flags, done, range);
+        fused_apply_kernel<K, double><<<blocks, PAR_THREADS, 0, st>>>(v, (uint32_t)ncells, row8, tile_tot, group_off,
+                                                                     total, range, cdf, masses);
+    }
+    if (guide_bits > 0) {
+        const uint64_t nwarps = (ncells + 31) / 32;
+        const int gblocks = (int)std::min<uint64_t>((nwarps + 7) / 8, 148 * 16);
+        guide_build_kernel<<<gblocks, 256, 0, st>>>(cdf, (uint32_t)ncells, guide_bits, guide, range);
+    }
+    return check_launch("lint_grid_build");
 }
 
 }  // namespace lint
@@ -808,8 +1026,40 @@ int lint_guide_build(const double *cdf_dev, int64_t n, int guide_bits, uint32_t 
         return fail(LINT_ERR_BAD_ARG, "lint_guide_build: guide_bits %d outside 1..30", guide_bits);
     const uint64_t nwarps = ((uint64_t)n + 31) / 32;
     const int blocks = (int)std::min<uint64_t>((nwarps + 7) / 8, 148 * 16);
-    guide_build_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cdf_dev, (uint32_t)n, guide_bits, guide_dev);
+    guide_build_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cdf_dev, (uint32_t)n, guide_bits, guide_dev,
+                                                                 nullptr);
     return check_launch("lint_guide_build");
+}
+
+size_t lint_grid_build_scratch_bytes(int64_t ncells) {
+    if (ncells < 1) return 0;
+    const size_t tiles = ((size_t)ncells + PAR_TILE - 1) / PAR_TILE;
+    const size_t groups = (tiles + PAR_GROUP - 1) / PAR_GROUP;
+    return (tiles + groups + 2) * sizeof(double);
+}
+
+int lint_grid_build(const lint_grid_t *g, double u_lo, double u_hi, double *cdf_dev, double *total_dev,
+                    uint32_t *guide_dev, int guide_bits, double *masses_dev, uint32_t *flags_dev,
+                    uint32_t *range_dev, void *scratch_dev, size_t scratch_bytes, lint_stream_t stream) {
+    uint64_t nc, nv;
+    if (int rc = validate_grid(g, false, &nc, &nv)) return rc;
+    if (!cdf_dev || !total_dev || !flags_dev || !range_dev)
+        return fail(LINT_ERR_BAD_ARG, "lint_grid_build: cdf_dev / total_dev / flags_dev / range_dev is NULL");
+    if (!(u_lo >= 0.0) || !(u_hi <= 1.0) || !(u_lo < u_hi))
+        return fail(LINT_ERR_BAD_ARG, "lint_grid_build: stratum [%g, %g) is not inside [0, 1]", u_lo, u_hi);
+    if (guide_bits < 0 || guide_bits > 30 || (guide_bits > 0 && !guide_dev))
+        return fail(LINT_ERR_BAD_ARG, "lint_grid_build: guide table inconsistent (bits=%d)", guide_bits);
+    if (!scratch_dev || scratch_bytes < lint_grid_build_scratch_bytes((int64_t)nc))
+        return fail(LINT_ERR_BAD_ARG, "lint_grid_build: scratch too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (g->dim) {
+        case 1: return fused_build_impl<1>(g, nc, u_lo, u_hi, cdf_dev, total_dev, guide_dev, guide_bits, masses_dev, flags_dev, range_dev, scratch_dev, st);
+        case 2: return fused_build_impl<2>(g, nc, u_lo, u_hi, cdf_dev, total_dev, guide_dev, guide_bits, masses_dev, flags_dev, range_dev, scratch_dev, st);
+        case 3: return fused_build_impl<3>(g, nc, u_lo, u_hi, cdf_dev, total_dev, guide_dev, guide_bits, masses_dev, flags_dev, range_dev, scratch_dev, st);
+        case 4: return fused_build_impl<4>(g, nc, u_lo, u_hi, cdf_dev, total_dev, guide_dev, guide_bits, masses_dev, flags_dev, range_dev, scratch_dev, st);
+        case 5: return fused_build_impl<5>(g, nc, u_lo, u_hi, cdf_dev, total_dev, guide_dev, guide_bits, masses_dev, flags_dev, range_dev, scratch_dev, st);
+        default: return fused_build_impl<6>(g, nc, u_lo, u_hi, cdf_dev, total_dev, guide_dev, guide_bits, masses_dev, flags_dev, range_dev, scratch_dev, st);
+    }
 }
 
 }  // extern "C"

@@ -42,8 +42,8 @@ size_t lint_cellmajor_scratch_bytes(int64_t ncells, int64_t N) {
 }
 
 int lint_grid_sample_cellmajor(const lint_grid_t *g, int64_t N, uint64_t seed, uint64_t offset,
-                               double u_lo, double u_hi, void *scratch_dev, size_t scratch_bytes, void *out_dev,
-                               int64_t *cell_idx_dev, lint_stream_t stream) {
+                               double u_lo, double u_hi, const uint32_t *cell_range_dev, void *scratch_dev,
+                               size_t scratch_bytes, void *out_dev, int64_t *cell_idx_dev, lint_stream_t stream) {
     uint64_t nc, nv;
     if (int rc = validate_grid(g, true, &nc, &nv)) return rc;
     if (int rc = check_common(N, nc, u_lo, u_hi, out_dev, scratch_dev, scratch_bytes, "lint_grid_sample_cellmajor")) return rc;
@@ -54,12 +54,12 @@ int lint_grid_sample_cellmajor(const lint_grid_t *g, int64_t N, uint64_t seed, u
     const Stratum u{u_lo, u_hi};
     int rc;
     switch (g->dim) {
-        case 1: rc = grid_cellmajor_k<1>(g, nc, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
-        case 2: rc = grid_cellmajor_k<2>(g, nc, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
-        case 3: rc = grid_cellmajor_k<3>(g, nc, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
-        case 4: rc = grid_cellmajor_k<4>(g, nc, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
-        case 5: rc = grid_cellmajor_k<5>(g, nc, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
-        default: rc = grid_cellmajor_k<6>(g, nc, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
+        case 1: rc = grid_cellmajor_k<1>(g, nc, N, key, offset, u, cell_range_dev, s, out_dev, cell_idx_dev, st); break;
+        case 2: rc = grid_cellmajor_k<2>(g, nc, N, key, offset, u, cell_range_dev, s, out_dev, cell_idx_dev, st); break;
+        case 3: rc = grid_cellmajor_k<3>(g, nc, N, key, offset, u, cell_range_dev, s, out_dev, cell_idx_dev, st); break;
+        case 4: rc = grid_cellmajor_k<4>(g, nc, N, key, offset, u, cell_range_dev, s, out_dev, cell_idx_dev, st); break;
+        case 5: rc = grid_cellmajor_k<5>(g, nc, N, key, offset, u, cell_range_dev, s, out_dev, cell_idx_dev, st); break;
+        default: rc = grid_cellmajor_k<6>(g, nc, N, key, offset, u, cell_range_dev, s, out_dev, cell_idx_dev, st); break;
     }
     if (rc) return rc;
     // rows [T, N): the u-driven sampler on the same stratum

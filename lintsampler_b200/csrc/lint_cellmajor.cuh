@@ -166,9 +166,12 @@ __device__ __forceinline__ double cell_lambda(const CdfSlice &t, uint32_t c, dou
 template <typename Cells>
 __global__ void __launch_bounds__(256)
 poisson_counts_kernel(Cells src, CdfSlice t, double lam_per_unit, uint2 key, uint64_t offset, bool split,
-                      uint32_t *__restrict__ counts_flat, uint32_t *__restrict__ counts_rest) {
+                      const uint32_t *__restrict__ range, uint32_t *__restrict__ counts_flat,
+                      uint32_t *__restrict__ counts_rest) {
     const uint32_t w2 = (uint32_t)offset, w3 = (uint32_t)(offset >> 32);
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < t.ncells; c += gridDim.x * blockDim.x) {
+    // cells [c0, c1): the slab of the stratum (lint_grid_build), or every cell
+    const uint32_t c0 = range ? range[0] : 0u, c1 = range ? range[1] : t.ncells;
+    for (uint32_t c = c0 + blockIdx.x * blockDim.x + threadIdx.x; c < c1; c += gridDim.x * blockDim.x) {
         const double lam = cell_lambda(t, c, lam_per_unit);
         if (!split) {
             CellRng rng{key, c, w2, w3};
@@ -204,9 +207,15 @@ __device__ __forceinline__ unsigned long long pack(uint32_t rows, uint32_t cells
 }
 
 static __global__ void __launch_bounds__(SCAN_THREADS)
-scan_compact_kernel(const uint32_t *counts, uint32_t ncells, uint32_t id_mul, uint32_t id_add,
-                    unsigned long long *tile_state, uint32_t *tile_counter, uint32_t *cid, uint32_t *coff,
-                    uint32_t *nnz_out, uint32_t *rows_out) {
+scan_compact_kernel(const uint32_t *counts, uint32_t ncells_all, const uint32_t *__restrict__ range,
+                    uint32_t id_mul, uint32_t id_add, unsigned long long *tile_state, uint32_t *tile_counter,
+                    uint32_t *cid, uint32_t *coff, uint32_t *nnz_out, uint32_t *rows_out) {
+    // cells [first, first + ncells) of the count array; ids are global cell indices
+    const uint32_t first = range ? range[0] : 0u;
+    const uint32_t ncells = range ? range[1] - range[0] : ncells_all;
+    counts += first;
+    id_add += first * id_mul;
+    if ((uint64_t)blockIdx.x * SCAN_TILE >= ncells) return;       // (the grid is sized for every cell)
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
     __shared__ unsigned long long s_excl;
@@ -978,26 +987,26 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
 // ---------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------
-static void scan_list(const uint32_t *counts, uint32_t n, uint32_t id_mul, uint32_t id_add, const SegList &l,
-                      cudaStream_t st) {
+static void scan_list(const uint32_t *counts, uint32_t n, const uint32_t *range, uint32_t id_mul, uint32_t id_add,
+                      const SegList &l, cudaStream_t st) {
     const uint32_t nscan = (n + SCAN_TILE - 1) / SCAN_TILE;
-    scan_compact_kernel<<<nscan, SCAN_THREADS, 0, st>>>(counts, n, id_mul, id_add, l.tile_state, l.tile_counter,
-                                                       l.cid, l.coff, l.nnz, l.rows);
+    scan_compact_kernel<<<nscan, SCAN_THREADS, 0, st>>>(counts, n, range, id_mul, id_add, l.tile_state,
+                                                       l.tile_counter, l.cid, l.coff, l.nnz, l.rows);
 }
 
 // counts -> offsets (+ compaction) -> row budget -> chunk starts, for both runs
 template <typename Cells>
 static int plan_rows(const Cells &src, const double *cdf, uint64_t ncells, uint64_t N, uint2 key,
-                     uint64_t offset, Stratum u, const Scratch &s, cudaStream_t st) {
+                     uint64_t offset, Stratum u, const uint32_t *range, const Scratch &s, cudaStream_t st) {
     const bool split = use_split(ncells, N);
     const CdfSlice t{cdf, (uint32_t)ncells, u.u_lo, u.u_hi};
     const double lam_per_unit = grouped_mean(N) / (u.u_hi - u.u_lo);
     const int cblocks = (int)std::min<uint64_t>((ncells + 255) / 256, 148 * 16);
     cudaMemsetAsync(s.zero_begin, 0, s.zero_bytes, st);
-    poisson_counts_kernel<<<cblocks, 256, 0, st>>>(src, t, lam_per_unit, key, offset, split, s.counts_flat,
+    poisson_counts_kernel<<<cblocks, 256, 0, st>>>(src, t, lam_per_unit, key, offset, split, range, s.counts_flat,
                                                    s.counts_rest);
-    if (split) scan_list(s.counts_flat, (uint32_t)ncells, 1, 0, s.flat, st);
-    scan_list(s.counts_rest, (uint32_t)ncells, split ? 2 : 1, split ? 1 : 0, s.rest, st);
+    if (split) scan_list(s.counts_flat, (uint32_t)ncells, range, 1, 0, s.flat, st);
+    scan_list(s.counts_rest, (uint32_t)ncells, range, split ? 2 : 1, split ? 1 : 0, s.rest, st);
     plan_totals_kernel<<<1, 1, 0, st>>>(split ? s.flat.rows : nullptr, s.rest.rows, (uint32_t)N, s.plan,
                                         s.chunk_counter);
     const uint32_t chunk_rows = emit_chunk_rows(N);
@@ -1062,14 +1071,14 @@ int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t 
 
 template <int K>
 int grid_cellmajor_k(const lint_grid_t *g, uint64_t nc, uint64_t N, uint2 key, uint64_t offset, Stratum u,
-                     const Scratch &s, void *out, int64_t *cell_idx, cudaStream_t st) {
+                     const uint32_t *range, const Scratch &s, void *out, int64_t *cell_idx, cudaStream_t st) {
     if (g->dtype == LINT_F32) {
         GridCells<K, float> src{make_grid_view<K>(g, nc, true)};
-        if (int rc = plan_rows(src, g->cdf_dev, nc, N, key, offset, u, s, st)) return rc;
+        if (int rc = plan_rows(src, g->cdf_dev, nc, N, key, offset, u, range, s, st)) return rc;
         return launch_emit<K, float>(src, g->cdf_dev, s, nc, N, key, offset, u, out, cell_idx, st);
     }
     GridCells<K, double> src{make_grid_view<K>(g, nc, true)};
-    if (int rc = plan_rows(src, g->cdf_dev, nc, N, key, offset, u, s, st)) return rc;
+    if (int rc = plan_rows(src, g->cdf_dev, nc, N, key, offset, u, range, s, st)) return rc;
     return launch_emit<K, double>(src, g->cdf_dev, s, nc, N, key, offset, u, out, cell_idx, st);
 }
 
@@ -1096,11 +1105,11 @@ int cells_cellmajor_k(const lint_cells_t *c, uint64_t N, uint2 key, uint64_t off
     const uint64_t nc = (uint64_t)c->ncells;
     if (c->dtype == LINT_F32) {
         ListCells<K, float> src{v};
-        if (int rc = plan_rows(src, c->cdf_dev, nc, N, key, offset, u, s, st)) return rc;
+        if (int rc = plan_rows(src, c->cdf_dev, nc, N, key, offset, u, nullptr, s, st)) return rc;
         return launch_emit<K, float>(src, c->cdf_dev, s, nc, N, key, offset, u, out, cell_idx, st);
     }
     ListCells<K, double> src{v};
-    if (int rc = plan_rows(src, c->cdf_dev, nc, N, key, offset, u, s, st)) return rc;
+    if (int rc = plan_rows(src, c->cdf_dev, nc, N, key, offset, u, nullptr, s, st)) return rc;
     return launch_emit<K, double>(src, c->cdf_dev, s, nc, N, key, offset, u, out, cell_idx, st);
 }
 

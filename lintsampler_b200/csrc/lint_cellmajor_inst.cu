@@ -11,8 +11,8 @@
 #include "lint_cellmajor_plan.h"
 namespace lint {
 template <int K>
-int grid_cellmajor_k(const lint_grid_t *, uint64_t, uint64_t, uint2, uint64_t, Stratum, const Scratch &, void *,
-                     int64_t *, cudaStream_t) {
+int grid_cellmajor_k(const lint_grid_t *, uint64_t, uint64_t, uint2, uint64_t, Stratum, const uint32_t *,
+                     const Scratch &, void *, int64_t *, cudaStream_t) {
     return fail(LINT_ERR_UNSUPPORTED, "cell-major kernels for dim %d were left out of this development build", K);
 }
 template <int K>
@@ -27,7 +27,7 @@ int cells_cellmajor_k(const lint_cells_t *, uint64_t, uint2, uint64_t, Stratum, 
 
 namespace lint {
 template int grid_cellmajor_k<LINT_K>(const lint_grid_t *, uint64_t, uint64_t, uint2, uint64_t, Stratum,
-                                      const Scratch &, void *, int64_t *, cudaStream_t);
+                                      const uint32_t *, const Scratch &, void *, int64_t *, cudaStream_t);
 template int cells_cellmajor_k<LINT_K>(const lint_cells_t *, uint64_t, uint2, uint64_t, Stratum,
                                        const Scratch &, void *, int64_t *, cudaStream_t);
 }  // namespace lint

@@ -91,7 +91,7 @@ inline bool use_split(uint64_t ncells, uint64_t N) { return N >= SPLIT_MIN_ROWS_
 // per-dimension entry points, instantiated in lint_cellmajor_inst.cu
 template <int K>
 int grid_cellmajor_k(const lint_grid_t *g, uint64_t nc, uint64_t N, uint2 key, uint64_t offset, Stratum u,
-                     const Scratch &s, void *out, int64_t *cell_idx, cudaStream_t st);
+                     const uint32_t *range, const Scratch &s, void *out, int64_t *cell_idx, cudaStream_t st);
 template <int K>
 int cells_cellmajor_k(const lint_cells_t *c, uint64_t N, uint2 key, uint64_t offset, Stratum u,
                       const Scratch &s, void *out, int64_t *cell_idx, cudaStream_t st);

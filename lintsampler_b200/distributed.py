@@ -138,14 +138,24 @@ class ShardedGrid:
         self.bounds = equal_mass_strata(self.world)
         self.shard_masses = None
         self._gather_buf = None
+        self.enqueue_build(gather=False)            # restrict the tables to this rank's stratum
         self.exchange_masses()
 
     # -- build -------------------------------------------------------------
-    def enqueue_build(self):
-        """Cell masses -> CDF -> guide table on the current stream, then the
-        all-gather of the per-shard masses (asynchronous; no host sync)."""
-        self.grid._enqueue_build()
-        self._enqueue_gather()
+    def enqueue_build(self, gather=True):
+        """This rank's share of the build on the current stream: every rank reduces the vertex
+        table to tile totals (total mass and tile offsets, identical on all ranks, no
+        communication) and scans only the slab of cells of its own stratum (the parallel CDF;
+        ``cdf_mode="sequential"`` builds the whole table).  ``gather``: also all-gather the
+        per-shard masses over NCCL (8 bytes per rank, asynchronous; equal-mass strata make it
+        redundant for the split of N, so the benchmark leaves it out)."""
+        lo, hi = float(self.bounds[self.rank]), float(self.bounds[self.rank + 1])
+        if self.grid.cdf_mode == "parallel":
+            self.grid._enqueue_build(stratum=(lo, hi))
+        else:
+            self.grid._enqueue_build()
+        if gather:
+            self._enqueue_gather()
 
     def _stratum_mass_tensor(self):
         """This rank's shard mass as a device scalar: (b_{g+1} - b_g) * total."""

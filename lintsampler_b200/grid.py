@@ -14,6 +14,12 @@ from .base import DensityStructure
 from .pdfs import FUSED_PDFS
 
 
+def torch_range(ncells, device):
+    """The whole-domain slab in lint_grid_build's layout: [first cell, end cell, first tile, end tile]."""
+    import torch
+    return torch.tensor([0, ncells, 0, (ncells + 2047) // 2048], dtype=torch.int32, device=device)
+
+
 def _is_flat_sequence(obj):
     """True for a sequence whose first element is not itself a sequence."""
     return hasattr(obj, "__len__") and not hasattr(obj[0], "__len__")
@@ -235,8 +241,10 @@ class DensityGrid(DensityStructure):
         self._gmm = gmm
         if gmm is not None:
             gmm._eval_on_grid(desc, self._scale, st)
-        self._masses = torch.empty(ncells, dtype=torch.float64, device=dev)
+        self._masses_t = None                       # cell masses on the device: computed on demand
         self._flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._range = torch.zeros(4, dtype=torch.int32, device=dev)     # slab of the last build (lint_grid_build)
+        self._stratum = (0.0, 1.0)
         self._cdf = torch.empty(ncells, dtype=torch.float64, device=dev)
         self._total = torch.empty(1, dtype=torch.float64, device=dev)
         self._guide_bits_planned = (int(self._guide_bits_arg) if self._guide_bits_arg is not None
@@ -245,15 +253,34 @@ class DensityGrid(DensityStructure):
         want_rec = self._cell_records_arg if self._cell_records_arg is not None else rec_bytes < (8 << 30)
         self._rec = torch.empty(ncells * 2 ** self._dim, dtype=tdt, device=dev) if want_rec else None
         self._guide = torch.empty((1 << self._guide_bits_planned) + 1, dtype=torch.int32, device=dev)
-        nbytes = _capi.load().lint_cdf_scratch_bytes(ncells)
+        nbytes = max(_capi.load().lint_cdf_scratch_bytes(ncells), _capi.load().lint_grid_build_scratch_bytes(ncells))
         self._scratch = torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device=dev)
         self._enqueue_build()
         self._check_build()
 
+    @property
+    def _masses(self):
+        """Device tensor of the cell masses (scaled like the stored densities).  The parallel
+        build never stores them; they are computed when somebody asks (grid.py:411)."""
+        if self._masses_t is None:
+            import torch
+            with torch.cuda.device(self.device):
+                self._masses_t = torch.empty(int(self.ncells), dtype=torch.float64, device=self.device)
+                flags = torch.zeros(1, dtype=torch.int32, device=self.device)
+                desc = self._descriptor()
+                _capi.call("lint_grid_masses", C.byref(desc), _device.ptr(self._masses_t), _device.ptr(flags),
+                           _device.stream_ptr(self.device))
+        return self._masses_t
+
     @_device.on_device
-    def _enqueue_build(self):
+    def _enqueue_build(self, stratum=(0.0, 1.0)):
         """Cell masses -> CDF -> guide table, enqueued on the current stream with no
-        host synchronisation (grid.py:411-412, 431; utils.py:195-196)."""
+        host synchronisation (grid.py:411-412, 431; utils.py:195-196).
+
+        ``cdf_mode="parallel"``: one fused call, masses computed on the fly and never stored;
+        with ``stratum=(u_lo, u_hi)`` only the slab of cells that stratum of the cell-selecting
+        uniform can touch is scanned (a rank of a sharded run).  ``"sequential"``: the
+        NumPy-identical path over stored masses, whole domain."""
         dev = self.device
         st = _device.stream_ptr(dev)
         ncells = int(self.ncells)
@@ -263,13 +290,26 @@ class DensityGrid(DensityStructure):
         self._guide_bits = 0
         desc = self._descriptor()
         self._flags.zero_()
-        _capi.call("lint_grid_masses", C.byref(desc), _device.ptr(self._masses), _device.ptr(self._flags), st)
+        self._masses_t = None
+        self._stratum = (float(stratum[0]), float(stratum[1]))
         if self._rec is not None:
             _capi.call("lint_grid_records", C.byref(desc), _device.ptr(self._rec), st)
-        _capi.call("lint_cdf_build", _device.ptr(self._masses), ncells, mode, _device.ptr(self._cdf),
-                   _device.ptr(self._total), _device.ptr(self._scratch), self._scratch.numel(), st)
-        _capi.call("lint_guide_build", _device.ptr(self._cdf), ncells, self._guide_bits_planned,
-                   _device.ptr(self._guide), st)
+        if mode == _capi.LINT_CDF_PARALLEL:
+            _capi.call("lint_grid_build", C.byref(desc), C.c_double(self._stratum[0]), C.c_double(self._stratum[1]),
+                       _device.ptr(self._cdf), _device.ptr(self._total), _device.ptr(self._guide),
+                       self._guide_bits_planned, None, _device.ptr(self._flags), _device.ptr(self._range),
+                       _device.ptr(self._scratch), self._scratch.numel(), st)
+        else:
+            if self._stratum != (0.0, 1.0):
+                raise ValueError("DensityGrid: a stratum-restricted build needs cdf_mode='parallel'")
+            import torch
+            self._masses_t = masses = torch.empty(ncells, dtype=torch.float64, device=dev)
+            _capi.call("lint_grid_masses", C.byref(desc), _device.ptr(masses), _device.ptr(self._flags), st)
+            _capi.call("lint_cdf_build", _device.ptr(masses), ncells, mode, _device.ptr(self._cdf),
+                       _device.ptr(self._total), _device.ptr(self._scratch), self._scratch.numel(), st)
+            _capi.call("lint_guide_build", _device.ptr(self._cdf), ncells, self._guide_bits_planned,
+                       _device.ptr(self._guide), st)
+            self._range.copy_(torch_range(ncells, dev))
         self._guide_bits = self._guide_bits_planned
         self._masses_host = None
         self._total_stale = True
@@ -339,6 +379,9 @@ class DensityGrid(DensityStructure):
     @_device.on_device
     def _sample_philox(self, N, seed, offset, want_cells=False, out=None, stratum=(0.0, 1.0)):
         import torch
+        if not (self._stratum[0] <= stratum[0] and stratum[1] <= self._stratum[1]):
+            raise ValueError(f"DensityGrid: the tables were built for the stratum {self._stratum}; "
+                             f"cannot draw from {tuple(stratum)}")
         if out is None:
             out = torch.empty((N, self._dim), dtype=_device.torch_dtype(self.dtype), device=self.device)
         cells = torch.empty(N, dtype=torch.int64, device=self.device) if want_cells else None
@@ -352,6 +395,9 @@ class DensityGrid(DensityStructure):
         """Throughput mode: rows grouped by cell (C order); exact multinomial cell
         counts, no per-sample search (``lint_grid_sample_cellmajor``)."""
         import torch
+        if not (self._stratum[0] <= stratum[0] and stratum[1] <= self._stratum[1]):
+            raise ValueError(f"DensityGrid: the tables were built for the stratum {self._stratum}; "
+                             f"cannot draw from {tuple(stratum)}")
         if out is None:
             out = torch.empty((N, self._dim), dtype=_device.torch_dtype(self.dtype), device=self.device)
         cells = torch.empty(N, dtype=torch.int64, device=self.device) if want_cells else None
@@ -360,7 +406,8 @@ class DensityGrid(DensityStructure):
             scratch, nbytes = _device.cellmajor_scratch(self, int(self.ncells), rows)
             _capi.call("lint_grid_sample_cellmajor", C.byref(desc), rows, C.c_uint64(seed),
                        C.c_uint64(offset + start), C.c_double(stratum[0]), C.c_double(stratum[1]),
-                       _device.ptr(scratch), nbytes, _device.ptr(out[start:start + rows]),
+                       _device.ptr(self._range), _device.ptr(scratch), nbytes,
+                       _device.ptr(out[start:start + rows]),
                        _device.ptr(cells[start:start + rows] if cells is not None else None),
                        _device.stream_ptr(self.device))
         return (out, cells) if want_cells else out

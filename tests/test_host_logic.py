@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     declared = set(re.findall(r"^(?:int|size_t|const char \*)\s*\*?(lint_\w+)\s*\(", hdr, flags=re.M))
     assert declared == set(_capi.PROTOTYPES), declared ^ set(_capi.PROTOTYPES)
     lib = _capi.load()                       # resolves each symbol or raises
-    assert lib.lint_abi_version() == 1
+    assert lib.lint_abi_version() == 2
     assert lib.lint_cdf_scratch_bytes(1 << 24) > 0
 
 
