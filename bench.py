@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark (BASELINE.json): samples/s for a 256^3 3-D DensityGrid,
-N = 1e9 samples per GPU, fp32 samples / fp64 CDF, synthetic K=4 Gaussian mixture.
+N = 1e9 samples per step in total (strong scaling over the GPUs: each rank owns an equal-mass
+stratum of the cell CDF), fp32 samples / fp64 CDF, synthetic K=4 Gaussian mixture.
 
     python bench.py --gpus N --steps K --warmup W            # this build
     python bench.py --impl reference ...                      # CPU reference arm
@@ -178,10 +179,27 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------- GPU arm
+def emit_traffic(order, rows_flat, rows_general, n_rows):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, scaled from the ncu
+    --set full capture recorded in profiles/traffic.json (bytes per row, with the commit and the
+    profile file it came from)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None, None
+    if order == "cell":
+        k = t.get("emit_flat_kernel<3,float>")
+        return (k["dram_bytes_per_row"] * rows_flat, k["source"]) if k else (None, None)
+    k = t.get("sample_kernel<3,float,GridSource,UniformsPhilox>")
+    return (k["dram_bytes_per_row"] * n_rows, k["source"]) if k else (None, None)
+
+
 def run_b200(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     import lintsampler_b200 as lb
+    from lintsampler_b200 import _capi
     from lintsampler_b200 import distributed as lbd
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -194,8 +212,9 @@ def run_b200(args):
 
     edges, w, means, sig = synthetic_c3()
     gmm = lb.GaussianMixture(w, means, sigmas=sig)
-    n_local = args.samples
-    # domain: the whole grid at world 1, this rank's equal-mass shard otherwise
+    # strong scaling: N samples in total, split multinomially over the ranks'
+    # equal-mass strata with a seed every rank shares (no communication); --weak: N per rank
+    n_total = args.samples * (world if args.weak else 1)
     grid_kw = {}
     if args.order == "cell":
         # the grouped emitter loads each cell once, so it needs neither per-cell records
@@ -207,19 +226,31 @@ def run_b200(args):
         grid_kw["cell_records"] = False
     shard = lbd.ShardedGrid(edges, gmm, dtype=np.float32, device=dev, rank=rank, world=world,
                             group=dist.group.WORLD if world > 1 else None, **grid_kw)
-    out = torch.empty((n_local, DIM), dtype=torch.float32, device=dev)
+    cap = n_total if world == 1 else int(n_total / world + 8 * np.sqrt(n_total) + 64)
+    out = torch.empty((cap, DIM), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream(dev)
 
+    def share(i):
+        """(rows, first row) of this rank in step i: Multinomial(N, 1/G ... 1/G), shared seed."""
+        if world == 1:
+            return n_total, 0
+        counts = lbd.split_counts(n_total, np.full(world, 1.0 / world), SEED * 1_000_003 + i)
+        return int(counts[rank]), int(counts[:rank].sum())
+
     def step(i, ev=None, order=None):
-        shard.enqueue_build()                       # masses -> CDF -> guide (+ tiny all-gather)
+        n, first = share(i)
         if ev:
             ev[0].record(stream)
-        if (order or args.order) == "cell":
-            shard.sample_cellmajor_into(out, seed=SEED, offset=i * n_local * world)
-        else:
-            shard.sample_philox_into(out, seed=SEED, offset=i * n_local * world)
+        shard.enqueue_build(gather=False)           # tile totals of the whole grid, CDF + guide of the own slab
         if ev:
             ev[1].record(stream)
+        if (order or args.order) == "cell":
+            shard.sample_cellmajor_into(out[:n], seed=SEED, offset=i * n_total + first)
+        else:
+            shard.sample_philox_into(out[:n], seed=SEED, offset=i * n_total + first)
+        if ev:
+            ev[2].record(stream)
+        return n
 
     def barrier():
         if world > 1:
@@ -229,8 +260,7 @@ def run_b200(args):
     for i in range(args.warmup):
         step(i)
     barrier()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         barrier()
@@ -240,24 +270,40 @@ def run_b200(args):
         t_end.record(stream)
         barrier()
     ms_total = t_beg.elapsed_time(t_end)
-    ms_sample = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    t = torch.tensor([ms_total, ms_sample], dtype=torch.float64, device=dev)
+    ms_build = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    ms_sample = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    t = torch.tensor([ms_total, ms_build, ms_sample], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_sample = t.tolist()
+    ms_total, ms_build, ms_sample = t.tolist()
     ms_step = ms_total / args.steps
-    value = n_local * world / (ms_step * 1e-3)
+    value = n_total / (ms_step * 1e-3)
+
+    # ---- the dominant kernels on their own: CUDA events recorded by the library around the flat
+    # emitter and the general emitter (3 extra steps, after the timed region)
+    kern = None
+    if args.order == "cell":
+        _capi.call("lint_cellmajor_timing", 1)
+        acc = np.zeros(5)
+        reps = 3
+        for i in range(reps):
+            step(10_000 + i)
+            buf = (C.c_double * 5)()
+            _capi.call("lint_cellmajor_last_times", buf)
+            acc += np.array(list(buf))
+        _capi.call("lint_cellmajor_timing", 0)
+        kern = dict(zip(["ms_flat", "ms_general", "rows_flat", "rows_general", "rows_grouped"], acc / reps))
+    barrier()
 
     # the other row order, for the record (2 steps, same workload)
     other = "draw" if args.order == "cell" else "cell"
     other_line = None
-    if not args.no_other:
+    if not args.no_other and world == 1:
         # its own tables: the u-driven kernel wants per-cell records and a fine guide table
         shard.grid.__dict__.pop("_cm_scratch", None)
         okw = dict(cell_records=False, guide_bits=16) if other == "cell" else dict(guide_bits=22)
         shard_main, shard = shard, lbd.ShardedGrid(edges, gmm, dtype=np.float32, device=dev, rank=rank,
-                                                   world=world, group=dist.group.WORLD if world > 1 else None,
-                                                   **okw)
+                                                   world=world, group=None, **okw)
         step(0, order=other)
         barrier()
         o_beg, o_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -266,17 +312,16 @@ def run_b200(args):
             step(100 + i, order=other)
         o_end.record(stream)
         barrier()
-        t2 = torch.tensor([o_beg.elapsed_time(o_end) / 2], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        other_line = {"order": other, "value": n_local * world / (float(t2.item()) * 1e-3),
-                      "ms_per_step": float(t2.item()), "steps": 2}
+        ms_other = o_beg.elapsed_time(o_end) / 2
+        other_line = {"order": other, "value": n_total / (ms_other * 1e-3), "ms_per_step": ms_other, "steps": 2}
         shard = shard_main
 
-    # ---- e2e: public API, host buffers in and out, N=1 GPU semantics per rank
+    # ---- e2e: public API, host buffers in and out
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, lb, edges, gmm, dev, world)
+        del out
+        torch.cuda.empty_cache()
+        e2e = run_e2e(args, lb, edges, gmm, dev, world, n_total)
 
     if rank == 0:
         peaks = {}
@@ -285,17 +330,26 @@ def run_b200(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        b_mass, b_scan, b_sample = algorithmic_bytes(n_local)
-        achieved = b_sample / (ms_sample * 1e-3) / 1e9
+        b_mass, b_scan, b_sample = algorithmic_bytes(n_total)
+        step_bytes_per_gpu = (b_mass + b_scan + b_sample) / world
+        if args.order == "cell":
+            rows_dom, ms_dom = kern["rows_flat"], kern["ms_flat"]
+            name = "emit_flat_kernel<3,float> (rows of the constant parts of the split cells)"
+        else:
+            rows_dom, ms_dom = n_total / world, ms_sample
+            name = "sample_kernel<3,float,GridSource<3,float>,UniformsPhilox<3>>"
+        achieved = rows_dom * DIM * 4 / (ms_dom * 1e-3) / 1e9
+        traffic, traffic_src = emit_traffic(args.order, rows_dom, kern["rows_general"] if kern else 0, n_total / world)
         line = {
             "metric": "samples/s", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": "C3: 3-D DensityGrid 256^3 (257^3 fp32 vertex densities, fp64 CDF), "
-                            "K=4 isotropic GMM on [-4,4]^3, N=%d samples per GPU per step" % n_local,
-                "samples_per_gpu": n_local, "l2": "outputs (12 GB/step) and tables (>260 MB) exceed L2",
+                            "K=4 isotropic GMM on [-4,4]^3, N=%d samples per step in total" % n_total,
+                "samples_total": n_total, "samples_per_gpu": n_total / world,
+                "l2": "outputs (12 GB/step in total) and tables (>200 MB) exceed L2",
                 "sharding": shard.describe(),
                 "order": ("rows grouped by cell: exact multinomial cell counts (Poisson counts + u-driven "
                           "top-up), i.i.d. as a multiset, NOT exchangeable in row order"
@@ -303,20 +357,19 @@ def run_b200(args):
                           "rows in draw order (i.i.d. Philox rows, exchangeable like the reference's shuffle)"),
             },
             "roofline": {
-                "bound": "hbm",
-                "kernel": ("emit_kernel<3,float,GridCells<3,float>> incl. its row planning (poisson_counts, "
-                           "scan_compact, chunk_start) and the sample_kernel top-up" if args.order == "cell"
-                           else "sample_kernel<3,float,GridSource<3,float>,UniformsPhilox<3>>"),
+                "bound": "hbm", "kernel": name,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
-                # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch at
-                # N=1e9, from the ncu --set full captures summarised in profiles/README.md
-                "traffic": ((12.16e9 if args.order == "cell" else 59.7e9) * n_local / 1e9
-                            if GRID_N == 256 else None),
-                "traffic_source": ("profiles/r1o_emit_kernel_metrics.txt" if args.order == "cell"
-                                   else "profiles/r1b_sample_kernel_metrics.txt"),
-                "ms_per_launch": ms_sample,
-                "step_frac_of_hbm_roofline": (b_mass + b_scan + b_sample) / (ms_step * 1e-3) / 1e9 / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured; a copy: a pure write stream "
+                               "reaches ~7470 GB/s on this part, scripts/time_emit.py)" if peaks else "fallback 6650",
+                "algorithmic_bytes_per_launch": rows_dom * DIM * 4, "ms_per_launch": ms_dom,
+                "timing": "CUDA events recorded by the library on the launching stream around this kernel",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "stages_ms": {"build": ms_build, "sampling": ms_sample,
+                              **({"emit_flat": kern["ms_flat"], "emit_general": kern["ms_general"],
+                                  "planning_and_topup": ms_sample - kern["ms_flat"] - kern["ms_general"]}
+                                 if kern else {})},
+                "rows": ({k: kern[k] for k in ("rows_flat", "rows_general", "rows_grouped")} if kern else None),
+                "step_frac_of_hbm_roofline": step_bytes_per_gpu / (ms_step * 1e-3) / 1e9 / peak,
             },
             "clocks": clocks.summary(),
             "gpu_launches": shard.launches_per_step(args.order) * args.steps,
@@ -332,10 +385,19 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, lb, edges, gmm, dev, world):
+def _numa_summary():
+    """Where the pinned staging memory can live: NUMA nodes of the host and of this process."""
+    try:
+        nodes = sorted(d for d in os.listdir("/sys/devices/system/node") if d.startswith("node"))
+        return {"host_numa_nodes": len(nodes), "cpus_allowed": len(os.sched_getaffinity(0))}
+    except Exception:
+        return None
+
+
+def run_e2e(args, lb, edges, gmm, dev, world, n_total):
     import torch
     import torch.distributed as dist
-    n = args.samples
+    n = n_total // world                                    # rows per rank (equal-mass strata)
     steps = max(1, min(args.steps, 3))
     # host inputs: pinned fp32 vertex densities (evaluated once, outside the timed region)
     kw = dict(cell_records=False, guide_bits=16) if args.order == "cell" else dict(guide_bits=22)
@@ -347,8 +409,8 @@ def run_e2e(args, lb, edges, gmm, dev, world):
     torch.cuda.synchronize(dev)
 
     def one():
-        g0.update_densities(v_host, check=False)            # H2D + masses + CDF + guide
-        sampler.sample_to_host(n, out=out_host)              # sample + D2H, pipelined
+        g0.update_densities(v_host, check=True)              # H2D + masses + CDF + guide + validity read-back
+        sampler.sample_to_host(n, out=out_host)              # sample + D2H, pipelined; returns when the rows are in host memory
     one()
     torch.cuda.synchronize(dev)
     if world > 1:
@@ -363,9 +425,11 @@ def run_e2e(args, lb, edges, gmm, dev, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
     assert np.isfinite(out_host[-1].numpy()).all()
+    d2h = int(n * DIM * 4)
     return {"value": n * world / dt, "unit": "samples/s", "h2d_bytes_per_step": int(v_host.numel() * 4),
-            "d2h_bytes_per_step": int(n * DIM * 4), "ms_per_step": dt * 1e3, "steps": steps,
-            "api": "DensityGrid.update_densities(pinned) + LintSampler.sample_to_host(N, out=pinned)"}
+            "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": steps,
+            "d2h_gb_per_s_per_gpu": d2h / dt / 1e9, "numa": _numa_summary(),
+            "api": "DensityGrid.update_densities(pinned, check=True) + LintSampler.sample_to_host(N, out=pinned)"}
 
 
 def main():
@@ -374,7 +438,9 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--samples", type=int, default=N_SAMPLES, help="samples per GPU per step")
+    ap.add_argument("--samples", type=int, default=N_SAMPLES,
+                    help="samples per step in total (strong scaling); with --weak: per GPU")
+    ap.add_argument("--weak", action="store_true", help="weak scaling: --samples rows per GPU per step")
     ap.add_argument("--order", default="cell", choices=["cell", "draw"],
                     help="cell: rows grouped by cell (throughput mode); draw: u-driven per-sample search")
     ap.add_argument("--no-e2e", action="store_true")

@@ -205,19 +205,23 @@ int lint_cdf_build(const double *masses_dev, int64_t n, int mode, double *cdf_de
                    double *total_dev, void *scratch_dev, size_t scratch_bytes,
                    lint_stream_t stream);
 
-/* Fused parallel build for a grid: cell masses [grid.py:469-518, 411] -> normalised inclusive
- * CDF [grid.py:431 + utils.py:195-196] -> guide table, with the masses computed on the fly from
- * the vertex densities in both scan passes and never stored (masses_dev == NULL) — the values are
- * bit-identical to lint_grid_masses + lint_cdf_build(LINT_CDF_PARALLEL) + lint_guide_build.
+/* Parallel build for a grid: cell masses [grid.py:469-518, 411] -> normalised inclusive CDF
+ * [grid.py:431 + utils.py:195-196] -> guide table, hierarchical and without ever storing the
+ * masses (masses_dev == NULL).  The cells are cut into groups of consecutive cell rows (~16 K
+ * cells); group totals come from one streaming pass over the vertex table (separable trapezoid
+ * weights; it also performs the validity check of grid.py:401-404 on every vertex), and inside
+ * a group the CDF is the exact chained scan of the cell masses laid on the group's offset:
+ *     cdf_i = min(min(Off[g] + L_i, Off[g + 1]) * (1 / total), 1),   cdf[n - 1] = 1.
+ * Non-decreasing, equal to its predecessor on zero-mass cells (utils.py:197 never selects them),
+ * bit-reproducible, within ~1e-15 of the NumPy-sequential table.
  * [u_lo, u_hi) is the stratum of the cell-selecting uniform the caller will draw from ((0, 1) =
- * whole domain): every rank of a sharded run reduces the whole vertex table to tile totals (which
- * yields the total mass and every tile's offset without communication) but scans, and writes
- * cdf_dev / masses_dev / guide_dev for, only the slab of cells its stratum can touch, plus a
- * margin.  range_dev (4 words, device) receives that slab: [0] first cell, [1] end cell, [2], [3]
- * the same in tiles of 2048 cells; hand it to lint_grid_sample_cellmajor.  Outside the slab the
- * three tables are left untouched.  Validity flags as lint_grid_masses (every vertex is checked).
- * total_dev receives the total mass. */
-size_t lint_grid_build_scratch_bytes(int64_t ncells);
+ * whole domain): every rank of a sharded run does the cheap vertex pass (total mass and group
+ * offsets, identical on all ranks, no communication) but scans, and writes cdf_dev / masses_dev /
+ * guide_dev for, only the groups its stratum can touch plus one group of margin.  range_dev
+ * (4 words, device) receives that slab: [0] first cell, [1] end cell, [2] first group, [3] end
+ * group; hand it to lint_grid_sample_cellmajor.  Outside the slab (and the one CDF entry before
+ * it) the tables are left untouched.  total_dev receives the total mass. */
+size_t lint_grid_build_scratch_bytes(const lint_grid_t *g);
 int lint_grid_build(const lint_grid_t *g, double u_lo, double u_hi, double *cdf_dev, double *total_dev,
                     uint32_t *guide_dev, int guide_bits, double *masses_dev, uint32_t *flags_dev,
                     uint32_t *range_dev, void *scratch_dev, size_t scratch_bytes, lint_stream_t stream);
@@ -310,6 +314,14 @@ int lint_grid_sample_cellmajor(const lint_grid_t *g, int64_t N, uint64_t seed, u
 int lint_cells_sample_cellmajor(const lint_cells_t *c, int64_t N, uint64_t seed, uint64_t offset,
                                 double u_lo, double u_hi, void *scratch_dev, size_t scratch_bytes, void *out_dev,
                                 int64_t *cell_idx_dev, lint_stream_t stream);
+
+/* Measurement aid: with timing enabled every cell-major call records CUDA events on its stream
+ * around the flat emitter and around the general emitter.  lint_cellmajor_last_times waits for
+ * the last timed call and returns [0] ms of the flat emitter, [1] ms of the general emitter,
+ * [2] rows of the flat run T_f, [3] rows of the general run T_r, [4] T_f + T_r (first top-up
+ * row).  Process-wide, not thread-safe: for benchmarks. */
+int lint_cellmajor_timing(int enable);
+int lint_cellmajor_last_times(double *out5);
 
 /* ---- row order ------------------------------------------------------------------- */
 

@@ -93,7 +93,7 @@ PROTOTYPES = {
     "lint_sum_numpy_f64": (C.c_int, [_P, _I64, _P, _P, C.c_size_t, _P]),
     "lint_cdf_build": (C.c_int, [_P, _I64, C.c_int, _P, _P, _P, C.c_size_t, _P]),
     "lint_guide_build": (C.c_int, [_P, _I64, C.c_int, _P, _P]),
-    "lint_grid_build_scratch_bytes": (C.c_size_t, [_I64]),
+    "lint_grid_build_scratch_bytes": (C.c_size_t, [C.POINTER(LintGrid)]),
     "lint_grid_build": (C.c_int, [C.POINTER(LintGrid), C.c_double, C.c_double, _P, _P, _P, C.c_int, _P, _P, _P,
                                   _P, C.c_size_t, _P]),
     "lint_grid_sample_u": (C.c_int, [C.POINTER(LintGrid), _P, _I64, _P, _P, _P]),
@@ -109,6 +109,8 @@ PROTOTYPES = {
     "lint_sobol_uniforms": (C.c_int, [C.c_int, _I64, C.POINTER(LintSobol), _P, _P]),
     "lint_permute_rows": (C.c_int, [_P, _P, _I64, C.c_int32, C.c_int32, _U64, _P]),
     "lint_cellmajor_scratch_bytes": (C.c_size_t, [_I64, _I64]),
+    "lint_cellmajor_timing": (C.c_int, [C.c_int]),
+    "lint_cellmajor_last_times": (C.c_int, [C.POINTER(C.c_double)]),
     "lint_grid_sample_cellmajor": (C.c_int, [C.POINTER(LintGrid), _I64, _U64, _U64, C.c_double, C.c_double,
                                              _P, _P, C.c_size_t, _P, _P, _P]),
     "lint_cells_sample_cellmajor": (C.c_int, [C.POINTER(LintCells), _I64, _U64, _U64, C.c_double,

@@ -7,6 +7,11 @@ namespace lint {
 
 int validate_grid(const lint_grid_t *g, bool need_cdf, uint64_t *ncells_out, uint64_t *nverts_out);
 
+EmitTimers &emit_timers() {
+    static EmitTimers t;
+    return t;
+}
+
 static int check_common(int64_t N, uint64_t ncells, double u_lo, double u_hi, void *out, void *scratch,
                         size_t scratch_bytes, const char *what) {
     if (!(u_lo >= 0.0) || !(u_hi <= 1.0) || !(u_lo < u_hi))
@@ -35,6 +40,31 @@ int topup_cells(const lint_cells_t *c, int64_t N, const uint32_t *first_row_dev,
 using namespace lint;
 
 extern "C" {
+
+int lint_cellmajor_timing(int enable) {
+    EmitTimers &t = emit_timers();
+    if (enable && !t.ev[0]) {
+        for (auto &e : t.ev)
+            if (cudaEventCreate(&e) != cudaSuccess) return fail(LINT_ERR_CUDA, "lint_cellmajor_timing: cudaEventCreate failed");
+    }
+    t.enabled = enable != 0;
+    return LINT_OK;
+}
+
+int lint_cellmajor_last_times(double *out5) {
+    EmitTimers &t = emit_timers();
+    if (!out5) return fail(LINT_ERR_BAD_ARG, "lint_cellmajor_last_times: out is NULL");
+    if (!t.enabled || !t.plan_dev) return fail(LINT_ERR_BAD_ARG, "lint_cellmajor_last_times: no timed call yet");
+    if (cudaEventSynchronize(t.ev[3]) != cudaSuccess) return fail(LINT_ERR_CUDA, "lint_cellmajor_last_times: sync failed");
+    float a = 0.f, b = 0.f;
+    if (t.flat_ran) cudaEventElapsedTime(&a, t.ev[0], t.ev[1]);
+    cudaEventElapsedTime(&b, t.ev[2], t.ev[3]);
+    uint32_t plan[3] = {0, 0, 0};
+    if (cudaMemcpy(plan, t.plan_dev, sizeof plan, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return fail(LINT_ERR_CUDA, "lint_cellmajor_last_times: reading the row budget failed");
+    out5[0] = a; out5[1] = b; out5[2] = plan[0]; out5[3] = plan[1]; out5[4] = plan[2];
+    return LINT_OK;
+}
 
 size_t lint_cellmajor_scratch_bytes(int64_t ncells, int64_t N) {
     if (ncells < 1 || N < 0) return 0;

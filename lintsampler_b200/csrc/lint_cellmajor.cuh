@@ -86,59 +86,66 @@ __device__ __forceinline__ double log_factorial(double k) {
 }
 
 // Poisson(lam): sequential inversion with one uniform below 10, Hörmann's
-// transformed rejection with squeeze (PTRS, 1993) above.
-__device__ __forceinline__ uint32_t poisson(double lam, CellRng &rng) {
-    if (!(lam > 0.0)) return 0;
-    if (lam < 10.0) {
-        double u, unused;
-        rng.next(u, unused);
-        // exp(-lam) >= 1 - lam: most cells of a fine grid hold lam << 1 and end here,
-        // without the exponential
-        if (u <= 1.0 - lam) return 0;
-        const double p0 = exp(-lam);
-        for (;;) {
-            double p = p0;
-            uint32_t x = 0;
-            bool ok = true;
-            while (u > p) {
-                u -= p;
-                ++x;
-                if (x > 200) { ok = false; break; }     // fp dust past the far tail: redraw
-                p *= lam * __drcp_rn((double)x);
-            }
-            if (ok) return x;
-            rng.next(u, unused);
-        }
-    }
-    const double b = 0.931 + 2.53 * sqrt(lam);
-    const double a = -0.059 + 0.02483 * b;
-    const double vr = 0.9277 - 3.6224 / (b - 2.0);
+// transformed rejection with squeeze (PTRS, 1993) above.  Split in two so that the count pass
+// can settle the common cases at once (zero mean; lam < 10 and u <= 1 - lam <= exp(-lam): no
+// rows, most cells of a fine grid) and queue the others for a second phase in which every lane
+// of a warp has real work of the same kind.
+constexpr double POISSON_PTRS_FROM = 10.0;
+
+// lam < 10, first uniform u already drawn (rng.attempt == 1) and u > 1 - lam
+__device__ __forceinline__ uint32_t poisson_inversion(double lam, double u, CellRng &rng) {
+    const double p0 = exp(-lam);
     for (;;) {
-        double u, v;
-        rng.next(u, v);
-        u -= 0.5;
-        const double us = 0.5 - fabs(u);
-        const double k = floor((2.0 * a / us + b) * u + lam + 0.43);
-        if (us >= 0.07 && v <= vr) return (uint32_t)k;            // the squeeze accepts ~86 %
-        if (k < 0.0 || (us < 0.013 && v > us)) continue;
-        const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
-        const double lhs_arg = v * invalpha / (a / (us * us) + b);
-        // Acceptance test log(lhs_arg) <= -lam + k log(lam) - log(k!).  ~14 % of the draws get
-        // here, i.e. nearly every warp, so it is first decided in fp32 wherever the margin
-        // exceeds a generous bound on the fp32 error; the fp64 test below settles the rest
-        // (a few per thousand).  With k1 = k + 1, d = k1 - lam, x = d / k1 and Stirling's
-        // series the right-hand side is  k log1p(-x) + d - log(k1)/2 - log(2 pi)/2 - s(k1).
-        if (k >= 4.0 && lam < 1.0e5) {
-            const float d = (float)(k + 1.0 - lam), k1 = (float)k + 1.0f, x = d / k1;
-            const float series = (1.0f / 12.0f - (1.0f / 360.0f) / (k1 * k1)) / k1;
-            const float rhs = ((float)k * log1pf(-x) + d) - 0.5f * __logf(k1) - 0.9189385f - series;
-            const float t = __logf((float)lhs_arg) - rhs;
-            const float tol = 2e-3f + 4e-6f * fabsf(d);
-            if (t < -tol) return (uint32_t)k;
-            if (t > tol) continue;
+        double p = p0;
+        uint32_t x = 0;
+        bool ok = true;
+        while (u > p) {
+            u -= p;
+            ++x;
+            if (x > 200) { ok = false; break; }     // fp dust past the far tail: redraw
+            p *= lam * __drcp_rn((double)x);
         }
-        if (log(lhs_arg) <= -lam + k * log(lam) - log_factorial(k)) return (uint32_t)k;
+        if (ok) return x;
+        double unused;
+        rng.next(u, unused);
     }
+}
+
+// PTRS in two stages, so that the count pass can run each stage with full warps.
+// Stage A, one attempt: proposal k and the squeeze.  Returns 1 accepted (k final), 0 rejected
+// outright (try again), 2 undecided: stage B must test (k, lhs_arg).
+__device__ __forceinline__ int ptrs_propose(double lam, double b, CellRng &rng, double &k, double &lhs_arg) {
+    const double a = -0.059 + 0.02483 * b;
+    const double vr = 0.9277 - 3.6224 * __drcp_rn(b - 2.0);
+    double u, v;
+    rng.next(u, v);
+    u -= 0.5;
+    const double us = 0.5 - fabs(u);
+    const double ius = __drcp_rn(us);
+    k = floor((2.0 * a * ius + b) * u + lam + 0.43);
+    if (us >= 0.07 && v <= vr) return 1;                          // the squeeze accepts ~86 %
+    if (k < 0.0 || (us < 0.013 && v > us)) return 0;
+    const double invalpha = 1.1239 + 1.1328 * __drcp_rn(b - 3.4);
+    lhs_arg = v * invalpha * __drcp_rn(a * ius * ius + b);
+    return 2;
+}
+
+// Stage B: the acceptance test log(lhs_arg) <= -lam + k log(lam) - log(k!).  It is first decided
+// in fp32 wherever the margin exceeds a generous bound on the fp32 error; the fp64 test settles
+// the rest (a few per thousand).  With k1 = k + 1, d = k1 - lam, x = d / k1 and Stirling's series
+// the right-hand side is  k log1p(-x) + d - log(k1)/2 - log(2 pi)/2 - s(k1).
+// (scripts/ptrs_fp32_screen_check.py replays this screen and bounds its error.)
+__device__ __forceinline__ bool ptrs_accept(double lam, double k, double lhs_arg) {
+    if (k >= 4.0 && lam < 1.0e5) {
+        const float d = (float)(k + 1.0 - lam), k1 = (float)k + 1.0f, x = d / k1;
+        const float series = (1.0f / 12.0f - (1.0f / 360.0f) / (k1 * k1)) / k1;
+        const float rhs = ((float)k * log1pf(-x) + d) - 0.5f * __logf(k1) - 0.9189385f - series;
+        const float t = __logf((float)lhs_arg) - rhs;
+        const float tol = 2e-3f + 4e-6f * fabsf(d);
+        if (t < -tol) return true;
+        if (t > tol) return false;
+    }
+    return log(lhs_arg) <= -lam + k * log(lam) - log_factorial(k);
 }
 
 // The table the counts are read from: the normalised CDF restricted to the stratum
@@ -160,11 +167,33 @@ __device__ __forceinline__ double cell_lambda(const CdfSlice &t, uint32_t c, dou
 }
 
 
+// One Poisson draw from the stream of (cell, part)
+__device__ __forceinline__ uint32_t poisson(double lam, CellRng &rng) {
+    if (!(lam > 0.0)) return 0;
+    if (lam < POISSON_PTRS_FROM) {
+        double u, unused;
+        rng.next(u, unused);
+        // exp(-lam) >= 1 - lam: most cells of a fine grid hold lam << 1 and end here,
+        // without the exponential
+        if (u <= 1.0 - lam) return 0;
+        return poisson_inversion(lam, u, rng);
+    }
+    const double b = 0.931 + 2.53 * sqrt(lam);
+    for (;;) {
+        double k, arg;
+        const int verdict = ptrs_propose(lam, b, rng, k, arg);
+        if (verdict == 1 || (verdict == 2 && ptrs_accept(lam, k, arg))) return (uint32_t)k;
+    }
+}
+
 // counts_rest[c] = rows of cell c drawn from its full interpolant (no split), or with the
 // split: counts_flat[c] = flat rows, counts_rest[c] = residual rows — or all rows of a cell
-// that is not split
+// that is not split.  (Settling the cheap cases first and working the expensive ones off from
+// shared-memory queues with full warps was tried twice and lost to this plain form by 30-45 %:
+// profiles/README.md, r2e.)
+constexpr int POISSON_THREADS = 256;
 template <typename Cells>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(POISSON_THREADS)
 poisson_counts_kernel(Cells src, CdfSlice t, double lam_per_unit, uint2 key, uint64_t offset, bool split,
                       const uint32_t *__restrict__ range, uint32_t *__restrict__ counts_flat,
                       uint32_t *__restrict__ counts_rest) {
@@ -1001,9 +1030,9 @@ static int plan_rows(const Cells &src, const double *cdf, uint64_t ncells, uint6
     const bool split = use_split(ncells, N);
     const CdfSlice t{cdf, (uint32_t)ncells, u.u_lo, u.u_hi};
     const double lam_per_unit = grouped_mean(N) / (u.u_hi - u.u_lo);
-    const int cblocks = (int)std::min<uint64_t>((ncells + 255) / 256, 148 * 16);
+    const int cblocks = (int)std::min<uint64_t>((ncells + POISSON_THREADS - 1) / POISSON_THREADS, 148 * 32);
     cudaMemsetAsync(s.zero_begin, 0, s.zero_bytes, st);
-    poisson_counts_kernel<<<cblocks, 256, 0, st>>>(src, t, lam_per_unit, key, offset, split, range, s.counts_flat,
+    poisson_counts_kernel<<<cblocks, POISSON_THREADS, 0, st>>>(src, t, lam_per_unit, key, offset, split, range, s.counts_flat,
                                                    s.counts_rest);
     if (split) scan_list(s.counts_flat, (uint32_t)ncells, range, 1, 0, s.flat, st);
     scan_list(s.counts_rest, (uint32_t)ncells, range, split ? 2 : 1, split ? 1 : 0, s.rest, st);
@@ -1038,6 +1067,12 @@ int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t 
     const uint32_t chunk_rows = emit_chunk_rows(N);
     const uint32_t nchunks = (uint32_t)((N + 1 + chunk_rows - 1) / chunk_rows);     // (+1: the general emitter's frame)
     const size_t smem = src.smem_bytes(sizeof(T));
+    EmitTimers &tm = emit_timers();
+    if (tm.enabled) {
+        tm.flat_ran = split;
+        tm.plan_dev = s.plan;
+        cudaEventRecord(tm.ev[0], st);
+    }
     if (split) {
         const uint32_t fper = FLAT_THREADS / 32;
         const int fblocks = (int)std::min<uint32_t>((nchunks + fper - 1) / fper,
@@ -1055,6 +1090,10 @@ int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t 
                 philox_round_keys(key), offset, (T *)out, cell_idx);
         if (int rc = check_launch("cell-major flat emission")) return rc;
     }
+    if (tm.enabled) {
+        cudaEventRecord(tm.ev[1], st);
+        cudaEventRecord(tm.ev[2], st);
+    }
     const uint32_t per_cta = EMIT_THREADS / 32;
     const int blocks = (int)std::min<uint32_t>((nchunks + per_cta - 1) / per_cta,
                                                 148u * env_int("LINT_REST_BPS", 8));
@@ -1066,6 +1105,7 @@ int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t 
         emit_kernel<K, T, Cells, false><<<blocks, EMIT_THREADS, smem, st>>>(
             src, s.rest.cid, s.rest.coff, s.rest.nnz, s.plan, s.rest.chunk_start, chunk_rows,
             philox_round_keys(key), offset, split ? 1u : 0u, t, lam_per_unit, (T *)out, cell_idx);
+    if (tm.enabled) cudaEventRecord(tm.ev[3], st);
     return check_launch("cell-major emission");
 }
 

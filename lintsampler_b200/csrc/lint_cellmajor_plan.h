@@ -88,6 +88,16 @@ constexpr uint64_t SPLIT_MIN_ROWS_PER_CELL = 32;
 inline bool use_split(uint64_t ncells, uint64_t N) { return N >= SPLIT_MIN_ROWS_PER_CELL * ncells; }
 
 
+// Optional timing of the two emitters (lint_cellmajor_timing): CUDA events recorded on the
+// caller's stream around each of them.  Defined in lint_cellmajor.cu.
+struct EmitTimers {
+    bool enabled = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // flat begin/end, general begin/end
+    bool flat_ran = false;
+    const uint32_t *plan_dev = nullptr;                          // row budget of the timed call
+};
+EmitTimers &emit_timers();
+
 // per-dimension entry points, instantiated in lint_cellmajor_inst.cu
 template <int K>
 int grid_cellmajor_k(const lint_grid_t *g, uint64_t nc, uint64_t N, uint2 key, uint64_t offset, Stratum u,

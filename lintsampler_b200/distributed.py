@@ -47,6 +47,11 @@ def all_gather_masses(local_mass, world, group=None, out=None):
     return out
 
 
+def _collectives_available():
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized()
+
+
 def route_rows(u_cell, bounds):
     """Parity-mode routing of caller-supplied uniforms: rank of each row and its
     cell uniform rescaled into that rank's stratum, exactly the list-of-domains
@@ -160,10 +165,17 @@ class ShardedGrid:
     def _stratum_mass_tensor(self):
         """This rank's shard mass as a device scalar: (b_{g+1} - b_g) * total."""
         lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
-        return self.grid._total * (hi - lo)
+        return self.grid._total * ((hi - lo) / self.grid._scale)
 
     def _enqueue_gather(self):
-        # NCCL all-gather, 8 bytes per rank
+        # NCCL all-gather, 8 bytes per rank.  Without a process group (ranks emulated one after the
+        # other in one process, as the single-GPU tests do) the masses are filled in locally: with
+        # equal-mass strata every rank can compute all of them from the total.
+        if self.world > 1 and not _collectives_available():
+            import torch
+            widths = torch.as_tensor(np.diff(self.bounds), dtype=torch.float64, device=self.device)
+            self._gather_buf = self.grid._total * (widths / self.grid._scale)
+            return
         self._gather_buf = all_gather_masses(self._stratum_mass_tensor(), self.world, self.group,
                                              self._gather_buf)
 
@@ -175,19 +187,20 @@ class ShardedGrid:
 
     # -- sampling ------------------------------------------------------------
     def sample_cellmajor_into(self, out, seed, offset):
-        """Throughput mode: this rank's rows grouped by cell (see DensityGrid._sample_cellmajor)."""
+        """Throughput mode: this rank's rows grouped by cell (see DensityGrid._sample_cellmajor).
+        ``offset``: this rank's position in the Philox stream — ranks must pass disjoint ranges
+        ``[offset, offset + len(out))`` (e.g. the prefix sums of the split of N)."""
         n = out.shape[0]
         lo, hi = float(self.bounds[self.rank]), float(self.bounds[self.rank + 1])
-        self.grid._sample_cellmajor(n, seed, offset + self.rank * n, out=out, stratum=(lo, hi))
+        self.grid._sample_cellmajor(n, seed, offset, out=out, stratum=(lo, hi))
         return out
 
     def sample_philox_into(self, out, seed, offset):
-        """Fill the device tensor ``out`` (n, k) with this rank's rows.  Row i of
-        rank g uses Philox counter ``offset + g * n + i`` so ranks never share a
-        counter."""
+        """Fill the device tensor ``out`` (n, k) with this rank's rows.  Row i uses Philox
+        counter ``offset + i``: ranks must pass disjoint ranges ``[offset, offset + n)``."""
         n = out.shape[0]
         lo, hi = float(self.bounds[self.rank]), float(self.bounds[self.rank + 1])
-        self.grid._sample_philox(n, seed, offset + self.rank * n, out=out, stratum=(lo, hi))
+        self.grid._sample_philox(n, seed, offset, out=out, stratum=(lo, hi))
         return out
 
     def sample(self, n_total, seed, offset=0):
@@ -206,15 +219,16 @@ class ShardedGrid:
 
     # -- reporting -------------------------------------------------------------
     def launches_per_step(self, order="draw"):
-        """Kernels of this library launched by enqueue_build + one sampling call:
-        masses 1, cell records 0/1, parallel CDF 4, guide 1; then the u-driven
-        sampler (1) or the grouped path (Poisson counts, 2 x scan+compact, row budget,
-        2 x chunk starts, general emitter, flat emitter, top-up = 9)."""
-        build = 6 + (1 if self.grid._rec is not None else 0)
-        return build + (9 if order == "cell" else 1)
+        """Kernels of this library launched by enqueue_build + one sampling call: fused build 2
+        (tile totals, apply), guide 1, cell records 0/1; then the u-driven sampler (1) or the
+        grouped path (Poisson counts, 2 x scan+compact, row budget, 2 x chunk starts, flat
+        boxes, flat emitter, general emitter, top-up = 10)."""
+        build = 3 + (1 if self.grid._rec is not None else 0)
+        return build + (10 if order == "cell" else 1)
 
     def describe(self):
         if self.world == 1:
             return "single GPU"
         return (f"{self.world} ranks, equal-mass strata of the flat cell CDF (contiguous dim-0-major "
-                "cell ranges); one 8-byte-per-rank NCCL all-gather of shard masses per build")
+                "cell ranges): every rank reduces the vertex table to tile totals, scans only its own slab; "
+                "N split multinomially with a shared seed; no sample data crosses NVLink")

@@ -15,9 +15,9 @@ from .pdfs import FUSED_PDFS
 
 
 def torch_range(ncells, device):
-    """The whole-domain slab in lint_grid_build's layout: [first cell, end cell, first tile, end tile]."""
+    """The whole-domain slab in lint_grid_build's layout (the cell-major sampler reads the cell range)."""
     import torch
-    return torch.tensor([0, ncells, 0, (ncells + 2047) // 2048], dtype=torch.int32, device=device)
+    return torch.tensor([0, ncells, 0, 0], dtype=torch.int32, device=device)
 
 
 def _is_flat_sequence(obj):
@@ -253,7 +253,8 @@ class DensityGrid(DensityStructure):
         want_rec = self._cell_records_arg if self._cell_records_arg is not None else rec_bytes < (8 << 30)
         self._rec = torch.empty(ncells * 2 ** self._dim, dtype=tdt, device=dev) if want_rec else None
         self._guide = torch.empty((1 << self._guide_bits_planned) + 1, dtype=torch.int32, device=dev)
-        nbytes = max(_capi.load().lint_cdf_scratch_bytes(ncells), _capi.load().lint_grid_build_scratch_bytes(ncells))
+        nbytes = max(_capi.load().lint_cdf_scratch_bytes(ncells),
+                     _capi.load().lint_grid_build_scratch_bytes(C.byref(self._descriptor())))
         self._scratch = torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device=dev)
         self._enqueue_build()
         self._check_build()
