@@ -61,8 +61,9 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, enabled=True):
         self.index = index
+        self.enabled = enabled
         self.rows = []
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -77,15 +78,17 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.05)
 
     def __enter__(self):
-        self._t.start()
+        if self.enabled:
+            self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self.enabled:
+            self._t.join(timeout=6)
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
@@ -237,45 +240,72 @@ def run_b200(args):
         counts = lbd.split_counts(n_total, np.full(world, 1.0 / world), SEED * 1_000_003 + i)
         return int(counts[rank]), int(counts[:rank].sum())
 
-    def step(i, ev=None, order=None):
-        n, first = share(i)
-        if ev:
-            ev[0].record(stream)
-        shard.enqueue_build(gather=False)           # tile totals of the whole grid, CDF + guide of the own slab
-        if ev:
-            ev[1].record(stream)
-        if (order or args.order) == "cell":
-            shard.sample_cellmajor_into(out[:n], seed=SEED, offset=i * n_total + first)
-        else:
-            shard.sample_philox_into(out[:n], seed=SEED, offset=i * n_total + first)
-        if ev:
-            ev[2].record(stream)
-        return n
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # The split of N over the ranks is drawn once (shared seed) and kept for the run, so that a step
+    # is one CUDA graph replay; the graph starts by advancing a device-resident Philox offset, so
+    # every replay draws fresh samples (lint_set_offset_counter / lint_advance_counter).
+    n_mine, first_mine = share(0)
+    counter = torch.zeros(1, dtype=torch.int64, device=dev)
+    _capi.call("lint_set_offset_counter", C.c_void_p(counter.data_ptr()))
+
+    def body(ev=None, order=None):
+        if ev:
+            ev[0].record(stream_now())
+        _capi.call("lint_advance_counter", C.c_void_p(counter.data_ptr()), C.c_uint64(n_total),
+                   C.c_void_p(stream_now().cuda_stream))
+        shard.enqueue_build(gather=False)           # vertex row sums + group offsets of the whole grid, CDF + guide of the own slab
+        if ev:
+            ev[1].record(stream_now())
+        if (order or args.order) == "cell":
+            shard.sample_cellmajor_into(out[:n_mine], seed=SEED, offset=first_mine)
+        else:
+            shard.sample_philox_into(out[:n_mine], seed=SEED, offset=first_mine)
+        if ev:
+            ev[2].record(stream_now())
+
+    def stream_now():
+        return torch.cuda.current_stream(dev)
+
     for i in range(args.warmup):
-        step(i)
+        body()
     barrier()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    graph = None
+    if not args.no_graph:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body()
+        for _ in range(2):
+            graph.replay()
         barrier()
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local, enabled=rank == 0) as clocks:
+        barrier()
+        h0 = time.perf_counter()
         t_beg.record(stream)
         for i in range(args.steps):
-            step(args.warmup + i, evs[i])
+            if graph is not None:
+                graph.replay()
+            else:
+                body()
         t_end.record(stream)
+        host_ms = (time.perf_counter() - h0) * 1e3 / args.steps      # host time to enqueue a step
         barrier()
     ms_total = t_beg.elapsed_time(t_end)
+    # stage breakdown: a few eager steps with events between the stages
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(3)]
+    for e in evs:
+        body(e)
+    barrier()
     ms_build = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
     ms_sample = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
-    t = torch.tensor([ms_total, ms_build, ms_sample], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_build, ms_sample, host_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_build, ms_sample = t.tolist()
+    ms_total, ms_build, ms_sample, host_ms = t.tolist()
     ms_step = ms_total / args.steps
     value = n_total / (ms_step * 1e-3)
 
@@ -287,7 +317,7 @@ def run_b200(args):
         acc = np.zeros(5)
         reps = 3
         for i in range(reps):
-            step(10_000 + i)
+            body()
             buf = (C.c_double * 5)()
             _capi.call("lint_cellmajor_last_times", buf)
             acc += np.array(list(buf))
@@ -304,18 +334,19 @@ def run_b200(args):
         okw = dict(cell_records=False, guide_bits=16) if other == "cell" else dict(guide_bits=22)
         shard_main, shard = shard, lbd.ShardedGrid(edges, gmm, dtype=np.float32, device=dev, rank=rank,
                                                    world=world, group=None, **okw)
-        step(0, order=other)
+        body(order=other)
         barrier()
         o_beg, o_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         o_beg.record(stream)
         for i in range(2):
-            step(100 + i, order=other)
+            body(order=other)
         o_end.record(stream)
         barrier()
         ms_other = o_beg.elapsed_time(o_end) / 2
         other_line = {"order": other, "value": n_total / (ms_other * 1e-3), "ms_per_step": ms_other, "steps": 2}
         shard = shard_main
 
+    _capi.call("lint_set_offset_counter", None)
     # ---- e2e: public API, host buffers in and out
     e2e = None
     if not args.no_e2e:
@@ -338,7 +369,7 @@ def run_b200(args):
         else:
             rows_dom, ms_dom = n_total / world, ms_sample
             name = "sample_kernel<3,float,GridSource<3,float>,UniformsPhilox<3>>"
-        achieved = rows_dom * DIM * 4 / (ms_dom * 1e-3) / 1e9
+        achieved = rows_dom * DIM * 4 / (max(ms_dom, 1e-9) * 1e-3) / 1e9
         traffic, traffic_src = emit_traffic(args.order, rows_dom, kern["rows_general"] if kern else 0, n_total / world)
         line = {
             "metric": "samples/s", "value": value, "unit": "samples/s", "n_gpus": world,
@@ -351,6 +382,11 @@ def run_b200(args):
                 "samples_total": n_total, "samples_per_gpu": n_total / world,
                 "l2": "outputs (12 GB/step in total) and tables (>200 MB) exceed L2",
                 "sharding": shard.describe(),
+                "launch": ("one CUDA graph replay per step: %d kernels captured once; the graph advances a "
+                           "device-resident Philox offset, so every step draws fresh samples; the multinomial "
+                           "split of N over the ranks is drawn once per run from the shared seed"
+                           % shard.launches_per_step(args.order)) if graph is not None else "eager launches",
+                "host_ms_per_step": host_ms,
                 "order": ("rows grouped by cell: exact multinomial cell counts (Poisson counts + u-driven "
                           "top-up), i.i.d. as a multiset, NOT exchangeable in row order"
                           if args.order == "cell" else
@@ -444,6 +480,7 @@ def main():
     ap.add_argument("--order", default="cell", choices=["cell", "draw"],
                     help="cell: rows grouped by cell (throughput mode); draw: u-driven per-sample search")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the 2-step run of the other row order")
     ap.add_argument("--guide-bits", type=int, default=None, help="tuning: log2 guide-table size")

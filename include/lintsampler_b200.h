@@ -149,6 +149,13 @@ typedef struct lint_halos {
 int lint_abi_version(void);
 const char *lint_last_error(void);
 
+/* Device-resident stream position (for CUDA graphs).  While a counter is set, every sampling call
+ * draws at Philox offset `offset + *counter_dev` (read on the device when the kernels run), so a
+ * captured graph that contains lint_advance_counter draws fresh samples at every replay.
+ * Process-wide setting, not thread-safe; NULL clears it. */
+int lint_set_offset_counter(const uint64_t *counter_dev);
+int lint_advance_counter(uint64_t *counter_dev, uint64_t by, lint_stream_t stream);
+
 /* ---- grid build ------------------------------------------------------------- */
 
 /* Fused vertex evaluation of a built-in analytic pdf on the grid vertices;

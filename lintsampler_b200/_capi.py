@@ -82,6 +82,8 @@ _U64 = C.c_uint64
 PROTOTYPES = {
     "lint_abi_version": (C.c_int, []),
     "lint_last_error": (C.c_char_p, []),
+    "lint_set_offset_counter": (C.c_int, [_P]),
+    "lint_advance_counter": (C.c_int, [_P, _U64, _P]),
     "lint_grid_eval_gmm": (C.c_int, [C.POINTER(LintGrid), C.POINTER(LintGmm), C.c_double, _P]),
     "lint_grid_eval_halos": (C.c_int, [C.POINTER(LintGrid), C.POINTER(LintHalos), C.c_double, _P]),
     "lint_grid_masses": (C.c_int, [C.POINTER(LintGrid), _P, _P, _P]),

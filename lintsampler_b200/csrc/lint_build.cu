@@ -25,6 +25,11 @@ int fail(int code, const char *fmt, ...) {
     return code;
 }
 
+static const uint64_t *g_offset_counter = nullptr;
+const uint64_t *offset_counter() { return g_offset_counter; }
+
+__global__ void advance_counter_kernel(uint64_t *counter, uint64_t by) { *counter += by; }
+
 int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LINT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
@@ -928,6 +933,17 @@ using namespace lint;
 extern "C" {
 
 int lint_abi_version(void) { return LINT_ABI_VERSION; }
+
+int lint_set_offset_counter(const uint64_t *counter_dev) {
+    g_offset_counter = counter_dev;
+    return LINT_OK;
+}
+
+int lint_advance_counter(uint64_t *counter_dev, uint64_t by, lint_stream_t stream) {
+    if (!counter_dev) return fail(LINT_ERR_BAD_ARG, "lint_advance_counter: counter_dev is NULL");
+    advance_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter_dev, by);
+    return check_launch("lint_advance_counter");
+}
 const char *lint_last_error(void) { return last_error_slot().c_str(); }
 
 int lint_grid_eval_gmm(const lint_grid_t *g, const lint_gmm_t *gmm, double scale,

@@ -194,9 +194,10 @@ __device__ __forceinline__ uint32_t poisson(double lam, CellRng &rng) {
 constexpr int POISSON_THREADS = 256;
 template <typename Cells>
 __global__ void __launch_bounds__(POISSON_THREADS)
-poisson_counts_kernel(Cells src, CdfSlice t, double lam_per_unit, uint2 key, uint64_t offset, bool split,
+poisson_counts_kernel(Cells src, CdfSlice t, double lam_per_unit, uint2 key, StreamPos pos, bool split,
                       const uint32_t *__restrict__ range, uint32_t *__restrict__ counts_flat,
                       uint32_t *__restrict__ counts_rest) {
+    const uint64_t offset = pos.get();
     const uint32_t w2 = (uint32_t)offset, w3 = (uint32_t)(offset >> 32);
     // cells [c0, c1): the slab of the stratum (lint_grid_build), or every cell
     const uint32_t c0 = range ? range[0] : 0u, c1 = range ? range[1] : t.ncells;
@@ -566,9 +567,10 @@ __global__ void __launch_bounds__(FLAT_THREADS, LINT_FLAT_MINB)
 emit_flat_kernel(const T *__restrict__ boxes, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
                  const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ plan,
                  const uint32_t *__restrict__ chunk_start, uint32_t chunk_rows, uint32_t *chunk_counter,
-                 const __grid_constant__ PhiloxKeys key, uint64_t offset, T *__restrict__ out,
+                 const __grid_constant__ PhiloxKeys key, StreamPos pos, T *__restrict__ out,
                  int64_t *__restrict__ cell_idx) {
     using FT = FlatTraits<T>;
+    const uint64_t offset = pos.get();
     const uint32_t fm = key.field_mask, fo = key.field_one;      // see FlatTraits<float>::uniform
     constexpr int VEC = FT::VEC, NF = FT::FIELDS;
     constexpr int J = flat_vectors_per_lane<K, VEC>();
@@ -817,9 +819,10 @@ __global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 ? (K <= 3 ? LINT_
 emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
             const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ plan,
             const uint32_t *__restrict__ chunk_start, uint32_t chunk_rows, const __grid_constant__ PhiloxKeys key,
-            uint64_t offset, uint32_t split, CdfSlice table, double lam_per_unit, T *__restrict__ out,
+            StreamPos pos, uint32_t split, CdfSlice table, double lam_per_unit, T *__restrict__ out,
             int64_t *__restrict__ cell_idx) {
     using FT = FlatTraits<T>;
+    const uint64_t offset = pos.get();
     constexpr int NF = FT::FIELDS, NB = (2 * K + NF - 1) / NF;       // Philox blocks per pair of rows
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sedges = reinterpret_cast<T *>(smem_raw);
@@ -1027,12 +1030,12 @@ static void scan_list(const uint32_t *counts, uint32_t n, const uint32_t *range,
 template <typename Cells>
 static int plan_rows(const Cells &src, const double *cdf, uint64_t ncells, uint64_t N, uint2 key,
                      uint64_t offset, Stratum u, const uint32_t *range, const Scratch &s, cudaStream_t st) {
-    const bool split = use_split(ncells, N);
+    const bool split = use_split(ncells, N, u.u_hi - u.u_lo);
     const CdfSlice t{cdf, (uint32_t)ncells, u.u_lo, u.u_hi};
     const double lam_per_unit = grouped_mean(N) / (u.u_hi - u.u_lo);
     const int cblocks = (int)std::min<uint64_t>((ncells + POISSON_THREADS - 1) / POISSON_THREADS, 148 * 32);
     cudaMemsetAsync(s.zero_begin, 0, s.zero_bytes, st);
-    poisson_counts_kernel<<<cblocks, POISSON_THREADS, 0, st>>>(src, t, lam_per_unit, key, offset, split, range, s.counts_flat,
+    poisson_counts_kernel<<<cblocks, POISSON_THREADS, 0, st>>>(src, t, lam_per_unit, key, StreamPos{offset, offset_counter()}, split, range, s.counts_flat,
                                                    s.counts_rest);
     if (split) scan_list(s.counts_flat, (uint32_t)ncells, range, 1, 0, s.flat, st);
     scan_list(s.counts_rest, (uint32_t)ncells, range, split ? 2 : 1, split ? 1 : 0, s.rest, st);
@@ -1061,7 +1064,7 @@ inline int env_int(const char *name, int fallback) {
 template <int K, typename T, typename Cells>
 int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t ncells, uint64_t N, uint2 key,
                 uint64_t offset, Stratum u, void *out, int64_t *cell_idx, cudaStream_t st) {
-    const bool split = use_split(ncells, N);
+    const bool split = use_split(ncells, N, u.u_hi - u.u_lo);
     const CdfSlice t{cdf, (uint32_t)ncells, u.u_lo, u.u_hi};
     const double lam_per_unit = grouped_mean(N) / (u.u_hi - u.u_lo);
     const uint32_t chunk_rows = emit_chunk_rows(N);
@@ -1083,11 +1086,11 @@ int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t 
         if (cell_idx)
             emit_flat_kernel<K, T, true><<<fblocks, FLAT_THREADS, 0, st>>>(
                 boxes, s.flat.cid, s.flat.coff, s.flat.nnz, s.plan, s.flat.chunk_start, chunk_rows, s.chunk_counter,
-                philox_round_keys(key), offset, (T *)out, cell_idx);
+                philox_round_keys(key), StreamPos{offset, offset_counter()}, (T *)out, cell_idx);
         else
             emit_flat_kernel<K, T, false><<<fblocks, FLAT_THREADS, 0, st>>>(
                 boxes, s.flat.cid, s.flat.coff, s.flat.nnz, s.plan, s.flat.chunk_start, chunk_rows, s.chunk_counter,
-                philox_round_keys(key), offset, (T *)out, cell_idx);
+                philox_round_keys(key), StreamPos{offset, offset_counter()}, (T *)out, cell_idx);
         if (int rc = check_launch("cell-major flat emission")) return rc;
     }
     if (tm.enabled) {
@@ -1100,11 +1103,11 @@ int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t 
     if (cell_idx)
         emit_kernel<K, T, Cells, true><<<blocks, EMIT_THREADS, smem, st>>>(
             src, s.rest.cid, s.rest.coff, s.rest.nnz, s.plan, s.rest.chunk_start, chunk_rows,
-            philox_round_keys(key), offset, split ? 1u : 0u, t, lam_per_unit, (T *)out, cell_idx);
+            philox_round_keys(key), StreamPos{offset, offset_counter()}, split ? 1u : 0u, t, lam_per_unit, (T *)out, cell_idx);
     else
         emit_kernel<K, T, Cells, false><<<blocks, EMIT_THREADS, smem, st>>>(
             src, s.rest.cid, s.rest.coff, s.rest.nnz, s.plan, s.rest.chunk_start, chunk_rows,
-            philox_round_keys(key), offset, split ? 1u : 0u, t, lam_per_unit, (T *)out, cell_idx);
+            philox_round_keys(key), StreamPos{offset, offset_counter()}, split ? 1u : 0u, t, lam_per_unit, (T *)out, cell_idx);
     if (tm.enabled) cudaEventRecord(tm.ev[3], st);
     return check_launch("cell-major emission");
 }

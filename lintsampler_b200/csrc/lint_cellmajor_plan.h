@@ -42,8 +42,7 @@ struct Scratch {
 constexpr double SPLIT_MIN_LAMBDA = LINT_SPLIT_MIN_LAMBDA;
 
 // `box_bytes`: bytes of one flat segment's box (2 * dim values of the output type; the default is
-// the largest).  Only split cells have a flat segment: a draw splits cells at all when
-// N >= SPLIT_MIN_ROWS_PER_CELL * ncells, and then those expecting >= SPLIT_MIN_LAMBDA rows, of
+// the largest).  Only split cells have a flat segment: those expecting >= SPLIT_MIN_LAMBDA rows, of
 // which there are at most N / SPLIT_MIN_LAMBDA.
 inline Scratch carve(void *base, uint64_t ncells, uint64_t N, size_t box_bytes = 2 * LINT_MAX_DIM * 8) {
     const uint64_t nscan = (ncells + SCAN_TILE - 1) / SCAN_TILE;
@@ -58,7 +57,7 @@ inline Scratch carve(void *base, uint64_t ncells, uint64_t N, size_t box_bytes =
         l->coff = (uint32_t *)take((ncells + 1) * 4);
         l->chunk_start = (uint32_t *)take(std::max<uint64_t>(nchunks, 1) * 4);
     }
-    const uint64_t nbox = N >= 32 * ncells ? std::min<uint64_t>(ncells, (uint64_t)((double)N / SPLIT_MIN_LAMBDA) + 1) : 0;
+    const uint64_t nbox = std::min<uint64_t>(ncells, (uint64_t)((double)N / SPLIT_MIN_LAMBDA) + 1);
     s.boxes = take(nbox * box_bytes);
     s.plan = (uint32_t *)take(16);
     s.chunk_counter = (uint32_t *)take(4);
@@ -85,7 +84,11 @@ inline uint64_t topup_bound(uint64_t N) {
 struct Stratum { double u_lo, u_hi; };
 
 constexpr uint64_t SPLIT_MIN_ROWS_PER_CELL = 32;
-inline bool use_split(uint64_t ncells, uint64_t N) { return N >= SPLIT_MIN_ROWS_PER_CELL * ncells; }
+// (a draw from a stratum of width w of the cell CDF is judged as the N / w rows of the whole
+// domain it is a part of: a rank of a sharded run splits exactly the cells a single GPU would)
+inline bool use_split(uint64_t ncells, uint64_t N, double stratum_width = 1.0) {
+    return (double)N >= (double)(SPLIT_MIN_ROWS_PER_CELL * ncells) * stratum_width;
+}
 
 
 // Optional timing of the two emitters (lint_cellmajor_timing): CUDA events recorded on the

@@ -73,6 +73,16 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, const PhiloxKeys &k) {
     return ctr;
 }
 
+// Position in the Philox stream: the `offset` argument of a call plus, optionally, a counter that
+// lives in device memory (lint_set_offset_counter) — a captured CUDA graph can then draw fresh
+// samples at every replay by advancing the counter on the device (lint_advance_counter).
+struct StreamPos {
+    uint64_t base;
+    const uint64_t *extra;
+    __device__ __forceinline__ uint64_t get() const { return base + (extra ? *extra : 0ull); }
+};
+const uint64_t *offset_counter();          // the process-wide setting (lint_build.cu)
+
 __host__ __device__ __forceinline__ double u53(uint32_t lo, uint32_t hi) {
     // same construction as NumPy's Generator.random: top 53 bits * 2^-53
     const uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;
@@ -514,7 +524,7 @@ struct UniformsFromArray {        // caller-supplied (N, K+1) fp64  [lintsampler
 template <int K>
 struct UniformsPhilox {
     uint2 key;
-    uint64_t offset;
+    StreamPos pos;
     double u_lo, u_span;           // cell-uniform stratum [u_lo, u_lo + u_span); (0, 1) = whole domain
     __host__ size_t smem_words() const { return 0; }
     __device__ __forceinline__ const uint32_t *stage(uint32_t *) const { return nullptr; }
@@ -523,7 +533,7 @@ struct UniformsPhilox {
     }
     // fp64 rows: cell uniform from words (0,1), coordinate d from words (2+2d, 3+2d)
     __device__ __forceinline__ void get(int64_t row, double &ucell, double (&uc)[K], const uint32_t *) const {
-        const uint64_t i = offset + (uint64_t)row;
+        const uint64_t i = pos.get() + (uint64_t)row;
         constexpr int NCALL = (K + 2) / 2;
         uint32_t w[4 * NCALL];
 #pragma unroll
@@ -539,7 +549,7 @@ struct UniformsPhilox {
     // top bits of words 2,3; d=2 from the otherwise unused low bytes of words
     // 2, 3 and 0; d=3..5 from a second block.
     __device__ __forceinline__ void get(int64_t row, double &ucell, float (&uc)[K], const uint32_t *) const {
-        const uint64_t i = offset + (uint64_t)row;
+        const uint64_t i = pos.get() + (uint64_t)row;
         const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0, 0), key);
         ucell = stratum(u53(r.x, r.y));
         constexpr float S = 1.0f / 16777216.0f;

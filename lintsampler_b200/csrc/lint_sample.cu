@@ -236,8 +236,8 @@ struct PhiloxMaker {
     uint64_t seed, offset;
     double u_lo = 0.0, u_hi = 1.0;
     template <int K> UniformsPhilox<K> make() const {
-        return UniformsPhilox<K>{make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), offset,
-                                 u_lo, u_hi - u_lo};
+        return UniformsPhilox<K>{make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)),
+                                 StreamPos{offset, offset_counter()}, u_lo, u_hi - u_lo};
     }
 };
 
