@@ -228,8 +228,10 @@ def run_b200(args):
     if args.no_records:
         grid_kw["cell_records"] = False
     shard = lbd.ShardedGrid(edges, gmm, dtype=np.float32, device=dev, rank=rank, world=world,
-                            group=dist.group.WORLD if world > 1 else None, **grid_kw)
-    cap = n_total if world == 1 else int(n_total / world + 8 * np.sqrt(n_total) + 64)
+                            group=dist.group.WORLD if world > 1 else None,
+                            balance_rows=None if args.equal_mass else n_total, **grid_kw)
+    widths = np.diff(shard.bounds)                   # shard probabilities (identical on every rank)
+    cap = n_total if world == 1 else int(n_total * widths.max() + 8 * np.sqrt(n_total) + 64)
     out = torch.empty((cap, DIM), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream(dev)
 
@@ -237,7 +239,7 @@ def run_b200(args):
         """(rows, first row) of this rank in step i: Multinomial(N, 1/G ... 1/G), shared seed."""
         if world == 1:
             return n_total, 0
-        counts = lbd.split_counts(n_total, np.full(world, 1.0 / world), SEED * 1_000_003 + i)
+        counts = lbd.split_counts(n_total, widths, SEED * 1_000_003 + i)
         return int(counts[rank]), int(counts[:rank].sum())
 
     def barrier():
@@ -433,7 +435,7 @@ def _numa_summary():
 def run_e2e(args, lb, edges, gmm, dev, world, n_total):
     import torch
     import torch.distributed as dist
-    n = n_total // world                                    # rows per rank (equal-mass strata)
+    n = n_total // world                                    # rows per rank
     steps = max(1, min(args.steps, 3))
     # host inputs: pinned fp32 vertex densities (evaluated once, outside the timed region)
     kw = dict(cell_records=False, guide_bits=16) if args.order == "cell" else dict(guide_bits=22)
@@ -480,6 +482,8 @@ def main():
     ap.add_argument("--order", default="cell", choices=["cell", "draw"],
                     help="cell: rows grouped by cell (throughput mode); draw: u-driven per-sample search")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--equal-mass", action="store_true",
+                    help="equal-mass strata instead of cost-balanced ones (multi-GPU)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the 2-step run of the other row order")

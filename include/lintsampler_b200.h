@@ -214,7 +214,7 @@ int lint_cdf_build(const double *masses_dev, int64_t n, int mode, double *cdf_de
 
 /* Parallel build for a grid: cell masses [grid.py:469-518, 411] -> normalised inclusive CDF
  * [grid.py:431 + utils.py:195-196] -> guide table, hierarchical and without ever storing the
- * masses (masses_dev == NULL).  The cells are cut into groups of consecutive cell rows (~16 K
+ * masses (masses_dev == NULL).  The cells are cut into groups of consecutive cell rows (~2 K
  * cells); group totals come from one streaming pass over the vertex table (separable trapezoid
  * weights; it also performs the validity check of grid.py:401-404 on every vertex), and inside
  * a group the CDF is the exact chained scan of the cell masses laid on the group's offset:
@@ -229,6 +229,9 @@ int lint_cdf_build(const double *masses_dev, int64_t n, int mode, double *cdf_de
  * group; hand it to lint_grid_sample_cellmajor.  Outside the slab (and the one CDF entry before
  * it) the tables are left untouched.  total_dev receives the total mass. */
 size_t lint_grid_build_scratch_bytes(const lint_grid_t *g);
+/* cells per group of lint_grid_build (whole cell rows, about 2 K cells): group b starts at cell
+ * b * lint_grid_group_cells(g).  A stratum cut at a group boundary has no straddling cell. */
+int64_t lint_grid_group_cells(const lint_grid_t *g);
 int lint_grid_build(const lint_grid_t *g, double u_lo, double u_hi, double *cdf_dev, double *total_dev,
                     uint32_t *guide_dev, int guide_bits, double *masses_dev, uint32_t *flags_dev,
                     uint32_t *range_dev, void *scratch_dev, size_t scratch_bytes, lint_stream_t stream);

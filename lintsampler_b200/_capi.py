@@ -96,6 +96,7 @@ PROTOTYPES = {
     "lint_cdf_build": (C.c_int, [_P, _I64, C.c_int, _P, _P, _P, C.c_size_t, _P]),
     "lint_guide_build": (C.c_int, [_P, _I64, C.c_int, _P, _P]),
     "lint_grid_build_scratch_bytes": (C.c_size_t, [C.POINTER(LintGrid)]),
+    "lint_grid_group_cells": (_I64, [C.POINTER(LintGrid)]),
     "lint_grid_build": (C.c_int, [C.POINTER(LintGrid), C.c_double, C.c_double, _P, _P, _P, C.c_int, _P, _P, _P,
                                   _P, C.c_size_t, _P]),
     "lint_grid_sample_u": (C.c_int, [C.POINTER(LintGrid), _P, _I64, _P, _P, _P]),

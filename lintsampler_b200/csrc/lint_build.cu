@@ -684,7 +684,7 @@ guide_build_kernel(const double *cdf, uint32_t n, int bits, uint32_t *guide, con
 // hierarchical parallel build for grids: vertices -> group totals -> slab CDF
 // ---------------------------------------------------------------------------
 // The grid's cells are cut into GROUPS of consecutive cell rows (a row = the n_last cells along
-// the last dimension), about 16 K cells each.
+// the last dimension), about 2 K cells each (whole rows: more where a row is longer).
 //   1. Group totals the cheap way.  The trapezoid mass of a set of whole rows is a weighted sum
 //      of vertex densities with separable weights: for every vertex row, Q = sum_i V[i] omega[i]
 //      (omega = half the widths of the adjacent last-dim cells); the mass of a cell row is
@@ -702,7 +702,7 @@ guide_build_kernel(const double *cdf, uint32_t n, int bits, uint32_t *guide, con
 // is all a rank needs to know the total mass and where its stratum lies.  Step 2, the expensive
 // one, runs only over the groups the rank's stratum [u_lo, u_hi) can touch (plus one group of
 // margin on either side).  Cell masses are computed once and never stored.
-constexpr uint32_t GROUP_TARGET_CELLS = 16384;
+constexpr uint32_t GROUP_TARGET_CELLS = PAR_TILE;      // one scan tile: a group is one block-step of the scan
 
 struct GroupPlan {
     uint32_t n_last, nrow, nvrow, rows_per_group, ngroups, group_cells;
@@ -749,8 +749,6 @@ __global__ void __launch_bounds__(256)
 group_totals_kernel(GridView<K> g, GroupPlan plan, uint32_t ncells, const double *__restrict__ Q, double *Off,
                     double *total, uint32_t *done_counter, uint32_t *range_out) {
     __shared__ bool s_last;
-    __shared__ double s_chain[2048];
-    __shared__ double s_run;
     const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gi < plan.ngroups; gi += warps) {
         const uint32_t r0 = gi * plan.rows_per_group, r1 = min(r0 + plan.rows_per_group, plan.nrow);
@@ -780,26 +778,31 @@ group_totals_kernel(GridView<K> g, GroupPlan plan, uint32_t ncells, const double
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // Off[g + 1] <- Gt[0] + ... + Gt[g], left to right, in chunks staged through shared memory
+    // Off[g + 1] <- Gt[0] (+) ... (+) Gt[g]: chunks of 2048 totals scanned with the nested exact
+    // chains of tile_scan (an offset is always the inclusive value before it: non-decreasing),
+    // chunk after chunk
     volatile double *vo = Off;
-    if (threadIdx.x == 0) s_run = 0.0;
-    for (uint32_t c0 = 0; c0 < plan.ngroups; c0 += 2048) {
-        const uint32_t m = min(2048u, plan.ngroups - c0);
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) s_chain[i] = vo[c0 + 1 + i];
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double run = s_run;
-            for (uint32_t i = 0; i < m; ++i) { run += s_chain[i]; s_chain[i] = run; }
-            s_run = run;
+    __shared__ double warp_tot[PAR_THREADS / 32];
+    double carry = 0.0;
+    for (uint32_t c0 = 0; c0 < plan.ngroups; c0 += PAR_TILE) {
+        double x[PAR_ITEMS];
+#pragma unroll
+        for (int j = 0; j < PAR_ITEMS; ++j) {
+            const uint32_t i = c0 + threadIdx.x * PAR_ITEMS + j;
+            x[j] = i < plan.ngroups ? vo[i + 1] : 0.0;
         }
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) vo[c0 + 1 + i] = s_chain[i];
+        const double chunk_total = tile_scan(x, warp_tot);
+#pragma unroll
+        for (int j = 0; j < PAR_ITEMS; ++j) {
+            const uint32_t i = c0 + threadIdx.x * PAR_ITEMS + j;
+            if (i < plan.ngroups) vo[i + 1] = c0 == 0 ? x[j] : __dadd_rn(carry, x[j]);
+        }
+        carry = c0 == 0 ? chunk_total : __dadd_rn(carry, chunk_total);
     }
+    __threadfence();
     __syncthreads();
     if (threadIdx.x != 0) return;
-    __threadfence();
-    const double run = s_run;
+    const double run = carry;
     vo[0] = 0.0;
     *total = run;
     *done_counter = 0;
@@ -1097,6 +1100,12 @@ int lint_guide_build(const double *cdf_dev, int64_t n, int guide_bits, uint32_t 
     guide_build_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cdf_dev, (uint32_t)n, guide_bits, guide_dev,
                                                                  nullptr);
     return check_launch("lint_guide_build");
+}
+
+int64_t lint_grid_group_cells(const lint_grid_t *g) {
+    uint64_t nc, nv;
+    if (validate_grid(g, false, &nc, &nv)) return 0;
+    return (int64_t)make_group_plan(g, nc, 0.0, 1.0).group_cells;
 }
 
 size_t lint_grid_build_scratch_bytes(const lint_grid_t *g) {

@@ -70,6 +70,47 @@ def equal_mass_strata(world):
     return np.arange(world + 1, dtype=np.float64) / world
 
 
+# Cost model of one rank's step (ns), measured on B200 at the 256^3 / N = 1e9 benchmark
+# (profiles/README.md, r2g): a row of a split cell (94 % flat rows at ~1.9 ns, 6 % residual rows at
+# ~6.4 ns), a row of a cell too small to split, and the per-cell work of the count / scan / build passes.
+COST_NS_ROW_SPLIT, COST_NS_ROW_SMALL, COST_NS_CELL = 2.2, 6.4, 0.04
+SPLIT_MIN_LAMBDA = 128.0          # csrc/lint_cellmajor_plan.h
+
+
+def cost_balanced_strata(grid, world, n_rows):
+    """Stratum boundaries that equalise the modelled cost of the ranks instead of their mass.
+
+    Equal-mass strata give every rank the same number of rows but very different numbers of
+    cells: the ranks that own the tails of the density visit several times more cells (count,
+    scan and build passes) and draw most of their rows from cells too small to split (the dearer
+    emitter).  The cuts are placed at group boundaries of the grid's build (no cell straddles a
+    cut) where the cumulative cost ``rows * c_row + cells * c_cell`` crosses g / world; every rank
+    derives the same cuts from the same CDF entries, without communication.  ``n_rows``: the
+    number of rows the whole domain will draw per call (sets rows per cell, hence which cells are
+    split)."""
+    import ctypes as C
+    import torch
+    from . import _capi
+    ncells = int(grid.ncells)
+    gc = int(_capi.load().lint_grid_group_cells(C.byref(grid._descriptor())))
+    if world == 1 or gc <= 0 or ncells <= gc:
+        return equal_mass_strata(world)
+    ends_idx = torch.arange(gc - 1, ncells, gc, device=grid.device)
+    if int(ends_idx[-1]) != ncells - 1:
+        ends_idx = torch.cat([ends_idx, torch.tensor([ncells - 1], device=grid.device)])
+    ends = grid._cdf[ends_idx].cpu().numpy()                       # CDF at the end of every group
+    cells = np.diff(np.concatenate([[0], ends_idx.cpu().numpy() + 1])).astype(np.float64)
+    rows = float(n_rows) * np.diff(np.concatenate([[0.0], ends]))
+    lam = rows / cells
+    cost = rows * np.where(lam >= SPLIT_MIN_LAMBDA, COST_NS_ROW_SPLIT, COST_NS_ROW_SMALL) + cells * COST_NS_CELL
+    cum = np.cumsum(cost)
+    cuts = np.searchsorted(cum, cum[-1] * np.arange(1, world) / world)
+    bounds = np.concatenate([[0.0], ends[np.minimum(cuts, len(ends) - 1)], [1.0]])
+    if np.any(np.diff(bounds) <= 0):
+        return equal_mass_strata(world)
+    return bounds
+
+
 def slab_bounds(n0, world):
     """Cell-plane ranges along dim 0, one contiguous slab per rank:
     rank g owns cell planes [b[g], b[g+1]) and vertex planes [b[g], b[g+1]]."""
@@ -135,12 +176,16 @@ class ShardedGrid:
     """
 
     def __init__(self, edges, pdf, *, dtype=np.float64, device=None, rank=0, world=1,
-                 group=None, vectorizedpdf=True, cdf_mode="parallel", **grid_kw):
+                 group=None, vectorizedpdf=True, cdf_mode="parallel", balance_rows=None, **grid_kw):
         self.rank, self.world, self.group = int(rank), int(world), group
         self.grid = DensityGrid(edges, pdf, vectorizedpdf=vectorizedpdf, dtype=dtype, device=device,
                                 cdf_mode=cdf_mode, **grid_kw)
         self.device = self.grid.device
-        self.bounds = equal_mass_strata(self.world)
+        # strata of the cell-selecting uniform, one per rank: equal mass, or (balance_rows = rows
+        # per call over the whole domain) equal modelled cost — see cost_balanced_strata
+        self.balanced = bool(balance_rows) and cdf_mode == "parallel" and self.world > 1
+        self.bounds = (cost_balanced_strata(self.grid, self.world, balance_rows) if self.balanced
+                       else equal_mass_strata(self.world))
         self.shard_masses = None
         self._gather_buf = None
         self.enqueue_build(gather=False)            # restrict the tables to this rank's stratum
@@ -229,6 +274,7 @@ class ShardedGrid:
     def describe(self):
         if self.world == 1:
             return "single GPU"
-        return (f"{self.world} ranks, equal-mass strata of the flat cell CDF (contiguous dim-0-major "
+        kind = "cost-balanced strata (cut at group boundaries of the build)" if self.balanced else "equal-mass strata"
+        return (f"{self.world} ranks, {kind} of the flat cell CDF (contiguous dim-0-major "
                 "cell ranges): every rank reduces the vertex table to tile totals, scans only its own slab; "
                 "N split multinomially with a shared seed; no sample data crosses NVLink")

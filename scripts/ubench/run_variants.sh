@@ -1,3 +1,6 @@
-python -m pytest tests -m gpu -q -x -k "(cellmajor_structure and g3d) or (flat_residual and 3-) or cell_order or sample_to_host" 2>&1 | tail -3
-python scripts/time_emit.py 1e9 3 > gpurun_out/m_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/m_launches.csv python scripts/time_emit.py 1e9 1 > gpurun_out/m_ncu.log 2>&1
-head -1 gpurun_out/m_plain.log; python scripts/launch_summary.py gpurun_out/m_launches.csv > gpurun_out/m_sum.txt; grep -E "emit|boxes|poisson|scan_compact|chunk_start|sample_kernel" gpurun_out/m_sum.txt
+python -m pytest tests -m gpu -q -x 2>&1 | tail -4
+for r in 0 1 2 3 4 5 6 7; do
+  python scripts/emulate_rank.py $r 8 1e9 3 2>&1 | tail -1
+done
+python scripts/emulate_rank.py 0 8 1e9 3 > gpurun_out/v_plain_0.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/v_launches_0.csv python scripts/emulate_rank.py 0 8 1e9 1 > gpurun_out/v_ncu_0.log 2>&1
+python scripts/launch_summary.py gpurun_out/v_launches_0.csv > gpurun_out/v_sum_0.txt; head -14 gpurun_out/v_sum_0.txt

@@ -28,7 +28,8 @@ def lb():
 
 @pytest.mark.parametrize("world", [2, 8])
 @pytest.mark.parametrize("order", ["cell", "draw"])
-def test_emulated_ranks_reproduce_the_cell_distribution(lb, world, order):
+@pytest.mark.parametrize("balanced", [False, True])
+def test_emulated_ranks_reproduce_the_cell_distribution(lb, world, order, balanced):
     """Strong-scaling decomposition of bench.py: N split multinomially (shared seed) over equal-mass
     strata, rank g builds only its slab (lint_grid_build) and draws its rows; the combined per-cell
     histogram must match the exact cell probabilities, the slabs must tile the cells the strata
@@ -41,12 +42,18 @@ def test_emulated_ranks_reproduce_the_cell_distribution(lb, world, order):
     edges = tuple(np.linspace(-4, 4, n + 1) for _ in range(3))
     gmm = lb.GaussianMixture(rng.dirichlet(np.ones(4)), rng.uniform(-2, 2, (4, 3)), sigmas=rng.uniform(0.3, 0.8, 4))
     N = 20_000_000
-    counts = lbd.split_counts(N, np.full(world, 1.0 / world), 5)
+    counts = None
     hist = torch.zeros(n ** 3, dtype=torch.float64, device="cuda")
     totals, slabs = [], []
     for rank in range(world):
         sh = lbd.ShardedGrid(edges, gmm, dtype=np.float32, rank=rank, world=world, cell_records=False,
-                             guide_bits=14)
+                             guide_bits=14, balance_rows=N if balanced else None)
+        if counts is None:                                         # shard probabilities = stratum widths
+            widths = np.diff(sh.bounds)
+            assert abs(widths.sum() - 1) < 1e-15 and (balanced or np.allclose(widths, 1.0 / world))
+            counts = lbd.split_counts(N, widths, 5)
+        else:
+            assert np.array_equal(np.diff(sh.bounds), widths)      # every rank derives the same strata
         x = torch.empty((int(counts[rank]), 3), dtype=torch.float32, device="cuda")
         first = int(counts[:rank].sum())
         if order == "cell":
@@ -57,7 +64,7 @@ def test_emulated_ranks_reproduce_the_cell_distribution(lb, world, order):
         hist += torch.bincount((idx[:, 0] * n + idx[:, 1]) * n + idx[:, 2], minlength=n ** 3).double()
         totals.append(float(sh.grid._total.item()))
         slabs.append(sh.grid._range.tolist()[:2])
-        np.testing.assert_allclose(sh.shard_masses, sh.grid.total_mass / world, rtol=1e-12)
+        np.testing.assert_allclose(sh.shard_masses, sh.grid.total_mass * widths, rtol=1e-12)
     assert len(set(totals)) == 1                                   # same tile totals on every rank, bit for bit
     assert slabs[0][0] == 0 and slabs[-1][1] == n ** 3
     assert all(a[1] > b[0] for a, b in zip(slabs[:-1], slabs[1:]))  # consecutive slabs overlap (margins): no gap

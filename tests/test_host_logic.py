@@ -30,7 +30,7 @@ def _no_gpu():
 # ----------------------------------------------------------------------------- C ABI
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "lintsampler_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|size_t|const char \*)\s*\*?(lint_\w+)\s*\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|size_t|const char \*)\s*\*?(lint_\w+)\s*\(", hdr, flags=re.M))
     assert declared == set(_capi.PROTOTYPES), declared ^ set(_capi.PROTOTYPES)
     lib = _capi.load()                       # resolves each symbol or raises
     assert lib.lint_abi_version() == 2
