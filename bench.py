@@ -230,6 +230,8 @@ def run_b200(args):
     shard = lbd.ShardedGrid(edges, gmm, dtype=np.float32, device=dev, rank=rank, world=world,
                             group=dist.group.WORLD if world > 1 else None,
                             balance_rows=None if args.equal_mass else n_total, **grid_kw)
+    if world > 1 and not args.equal_mass and not args.no_calibrate and args.order == "cell":
+        shard.calibrate(n_total, seed=SEED)          # strata re-cut from measured step times (setup, collective)
     widths = np.diff(shard.bounds)                   # shard probabilities (identical on every rank)
     cap = n_total if world == 1 else int(n_total * widths.max() + 8 * np.sqrt(n_total) + 64)
     out = torch.empty((cap, DIM), dtype=torch.float32, device=dev)
@@ -384,6 +386,7 @@ def run_b200(args):
                 "samples_total": n_total, "samples_per_gpu": n_total / world,
                 "l2": "outputs (12 GB/step in total) and tables (>200 MB) exceed L2",
                 "sharding": shard.describe(),
+                "strata": [float(b) for b in shard.bounds],
                 "launch": ("one CUDA graph replay per step: %d kernels captured once; the graph advances a "
                            "device-resident Philox offset, so every step draws fresh samples; the multinomial "
                            "split of N over the ranks is drawn once per run from the shared seed"
@@ -484,6 +487,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--equal-mass", action="store_true",
                     help="equal-mass strata instead of cost-balanced ones (multi-GPU)")
+    ap.add_argument("--no-calibrate", action="store_true",
+                    help="keep the analytic cost-balanced strata (no timed trial steps at setup)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the 2-step run of the other row order")

@@ -323,35 +323,41 @@ scan_compact_kernel(const uint32_t *counts, uint32_t ncells_all, const uint32_t 
     }
 }
 
-// Row budget of the two grouped runs.  T_f + T_r <= N but for an 8-sigma event of the Poisson
-// total; clamping keeps every writer inside the output whatever happened.  Also resets the
-// flat emitter's chunk counter.  plan[0] = T_f, plan[1] = T_r, plan[2] = T_f + T_r.
-static __global__ void plan_totals_kernel(const uint32_t *rows_flat, const uint32_t *rows_rest, uint32_t n_requested,
-                                   uint32_t *plan, uint32_t *chunk_counter) {
-    const uint32_t tf = rows_flat ? min(*rows_flat, n_requested) : 0u;
-    const uint32_t tr = min(*rows_rest, n_requested - tf);
-    plan[0] = tf;
-    plan[1] = tr;
-    plan[2] = tf + tr;
-    *chunk_counter = 0;
-}
-
-// First segment of every output chunk: last j with coff[j] <= first row of the chunk.  Chunk t
-// holds the rows r with t * chunk_rows <= r + shift < (t + 1) * chunk_rows, shift = *shift_p & 1
-// (the general emitter lays its chunks over even global rows, see emit_kernel) or 0.
-static __global__ void chunk_start_kernel(const uint32_t *coff, const uint32_t *nnz_p, const uint32_t *rows_p,
-                                          const uint32_t *shift_p, uint32_t chunk_rows, uint32_t *chunk_start) {
-    const uint32_t nnz = *nnz_p;
-    const uint32_t shift = shift_p ? (*shift_p & 1u) : 0u;
-    const uint32_t nchunks = *rows_p ? (*rows_p + shift + chunk_rows - 1) / chunk_rows : 0u;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nchunks; t += gridDim.x * blockDim.x) {
-        const uint32_t r0 = max(t * chunk_rows, shift) - shift;
-        uint32_t lo = 0, hi = nnz;                                 // coff[nnz] = N > r0
+// Row budget of the two grouped runs and the first segment of every output chunk, one launch.
+// T_f + T_r <= N but for an 8-sigma event of the Poisson total; clamping keeps every writer
+// inside the output whatever happened.  plan[0] = T_f, plan[1] = T_r, plan[2] = T_f + T_r; the
+// flat emitter's chunk counter is reset.
+// Chunk t of a run holds the rows r with t * chunk_rows <= r + shift < (t + 1) * chunk_rows
+// (shift = T_f & 1 for the general run, whose chunks are laid over even global rows, see
+// emit_kernel; 0 for the flat run); its first segment is the last j with coff[j] <= its first row.
+struct SegTable {
+    const uint32_t *coff, *nnz, *rows;
+    uint32_t *chunk_start;
+};
+static __global__ void plan_chunks_kernel(SegTable flat, SegTable rest, uint32_t n_requested, uint32_t chunk_rows,
+                                          uint32_t *plan, uint32_t *chunk_counter) {
+    const uint32_t tf = flat.rows ? min(*flat.rows, n_requested) : 0u;
+    const uint32_t tr = min(*rest.rows, n_requested - tf);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        plan[0] = tf;
+        plan[1] = tr;
+        plan[2] = tf + tr;
+        *chunk_counter = 0;
+    }
+    const uint32_t shift = tf & 1u;
+    const uint32_t nflat = tf ? (tf + chunk_rows - 1) / chunk_rows : 0u;
+    const uint32_t nrest = tr ? (tr + shift + chunk_rows - 1) / chunk_rows : 0u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nflat + nrest; i += gridDim.x * blockDim.x) {
+        const bool is_rest = i >= nflat;
+        const SegTable &l = is_rest ? rest : flat;
+        const uint32_t t = is_rest ? i - nflat : i, sh = is_rest ? shift : 0u;
+        const uint32_t r0 = max(t * chunk_rows, sh) - sh;
+        uint32_t lo = 0, hi = *l.nnz;                              // coff[nnz] = rows of the run > r0
         while (lo < hi) {                                          // first j with coff[j] > r0
             const uint32_t mid = lo + ((hi - lo) >> 1);
-            if (__ldg(coff + mid) > r0) hi = mid; else lo = mid + 1;
+            if (__ldg(l.coff + mid) > r0) hi = mid; else lo = mid + 1;
         }
-        chunk_start[t] = lo - 1;
+        l.chunk_start[t] = lo - 1;
     }
 }
 
@@ -1039,16 +1045,12 @@ static int plan_rows(const Cells &src, const double *cdf, uint64_t ncells, uint6
                                                    s.counts_rest);
     if (split) scan_list(s.counts_flat, (uint32_t)ncells, range, 1, 0, s.flat, st);
     scan_list(s.counts_rest, (uint32_t)ncells, range, split ? 2 : 1, split ? 1 : 0, s.rest, st);
-    plan_totals_kernel<<<1, 1, 0, st>>>(split ? s.flat.rows : nullptr, s.rest.rows, (uint32_t)N, s.plan,
-                                        s.chunk_counter);
     const uint32_t chunk_rows = emit_chunk_rows(N);
-    const uint32_t nchunks = (uint32_t)((N + chunk_rows - 1) / chunk_rows);
+    const uint32_t nchunks = (uint32_t)((N + chunk_rows - 1) / chunk_rows) + 2;
     const int sblocks = (int)std::max(1u, std::min((nchunks + 255) / 256, 148u * 8));
-    if (split)
-        chunk_start_kernel<<<sblocks, 256, 0, st>>>(s.flat.coff, s.flat.nnz, s.plan + 0, nullptr, chunk_rows,
-                                                    s.flat.chunk_start);
-    chunk_start_kernel<<<sblocks, 256, 0, st>>>(s.rest.coff, s.rest.nnz, s.plan + 1, s.plan + 0, chunk_rows,
-                                                s.rest.chunk_start);
+    const SegTable tf{s.flat.coff, s.flat.nnz, split ? s.flat.rows : nullptr, s.flat.chunk_start};
+    const SegTable tr{s.rest.coff, s.rest.nnz, s.rest.rows, s.rest.chunk_start};
+    plan_chunks_kernel<<<sblocks, 256, 0, st>>>(tf, tr, (uint32_t)N, chunk_rows, s.plan, s.chunk_counter);
     return check_launch("cell-major row planning");
 }
 

@@ -77,6 +77,20 @@ COST_NS_ROW_SPLIT, COST_NS_ROW_SMALL, COST_NS_CELL = 2.2, 6.4, 0.04
 SPLIT_MIN_LAMBDA = 128.0          # csrc/lint_cellmajor_plan.h
 
 
+def _group_end_values(grid):
+    """CDF value at the end of every group of the grid's build (host array): the places where a
+    stratum can be cut without a straddling cell."""
+    import ctypes as C
+    import torch
+    from . import _capi
+    ncells = int(grid.ncells)
+    gc = int(_capi.load().lint_grid_group_cells(C.byref(grid._descriptor())))
+    idx = torch.arange(gc - 1, ncells, gc, device=grid.device)
+    if idx.numel() == 0 or int(idx[-1]) != ncells - 1:
+        idx = torch.cat([idx, torch.tensor([ncells - 1], device=grid.device)])
+    return grid._cdf[idx].cpu().numpy()
+
+
 def cost_balanced_strata(grid, world, n_rows):
     """Stratum boundaries that equalise the modelled cost of the ranks instead of their mass.
 
@@ -263,13 +277,62 @@ class ShardedGrid:
         return out, counts
 
     # -- reporting -------------------------------------------------------------
+    # -- calibration -----------------------------------------------------------
+    def calibrate(self, n_rows, seed=0, iters=3, fixed_ms=0.08):
+        """Re-cut the strata from MEASURED step times (multi-GPU, collective).  The analytic cost
+        model of ``cost_balanced_strata`` misjudges the ranks that own the tails of the density
+        (their rows are dearer than the model's average).  Every iteration each rank times its
+        own step (build of its slab + its share of ``n_rows`` grouped rows) with CUDA events, the
+        times are all-gathered, the cost per unit of CDF mass is taken as constant inside each
+        current stratum and the cuts are moved to equalise it, snapped to group boundaries of the
+        build.  ``fixed_ms``: the part of a step that does not shrink with the stratum.  All ranks
+        compute the same cuts from the same gathered numbers."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1 or not _collectives_available() or self.grid.cdf_mode != "parallel":
+            return self.bounds
+        ends = _group_end_values(self.grid)
+        for it in range(iters):
+            widths = np.diff(self.bounds)
+            counts = split_counts(n_rows, widths, seed + it)
+            n = int(counts[self.rank])
+            out = torch.empty((max(n, 1), self.grid.dim), dtype=_device.torch_dtype(self.grid.dtype),
+                              device=self.device)
+            best = float("inf")
+            for rep in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                self.enqueue_build(gather=False)
+                self.sample_cellmajor_into(out[:n], seed=seed, offset=int(counts[:self.rank].sum()))
+                b.record()
+                torch.cuda.synchronize(self.device)
+                if rep:
+                    best = min(best, a.elapsed_time(b))
+            times = torch.tensor([best], dtype=torch.float64, device=self.device)
+            gathered = torch.empty(self.world, dtype=torch.float64, device=self.device)
+            dist.all_gather_into_tensor(gathered, times, group=self.group)
+            t = np.maximum(gathered.cpu().numpy() - fixed_ms, 1e-3)
+            # piecewise-constant cost density t_r / width_r: cumulative cost at the current cuts
+            cum = np.concatenate([[0.0], np.cumsum(t)])
+            targets = cum[-1] * np.arange(1, self.world) / self.world
+            cuts = np.interp(targets, cum, self.bounds)                    # new cuts in u
+            snapped = ends[np.clip(np.searchsorted(ends, cuts), 0, len(ends) - 1)]
+            new = np.concatenate([[0.0], snapped, [1.0]])
+            if np.any(np.diff(new) <= 0):
+                break
+            self.bounds = new
+            self.balanced = True
+            self.enqueue_build(gather=False)
+        torch.cuda.synchronize(self.device)
+        return self.bounds
+
     def launches_per_step(self, order="draw"):
-        """Kernels of this library launched by enqueue_build + one sampling call: fused build 2
-        (tile totals, apply), guide 1, cell records 0/1; then the u-driven sampler (1) or the
-        grouped path (Poisson counts, 2 x scan+compact, row budget, 2 x chunk starts, flat
-        boxes, flat emitter, general emitter, top-up = 10)."""
-        build = 3 + (1 if self.grid._rec is not None else 0)
-        return build + (10 if order == "cell" else 1)
+        """Kernels of this library launched by enqueue_build + one sampling call: build 4 (vertex
+        row sums, group totals, group scan, guide), cell records 0/1; then the u-driven sampler
+        (1) or the grouped path (Poisson counts, 2 x scan+compact, row budget + chunk starts, flat
+        boxes, flat emitter, general emitter, top-up = 8)."""
+        build = 4 + (1 if self.grid._rec is not None else 0)
+        return build + (8 if order == "cell" else 1)
 
     def describe(self):
         if self.world == 1:
