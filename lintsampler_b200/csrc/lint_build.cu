@@ -892,6 +892,38 @@ static GroupPlan make_group_plan(const lint_grid_t *g, uint64_t ncells, double u
     return p;
 }
 
+// Small guide tables (far fewer bins than cells of the slab): one thread per bin searches the
+// slab for the first cell with cdf > j / G instead of every cell looking for the bins it owns.
+// Same table, same flags; only bins whose answer lies in the slab [c0, c1) are written.
+__global__ void __launch_bounds__(256)
+guide_search_kernel(const double *__restrict__ cdf, uint32_t n, int bits, uint32_t *guide,
+                    const uint32_t *__restrict__ range) {
+    const uint32_t Gi = 1u << bits;
+    const double G = (double)Gi;
+    const uint32_t c0 = range ? range[0] : 0u, c1 = range ? range[1] : n;
+    // bins a slab cell can own: ceil(cdf[c0 - 1] G) <= j < ceil(cdf[c1 - 1] G)  (the last cell of the
+    // table also owns j = G)
+    const double before = c0 > 0 ? __ldg(cdf + c0 - 1) : 0.0, last = __ldg(cdf + c1 - 1);
+    const uint32_t j_lo = (uint32_t)fmin(ceil(before * G), G);
+    const uint32_t j_hi = c1 == n ? Gi : (uint32_t)fmin(ceil(last * G), G);           // inclusive, generous
+    for (uint32_t j = j_lo + blockIdx.x * blockDim.x + threadIdx.x; j <= j_hi; j += gridDim.x * blockDim.x) {
+        const double u = (double)j / G;
+        uint32_t lo = c0, hi = c1;                               // first i in [c0, c1) with cdf[i] > j / G, or c1
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (__ldg(cdf + mid) > u) hi = mid; else lo = mid + 1;
+        }
+        uint32_t i = lo;
+        if (i >= c1) {
+            if (c1 != n) continue;                               // the owner lies beyond the slab: not ours
+            i = n - 1;                                           // j = G: the last cell
+        }
+        // flagged when the next bin has the same owner: the whole bin lies inside cell i
+        const bool same = i == n - 1 ? j < Gi : __ldg(cdf + i) > (double)(j + 1) / G;
+        guide[j] = same ? (i | GUIDE_SAME) : i;
+    }
+}
+
 template <int K>
 int group_build_impl(const lint_grid_t *g, uint64_t ncells, double u_lo, double u_hi, double *cdf, double *total,
                      uint32_t *guide, int guide_bits, double *masses, uint32_t *flags, uint32_t *range,
@@ -918,7 +950,10 @@ int group_build_impl(const lint_grid_t *g, uint64_t ncells, double u_lo, double 
                                                                 masses);
     };
     if (g->dtype == LINT_F32) run(float{}); else run(double{});
-    if (guide_bits > 0) {
+    if (guide_bits > 0 && (1ull << guide_bits) * 16 <= ncells) {
+        const int gblocks = (int)std::min<uint64_t>(((1ull << guide_bits) + 256) / 256, 148 * 8);
+        guide_search_kernel<<<gblocks, 256, 0, st>>>(cdf, (uint32_t)ncells, guide_bits, guide, range);
+    } else if (guide_bits > 0) {
         const uint64_t nwarps = (ncells + 31) / 32;
         const int gblocks = (int)std::min<uint64_t>((nwarps + 7) / 8, 148 * 16);
         guide_build_kernel<<<gblocks, 256, 0, st>>>(cdf, (uint32_t)ncells, guide_bits, guide, range);

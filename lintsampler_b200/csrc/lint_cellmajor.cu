@@ -1,5 +1,6 @@
 // C ABI of the cell-major ("grouped") sampling path.  The kernels live in
 // lint_cellmajor.cuh and are compiled per dimension by lint_cellmajor_inst.cu.
+#include <cstdlib>
 #include "lint_device.cuh"
 #include "lint_cellmajor_plan.h"
 
@@ -10,6 +11,22 @@ int validate_grid(const lint_grid_t *g, bool need_cdf, uint64_t *ncells_out, uin
 EmitTimers &emit_timers() {
     static EmitTimers t;
     return t;
+}
+
+Lanes *side_lanes() {
+    static Lanes table[64];
+    static const bool off = [] { const char *v = getenv("LINT_SIDE"); return v && *v == '0'; }();
+    if (off || emit_timers().enabled) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    Lanes &l = table[dev];
+    if (!l.side[0]) {
+        for (auto &s : l.side)
+            if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (auto &e : l.ev)
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    return &l;
 }
 
 static int check_common(int64_t N, uint64_t ncells, double u_lo, double u_hi, void *out, void *scratch,
@@ -92,9 +109,20 @@ int lint_grid_sample_cellmajor(const lint_grid_t *g, int64_t N, uint64_t seed, u
         default: rc = grid_cellmajor_k<6>(g, nc, N, key, offset, u, cell_range_dev, s, out_dev, cell_idx_dev, st); break;
     }
     if (rc) return rc;
-    // rows [T, N): the u-driven sampler on the same stratum
-    return topup_grid(g, N, s.plan + 2, (int64_t)topup_bound((uint64_t)N), seed, offset, u_lo, u_hi, out_dev,
-                      cell_idx_dev, st);
+    // rows [T, N): the u-driven sampler on the same stratum, beside the emitters
+    Lanes *L = side_lanes();
+    cudaStream_t st_top = st;
+    if (L) {
+        cudaStreamWaitEvent(L->side[1], L->ev[4], 0);           // the row budget is known (grid_cellmajor_k)
+        st_top = L->side[1];
+    }
+    rc = topup_grid(g, N, s.plan + 2, (int64_t)topup_bound((uint64_t)N), seed, offset, u_lo, u_hi, out_dev,
+                    cell_idx_dev, st_top);
+    if (L) {
+        cudaEventRecord(L->ev[5], st_top);
+        cudaStreamWaitEvent(st, L->ev[5], 0);
+    }
+    return rc;
 }
 
 int lint_cells_sample_cellmajor(const lint_cells_t *c, int64_t N, uint64_t seed, uint64_t offset,
@@ -120,8 +148,19 @@ int lint_cells_sample_cellmajor(const lint_cells_t *c, int64_t N, uint64_t seed,
         default: rc = cells_cellmajor_k<6>(c, N, key, offset, u, s, out_dev, cell_idx_dev, st); break;
     }
     if (rc) return rc;
-    return topup_cells(c, N, s.plan + 2, (int64_t)topup_bound((uint64_t)N), seed, offset, u_lo, u_hi, out_dev,
-                       cell_idx_dev, st);
+    Lanes *L = side_lanes();
+    cudaStream_t st_top = st;
+    if (L) {
+        cudaStreamWaitEvent(L->side[1], L->ev[4], 0);
+        st_top = L->side[1];
+    }
+    rc = topup_cells(c, N, s.plan + 2, (int64_t)topup_bound((uint64_t)N), seed, offset, u_lo, u_hi, out_dev,
+                     cell_idx_dev, st_top);
+    if (L) {
+        cudaEventRecord(L->ev[5], st_top);
+        cudaStreamWaitEvent(st, L->ev[5], 0);
+    }
+    return rc;
 }
 
 }  // extern "C"

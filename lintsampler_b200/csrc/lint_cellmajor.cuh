@@ -1043,14 +1043,24 @@ static int plan_rows(const Cells &src, const double *cdf, uint64_t ncells, uint6
     cudaMemsetAsync(s.zero_begin, 0, s.zero_bytes, st);
     poisson_counts_kernel<<<cblocks, POISSON_THREADS, 0, st>>>(src, t, lam_per_unit, key, StreamPos{offset, offset_counter()}, split, range, s.counts_flat,
                                                    s.counts_rest);
-    if (split) scan_list(s.counts_flat, (uint32_t)ncells, range, 1, 0, s.flat, st);
+    Lanes *L = split ? side_lanes() : nullptr;
+    if (L) {                                                   // the two scans side by side
+        cudaEventRecord(L->ev[0], st);
+        cudaStreamWaitEvent(L->side[0], L->ev[0], 0);
+        scan_list(s.counts_flat, (uint32_t)ncells, range, 1, 0, s.flat, L->side[0]);
+        cudaEventRecord(L->ev[1], L->side[0]);
+    } else if (split) {
+        scan_list(s.counts_flat, (uint32_t)ncells, range, 1, 0, s.flat, st);
+    }
     scan_list(s.counts_rest, (uint32_t)ncells, range, split ? 2 : 1, split ? 1 : 0, s.rest, st);
+    if (L) cudaStreamWaitEvent(st, L->ev[1], 0);
     const uint32_t chunk_rows = emit_chunk_rows(N);
     const uint32_t nchunks = (uint32_t)((N + chunk_rows - 1) / chunk_rows) + 2;
     const int sblocks = (int)std::max(1u, std::min((nchunks + 255) / 256, 148u * 8));
     const SegTable tf{s.flat.coff, s.flat.nnz, split ? s.flat.rows : nullptr, s.flat.chunk_start};
     const SegTable tr{s.rest.coff, s.rest.nnz, s.rest.rows, s.rest.chunk_start};
     plan_chunks_kernel<<<sblocks, 256, 0, st>>>(tf, tr, (uint32_t)N, chunk_rows, s.plan, s.chunk_counter);
+    if (Lanes *L2 = side_lanes()) cudaEventRecord(L2->ev[4], st);       // the row budget is known: the top-up may start
     return check_launch("cell-major row planning");
 }
 
@@ -1078,6 +1088,13 @@ int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t 
         tm.plan_dev = s.plan;
         cudaEventRecord(tm.ev[0], st);
     }
+    Lanes *L = split ? side_lanes() : nullptr;                 // the flat emitter beside the general one
+    cudaStream_t st_main = st;
+    if (L) {
+        cudaEventRecord(L->ev[2], st);
+        cudaStreamWaitEvent(L->side[0], L->ev[2], 0);
+        st = L->side[0];
+    }
     if (split) {
         const uint32_t fper = FLAT_THREADS / 32;
         const int fblocks = (int)std::min<uint32_t>((nchunks + fper - 1) / fper,
@@ -1095,6 +1112,10 @@ int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t 
                 philox_round_keys(key), StreamPos{offset, offset_counter()}, (T *)out, cell_idx);
         if (int rc = check_launch("cell-major flat emission")) return rc;
     }
+    if (L) {
+        cudaEventRecord(L->ev[3], st);
+        st = st_main;
+    }
     if (tm.enabled) {
         cudaEventRecord(tm.ev[1], st);
         cudaEventRecord(tm.ev[2], st);
@@ -1111,6 +1132,7 @@ int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t 
             src, s.rest.cid, s.rest.coff, s.rest.nnz, s.plan, s.rest.chunk_start, chunk_rows,
             philox_round_keys(key), StreamPos{offset, offset_counter()}, split ? 1u : 0u, t, lam_per_unit, (T *)out, cell_idx);
     if (tm.enabled) cudaEventRecord(tm.ev[3], st);
+    if (L) cudaStreamWaitEvent(st, L->ev[3], 0);
     return check_launch("cell-major emission");
 }
 

@@ -101,6 +101,18 @@ struct EmitTimers {
 };
 EmitTimers &emit_timers();
 
+// Side streams of a draw (one set per device, created on first use; lint_cellmajor.cu).  The
+// pieces of a draw that do not depend on one another are enqueued side by side — the two
+// scans, the flat emitter next to the general one, the top-up next to both — joined by events,
+// so the call is still complete, in stream order, on the caller's stream (and a CUDA graph
+// captured from it holds the same fork / join structure).  NULL: everything on the caller's
+// stream (LINT_SIDE=0, or while lint_cellmajor_timing is on).
+struct Lanes {
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+Lanes *side_lanes();
+
 // per-dimension entry points, instantiated in lint_cellmajor_inst.cu
 template <int K>
 int grid_cellmajor_k(const lint_grid_t *g, uint64_t nc, uint64_t N, uint2 key, uint64_t offset, Stratum u,

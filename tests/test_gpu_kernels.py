@@ -412,6 +412,39 @@ def test_hierarchical_grid_build(lb, name, dtype):
             part._sample_philox(10, 5, 0, stratum=(0.0, 1.0))
 
 
+@pytest.mark.parametrize("name", ["g2d_fullcov", "g3d_iso", "g3d_holes", "g4d_iso"])
+@pytest.mark.parametrize("bits", [1, 3, 5])
+def test_small_guide_tables_by_bin_search_equal_the_cell_walk(lb, name, bits):
+    """A guide table with far fewer bins than cells is built by one binary search per bin
+    (lint_grid_build); it must be the very table the cell-walking lint_guide_build writes, on the
+    whole domain and, restricted to a stratum, on every bin a cell of the slab owns."""
+    import torch
+    from lintsampler_b200 import _capi, _device
+    g = load_golden(name)
+    grid = _grid_from_golden(lb, g, guide_bits=bits)
+    n = int(grid.ncells)
+    if (1 << bits) * 16 > n:
+        pytest.skip("this grid is too small for the bin-search path at this table size")
+    walk = torch.empty_like(grid._guide)
+    _capi.call("lint_guide_build", _device.ptr(grid._cdf), n, bits, _device.ptr(walk), _device.stream_ptr(grid.device))
+    assert torch.equal(walk, grid._guide)
+    cdf = grid._cdf.cpu().numpy()
+    part = _grid_from_golden(lb, g, guide_bits=bits)
+    part._guide.fill_(-7)
+    part._enqueue_build(stratum=(0.3, 0.6))
+    c0, c1 = part._range.tolist()[:2]
+    got, ref = part._guide.cpu().numpy(), walk.cpu().numpy()
+    owner = ref & 0x7fffffff
+    mine = (owner >= c0) & (owner < c1)
+    assert mine.any() and np.array_equal(got[mine], ref[mine]) and np.all(got[~mine] == -7)
+    # and the u-driven sampler finds the same cells through either table
+    u = np.random.default_rng(1).random((4000, len(grid.shape) + 1))
+    u[:, -1] = 0.3 + 0.3 * u[:, -1]
+    _, a = grid._sample_u(torch.as_tensor(u, device="cuda"), want_cells=True)
+    _, b = part._sample_u(torch.as_tensor(u, device="cuda"), want_cells=True)
+    assert torch.equal(a, b) and np.array_equal(a.cpu().numpy(), np.searchsorted(cdf, u[:, -1], side="right"))
+
+
 # ----------------------------------------------------------------------------- cell-major throughput mode
 def grouped_runs(cells, N):
     """Row layout of a cell-major draw: rows [0, T_f) flat parts grouped by cell, rows [T_f, T)
