@@ -47,6 +47,16 @@
 #include "lint_device.cuh"
 #include "lint_cellmajor_plan.h"
 
+// Checked build (-DLINT_CHECKED; scripts/checked_build.sh): every index the emitters and the scan
+// compute is asserted against its bounds on the device.  compute-sanitizer is closed on the GPU
+// pool this was developed on, so the cell-major tests are run once against this build instead.
+#ifdef LINT_CHECKED
+#include <cassert>
+#define LINT_CHECK(cond) assert(cond)
+#else
+#define LINT_CHECK(cond) ((void)0)
+#endif
+
 namespace lint {
 
 int validate_grid(const lint_grid_t *g, bool need_cdf, uint64_t *ncells_out, uint64_t *nverts_out);
@@ -310,6 +320,7 @@ scan_compact_kernel(const uint32_t *counts, uint32_t ncells_all, const uint32_t 
     for (int i = 0; i < SCAN_ITEMS; ++i) {
         if (c[i] != 0) {
             const uint32_t slot = (uint32_t)(pre >> 32);
+            LINT_CHECK(slot < ncells && base + i < ncells);
             cid[slot] = (base + i) * id_mul + id_add;
             coff[slot] = (uint32_t)pre;
         }
@@ -686,6 +697,7 @@ emit_flat_kernel(const T *__restrict__ boxes, const uint32_t *__restrict__ cid, 
                         const int t = (32 * VEC * jj + i) % K;
                         x[i] = affine_w(rlo[t], rw[t], u[jj][i]);
                     }
+                    LINT_CHECK((vl + 32u * jj + 1) * VEC <= (uint64_t)N * K && held == j && j < nnz);
                     FT::store(p + (size_t)32 * VEC * jj, x);
                 }
                 if (seg_end == R + STEP_ROWS) ++j;
@@ -705,6 +717,7 @@ emit_flat_kernel(const T *__restrict__ boxes, const uint32_t *__restrict__ cid, 
                         const T xa = affine_w(rlo[t], rw[t], u[jj][i]), xb = affine_w(blo[t], bw[t], u[jj][i]);
                         x[i] = VEC * (lane + 32u * jj) + i >= eb ? xb : xa;
                     }
+                    LINT_CHECK((vl + 32u * jj + 1) * VEC <= (uint64_t)N * K && j + 1 < nnz && eb > 0 && eb < STEP_ELEMS);
                     FT::store(p + (size_t)32 * VEC * jj, x);
                 }
 #pragma unroll
@@ -741,6 +754,7 @@ emit_flat_kernel(const T *__restrict__ boxes, const uint32_t *__restrict__ cid, 
                         for (int i = 0; i < VEC; ++i) {
                             const int t = (32 * VEC * jj + i) % K;
                             const uint32_t e = VEC * (lane + 32u * jj) + i;
+                            LINT_CHECK(!(e >= done && e < upto) || (sidx[i] >= first && sidx[i] < first + ns && sidx[i] < 31));
                             if (e >= done && e < upto)
                                 u[jj][i] = affine_w(s_box[sidx[i] * SLOT + dsel[t]], s_box[sidx[i] * SLOT + K + dsel[t]],
                                                     u[jj][i]);
@@ -764,6 +778,7 @@ emit_flat_kernel(const T *__restrict__ boxes, const uint32_t *__restrict__ cid, 
 #pragma unroll
                 for (int jj = 0; jj < J; ++jj) {
                     const uint32_t e0 = VEC * (lane + 32u * jj);
+                    LINT_CHECK(lim <= STEP_ELEMS && (uint64_t)R * K + lim <= (uint64_t)N * K && done >= lim);
                     if (e0 + VEC <= lim) {
                         FT::store(p + (size_t)32 * VEC * jj, u[jj]);
                     } else {
@@ -933,6 +948,8 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
         };
         // one row of segment sg: constants (staged, or fetched), in-cell draw, affine map
         auto draw_row = [&](uint32_t sg, bool staged, const T (&u)[K], T (&x)[K], uint32_t &cell) {
+            LINT_CHECK(sg >= jbase && sg - jbase < (uint32_t)EMIT_WIN && sg < nnz);
+            LINT_CHECK(!(PRE && staged) || (sg >= cbase && sg - cbase < EMIT_PRE));
             const uint32_t v = s_cid[sg - jbase];
             cell = v >> split;
             T xlo[K], xw[K], z[K];
@@ -998,6 +1015,8 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
                 draw_row(va ? sa : sb, staged, ua, xa, ca);
                 draw_row(vb ? sb : sa, staged, ub, xb, cb);
                 T *p = out + (size_t)ra * K;
+                LINT_CHECK(sa >= j && sb <= j + nstart && (!va || (off(sa) <= ra && ra < off(sa + 1))) &&
+                           (!vb || (off(sb) <= ra + 1 && ra + 1 < off(sb + 1))));
                 if (va && vb) {
                     T e[2 * K];
 #pragma unroll
