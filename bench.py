@@ -351,10 +351,38 @@ def run_b200(args):
         shard = shard_main
 
     _capi.call("lint_set_offset_counter", None)
+    # ---- the same workload in the reference's own precision (fp64 densities and samples), 3 steps
+    f64_line = None
+    if world == 1 and not args.no_other:
+        out = None
+        torch.cuda.empty_cache()
+        g64 = lb.DensityGrid(edges, gmm, vectorizedpdf=True, dtype=np.float64, device=dev, cell_records=False,
+                             guide_bits=16)
+        out64 = torch.empty((n_total, DIM), dtype=torch.float64, device=dev)
+        for i in range(2):
+            g64._enqueue_build()
+            g64._sample_cellmajor(n_total, SEED, i * n_total, out=out64)
+        barrier()
+        o_beg, o_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o_beg.record(stream)
+        for i in range(3):
+            g64._enqueue_build()
+            g64._sample_cellmajor(n_total, SEED, (2 + i) * n_total, out=out64)
+        o_end.record(stream)
+        barrier()
+        ms64 = o_beg.elapsed_time(o_end) / 3
+        bm, bs, bo = algorithmic_bytes(n_total, 8, 8)
+        f64_line = {"dtype": "f64", "value": n_total / (ms64 * 1e-3), "ms_per_step": ms64, "steps": 3,
+                    "step_frac_of_hbm_roofline": (bm + bs + bo) / (ms64 * 1e-3) / 1e9 /
+                    float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+                    if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None}
+        del g64, out64
+        torch.cuda.empty_cache()
+        out = None
     # ---- e2e: public API, host buffers in and out
     e2e = None
     if not args.no_e2e:
-        del out
+        out = None
         torch.cuda.empty_cache()
         e2e = run_e2e(args, lb, edges, gmm, dev, world, n_total)
 
@@ -417,6 +445,8 @@ def run_b200(args):
         }
         if other_line:
             line["other_order"] = other_line
+        if f64_line:
+            line["c3_f64"] = f64_line
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu:
@@ -473,6 +503,115 @@ def run_e2e(args, lb, edges, gmm, dev, world, n_total):
             "api": "DensityGrid.update_densities(pinned, check=True) + LintSampler.sample_to_host(N, out=pinned)"}
 
 
+# --------------------------------------------------------------------------- the other named configs
+def _gmm(lb, k, K, smin, smax, full=False):
+    """SURVEY.md 8(d) generators: all draws from default_rng(0) in this order."""
+    rng = np.random.default_rng(0)
+    means = rng.uniform(-2, 2, size=(K, k))
+    if full:
+        A = rng.uniform(-0.5, 0.5, size=(K, k, k))
+        covs = A @ np.swapaxes(A, 1, 2) + 0.05 * np.eye(k)
+        return lb.GaussianMixture(rng.dirichlet(np.ones(K)), means, covs=covs)
+    sig = rng.uniform(smin, smax, size=K)
+    return lb.GaussianMixture(rng.dirichlet(np.ones(K)), means, sigmas=sig)
+
+
+def run_config(args):
+    """`--config C2|C3f64|C4|C5`: the other configurations BASELINE.json names, one
+    GPU, the same JSON shape.  A step = build of the tables (grids) + the N-row draw through the
+    same entry points the headline uses; `roofline` is the step against its algorithmic bytes."""
+    import warnings
+    import torch
+    import lintsampler_b200 as lb
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    name = args.config.upper()
+    dtype, qmc, tree = np.float32, False, None
+    if name == "C2":
+        edges = tuple(np.linspace(-4, 4, 1025) for _ in range(2))
+        pdf, N = _gmm(lb, 2, 4, 0, 0, full=True), 100_000_000
+        what = "C2: 2-D DensityGrid 1024^2, K=4 full-covariance GMM, N=1e8, fp32"
+    elif name == "C3F64":
+        edges, w, means, sig = synthetic_c3()
+        pdf, N, dtype = lb.GaussianMixture(w, means, sigmas=sig), 1_000_000_000, np.float64
+        what = "C3 in the reference's precision: 3-D DensityGrid 256^3, N=1e9, fp64 densities and samples"
+    elif name == "C4":
+        edges = tuple(np.linspace(-4, 4, 33) for _ in range(5))
+        pdf, N, qmc = _gmm(lb, 5, 4, 0.5, 0.9), 100_000_000, True
+        what = ("C4: 5-D DensityGrid 32^5 (32 corners per cell), N=1e8, qmc=True: device Sobol points "
+                "bit-identical to scipy's Sobol(d=6, bits=32, seed=1), rows permuted on the device")
+    elif name == "C5":
+        pdf, N = _gmm(lb, 3, 8, 0.02, 0.2), 100_000_000
+        t0 = time.perf_counter()
+        tree = lb.DensityTree([-4.0] * 3, [4.0] * 3, pdf, vectorizedpdf=True, min_openings=4, dtype=np.float32)
+        tree.refine(1e-3, leaf_tol=1e-3)
+        tree_s = time.perf_counter() - t0
+        what = ("C5: 3-D DensityTree, K=8 sharp GMM, min_openings=4, refine(1e-3, leaf_tol=1e-3): %d leaves "
+                "(built on the host in %.2f s, outside the timed region), N=1e8, fp32" % (len(tree.leaves), tree_s))
+    else:
+        raise SystemExit(f"unknown --config {args.config}")
+    isz = np.dtype(dtype).itemsize
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    if tree is None:
+        kw = {} if qmc else dict(cell_records=False, guide_bits=16)
+        grid = lb.DensityGrid(edges, pdf, vectorizedpdf=True, dtype=dtype, device=dev, **kw)
+        k, C_, V_ = grid.dim, int(grid.ncells), int(np.prod([len(e) for e in edges]))
+        alg = V_ * isz + C_ * 8 + 2 * C_ * 8 + N * k * isz
+    else:
+        tree._ensure_device()
+        k = 3
+        alg = N * k * isz + len(tree.leaves) * (8 + 2 * 3) * isz
+    out = None if qmc else torch.empty((N, k), dtype=tdt, device=dev)
+    sampler = None
+    if qmc:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sampler = lb.LintSampler(grid, seed=SEED, qmc=True, return_tensor=True)
+
+    def step(i):
+        if tree is not None:
+            tree._sample_cellmajor(N, SEED, i * N, out=out)
+        elif qmc:
+            grid._enqueue_build()
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")                 # scipy's non-power-of-two warning
+                sampler.sample(N)
+        else:
+            grid._enqueue_build()
+            grid._sample_cellmajor(N, SEED, i * N, out=out)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clocks:
+        a.record()
+        for i in range(args.steps):
+            step(args.warmup + i)
+        b.record()
+        torch.cuda.synchronize(dev)
+    ms = a.elapsed_time(b) / args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg / (ms * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": "samples/s", "value": N / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32" if dtype == np.float32 else "f64", "data": "synthetic",
+        "config": {"workload": what, "samples_total": N,
+                   "order": "scipy-identical Sobol point set, device row permutation" if qmc else
+                            "rows grouped by cell (order=\"cell\")"},
+        "roofline": {"bound": "hbm", "kernel": "whole step (tables + draw)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "algorithmic_bytes_per_step": alg, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650"},
+        "clocks": clocks.summary(),
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -482,6 +621,7 @@ def main():
     ap.add_argument("--samples", type=int, default=N_SAMPLES,
                     help="samples per step in total (strong scaling); with --weak: per GPU")
     ap.add_argument("--weak", action="store_true", help="weak scaling: --samples rows per GPU per step")
+    ap.add_argument("--config", default=None, help="one of the other named configs: C2, C3f64, C4, C5 (one GPU)")
     ap.add_argument("--order", default="cell", choices=["cell", "draw"],
                     help="cell: rows grouped by cell (throughput mode); draw: u-driven per-sample search")
     ap.add_argument("--no-e2e", action="store_true")
@@ -502,6 +642,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.config:
+        run_config(args)
     else:
         run_b200(args)
 

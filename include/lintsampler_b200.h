@@ -297,6 +297,29 @@ int lint_cells_sample_sobol(const lint_cells_t *c, int64_t N, const lint_sobol_t
 int lint_sobol_uniforms(int dim, int64_t N, const lint_sobol_t *sobol, double *u_dev,
                         lint_stream_t stream);
 
+/* ---- sampling: a list of grids as one domain, one launch ------------------------------ */
+
+/* == the list-of-domains branch of LintSampler.sample [lintsampler.py:281-307] for grids of one
+ * dimension and dtype: per row, the cell-selecting uniform picks the grid (`_choice` on the
+ * normalised cumulative grid masses, :286-290 — choice_cdf[i] = c[i] / c[-1], c = p.cumsum()), is
+ * rescaled into that grid's interval exactly as :306 does, (u - bounds[i]) / (bounds[i+1] - bounds[i])
+ * with bounds = np.append(0, p.cumsum()) (:293-297), and then selects the cell and the in-cell
+ * position as lint_grid_sample_*.  `grids`, `choice_cdf` (ndomains), `bounds` (ndomains + 1) are HOST
+ * arrays; 1 <= ndomains <= 16.  Rows come out in the order of the uniforms (draw order), not
+ * grouped by grid as the reference's vstack leaves them: cell_idx_dev numbers the cells through
+ * the concatenation of the grids, so the caller can regroup (a stable partition by grid
+ * reproduces the reference's row order exactly).  scratch_dev: lint_multi_scratch_bytes. */
+size_t lint_multi_scratch_bytes(int dim, int ndomains);
+int lint_multi_grid_sample_u(const lint_grid_t *grids, int ndomains, const double *choice_cdf, const double *bounds,
+                             const double *u_dev, int64_t N, void *scratch_dev, size_t scratch_bytes, void *out_dev,
+                             int64_t *cell_idx_dev, lint_stream_t stream);
+int lint_multi_grid_sample_philox(const lint_grid_t *grids, int ndomains, const double *choice_cdf,
+                                  const double *bounds, int64_t N, uint64_t seed, uint64_t offset, void *scratch_dev,
+                                  size_t scratch_bytes, void *out_dev, int64_t *cell_idx_dev, lint_stream_t stream);
+int lint_multi_grid_sample_sobol(const lint_grid_t *grids, int ndomains, const double *choice_cdf,
+                                 const double *bounds, int64_t N, const lint_sobol_t *sobol, void *scratch_dev,
+                                 size_t scratch_bytes, void *out_dev, int64_t *cell_idx_dev, lint_stream_t stream);
+
 /* ---- sampling: cell-major throughput mode ----------------------------------------- */
 
 /* N i.i.d. draws as a multiset, emitted grouped by cell (C order of the flat cell

@@ -110,6 +110,14 @@ PROTOTYPES = {
     "lint_grid_sample_sobol": (C.c_int, [C.POINTER(LintGrid), _I64, C.POINTER(LintSobol), _P, _P, _P]),
     "lint_cells_sample_sobol": (C.c_int, [C.POINTER(LintCells), _I64, C.POINTER(LintSobol), _P, _P, _P]),
     "lint_sobol_uniforms": (C.c_int, [C.c_int, _I64, C.POINTER(LintSobol), _P, _P]),
+    "lint_multi_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "lint_multi_grid_sample_u": (C.c_int, [C.POINTER(LintGrid), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                           _P, _I64, _P, C.c_size_t, _P, _P, _P]),
+    "lint_multi_grid_sample_philox": (C.c_int, [C.POINTER(LintGrid), C.c_int, C.POINTER(C.c_double),
+                                                C.POINTER(C.c_double), _I64, _U64, _U64, _P, C.c_size_t, _P, _P, _P]),
+    "lint_multi_grid_sample_sobol": (C.c_int, [C.POINTER(LintGrid), C.c_int, C.POINTER(C.c_double),
+                                               C.POINTER(C.c_double), _I64, C.POINTER(LintSobol), _P, C.c_size_t, _P,
+                                               _P, _P]),
     "lint_permute_rows": (C.c_int, [_P, _P, _I64, C.c_int32, C.c_int32, _U64, _P]),
     "lint_cellmajor_scratch_bytes": (C.c_size_t, [_I64, _I64]),
     "lint_cellmajor_timing": (C.c_int, [C.c_int]),

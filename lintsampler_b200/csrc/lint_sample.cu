@@ -7,6 +7,8 @@
 #include <algorithm>
 #include "lint_device.cuh"
 
+extern "C" size_t lint_multi_scratch_bytes(int dim, int ndomains);
+
 namespace lint {
 
 int validate_grid(const lint_grid_t *g, bool need_cdf, uint64_t *ncells_out, uint64_t *nverts_out);
@@ -23,7 +25,7 @@ struct GridSource {
     template <typename T>
     __device__ __forceinline__ void prepare(T *smem) const { grid_stage_edges<K, T>(g, smem); }
     __device__ __forceinline__ bool prenormalised() const { return g.rec != nullptr; }
-    __device__ __forceinline__ void bracket(double u, uint32_t &lo, uint32_t &hi) const {
+    __device__ __forceinline__ void bracket(double &u, uint32_t &lo, uint32_t &hi) const {
         if (g.table.n == 1) { lo = hi = 0; return; }             // grid.py:427-428 shortcut
         guide_bracket(g.table, u, lo, hi);
     }
@@ -45,7 +47,7 @@ struct ListSource {
     template <typename T>
     __device__ __forceinline__ void prepare(T *) const {}
     __device__ __forceinline__ bool prenormalised() const { return s.rec != nullptr; }
-    __device__ __forceinline__ void bracket(double u, uint32_t &lo, uint32_t &hi) const {
+    __device__ __forceinline__ void bracket(double &u, uint32_t &lo, uint32_t &hi) const {
         guide_bracket(s.table, u, lo, hi);
     }
     __device__ __forceinline__ uint32_t resolve(double u, uint32_t lo, uint32_t hi) const {
@@ -55,6 +57,51 @@ struct ListSource {
     __device__ __forceinline__ void fetch(const T *, uint32_t idx, T (&c)[1 << K], T (&lo)[K],
                                           T (&hi)[K]) const {
         cells_fetch<K, DensT, T>(s, idx, c, lo, hi);
+    }
+};
+
+// A list of grids as ONE domain  [lintsampler.py:281-307]: the cell-selecting uniform first picks
+// the grid (`_choice` on the normalised cumulative grid masses, :286-290), is then rescaled into
+// that grid's interval exactly as the reference does, (u - start) / (end - start) (:306), and
+// finally picks the cell inside the grid.  Cells are numbered through the concatenation of the
+// grids (cell_off), which is also what cell_idx reports.
+constexpr int LINT_MULTI_MAX = 16;
+template <int K, typename DensT>
+struct MultiGridSource {
+    const GridView<K> *views;              // device table, one view per grid
+    int nd;
+    double choice_cdf[LINT_MULTI_MAX];     // c / c[-1], c = p.cumsum()          (utils.py:195-196)
+    double starts[LINT_MULTI_MAX], ends[LINT_MULTI_MAX];      // np.append(0, p.cumsum())   (:293-297)
+    uint32_t cell_off[LINT_MULTI_MAX + 1];
+    bool has_records;
+    __host__ size_t smem_bytes(size_t) const { return 0; }
+    __device__ __forceinline__ size_t smem_bytes_dev(size_t) const { return 0; }
+    template <typename T>
+    __device__ __forceinline__ void prepare(T *) const {}
+    __device__ __forceinline__ bool prenormalised() const { return has_records; }
+    __device__ __forceinline__ int domain_of(uint32_t cell) const {
+        int d = 0;
+        while (d + 1 < nd && cell >= cell_off[d + 1]) ++d;
+        return d;
+    }
+    __device__ __forceinline__ void bracket(double &u, uint32_t &lo, uint32_t &hi) const {
+        int d = 0;
+        while (d + 1 < nd && !(choice_cdf[d] > u)) ++d;           // searchsorted(side='right')
+        u = __ddiv_rn(__dsub_rn(u, starts[d]), __dsub_rn(ends[d], starts[d]));
+        const GridView<K> &g = views[d];
+        if (g.table.n == 1) { lo = hi = cell_off[d]; return; }
+        guide_bracket(g.table, u, lo, hi);
+        lo += cell_off[d];
+        hi += cell_off[d];
+    }
+    __device__ __forceinline__ uint32_t resolve(double u, uint32_t lo, uint32_t hi) const {
+        const int d = domain_of(lo);
+        return cell_off[d] + search_bracket(views[d].table, u, lo - cell_off[d], hi - cell_off[d]);
+    }
+    template <typename T>
+    __device__ __forceinline__ void fetch(const T *, uint32_t idx, T (&c)[1 << K], T (&lo)[K], T (&hi)[K]) const {
+        const int d = domain_of(idx);
+        grid_fetch<K, DensT, T>(views[d], (const T *)nullptr, idx - cell_off[d], c, lo, hi);
     }
 };
 
@@ -326,6 +373,74 @@ int uniforms_dispatch(int dim, int dtype, int64_t N, const Maker &mk, double *ou
     }
 }
 
+// list of grids: one launch
+template <int K, typename UnifMaker>
+int multi_dispatch_k(const lint_grid_t *grids, int nd, const double *choice_cdf, const double *bounds, int64_t N,
+                     void *views_dev, void *out, int64_t *cell_idx, cudaStream_t st, const UnifMaker &mk,
+                     const char *what) {
+    GridView<K> host_views[LINT_MULTI_MAX];
+    uint32_t off = 0;
+    bool all_rec = true;
+    uint32_t cell_off[LINT_MULTI_MAX + 1];
+    for (int d = 0; d < nd; ++d) {
+        uint64_t nc, nv;
+        if (int rc = validate_grid(&grids[d], true, &nc, &nv)) return rc;
+        if (grids[d].dim != K || grids[d].dtype != grids[0].dtype)
+            return fail(LINT_ERR_BAD_ARG, "%s: the grids of a list must share dimension and dtype", what);
+        host_views[d] = make_grid_view<K>(&grids[d], nc, false);
+        all_rec = all_rec && grids[d].cell_records_dev != nullptr;
+        cell_off[d] = off;
+        if ((uint64_t)off + nc >= (1ull << 31)) return fail(LINT_ERR_UNSUPPORTED, "%s: >= 2^31 cells in total", what);
+        off += (uint32_t)nc;
+    }
+    cell_off[nd] = off;
+    if (!all_rec)
+        for (int d = 0; d < nd; ++d) host_views[d].rec = nullptr;     // one convention for the whole list
+    if (cudaMemcpyAsync(views_dev, host_views, sizeof(GridView<K>) * nd, cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return fail(LINT_ERR_CUDA, "%s: copying the grid table failed", what);
+    auto fill = [&](auto &src) {
+        src.views = reinterpret_cast<const GridView<K> *>(views_dev);
+        src.nd = nd;
+        src.has_records = all_rec;
+        for (int d = 0; d < nd; ++d) {
+            src.choice_cdf[d] = choice_cdf[d];
+            src.starts[d] = bounds[d];
+            src.ends[d] = bounds[d + 1];
+        }
+        for (int d = 0; d <= nd; ++d) src.cell_off[d] = cell_off[d];
+    };
+    if (grids[0].dtype == LINT_F32) {
+        MultiGridSource<K, float> src;
+        fill(src);
+        return launch_sample<K, float>(src, mk.template make<K>(), N, out, cell_idx, st, what, RowWindow{});
+    }
+    MultiGridSource<K, double> src;
+    fill(src);
+    return launch_sample<K, double>(src, mk.template make<K>(), N, out, cell_idx, st, what, RowWindow{});
+}
+
+template <typename UnifMaker>
+int multi_dispatch(const lint_grid_t *grids, int nd, const double *choice_cdf, const double *bounds, int64_t N,
+                   void *views_dev, size_t views_bytes, void *out, int64_t *cell_idx, lint_stream_t stream,
+                   const UnifMaker &mk, const char *what) {
+    if (!grids || nd < 1 || nd > LINT_MULTI_MAX) return fail(LINT_ERR_BAD_ARG, "%s: 1..%d grids", what, LINT_MULTI_MAX);
+    if (!choice_cdf || !bounds) return fail(LINT_ERR_BAD_ARG, "%s: choice_cdf / bounds is NULL", what);
+    if (N < 0 || (N > 0 && !out)) return fail(LINT_ERR_BAD_ARG, "%s: bad N / out_dev", what);
+    if (N == 0) return LINT_OK;
+    if (!views_dev || views_bytes < lint_multi_scratch_bytes(grids[0].dim, nd))
+        return fail(LINT_ERR_BAD_ARG, "%s: scratch too small", what);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (grids[0].dim) {
+        case 1: return multi_dispatch_k<1>(grids, nd, choice_cdf, bounds, N, views_dev, out, cell_idx, st, mk, what);
+        case 2: return multi_dispatch_k<2>(grids, nd, choice_cdf, bounds, N, views_dev, out, cell_idx, st, mk, what);
+        case 3: return multi_dispatch_k<3>(grids, nd, choice_cdf, bounds, N, views_dev, out, cell_idx, st, mk, what);
+        case 4: return multi_dispatch_k<4>(grids, nd, choice_cdf, bounds, N, views_dev, out, cell_idx, st, mk, what);
+        case 5: return multi_dispatch_k<5>(grids, nd, choice_cdf, bounds, N, views_dev, out, cell_idx, st, mk, what);
+        case 6: return multi_dispatch_k<6>(grids, nd, choice_cdf, bounds, N, views_dev, out, cell_idx, st, mk, what);
+        default: return fail(LINT_ERR_BAD_ARG, "%s: dim outside 1..%d", what, LINT_MAX_DIM);
+    }
+}
+
 // packed leaf records (lint_cells_records)
 template <int K, typename DensT>
 __global__ void cells_records_kernel(CellsView s, uint32_t ncells, DensT *rec) {
@@ -385,6 +500,19 @@ int topup_cells(const lint_cells_t *c, int64_t N, const uint32_t *first_row_dev,
 using namespace lint;
 
 extern "C" {
+
+size_t lint_multi_scratch_bytes(int dim, int ndomains) {
+    if (ndomains < 1 || ndomains > LINT_MULTI_MAX) return 0;
+    switch (dim) {
+        case 1: return sizeof(GridView<1>) * ndomains;
+        case 2: return sizeof(GridView<2>) * ndomains;
+        case 3: return sizeof(GridView<3>) * ndomains;
+        case 4: return sizeof(GridView<4>) * ndomains;
+        case 5: return sizeof(GridView<5>) * ndomains;
+        case 6: return sizeof(GridView<6>) * ndomains;
+        default: return 0;
+    }
+}
 
 size_t lint_cells_record_bytes(int dim, int dtype) {
     switch (dim) {
@@ -492,6 +620,29 @@ int lint_sobol_uniforms(int dim, int64_t N, const lint_sobol_t *sobol, double *u
                         lint_stream_t stream) {
     if (int rc = check_sobol(sobol, N, "lint_sobol_uniforms")) return rc;
     return uniforms_dispatch(dim, LINT_F64, N, SobolMaker{sobol}, u_dev, stream);
+}
+
+int lint_multi_grid_sample_u(const lint_grid_t *grids, int ndomains, const double *choice_cdf, const double *bounds,
+                             const double *u_dev, int64_t N, void *scratch_dev, size_t scratch_bytes, void *out_dev,
+                             int64_t *cell_idx_dev, lint_stream_t stream) {
+    if (N > 0 && !u_dev) return fail(LINT_ERR_BAD_ARG, "lint_multi_grid_sample_u: u_dev is NULL");
+    return multi_dispatch(grids, ndomains, choice_cdf, bounds, N, scratch_dev, scratch_bytes, out_dev, cell_idx_dev,
+                          stream, ArrayMaker{u_dev}, "lint_multi_grid_sample_u");
+}
+
+int lint_multi_grid_sample_philox(const lint_grid_t *grids, int ndomains, const double *choice_cdf,
+                                  const double *bounds, int64_t N, uint64_t seed, uint64_t offset, void *scratch_dev,
+                                  size_t scratch_bytes, void *out_dev, int64_t *cell_idx_dev, lint_stream_t stream) {
+    return multi_dispatch(grids, ndomains, choice_cdf, bounds, N, scratch_dev, scratch_bytes, out_dev, cell_idx_dev,
+                          stream, PhiloxMaker{seed, offset, 0.0, 1.0}, "lint_multi_grid_sample_philox");
+}
+
+int lint_multi_grid_sample_sobol(const lint_grid_t *grids, int ndomains, const double *choice_cdf,
+                                 const double *bounds, int64_t N, const lint_sobol_t *sobol, void *scratch_dev,
+                                 size_t scratch_bytes, void *out_dev, int64_t *cell_idx_dev, lint_stream_t stream) {
+    if (int rc = check_sobol(sobol, N, "lint_multi_grid_sample_sobol")) return rc;
+    return multi_dispatch(grids, ndomains, choice_cdf, bounds, N, scratch_dev, scratch_bytes, out_dev, cell_idx_dev,
+                          stream, SobolMaker{sobol}, "lint_multi_grid_sample_sobol");
 }
 
 }  // extern "C"

@@ -40,6 +40,28 @@ from .base import DensityStructure
 from .grid import DensityGrid, _is_flat_sequence
 
 
+def sobol_advance(engine, n):
+    """``engine.fast_forward(n)`` for a scipy Sobol engine in O(bits) instead of O(n): after ``t``
+    points scipy keeps the integer coordinates of point ``t - 1`` in ``_quasi``, and point ``i`` is
+    ``shift ^ XOR_{b in gray(i)} sv[:, b]``, so the state can be written directly.
+    (``fast_forward`` walks the sequence: 0.3 s per 1e8 points, longer than the draw itself.)"""
+    try:
+        total = int(engine.num_generated) + int(n)
+        if total > 0:
+            g = (total - 1) ^ ((total - 1) >> 1)
+            x = engine._shift.copy()
+            b = 0
+            while g:
+                if g & 1:
+                    x ^= engine._sv[:, b]
+                g >>= 1
+                b += 1
+            engine._quasi[...] = x
+        engine.num_generated = total
+    except (AttributeError, TypeError, ValueError, IndexError):
+        engine.fast_forward(n)
+
+
 def sobol_sorted_inverse(sv_cell, m):
     """Columns (as ints) of A^-1 over GF(2), A = top m x m block of the generator matrix
     whose columns are the 32-bit direction numbers ``sv_cell``: with it,
@@ -272,7 +294,7 @@ class LintSampler:
             s = self._sobol_struct()
             _capi.call("lint_sobol_uniforms", self.dim, n, C.byref(s), _device.ptr(u),
                        _device.stream_ptr(dev))
-            self.qmc_engine.fast_forward(n)
+            sobol_advance(self.qmc_engine, n)
         else:
             _capi.call("lint_philox_uniforms", self.dim, _device.lint_dtype(self._domain_dtype()), n,
                        C.c_uint64(self._philox_key), C.c_uint64(self._philox_offset), _device.ptr(u),
@@ -324,7 +346,7 @@ class LintSampler:
             self._sobol_precheck(n)
             s = self._sobol_struct(sorted_n=n if self._sobol_sorted_ok(n) else None)
             x = grid._sample_sobol(n, s)
-            self.qmc_engine.fast_forward(n)
+            sobol_advance(self.qmc_engine, n)
             return x
         if self.order == "cell" and hasattr(grid, "_sample_cellmajor"):
             x = grid._sample_cellmajor(n, self._philox_key, self._philox_offset)
@@ -333,14 +355,69 @@ class LintSampler:
         self._philox_offset += n
         return x
 
+    def _fused_list(self):
+        """True when the list of domains can be drawn by one launch (lint_multi_grid_sample_*):
+        native grids of one dtype on one device, at most 16 of them."""
+        from .grid import DensityGrid
+        g0 = self.grids[0]
+        return (len(self.grids) <= 16 and all(type(g) is DensityGrid for g in self.grids)
+                and all(g.dtype == g0.dtype and g.device == g0.device for g in self.grids)
+                and all(g._stratum == (0.0, 1.0) for g in self.grids))
+
+    def _sample_multi_fused(self, n, p, mode, u=None):
+        """One launch over the whole list  [lintsampler.py:281-307].  Returns (rows in draw order,
+        grid index of every row)."""
+        import torch
+        g0 = self.grids[0]
+        with torch.cuda.device(g0.device):
+            nd = len(self.grids)
+            descs = (_capi.LintGrid * nd)(*[g._descriptor() for g in self.grids])
+            c = p.cumsum()
+            choice = (C.c_double * nd)(*(c / c[-1]))
+            bounds = (C.c_double * (nd + 1))(*np.append(0, p.cumsum()))
+            nbytes = int(_capi.load().lint_multi_scratch_bytes(self.dim, nd))
+            scratch = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=g0.device)
+            out = torch.empty((n, self.dim), dtype=_device.torch_dtype(g0.dtype), device=g0.device)
+            cells = torch.empty(n, dtype=torch.int64, device=g0.device)
+            st = _device.stream_ptr(g0.device)
+            if mode == "u":
+                _capi.call("lint_multi_grid_sample_u", descs, nd, choice, bounds, _device.ptr(u), n,
+                           _device.ptr(scratch), nbytes, _device.ptr(out), _device.ptr(cells), st)
+            elif mode == "philox":
+                _capi.call("lint_multi_grid_sample_philox", descs, nd, choice, bounds, n,
+                           C.c_uint64(self._philox_key), C.c_uint64(self._philox_offset), _device.ptr(scratch),
+                           nbytes, _device.ptr(out), _device.ptr(cells), st)
+                self._philox_offset += n
+            else:
+                self._sobol_precheck(n)
+                sob = self._sobol_struct()
+                _capi.call("lint_multi_grid_sample_sobol", descs, nd, choice, bounds, n, C.byref(sob),
+                           _device.ptr(scratch), nbytes, _device.ptr(out), _device.ptr(cells), st)
+                sobol_advance(self.qmc_engine, n)
+            ends = torch.as_tensor(np.cumsum([int(g.ncells) for g in self.grids]), device=g0.device)
+            return out, torch.bucketize(cells, ends, right=True)
+
     def _sample_multi(self, n):
         """List of domains  [lintsampler.py:281-307]: domain chosen by the same
         uniform that then (rescaled) chooses the cell; rows grouped by domain."""
         import torch
         masses = np.array([g.total_mass for g in self.grids])
         p = masses / masses.sum()
-        if (not self.qmc and self.rng_backend == "philox"
-                and all(hasattr(g, "_sample_philox") for g in self.grids)):
+        device_rows = (not self.qmc and self.rng_backend == "philox"
+                       and all(hasattr(g, "_sample_philox") for g in self.grids))
+        if self._fused_list() and not (device_rows and self.order == "cell"):
+            if device_rows:
+                # i.i.d. device rows in draw order are exchangeable as they are: no regrouping
+                x, _ = self._sample_multi_fused(n, p, "philox")
+                return x.to(torch.float64)
+            if self._uses_host_uniforms():
+                x, dom = self._sample_multi_fused(n, p, "u", self._host_uniforms(n))
+            else:
+                x, dom = self._sample_multi_fused(n, p, "sobol")
+            # the reference's vstack order: rows of grid 0 in draw order, then grid 1, ...
+            order = torch.sort(dom, stable=True).indices
+            return x[order].to(torch.float64)
+        if device_rows:
             # i.i.d. device rows: choosing a domain per row with probability p (what `_choice`
             # does row by row, lintsampler.py:290) is a Multinomial(n, p) split of the row
             # count; each domain then draws its rows with one fused kernel, no uniforms

@@ -115,6 +115,36 @@ def _ks_all_dims(x, y):
     return min(stats.ks_2samp(x[:, d], y[:, d]).pvalue for d in range(x.shape[1]))
 
 
+@pytest.mark.parametrize("qmc", [False, True])
+def test_list_of_grids_single_launch_equals_the_per_domain_path(lb, qmc, monkeypatch):
+    """A list of grids is drawn by ONE launch (lint_multi_grid_sample_*: grid choice, the u-rescaling
+    of lintsampler.py:306 and the cell choice fused); regrouped by grid it must be, bit for bit, what
+    the per-domain path (mask, rescale, one launch per grid, concatenate) returns — for host PCG64
+    uniforms and for the device Sobol stream — and the device Philox stream must keep the mixture."""
+    import warnings
+    pdf = pdfs.GMM(*pdfs.gmm_params(2, seed=1, full_cov=True))
+    xe, ye = np.linspace(-10, 10, 41), np.linspace(-5, 5, 25)
+    doms = [(xe[:21], ye[:13]), (xe[20:], ye[:13]), (xe[:21], ye[12:]), (xe[20:], ye[12:])]
+    outs = []
+    for fused in (True, False):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            s = lb.LintSampler(doms, pdf=pdf, vectorizedpdf=True, seed=11, qmc=qmc,
+                               rng_backend="numpy" if not qmc else "philox", cdf_mode="sequential")
+            if not fused:
+                monkeypatch.setattr(type(s), "_fused_list", lambda self: False)
+            outs.append(s.sample(5000))
+            monkeypatch.undo()
+    assert np.array_equal(outs[0], outs[1])
+    # device Philox rows of the fused launch: same mixture as the reference-stream rows
+    x = lb.LintSampler(doms, pdf=pdf, vectorizedpdf=True, seed=5).sample(200_000)
+    y = lb.LintSampler(doms, pdf=pdf, vectorizedpdf=True, seed=5, rng_backend="numpy").sample(200_000)
+    for d in range(2):
+        assert stats.ks_2samp(x[:, d], y[:, d]).pvalue > 1e-4
+    frac = [np.mean((x[:, 0] < 0) & (x[:, 1] < 0)), np.mean((y[:, 0] < 0) & (y[:, 1] < 0))]
+    assert abs(frac[0] - frac[1]) < 5e-3
+
+
 @pytest.mark.parametrize("name", ["g1d_nonuniform", "g2d_fullcov", "g3d_iso", "g4d_iso"])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_philox_samples_match_reference_distribution(lb, name, dtype):

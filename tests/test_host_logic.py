@@ -350,3 +350,25 @@ def test_ptrs_fp32_screen_never_decides_wrongly():
     assert res["proposals"] > 100_000
     assert res["wrong_decisions"] == 0
     assert res["max_err_over_tol"] < 0.5
+
+
+def test_sobol_advance_equals_fast_forward():
+    """The O(bits) state jump used after a device Sobol draw leaves the scipy engine exactly where
+    ``fast_forward`` would (next points identical, including across several jumps)."""
+    import warnings
+    from lintsampler_b200.sampler import sobol_advance
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for n1, n2, m in [(1000, 0, 7), (1, 5, 3), (12345, 678, 11), (2 ** 20, 3, 5), (100_000_000, 1, 4)]:
+            a, b = Sobol(d=4, bits=32, seed=7), Sobol(d=4, bits=32, seed=7)
+            if n1 <= 2 ** 20:
+                a.random(n1)
+                if n2:
+                    a.random(n2)
+            else:
+                a.fast_forward(n1 + n2)
+            sobol_advance(b, n1)
+            if n2:
+                sobol_advance(b, n2)
+            assert a.num_generated == b.num_generated
+            assert np.array_equal(a.random(m), b.random(m)), (n1, n2)
