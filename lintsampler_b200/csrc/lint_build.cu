@@ -705,15 +705,18 @@ guide_build_kernel(const double *cdf, uint32_t n, int bits, uint32_t *guide, con
 constexpr uint32_t GROUP_TARGET_CELLS = PAR_TILE;      // one scan tile: a group is one block-step of the scan
 
 struct GroupPlan {
-    uint32_t n_last, nrow, nvrow, rows_per_group, ngroups, group_cells;
+    uint32_t n_last, nrow, nvrow, rows_per_group, ngroups, group_cells, sub;
     double u_lo, u_hi;
 };
 
 // Q[vr] = sum_i V[vr, i] * omega_last[i], one warp per vertex row, fixed summation order
+constexpr int ROWSUM_BATCH = 8;
 template <int K, typename DensT>
 __global__ void __launch_bounds__(256)
-vertex_rowsum_kernel(GridView<K> g, GroupPlan plan, double *__restrict__ Q, uint32_t *flags) {
+vertex_rowsum_kernel(GridView<K> g, GroupPlan plan, double *__restrict__ Q, uint32_t *flags,
+                     uint32_t *done_counter) {
     extern __shared__ double s_omega[];                            // n_last + 1 weights
+    if (blockIdx.x == 0 && threadIdx.x == 0) *done_counter = 0;    // for group_totals_kernel, next in the stream
     const double *el = g.edges[K - 1];
     for (uint32_t i = threadIdx.x; i <= plan.n_last; i += blockDim.x) {
         const double wl = i > 0 ? __dsub_rn(__ldg(el + i), __ldg(el + i - 1)) : 0.0;
@@ -727,11 +730,19 @@ vertex_rowsum_kernel(GridView<K> g, GroupPlan plan, double *__restrict__ Q, uint
     for (uint32_t vr = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; vr < plan.nvrow; vr += warps) {
         const DensT *row = V + (size_t)vr * (plan.n_last + 1);
         double acc = 0.0;
-        for (uint32_t i = lane; i <= plan.n_last; i += 32) {
-            const double v = (double)__ldg(row + i);
-            if (v < 0.0) bad |= LINT_FLAG_NEGATIVE;
-            if (!isfinite(v)) bad |= LINT_FLAG_NONFINITE;
-            acc = fma(v, s_omega[i], acc);
+        // eight loads in flight per lane before the first dependent fma (same summation order)
+        for (uint32_t i0 = lane; i0 <= plan.n_last; i0 += 32 * ROWSUM_BATCH) {
+            DensT v[ROWSUM_BATCH];
+#pragma unroll
+            for (int j = 0; j < ROWSUM_BATCH; ++j)
+                v[j] = i0 + 32 * j <= plan.n_last ? __ldg(row + i0 + 32 * j) : DensT(0);
+#pragma unroll
+            for (int j = 0; j < ROWSUM_BATCH; ++j) {
+                const double x = (double)v[j];
+                if (x < 0.0) bad |= LINT_FLAG_NEGATIVE;
+                if (!isfinite(x)) bad |= LINT_FLAG_NONFINITE;
+                if (i0 + 32 * j <= plan.n_last) acc = fma(x, s_omega[i0 + 32 * j], acc);
+            }
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
@@ -750,10 +761,16 @@ group_totals_kernel(GridView<K> g, GroupPlan plan, uint32_t ncells, const double
                     double *total, uint32_t *done_counter, uint32_t *range_out) {
     __shared__ bool s_last;
     const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gi < plan.ngroups; gi += warps) {
-        const uint32_t r0 = gi * plan.rows_per_group, r1 = min(r0 + plan.rows_per_group, plan.nrow);
+    // plan.sub lanes per group (a power of two >= the rows of a group, at most 32): 32 / sub groups
+    // per warp step.  Lanes past the rows hold zero, so the sum is that of a full-warp tree.
+    const uint32_t sub = plan.sub, per_warp = 32 / sub, sl = lane & (sub - 1);
+    for (uint32_t g0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * per_warp; g0 < plan.ngroups;
+         g0 += warps * per_warp) {
+        const uint32_t gi = g0 + lane / sub;
+        const uint32_t r0 = gi * plan.rows_per_group;
+        const uint32_t r1 = gi < plan.ngroups ? min(r0 + plan.rows_per_group, plan.nrow) : r0;
         double sum = 0.0;
-        for (uint32_t rho = r0 + lane; rho < r1; rho += 32) {
+        for (uint32_t rho = r0 + sl; rho < r1; rho += sub) {
             uint32_t i[K];
             grid_unravel<K>(g, rho * plan.n_last, i);
             uint32_t vbase = 0;
@@ -769,8 +786,9 @@ group_totals_kernel(GridView<K> g, GroupPlan plan, uint32_t ncells, const double
             sum += pw * q;
         }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-        if (lane == 0) Off[gi + 1] = sum;                          // chained below
+        for (int d = 16; d > 0; d >>= 1)
+            if ((uint32_t)d < sub) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        if (sl == 0 && gi < plan.ngroups) Off[gi + 1] = sum;       // chained below
     }
     __threadfence();
     __syncthreads();
@@ -784,12 +802,18 @@ group_totals_kernel(GridView<K> g, GroupPlan plan, uint32_t ncells, const double
     volatile double *vo = Off;
     __shared__ double warp_tot[PAR_THREADS / 32];
     double carry = 0.0;
+    double x[PAR_ITEMS], nxt[PAR_ITEMS];
+#pragma unroll
+    for (int j = 0; j < PAR_ITEMS; ++j) {
+        const uint32_t i = threadIdx.x * PAR_ITEMS + j;
+        nxt[j] = i < plan.ngroups ? vo[i + 1] : 0.0;
+    }
     for (uint32_t c0 = 0; c0 < plan.ngroups; c0 += PAR_TILE) {
-        double x[PAR_ITEMS];
 #pragma unroll
         for (int j = 0; j < PAR_ITEMS; ++j) {
-            const uint32_t i = c0 + threadIdx.x * PAR_ITEMS + j;
-            x[j] = i < plan.ngroups ? vo[i + 1] : 0.0;
+            x[j] = nxt[j];
+            const uint32_t i = c0 + PAR_TILE + threadIdx.x * PAR_ITEMS + j;        // the next chunk, in flight
+            nxt[j] = i < plan.ngroups ? vo[i + 1] : 0.0;                           // during this one's scan
         }
         const double chunk_total = tile_scan(x, warp_tot);
 #pragma unroll
@@ -801,22 +825,32 @@ group_totals_kernel(GridView<K> g, GroupPlan plan, uint32_t ncells, const double
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x != 0) return;
     const double run = carry;
+    // groups the stratum can touch: Off[g + 1] / total > u_lo and Off[g] / total < u_hi.  Off is
+    // non-decreasing, so the two bracketing groups are counts (every thread tests a few entries):
+    //   lo = last g in [0, ngroups) with Off[g] / total <= u_lo   (Off[0] = 0 always passes)
+    //   a  = first g in [0, ngroups] with Off[g] / total >= u_hi
+    __shared__ uint32_t s_cnt[2];
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t n_le = 0, n_lt = 0;
+    for (uint32_t gi = threadIdx.x; gi < plan.ngroups; gi += blockDim.x) {
+        const double f = (gi == 0 ? 0.0 : vo[gi]) / run;
+        n_le += f <= plan.u_lo;
+        n_lt += f < plan.u_hi;
+    }
+    n_le = __reduce_add_sync(0xffffffffu, n_le);
+    n_lt = __reduce_add_sync(0xffffffffu, n_lt);
+    if (lane == 0) {
+        atomicAdd(&s_cnt[0], n_le);
+        atomicAdd(&s_cnt[1], n_lt);
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     vo[0] = 0.0;
     *total = run;
     *done_counter = 0;
-    // groups the stratum can touch: Off[g + 1] / total > u_lo and Off[g] / total < u_hi
-    uint32_t lo = 0, hi = plan.ngroups;                            // last g with Off[g] / total <= u_lo
-    while (hi - lo > 1) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (vo[mid] / run <= plan.u_lo) lo = mid; else hi = mid;
-    }
-    uint32_t a = 0, b = plan.ngroups;                              // first g with Off[g] / total >= u_hi
-    while (a < b) {
-        const uint32_t mid = a + ((b - a) >> 1);
-        if (vo[mid] / run >= plan.u_hi) b = mid; else a = mid + 1;
-    }
+    const uint32_t lo = s_cnt[0] > 0 ? s_cnt[0] - 1 : 0, a = s_cnt[1];
     uint32_t g_lo = lo > 0 ? lo - 1 : 0, g_hi = min(a + 1, plan.ngroups);      // one group of margin
     if (plan.u_lo <= 0.0) g_lo = 0;                                // a stratum that starts / ends with the domain
     if (plan.u_hi >= 1.0) g_hi = plan.ngroups;                     // covers its zero-mass head / tail too
@@ -887,6 +921,8 @@ static GroupPlan make_group_plan(const lint_grid_t *g, uint64_t ncells, double u
     p.rows_per_group = std::max<uint32_t>(1, GROUP_TARGET_CELLS / p.n_last);
     p.ngroups = (p.nrow + p.rows_per_group - 1) / p.rows_per_group;
     p.group_cells = p.rows_per_group * p.n_last;
+    p.sub = 1;
+    while (p.sub < 32 && p.sub < p.rows_per_group) p.sub <<= 1;
     p.u_lo = u_lo;
     p.u_hi = u_hi;
     return p;
@@ -934,17 +970,17 @@ int group_build_impl(const lint_grid_t *g, uint64_t ncells, double u_lo, double 
     double *Q = (double *)scratch;
     double *Off = Q + plan.nvrow;
     uint32_t *done = (uint32_t *)(Off + plan.ngroups + 1);
-    cudaMemsetAsync(done, 0, sizeof(uint32_t), st);
     const size_t smem = ((size_t)plan.n_last + 1) * sizeof(double);
     if (smem > 96 * 1024) return fail(LINT_ERR_UNSUPPORTED, "lint_grid_build: more than 12287 cells along the last dimension");
     const int qblocks = (int)std::min<uint64_t>(((uint64_t)plan.nvrow + 7) / 8, 148 * 8);
     const int sblocks = (int)std::min<uint32_t>(plan.ngroups, 148 * 8);
-    const int tblocks = (int)std::min<uint32_t>((plan.ngroups + 7) / 8, 148);
+    const uint32_t per_block = 8 * (32 / plan.sub);               // groups per block step
+    const int tblocks = (int)std::min<uint32_t>((plan.ngroups + per_block - 1) / per_block, 148 * 4);
     auto run = [&](auto tag) {
         using D = decltype(tag);
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(vertex_rowsum_kernel<K, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        vertex_rowsum_kernel<K, D><<<qblocks, 256, smem, st>>>(v, plan, Q, flags);
+        vertex_rowsum_kernel<K, D><<<qblocks, 256, smem, st>>>(v, plan, Q, flags, done);
         group_totals_kernel<K><<<tblocks, 256, 0, st>>>(v, plan, (uint32_t)ncells, Q, Off, total, done, range);
         group_scan_kernel<K, D><<<sblocks, PAR_THREADS, 0, st>>>(v, plan, (uint32_t)ncells, Off, total, range, cdf,
                                                                 masses);
