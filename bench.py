@@ -222,7 +222,7 @@ def run_b200(args):
     if args.order == "cell":
         # the grouped emitter loads each cell once, so it needs neither per-cell records
         # nor a fine guide table (only the ~2.5e-4 N top-up rows search the CDF)
-        grid_kw.update(cell_records=False, guide_bits=16)
+        grid_kw.update(cell_records=False, guide_bits=0)
     if args.guide_bits is not None:
         grid_kw["guide_bits"] = args.guide_bits
     if args.no_records:
@@ -255,13 +255,18 @@ def run_b200(args):
     n_mine, first_mine = share(0)
     counter = torch.zeros(1, dtype=torch.int64, device=dev)
     _capi.call("lint_set_offset_counter", C.c_void_p(counter.data_ptr()))
+    lane = torch.cuda.Stream(dev)
 
     def body(ev=None, order=None):
         if ev:
             ev[0].record(stream_now())
+        # the Philox offset advances beside the build (which draws nothing)
+        main = stream_now()
+        lane.wait_stream(main)
         _capi.call("lint_advance_counter", C.c_void_p(counter.data_ptr()), C.c_uint64(n_total),
-                   C.c_void_p(stream_now().cuda_stream))
-        shard.enqueue_build(gather=False)           # vertex row sums + group offsets of the whole grid, CDF + guide of the own slab
+                   C.c_void_p(lane.cuda_stream))
+        shard.enqueue_build(gather=False)           # vertex row sums + group offsets of the whole grid, CDF (+ guide) of the own slab
+        main.wait_stream(lane)
         if ev:
             ev[1].record(stream_now())
         if (order or args.order) == "cell":
@@ -335,7 +340,7 @@ def run_b200(args):
     if not args.no_other and world == 1:
         # its own tables: the u-driven kernel wants per-cell records and a fine guide table
         shard.grid.__dict__.pop("_cm_scratch", None)
-        okw = dict(cell_records=False, guide_bits=16) if other == "cell" else dict(guide_bits=22)
+        okw = dict(cell_records=False, guide_bits=0) if other == "cell" else dict(guide_bits=22)
         shard_main, shard = shard, lbd.ShardedGrid(edges, gmm, dtype=np.float32, device=dev, rank=rank,
                                                    world=world, group=None, **okw)
         body(order=other)
@@ -357,7 +362,7 @@ def run_b200(args):
         out = None
         torch.cuda.empty_cache()
         g64 = lb.DensityGrid(edges, gmm, vectorizedpdf=True, dtype=np.float64, device=dev, cell_records=False,
-                             guide_bits=16)
+                             guide_bits=0)
         out64 = torch.empty((n_total, DIM), dtype=torch.float64, device=dev)
         for i in range(2):
             g64._enqueue_build()
@@ -418,7 +423,7 @@ def run_b200(args):
                 "launch": ("one CUDA graph replay per step: %d kernels captured once; the graph advances a "
                            "device-resident Philox offset, so every step draws fresh samples; the multinomial "
                            "split of N over the ranks is drawn once per run from the shared seed"
-                           % shard.launches_per_step(args.order)) if graph is not None else "eager launches",
+                           % (shard.launches_per_step(args.order) + 1)) if graph is not None else "eager launches",
                 "host_ms_per_step": host_ms,
                 "order": ("rows grouped by cell: exact multinomial cell counts (Poisson counts + u-driven "
                           "top-up), i.i.d. as a multiset, NOT exchangeable in row order"
@@ -441,7 +446,7 @@ def run_b200(args):
                 "step_frac_of_hbm_roofline": step_bytes_per_gpu / (ms_step * 1e-3) / 1e9 / peak,
             },
             "clocks": clocks.summary(),
-            "gpu_launches": shard.launches_per_step(args.order) * args.steps,
+            "gpu_launches": (shard.launches_per_step(args.order) + 1) * args.steps,   # + the offset-counter kernel
         }
         if other_line:
             line["other_order"] = other_line
@@ -471,7 +476,7 @@ def run_e2e(args, lb, edges, gmm, dev, world, n_total):
     n = n_total // world                                    # rows per rank
     steps = max(1, min(args.steps, 3))
     # host inputs: pinned fp32 vertex densities (evaluated once, outside the timed region)
-    kw = dict(cell_records=False, guide_bits=16) if args.order == "cell" else dict(guide_bits=22)
+    kw = dict(cell_records=False, guide_bits=0) if args.order == "cell" else dict(guide_bits=22)
     g0 = lb.DensityGrid(edges, gmm, vectorizedpdf=True, dtype=np.float32, device=dev, **kw)
     v_host = torch.empty(g0._V.numel(), dtype=torch.float32, pin_memory=True)
     v_host.copy_(g0._V)
@@ -553,7 +558,7 @@ def run_config(args):
     isz = np.dtype(dtype).itemsize
     tdt = torch.float32 if dtype == np.float32 else torch.float64
     if tree is None:
-        kw = {} if qmc else dict(cell_records=False, guide_bits=16)
+        kw = {} if qmc else dict(cell_records=False, guide_bits=0)
         grid = lb.DensityGrid(edges, pdf, vectorizedpdf=True, dtype=dtype, device=dev, **kw)
         k, C_, V_ = grid.dim, int(grid.ncells), int(np.prod([len(e) for e in edges]))
         alg = V_ * isz + C_ * 8 + 2 * C_ * 8 + N * k * isz

@@ -724,28 +724,45 @@ vertex_rowsum_kernel(GridView<K> g, GroupPlan plan, double *__restrict__ Q, uint
         s_omega[i] = 0.5 * (wl + wr);
     }
     __syncthreads();
-    const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5, nv = plan.n_last + 1;
     const DensT *V = reinterpret_cast<const DensT *>(g.V);
     uint32_t bad = 0;
+    // Issue-bound like everything integer on this part (profiles/README.md r2a): five instructions
+    // per element — load, min, convert, weight, fma.  No per-element predicates (full 32-wide slots
+    // first, the leftover lanes once), and the validity check rides on the arithmetic: a negative
+    // element drags the running minimum below zero, a NaN or an infinity makes the row sum
+    // non-finite (finite fp32/fp64 densities times finite weights cannot overflow an fp64 sum).
+    const uint32_t nfull = nv >> 5, rem = nv & 31u;
     for (uint32_t vr = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; vr < plan.nvrow; vr += warps) {
-        const DensT *row = V + (size_t)vr * (plan.n_last + 1);
+        const DensT *row = V + (size_t)vr * nv + lane;
+        const double *om = s_omega + lane;
+        const DensT tail = lane < rem ? __ldg(row + nfull * 32) : DensT(0);    // in flight with the first batch
         double acc = 0.0;
-        // eight loads in flight per lane before the first dependent fma (same summation order)
-        for (uint32_t i0 = lane; i0 <= plan.n_last; i0 += 32 * ROWSUM_BATCH) {
+        DensT vmin = DensT(0);
+        uint32_t s = 0;
+        for (; s + ROWSUM_BATCH <= nfull; s += ROWSUM_BATCH) {
             DensT v[ROWSUM_BATCH];
 #pragma unroll
-            for (int j = 0; j < ROWSUM_BATCH; ++j)
-                v[j] = i0 + 32 * j <= plan.n_last ? __ldg(row + i0 + 32 * j) : DensT(0);
+            for (int j = 0; j < ROWSUM_BATCH; ++j) v[j] = __ldg(row + (s + j) * 32);
 #pragma unroll
             for (int j = 0; j < ROWSUM_BATCH; ++j) {
-                const double x = (double)v[j];
-                if (x < 0.0) bad |= LINT_FLAG_NEGATIVE;
-                if (!isfinite(x)) bad |= LINT_FLAG_NONFINITE;
-                if (i0 + 32 * j <= plan.n_last) acc = fma(x, s_omega[i0 + 32 * j], acc);
+                vmin = v[j] < vmin ? v[j] : vmin;
+                acc = fma((double)v[j], om[(s + j) * 32], acc);
             }
         }
+        for (; s < nfull; ++s) {
+            const DensT v = __ldg(row + s * 32);
+            vmin = v < vmin ? v : vmin;
+            acc = fma((double)v, om[s * 32], acc);
+        }
+        if (lane < rem) {
+            vmin = tail < vmin ? tail : vmin;
+            acc = fma((double)tail, om[nfull * 32], acc);
+        }
+        if (vmin < DensT(0)) bad |= LINT_FLAG_NEGATIVE;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (!isfinite(acc)) bad |= LINT_FLAG_NONFINITE;
         if (lane == 0) Q[vr] = acc;
     }
     bad = __reduce_or_sync(0xffffffffu, bad);
@@ -834,10 +851,21 @@ group_totals_kernel(GridView<K> g, GroupPlan plan, uint32_t ncells, const double
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     uint32_t n_le = 0, n_lt = 0;
-    for (uint32_t gi = threadIdx.x; gi < plan.ngroups; gi += blockDim.x) {
-        const double f = (gi == 0 ? 0.0 : vo[gi]) / run;
-        n_le += f <= plan.u_lo;
-        n_lt += f < plan.u_hi;
+    for (uint32_t base = threadIdx.x; base < plan.ngroups; base += blockDim.x * 8) {
+        double v[8];                                               // eight L2 loads in flight, not one
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t gi = base + j * blockDim.x;
+            v[j] = gi > 0 && gi < plan.ngroups ? __ldcg(Off + gi) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (base + j * blockDim.x < plan.ngroups) {
+                const double f = v[j] / run;
+                n_le += f <= plan.u_lo;
+                n_lt += f < plan.u_hi;
+            }
+        }
     }
     n_le = __reduce_add_sync(0xffffffffu, n_le);
     n_lt = __reduce_add_sync(0xffffffffu, n_lt);

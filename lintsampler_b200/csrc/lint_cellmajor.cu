@@ -46,8 +46,8 @@ static int check_common(int64_t N, uint64_t ncells, double u_lo, double u_hi, vo
 
 // defined in lint_sample.cu: u-driven rows [*first_row_dev, N), at most max_rows of them
 int topup_grid(const lint_grid_t *g, int64_t N, const uint32_t *first_row_dev, int64_t max_rows,
-               uint64_t seed, uint64_t offset, double u_lo, double u_hi, void *out, int64_t *cell_idx,
-               cudaStream_t st);
+               uint64_t seed, uint64_t offset, double u_lo, double u_hi, const uint32_t *cell_range_dev, void *out,
+               int64_t *cell_idx, cudaStream_t st);
 int topup_cells(const lint_cells_t *c, int64_t N, const uint32_t *first_row_dev, int64_t max_rows,
                 uint64_t seed, uint64_t offset, double u_lo, double u_hi, void *out, int64_t *cell_idx,
                 cudaStream_t st);
@@ -116,8 +116,8 @@ int lint_grid_sample_cellmajor(const lint_grid_t *g, int64_t N, uint64_t seed, u
         cudaStreamWaitEvent(L->side[1], L->ev[4], 0);           // the row budget is known (grid_cellmajor_k)
         st_top = L->side[1];
     }
-    rc = topup_grid(g, N, s.plan + 2, (int64_t)topup_bound((uint64_t)N), seed, offset, u_lo, u_hi, out_dev,
-                    cell_idx_dev, st_top);
+    rc = topup_grid(g, N, s.plan + 2, (int64_t)topup_bound((uint64_t)N), seed, offset, u_lo, u_hi, cell_range_dev,
+                    out_dev, cell_idx_dev, st_top);
     if (L) {
         cudaEventRecord(L->ev[5], st_top);
         cudaStreamWaitEvent(st, L->ev[5], 0);

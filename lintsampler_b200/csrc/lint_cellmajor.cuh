@@ -206,7 +206,11 @@ template <typename Cells>
 __global__ void __launch_bounds__(POISSON_THREADS)
 poisson_counts_kernel(Cells src, CdfSlice t, double lam_per_unit, uint2 key, StreamPos pos, bool split,
                       const uint32_t *__restrict__ range, uint32_t *__restrict__ counts_flat,
-                      uint32_t *__restrict__ counts_rest) {
+                      uint32_t *__restrict__ counts_rest, uint4 *__restrict__ zero, uint32_t nzero) {
+    // the scans' tile states and totals (Scratch::zero_begin), cleared here instead of by a memset
+    // node of its own: the scans are the next kernels in the stream
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nzero; i += gridDim.x * blockDim.x)
+        zero[i] = make_uint4(0u, 0u, 0u, 0u);
     const uint64_t offset = pos.get();
     const uint32_t w2 = (uint32_t)offset, w3 = (uint32_t)(offset >> 32);
     // cells [c0, c1): the slab of the stratum (lint_grid_build), or every cell
@@ -369,7 +373,7 @@ static __global__ void plan_chunks_kernel(SegTable flat, SegTable rest, uint32_t
             if (__ldg(l.coff + mid) > r0) hi = mid; else lo = mid + 1;
         }
         l.chunk_start[t] = lo - 1;
-    }
+}
 }
 
 // ---------------------------------------------------------------------------
@@ -1041,6 +1045,12 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
     }
 }
 
+// tuning overrides read from the environment at every call (profiling sweeps only)
+inline int env_int(const char *name, int fallback) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : fallback;
+}
+
 // ---------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------
@@ -1059,9 +1069,9 @@ static int plan_rows(const Cells &src, const double *cdf, uint64_t ncells, uint6
     const CdfSlice t{cdf, (uint32_t)ncells, u.u_lo, u.u_hi};
     const double lam_per_unit = grouped_mean(N) / (u.u_hi - u.u_lo);
     const int cblocks = (int)std::min<uint64_t>((ncells + POISSON_THREADS - 1) / POISSON_THREADS, 148 * 32);
-    cudaMemsetAsync(s.zero_begin, 0, s.zero_bytes, st);
-    poisson_counts_kernel<<<cblocks, POISSON_THREADS, 0, st>>>(src, t, lam_per_unit, key, StreamPos{offset, offset_counter()}, split, range, s.counts_flat,
-                                                   s.counts_rest);
+    poisson_counts_kernel<<<cblocks, POISSON_THREADS, 0, st>>>(
+        src, t, lam_per_unit, key, StreamPos{offset, offset_counter()}, split, range, s.counts_flat, s.counts_rest,
+        (uint4 *)s.zero_begin, (uint32_t)(s.zero_bytes / 16));
     Lanes *L = split ? side_lanes() : nullptr;
     if (L) {                                                   // the two scans side by side
         cudaEventRecord(L->ev[0], st);
@@ -1083,15 +1093,11 @@ static int plan_rows(const Cells &src, const double *cdf, uint64_t ncells, uint6
     return check_launch("cell-major row planning");
 }
 
-// tuning overrides read from the environment at every call (profiling sweeps only)
-inline int env_int(const char *name, int fallback) {
-    const char *v = getenv(name);
-    return v && *v ? atoi(v) : fallback;
-}
 
-// The two emitters run back to back on the caller's stream.  (Both are bound by integer
-// instruction issue — Philox's wide multiplies and XORs — so running them side by side on two
-// streams gains nothing: measured, profiles/README.md r2b.)
+// The flat emitter runs on a side lane beside the general one: the first fills the store path,
+// the second the issue slots (profiles/README.md r2g).  The box table is built on that lane just
+// before the flat emitter, which gives the general emitter a few microseconds of head start on
+// the SMs: moving it next to the scans (both emitters starting together) cost 4 % of the step.
 template <int K, typename T, typename Cells>
 int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t ncells, uint64_t N, uint2 key,
                 uint64_t offset, Stratum u, void *out, int64_t *cell_idx, cudaStream_t st) {
@@ -1170,8 +1176,8 @@ int grid_cellmajor_k(const lint_grid_t *g, uint64_t nc, uint64_t N, uint2 key, u
 
 // defined in lint_sample.cu: u-driven rows [*first_row_dev, N), at most max_rows of them
 int topup_grid(const lint_grid_t *g, int64_t N, const uint32_t *first_row_dev, int64_t max_rows,
-               uint64_t seed, uint64_t offset, double u_lo, double u_hi, void *out, int64_t *cell_idx,
-               cudaStream_t st);
+               uint64_t seed, uint64_t offset, double u_lo, double u_hi, const uint32_t *cell_range_dev, void *out,
+               int64_t *cell_idx, cudaStream_t st);
 int topup_cells(const lint_cells_t *c, int64_t N, const uint32_t *first_row_dev, int64_t max_rows,
                 uint64_t seed, uint64_t offset, double u_lo, double u_hi, void *out, int64_t *cell_idx,
                 cudaStream_t st);

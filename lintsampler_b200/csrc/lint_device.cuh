@@ -99,6 +99,7 @@ struct CdfView {
     const uint32_t *guide;
     uint32_t n;
     int guide_bits;
+    const uint32_t *range = nullptr;    // device [first cell, end cell) of a slab build; brackets the search when there is no guide table
 };
 
 // Guide entries carry a flag in bit 31: set when the whole bin lies inside one
@@ -157,6 +158,9 @@ __device__ __forceinline__ void guide_bracket(const CdfView &t, double u, uint32
         const uint32_t e = __ldg(t.guide + j);
         lo = e & ~GUIDE_SAME;
         hi = (e & GUIDE_SAME) ? lo : (__ldg(t.guide + j + 1) & ~GUIDE_SAME);
+    } else if (t.range) {
+        lo = __ldg(t.range);
+        hi = __ldg(t.range + 1) - 1;
     }
 }
 

@@ -172,6 +172,7 @@ sample_kernel(Source src, Uniforms unif, int64_t N, T *__restrict__ out,
 struct RowWindow {
     const uint32_t *first_row_dev = nullptr;
     int64_t max_rows = 0;
+    const uint32_t *cell_range_dev = nullptr;   // slab of the table that is valid (lint_grid_build)
 };
 
 template <int K, typename T, typename Source, typename Uniforms>
@@ -197,9 +198,11 @@ int grid_dispatch_k(const lint_grid_t *g, uint64_t ncells, int64_t N, void *out,
                     cudaStream_t st, const UnifMaker &mk, const char *what, const RowWindow &win) {
     if (g->dtype == LINT_F32) {
         GridSource<K, float> src{make_grid_view<K>(g, ncells, true)};
+        src.g.table.range = win.cell_range_dev;
         return launch_sample<K, float>(src, mk.template make<K>(), N, out, cell_idx, st, what, win);
     }
     GridSource<K, double> src{make_grid_view<K>(g, ncells, true)};
+    src.g.table.range = win.cell_range_dev;
     return launch_sample<K, double>(src, mk.template make<K>(), N, out, cell_idx, st, what, win);
 }
 
@@ -482,10 +485,10 @@ template <int K> static size_t cells_record_bytes_k(int dtype) {
 
 // u-driven top-up of rows [*first_row_dev, N) for the cell-major path
 int topup_grid(const lint_grid_t *g, int64_t N, const uint32_t *first_row_dev, int64_t max_rows,
-               uint64_t seed, uint64_t offset, double u_lo, double u_hi, void *out, int64_t *cell_idx,
-               cudaStream_t st) {
+               uint64_t seed, uint64_t offset, double u_lo, double u_hi, const uint32_t *cell_range_dev, void *out,
+               int64_t *cell_idx, cudaStream_t st) {
     return grid_dispatch(g, N, out, cell_idx, (lint_stream_t)st, PhiloxMaker{seed, offset, u_lo, u_hi},
-                         "cell-major top-up", RowWindow{first_row_dev, max_rows});
+                         "cell-major top-up", RowWindow{first_row_dev, max_rows, cell_range_dev});
 }
 
 int topup_cells(const lint_cells_t *c, int64_t N, const uint32_t *first_row_dev, int64_t max_rows,

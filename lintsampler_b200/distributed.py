@@ -327,11 +327,12 @@ class ShardedGrid:
         return self.bounds
 
     def launches_per_step(self, order="draw"):
-        """Kernels of this library launched by enqueue_build + one sampling call: build 4 (vertex
-        row sums, group totals, group scan, guide), cell records 0/1; then the u-driven sampler
+        """Kernels of this library launched by enqueue_build + one sampling call: build 3 (vertex
+        row sums, group totals, group scan) + 1 for the guide table when there is one, cell records
+        0/1; then the u-driven sampler
         (1) or the grouped path (Poisson counts, 2 x scan+compact, row budget + chunk starts, flat
         boxes, flat emitter, general emitter, top-up = 8)."""
-        build = 4 + (1 if self.grid._rec is not None else 0)
+        build = 3 + (1 if self.grid._guide_bits_planned > 0 else 0) + (1 if self.grid._rec is not None else 0)
         return build + (8 if order == "cell" else 1)
 
     def describe(self):

@@ -57,6 +57,8 @@ class DensityGrid(DensityStructure):
     pdf_on_device : if True the vectorised ``pdf`` is called with a torch CUDA
         tensor of shape (npts, k) and must return a torch tensor.
     guide_bits : log2 of the guide-table size (default: about one bin per cell).
+        0: no guide table — enough for ``order="cell"``, whose only searches
+        are its ~2.5e-4 N top-up rows.
     cell_records : keep a per-cell copy of the 2^k corner densities so a sample
         reads one contiguous record (default: on when it needs < 8 GiB).
     """
@@ -308,8 +310,9 @@ class DensityGrid(DensityStructure):
             _capi.call("lint_grid_masses", C.byref(desc), _device.ptr(masses), _device.ptr(self._flags), st)
             _capi.call("lint_cdf_build", _device.ptr(masses), ncells, mode, _device.ptr(self._cdf),
                        _device.ptr(self._total), _device.ptr(self._scratch), self._scratch.numel(), st)
-            _capi.call("lint_guide_build", _device.ptr(self._cdf), ncells, self._guide_bits_planned,
-                       _device.ptr(self._guide), st)
+            if self._guide_bits_planned > 0:
+                _capi.call("lint_guide_build", _device.ptr(self._cdf), ncells, self._guide_bits_planned,
+                           _device.ptr(self._guide), st)
             self._range.copy_(torch_range(ncells, dev))
         self._guide_bits = self._guide_bits_planned
         self._masses_host = None
@@ -383,6 +386,10 @@ class DensityGrid(DensityStructure):
         if not (self._stratum[0] <= stratum[0] and stratum[1] <= self._stratum[1]):
             raise ValueError(f"DensityGrid: the tables were built for the stratum {self._stratum}; "
                              f"cannot draw from {tuple(stratum)}")
+        if self._guide_bits == 0 and self._stratum != (0.0, 1.0):
+            # without a guide table the u-driven search brackets the whole CDF, and only the
+            # stratum's slab of it was built
+            raise ValueError("DensityGrid: u-driven draws from a stratum-restricted build need guide_bits > 0")
         if out is None:
             out = torch.empty((N, self._dim), dtype=_device.torch_dtype(self.dtype), device=self.device)
         cells = torch.empty(N, dtype=torch.int64, device=self.device) if want_cells else None

@@ -73,7 +73,7 @@ def grid_case(name, edges, pdf, N, qmc=False, dtype=np.float32):
     tdt = torch.float32 if dtype == np.float32 else torch.float64
     isz = 4 if dtype == np.float32 else 8
     for order in (("draw",) if qmc else ("cell", "draw")):
-        kw = dict(cell_records=False, guide_bits=16) if order == "cell" else {}
+        kw = dict(cell_records=False, guide_bits=0) if order == "cell" else {}
         t0 = time.perf_counter()
         grid = lb.DensityGrid(edges, pdf, vectorizedpdf=True, dtype=dtype, **kw)
         torch.cuda.synchronize()

@@ -26,7 +26,7 @@ n_total = int(float(sys.argv[3])) if len(sys.argv) > 3 else 1_000_000_000
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 10
 edges, w, means, sig = synthetic_c3()
 shard = lbd.ShardedGrid(edges, lb.GaussianMixture(w, means, sigmas=sig), dtype=np.float32, rank=rank, world=world,
-                        cell_records=False, guide_bits=16,
+                        cell_records=False, guide_bits=int(os.environ.get("GUIDE_BITS", "0")),
                         balance_rows=None if os.environ.get("EQUAL_MASS") else n_total)
 if len(sys.argv) > 5:
     for line in open(sys.argv[5]):
@@ -39,14 +39,17 @@ n, first = int(counts[rank]), int(counts[:rank].sum())
 out = torch.empty((n, 3), dtype=torch.float32, device="cuda")
 counter = torch.zeros(1, dtype=torch.int64, device="cuda")
 _capi.call("lint_set_offset_counter", C.c_void_p(counter.data_ptr()))
+lane = torch.cuda.Stream()
 
 
 def body(ev=None):
     st = torch.cuda.current_stream()
     if ev:
         ev[0].record(st)
-    _capi.call("lint_advance_counter", C.c_void_p(counter.data_ptr()), C.c_uint64(n_total), C.c_void_p(st.cuda_stream))
+    lane.wait_stream(st)
+    _capi.call("lint_advance_counter", C.c_void_p(counter.data_ptr()), C.c_uint64(n_total), C.c_void_p(lane.cuda_stream))
     shard.enqueue_build(gather=False)
+    st.wait_stream(lane)
     if ev:
         ev[1].record(st)
     shard.sample_cellmajor_into(out, seed=SEED, offset=first)

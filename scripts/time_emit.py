@@ -27,7 +27,7 @@ def main():
     edges, w, means, sig = synthetic_c3()
     dtype = np.float64 if os.environ.get("LINT_F64") else np.float32
     grid = lb.DensityGrid(edges, lb.GaussianMixture(w, means, sigmas=sig), vectorizedpdf=True,
-                          dtype=dtype, cell_records=False, guide_bits=16)
+                          dtype=dtype, cell_records=False, guide_bits=0)
     out = torch.empty((N, 3), dtype=torch.float32 if dtype == np.float32 else torch.float64, device="cuda")
     keys = sorted(sweeps)
     for combo in itertools.product(*(sweeps[k] for k in keys)) if keys else [()]:

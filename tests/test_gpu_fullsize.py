@@ -67,7 +67,7 @@ def test_full_size_draw_properties(lb, order):
     import torch
     from scipy import stats
     edges, w, means, sig = _c3()
-    kw = dict(cell_records=False, guide_bits=16) if order == "cell" else {}
+    kw = dict(cell_records=False, guide_bits=0) if order == "cell" else {}
     grid = lb.DensityGrid(edges, lb.GaussianMixture(w, means, sigmas=sig), vectorizedpdf=True,
                           dtype=np.float32, **kw)
     out = torch.empty((N_FULL, 3), dtype=torch.float32, device="cuda")

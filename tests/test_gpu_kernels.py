@@ -412,6 +412,46 @@ def test_hierarchical_grid_build(lb, name, dtype):
             part._sample_philox(10, 5, 0, stratum=(0.0, 1.0))
 
 
+@pytest.mark.parametrize("name", ["g2d_fullcov", "g3d_holes", "g1d_nonuniform"])
+def test_grid_without_a_guide_table(lb, name):
+    """guide_bits=0: no guide table is built; the u-driven kernels search the whole CDF (same cells
+    as NumPy's searchsorted), the grouped draw of a stratum-restricted build brackets its top-up
+    rows by the slab the build reports, and u-driven draws from such a build are refused."""
+    import torch
+    g = load_golden(name)
+    grid = _grid_from_golden(lb, g, guide_bits=0)
+    ref = _grid_from_golden(lb, g)
+    assert grid._guide_bits == 0 and torch.equal(grid._cdf, ref._cdf)
+    k = len(grid.shape)
+    u = np.random.default_rng(3).random((5000, k + 1))
+    xa, a = grid._sample_u(torch.as_tensor(u, device="cuda"), want_cells=True)
+    xb, b = ref._sample_u(torch.as_tensor(u, device="cuda"), want_cells=True)
+    assert torch.equal(a, b) and torch.equal(xa, xb)
+    assert np.array_equal(a.cpu().numpy(), np.searchsorted(grid._cdf.cpu().numpy(), u[:, -1], side="right"))
+    # grouped draw on a stratum: rows (top-up rows included) stay in cells the stratum touches
+    grid._enqueue_build(stratum=(0.25, 0.75))
+    cdf = ref._cdf.cpu().numpy()
+    c_lo = int(np.searchsorted(cdf, 0.25, side="right"))          # first / last cell the stratum touches
+    c_hi = int(np.searchsorted(cdf, 0.75, side="left"))
+    N = 200_000
+    x, cells = grid._sample_cellmajor(N, 11, 0, want_cells=True, stratum=(0.25, 0.75))
+    cells = cells.cpu().numpy()
+    assert cells.min() >= c_lo and cells.max() <= c_hi
+    # (the top-up tail is non-empty at this N: 8 sqrt(N) rows are held back)
+    counts = np.bincount(cells, minlength=len(cdf)).astype(np.float64)
+    p = np.diff(np.concatenate([[0.25], np.clip(cdf, 0.25, 0.75)])) / 0.5     # share of the stratum in each cell
+    big = p * N >= 20
+    if big.sum() > 1:
+        from scipy import stats
+        obs = np.append(counts[big], counts[~big].sum())
+        exp = np.append(p[big], p[~big].sum()) * N
+        keep = exp > 0
+        chi2 = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum()
+        assert stats.chi2.sf(chi2, keep.sum() - 1) > 1e-4
+    with pytest.raises(ValueError):
+        grid._sample_philox(10, 5, 0, stratum=(0.3, 0.6))
+
+
 @pytest.mark.parametrize("name", ["g2d_fullcov", "g3d_iso", "g3d_holes", "g4d_iso"])
 @pytest.mark.parametrize("bits", [1, 3, 5])
 def test_small_guide_tables_by_bin_search_equal_the_cell_walk(lb, name, bits):
