@@ -356,6 +356,47 @@ int lint_cells_sample_cellmajor(const lint_cells_t *c, int64_t N, uint64_t seed,
 int lint_cellmajor_timing(int enable);
 int lint_cellmajor_last_times(double *out5);
 
+/* ---- tree build (fused pdf families) ------------------------------------------------ */
+
+/* The cells of a DensityTree as a device table in structure-of-arrays form (caller-owned buffers
+ * of `capacity` cells; cell 0 is the root).  Replaces the _TreeCell objects of
+ * density_structures/tree.py:544-703 for pdfs the library can evaluate itself. */
+#define LINT_TREE_MAX_LEVEL 30            /* lattice coordinates are int32 */
+typedef struct lint_tree {
+    int32_t dim;
+    int32_t reserved;
+    double mins[LINT_MAX_DIM], maxs[LINT_MAX_DIM];   /* the root box (HOST values) */
+    int64_t capacity;
+    int32_t *origin_dev;    /* (capacity, dim) integer lattice coordinates of the cell at its level */
+    int32_t *level_dev;     /* (capacity) */
+    int32_t *parent_dev;    /* (capacity) parent cell, -1 for the root */
+    double *corners_dev;    /* (capacity, 2^dim) corner densities, corner order (dim 0 = most significant bit) */
+    double *mass_raw_dev;   /* (capacity) trapezoid mass, tree.py:608 */
+    double *est_dev;        /* (capacity, lint_tree_est_stride()) Romberg estimates e[0..level], tree.py:649-703 */
+} lint_tree_t;
+
+int lint_tree_est_stride(void);
+
+/* == _TreeCell.open + _evaluate_cell + _calculate_romberg_estimates for a batch [tree.py:615-647,
+ * 593-613, 649-703]: creates the 2^dim children of the n_open cells open_ids_dev[] (device int32,
+ * in the order the caller opens them) as cells first_new, first_new + 1, ... (children of one cell
+ * contiguous, in corner order); n_open == 0 creates the root (first_new must be 0).  Per new cell:
+ * pdf on its corners at mins + coords * ((maxs - mins) / 2^level), mass_raw = vol * mean(corners),
+ * the Richardson chain over its ancestors' corner tables — NumPy's operation order throughout.
+ * summary_dev: (new cells, 3) fp64 = mass_raw, mass_romberg (= e[-1]), |e[-1] - e[-2]|, all a caller
+ * needs to pick the next cells to open (tree.py:413-488).  Exactly one of gmm / halos is non-NULL
+ * (HOST structs).  ORs LINT_FLAG_* into *flags_dev for negative / non-finite densities
+ * (tree.py:598-605).  Levels beyond LINT_TREE_MAX_LEVEL are the caller's to refuse. */
+int lint_tree_open(const lint_tree_t *t, const lint_gmm_t *gmm, const lint_halos_t *halos,
+                   const int32_t *open_ids_dev, int64_t n_open, int64_t first_new, double *summary_dev,
+                   uint32_t *flags_dev, lint_stream_t stream);
+
+/* The same pdf at a list of points, points_dev (n, dim) fp64 -> out_dev (n) fp64: what a
+ * vectorised `pdf(x)` call of the reference returns (grid.py:398, tree.py:816), with the
+ * arithmetic of lint_grid_eval_* / lint_tree_open. */
+int lint_points_eval(int dim, const lint_gmm_t *gmm, const lint_halos_t *halos, const double *points_dev, int64_t n,
+                     double *out_dev, lint_stream_t stream);
+
 /* ---- row order ------------------------------------------------------------------- */
 
 /* out[i] = in[pi(i)] for a pseudo-random bijection pi of [0, N) keyed by `seed`

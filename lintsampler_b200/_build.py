@@ -17,12 +17,12 @@ OUT = os.path.join(OUT_DIR, "liblintsampler_b200.so")
 # (source, object stem, extra defines): the cell-major kernels are compiled once per
 # dimension so that the eight translation units build in parallel
 SOURCES = [("lint_build.cu", "lint_build", []), ("lint_sample.cu", "lint_sample", []),
-           ("lint_cellmajor.cu", "lint_cellmajor", [])]
+           ("lint_cellmajor.cu", "lint_cellmajor", []), ("lint_tree.cu", "lint_tree", [])]
 # LINT_DIMS=3 (development only): build the cell-major kernels of the listed dimensions, stubs for the rest
 _DIMS = [int(d) for d in os.environ.get("LINT_DIMS", "1,2,3,4,5,6").split(",")]
 SOURCES += [("lint_cellmajor_inst.cu", f"lint_cellmajor_k{k}",
              [f"-DLINT_K={k}"] + ([] if k in _DIMS else ["-DLINT_STUB"])) for k in range(1, 7)]
-HEADERS = ["lint_device.cuh", "lint_cellmajor.cuh", "lint_cellmajor_plan.h",
+HEADERS = ["lint_device.cuh", "lint_pdf.cuh", "lint_cellmajor.cuh", "lint_cellmajor_plan.h",
            os.path.join("..", "..", "include", "lintsampler_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

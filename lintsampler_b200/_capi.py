@@ -74,6 +74,16 @@ class LintGmm(C.Structure):
     ]
 
 
+class LintTree(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32), ("reserved", C.c_int32),
+        ("mins", C.c_double * LINT_MAX_DIM), ("maxs", C.c_double * LINT_MAX_DIM),
+        ("capacity", C.c_int64),
+        ("origin_dev", C.c_void_p), ("level_dev", C.c_void_p), ("parent_dev", C.c_void_p),
+        ("corners_dev", C.c_void_p), ("mass_raw_dev", C.c_void_p), ("est_dev", C.c_void_p),
+    ]
+
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _U64 = C.c_uint64
@@ -86,6 +96,10 @@ PROTOTYPES = {
     "lint_advance_counter": (C.c_int, [_P, _U64, _P]),
     "lint_grid_eval_gmm": (C.c_int, [C.POINTER(LintGrid), C.POINTER(LintGmm), C.c_double, _P]),
     "lint_grid_eval_halos": (C.c_int, [C.POINTER(LintGrid), C.POINTER(LintHalos), C.c_double, _P]),
+    "lint_tree_est_stride": (C.c_int, []),
+    "lint_tree_open": (C.c_int, [C.POINTER(LintTree), C.POINTER(LintGmm), C.POINTER(LintHalos), _P, _I64, _I64, _P,
+                                 _P, _P]),
+    "lint_points_eval": (C.c_int, [C.c_int, C.POINTER(LintGmm), C.POINTER(LintHalos), _P, _I64, _P, _P]),
     "lint_grid_masses": (C.c_int, [C.POINTER(LintGrid), _P, _P, _P]),
     "lint_grid_records": (C.c_int, [C.POINTER(LintGrid), _P, _P]),
     "lint_cells_record_bytes": (C.c_size_t, [C.c_int, C.c_int]),

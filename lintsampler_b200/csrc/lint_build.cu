@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cmath>
 #include "lint_device.cuh"
+#include "lint_pdf.cuh"
 
 namespace lint {
 
@@ -117,14 +118,6 @@ template GridView<6> make_grid_view<6>(const lint_grid_t *, uint64_t, bool);
 // ---------------------------------------------------------------------------
 // fused Gaussian-mixture vertex evaluation            [replaces grid.py:384-398]
 // ---------------------------------------------------------------------------
-template <int K>
-struct GmmParams {
-    int ncomp;
-    double log_norm[LINT_GMM_MAX_COMP];
-    double mean[LINT_GMM_MAX_COMP][K];
-    double U[LINT_GMM_MAX_COMP][K * (K + 1) / 2];   // upper triangle, row-major
-};
-
 template <int K, typename DensT>
 __global__ void __launch_bounds__(256)
 gmm_eval_kernel(GridView<K> g, GmmParams<K> p, double scale, uint32_t nverts, DensT *out) {
@@ -138,22 +131,7 @@ gmm_eval_kernel(GridView<K> g, GmmParams<K> p, double scale, uint32_t nverts, De
             if (d == 0) { i = r; } else { const uint32_t q = r / nd; i = r - q * nd; r = q; }
             x[d] = __ldg(g.edges[d] + i);
         }
-        double f = 0.0;
-        for (int j = 0; j < p.ncomp; ++j) {
-            double y[K];
-#pragma unroll
-            for (int d = 0; d < K; ++d) y[d] = x[d] - p.mean[j][d];
-            double q = 0.0;
-            int t = 0;
-#pragma unroll
-            for (int rr = 0; rr < K; ++rr) {
-                double s = 0.0;
-#pragma unroll
-                for (int cc = rr; cc < K; ++cc) s = fma(p.U[j][t++], y[cc], s);
-                q = fma(s, s, q);
-            }
-            f += exp(p.log_norm[j] - 0.5 * q);
-        }
+        const double f = p(x);
         out[v] = (DensT)(f * scale);
     }
 }
@@ -161,16 +139,7 @@ gmm_eval_kernel(GridView<K> g, GmmParams<K> p, double scale, uint32_t nverts, De
 template <int K>
 int eval_gmm_impl(const lint_grid_t *g, const lint_gmm_t *gmm, double scale, uint64_t nverts,
                   cudaStream_t st) {
-    GmmParams<K> p;
-    p.ncomp = gmm->ncomp;
-    for (int j = 0; j < gmm->ncomp; ++j) {
-        p.log_norm[j] = gmm->log_norm[j];
-        int t = 0;
-        for (int r = 0; r < K; ++r) {
-            p.mean[j][r] = gmm->mean[j * K + r];
-            for (int c = r; c < K; ++c) p.U[j][t++] = gmm->prec_chol[(j * K + r) * K + c];
-        }
-    }
+    const GmmParams<K> p = fill_gmm<K>(gmm);
     GridView<K> v = make_grid_view<K>(g, 1, false);
     const int threads = 256;
     const int blocks = (int)std::min<uint64_t>((nverts + threads - 1) / threads, 148 * 32);
@@ -186,14 +155,6 @@ int eval_gmm_impl(const lint_grid_t *g, const lint_gmm_t *gmm, double scale, uin
 // ---------------------------------------------------------------------------
 // fused double-power-law halo evaluation   [3_dark_matter.ipynb cells 11, 16 through grid.py:384-398]
 // ---------------------------------------------------------------------------
-template <int K>
-struct HaloParams {
-    int ncomp;
-    double rho0[LINT_GMM_MAX_COMP], inv_rs[LINT_GMM_MAX_COMP], centre[LINT_GMM_MAX_COMP][K];
-    double alpha, outer, gamma, eps, q_cut;      // outer = (beta - gamma) / alpha
-    bool nfw;                                    // alpha 1, beta 3, gamma 1: no pow()
-};
-
 template <int K, typename DensT>
 __global__ void __launch_bounds__(256)
 halo_eval_kernel(GridView<K> g, HaloParams<K> p, double scale, uint32_t nverts, DensT *out) {
@@ -207,17 +168,7 @@ halo_eval_kernel(GridView<K> g, HaloParams<K> p, double scale, uint32_t nverts, 
             if (d == 0) { i = r; } else { const uint32_t q = r / nd; i = r - q * nd; r = q; }
             x[d] = __ldg(g.edges[d] + i);
         }
-        double f = 0.0;
-        for (int j = 0; j < p.ncomp; ++j) {
-            double r2 = 0.0;
-#pragma unroll
-            for (int d = 0; d < K; ++d) { const double y = x[d] - p.centre[j][d]; r2 = fma(y, y, r2); }
-            const double q = sqrt(r2) * p.inv_rs[j];
-            if (p.q_cut > 0.0 && q > p.q_cut) continue;
-            const double den = p.nfw ? (q + p.eps) * (1.0 + q) * (1.0 + q)
-                                     : pow(q + p.eps, p.gamma) * pow(1.0 + pow(q, p.alpha), p.outer);
-            f += p.rho0[j] / den;
-        }
+        const double f = p(x);
         out[v] = (DensT)(f * scale);
     }
 }
@@ -225,19 +176,7 @@ halo_eval_kernel(GridView<K> g, HaloParams<K> p, double scale, uint32_t nverts, 
 template <int K>
 int eval_halos_impl(const lint_grid_t *g, const lint_halos_t *h, double scale, uint64_t nverts,
                     cudaStream_t st) {
-    HaloParams<K> p;
-    p.ncomp = h->ncomp;
-    for (int j = 0; j < h->ncomp; ++j) {
-        p.rho0[j] = h->rho0[j];
-        p.inv_rs[j] = 1.0 / h->r_s[j];
-        for (int d = 0; d < K; ++d) p.centre[j][d] = h->centre[j * K + d];
-    }
-    p.alpha = h->alpha;
-    p.outer = (h->beta - h->gamma) / h->alpha;
-    p.gamma = h->gamma;
-    p.eps = h->eps;
-    p.q_cut = h->q_cut;
-    p.nfw = h->alpha == 1.0 && h->beta == 3.0 && h->gamma == 1.0;
+    const HaloParams<K> p = fill_halos<K>(h);
     GridView<K> v = make_grid_view<K>(g, 1, false);
     const int threads = 256;
     const int blocks = (int)std::min<uint64_t>((nverts + threads - 1) / threads, 148 * 32);

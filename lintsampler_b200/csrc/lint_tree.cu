@@ -1,0 +1,274 @@
+// lintsampler_b200 — tree construction on the device for fused pdf families.
+//
+// Reference: DensityTree / _TreeCell, density_structures/tree.py:228-292 (construction),
+// 357-488 (refine), 593-613 (_evaluate_cell), 615-647 (open), 649-703 (Romberg estimates).
+//
+// The tree is a table of cells in structure-of-arrays form, appended to as cells are opened.
+// `lint_tree_open` creates the 2^k children of a batch of cells: one thread per child evaluates the
+// pdf on its 2^k corners, the trapezoid mass and the chain of Richardson-extrapolated masses from
+// the corner tables of its ancestors — the arithmetic of tree.py:608 and 649-703 in NumPy's
+// operation order (the sums over corners are NumPy's pairwise add.reduce), so that a tree built
+// here and one built by the host code from the same corner densities agree bit for bit.  Which
+// cells to open, and in which order (it fixes the leaf order and with it the leaf CDF,
+// tree.py:335-338), stays with the caller: it needs only the three numbers per new cell returned in
+// `summary_dev`.
+#include <algorithm>
+#include "lint_device.cuh"
+#include "lint_pdf.cuh"
+
+namespace lint {
+
+constexpr int TREE_MAX_LEVEL = LINT_TREE_MAX_LEVEL;       // int32 lattice coordinates
+constexpr int TREE_EST = LINT_TREE_MAX_LEVEL + 2;         // Romberg estimates kept per cell (stride)
+
+template <int K>
+struct TreeTable {
+    double mins[K], span[K];
+    int32_t *origin;        // (cap, K) lattice coordinates at the cell's level
+    int32_t *level;         // (cap)
+    int32_t *parent;        // (cap), -1 for the root
+    double *corners;        // (cap, 2^K) corner densities, corner order (dim 0 = most significant bit)
+    double *mass_raw;       // (cap)
+    double *est;            // (cap, TREE_EST) Romberg estimates e[0..level]
+};
+
+// NumPy's add.reduce over N contiguous doubles (np.sum(a, axis=1) of an (n, N) array):
+// below 8 elements a running sum from -0.0, otherwise eight accumulators combined pairwise.
+template <int N>
+__device__ __forceinline__ double numpy_sum(const double (&a)[N]) {
+    if constexpr (N < 8) {
+        double r = -0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) r = __dadd_rn(r, a[i]);
+        return r;
+    } else {
+        double r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+#pragma unroll
+        for (int i = 8; i < N; i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+        }
+        return __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    }
+}
+
+// dx = span / 2^level per dimension, vol = np.prod(dx) (a running product from 1.0)
+template <int K>
+__device__ __forceinline__ double cell_volume(const double (&span)[K], int level) {
+    double vol = 1.0;
+#pragma unroll
+    for (int d = 0; d < K; ++d) vol = __dmul_rn(vol, scalbn(span[d], -level));
+    return vol;
+}
+
+// One thread per new cell.  Cell `first + t` is child `t mod 2^K` of open_ids[t / 2^K]
+// (root: the single cell 0 with no parent, n_open == 0).
+template <int K, typename Pdf>
+__global__ void __launch_bounds__(128)
+tree_open_kernel(TreeTable<K> tb, Pdf pdf, const int32_t *__restrict__ open_ids, uint32_t n_new, uint32_t first,
+                 bool root, double *__restrict__ summary, uint32_t *flags) {
+    constexpr int NC = 1 << K;
+    uint32_t bad = 0;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_new; t += gridDim.x * blockDim.x) {
+        const uint32_t id = first + t;
+        int32_t org[K];
+        int level = 0, par = -1;
+        if (root) {
+#pragma unroll
+            for (int d = 0; d < K; ++d) org[d] = 0;
+        } else {
+            par = open_ids[t >> K];
+            const uint32_t c = t & (NC - 1);
+            level = tb.level[par] + 1;
+#pragma unroll
+            for (int d = 0; d < K; ++d)                                      // tree.py:632-640
+                org[d] = 2 * tb.origin[(size_t)par * K + d] + (int32_t)((c >> (K - 1 - d)) & 1u);
+        }
+        // corner densities at mins + coords * (span / 2^level)            [tree.py:593-596, 866-867]
+        double f[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            double x[K];
+#pragma unroll
+            for (int d = 0; d < K; ++d) {
+                const int32_t coord = org[d] + (int32_t)((c >> (K - 1 - d)) & 1);
+                x[d] = __dadd_rn(tb.mins[d], __dmul_rn((double)coord, scalbn(tb.span[d], -level)));
+            }
+            f[c] = pdf(x);
+            if (f[c] < 0.0) bad |= LINT_FLAG_NEGATIVE;                       // tree.py:598-601
+            if (!isfinite(f[c])) bad |= LINT_FLAG_NONFINITE;                 // tree.py:602-605
+        }
+        const double vol = cell_volume<K>(tb.span, level);
+        const double raw = __dmul_rn(vol, __ddiv_rn(numpy_sum<NC>(f), (double)NC));     // tree.py:608
+        tb.level[id] = level;
+        tb.parent[id] = par;
+#pragma unroll
+        for (int d = 0; d < K; ++d) tb.origin[(size_t)id * K + d] = org[d];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) tb.corners[(size_t)id * NC + c] = f[c];
+        tb.mass_raw[id] = raw;
+
+        // Romberg chain [tree.py:649-703]: cur[0] the cell's own trapezoid mass, cur[j] the mass its
+        // j-th ancestor's multilinear interpolant gives it (value at the cell's midpoint x volume)
+        double cur[TREE_MAX_LEVEL + 1];
+        cur[0] = raw;
+        int anc = par;
+        for (int j = 1; j <= level; ++j) {
+            double w[NC];
+            w[0] = 1.0;
+            // midpoint of the cell in the ancestor's unit cube (dyadic, exact); weights built dimension
+            // by dimension, ((w0 * w1) * w2) ..., corner index with dim 0 as the most significant bit
+#pragma unroll
+            for (int d = 0; d < K; ++d) {
+                const double mid = scalbn((double)org[d] + 0.5, -j) - (double)tb.origin[(size_t)anc * K + d];
+                const int have = 1 << d;
+#pragma unroll
+                for (int c = have - 1; c >= 0; --c) {
+                    const double base = w[c];
+                    w[2 * c + 1] = d == 0 ? mid : __dmul_rn(base, mid);
+                    w[2 * c] = d == 0 ? 1.0 - mid : __dmul_rn(base, 1.0 - mid);
+                }
+            }
+            double prod[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) prod[c] = __dmul_rn(tb.corners[(size_t)anc * NC + c], w[c]);
+            const double fmid = numpy_sum<NC>(prod);
+            const double avol = cell_volume<K>(tb.span, level - j);
+            cur[j] = scalbn(__dmul_rn(fmid, avol), -(j * K));                // fmid * anc.vol / 2^(j k)
+            anc = tb.parent[anc];
+        }
+        double *est = tb.est + (size_t)id * TREE_EST;
+        est[0] = raw;
+        double prev = raw, last = raw;
+        for (int i = 0; i < level; ++i) {                                    // Richardson extrapolation
+            const double denom = scalbn(1.0, 2 * (i + 1)) - 1.0;             // 4^(i+1) - 1
+            for (int j = 0; j < level - i; ++j)
+                cur[j] = __dsub_rn(cur[j], __ddiv_rn(__dsub_rn(cur[j + 1], cur[j]), denom));
+            prev = last;
+            last = cur[0];
+            est[i + 1] = last;
+        }
+        summary[(size_t)t * 3 + 0] = raw;
+        summary[(size_t)t * 3 + 1] = last;                                   // mass_romberg
+        summary[(size_t)t * 3 + 2] = fabs(__dsub_rn(last, prev));            // |e[-1] - e[-2]| (0 for the root)
+    }
+    if (bad) atomicOr(flags, bad);
+}
+
+// pdf on a list of points (the host tree builder's vectorised pdf call; parity tests)
+template <int K, typename Pdf>
+__global__ void __launch_bounds__(256)
+points_eval_kernel(Pdf pdf, const double *__restrict__ pts, uint32_t n, double *__restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double x[K];
+#pragma unroll
+        for (int d = 0; d < K; ++d) x[d] = pts[(size_t)i * K + d];
+        out[i] = pdf(x);
+    }
+}
+
+template <int K, typename Pdf>
+int tree_open_launch(const lint_tree_t *t, const Pdf &pdf, const int32_t *open_ids, int64_t n_open,
+                     int64_t first, double *summary, uint32_t *flags, cudaStream_t st) {
+    TreeTable<K> tb;
+    for (int d = 0; d < K; ++d) {
+        tb.mins[d] = t->mins[d];
+        tb.span[d] = t->maxs[d] - t->mins[d];
+    }
+    tb.origin = t->origin_dev;
+    tb.level = t->level_dev;
+    tb.parent = t->parent_dev;
+    tb.corners = t->corners_dev;
+    tb.mass_raw = t->mass_raw_dev;
+    tb.est = t->est_dev;
+    const bool root = n_open == 0;
+    const uint32_t n_new = root ? 1u : (uint32_t)(n_open << K);
+    const int blocks = (int)std::min<uint32_t>((n_new + 127) / 128, 148 * 8);
+    tree_open_kernel<K, Pdf><<<blocks, 128, 0, st>>>(tb, pdf, open_ids, n_new, (uint32_t)first, root, summary, flags);
+    return check_launch("lint_tree_open");
+}
+
+template <int K>
+int tree_open_k(const lint_tree_t *t, const lint_gmm_t *gmm, const lint_halos_t *halos, const int32_t *open_ids,
+                int64_t n_open, int64_t first, double *summary, uint32_t *flags, cudaStream_t st) {
+    if (gmm) return tree_open_launch<K>(t, fill_gmm<K>(gmm), open_ids, n_open, first, summary, flags, st);
+    return tree_open_launch<K>(t, fill_halos<K>(halos), open_ids, n_open, first, summary, flags, st);
+}
+
+template <int K>
+int points_eval_k(const lint_gmm_t *gmm, const lint_halos_t *halos, const double *pts, int64_t n, double *out,
+                  cudaStream_t st) {
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    if (gmm) points_eval_kernel<K><<<blocks, 256, 0, st>>>(fill_gmm<K>(gmm), pts, (uint32_t)n, out);
+    else points_eval_kernel<K><<<blocks, 256, 0, st>>>(fill_halos<K>(halos), pts, (uint32_t)n, out);
+    return check_launch("lint_points_eval");
+}
+
+static int check_pdf(const char *what, int dim, const lint_gmm_t *gmm, const lint_halos_t *halos) {
+    if ((gmm != nullptr) == (halos != nullptr))
+        return fail(LINT_ERR_BAD_ARG, "%s: exactly one of gmm / halos must be given", what);
+    if (dim < 1 || dim > LINT_MAX_DIM) return fail(LINT_ERR_BAD_ARG, "%s: dim %d outside 1..%d", what, dim, LINT_MAX_DIM);
+    const int pdim = gmm ? gmm->dim : halos->dim, nc = gmm ? gmm->ncomp : halos->ncomp;
+    if (pdim != dim) return fail(LINT_ERR_BAD_ARG, "%s: pdf has %d dimensions, the domain %d", what, pdim, dim);
+    if (nc < 1 || nc > LINT_GMM_MAX_COMP)
+        return fail(LINT_ERR_BAD_ARG, "%s: %d components outside 1..%d", what, nc, LINT_GMM_MAX_COMP);
+    return LINT_OK;
+}
+
+}  // namespace lint
+
+using namespace lint;
+
+extern "C" {
+
+int lint_tree_est_stride(void) { return TREE_EST; }
+
+int lint_tree_open(const lint_tree_t *t, const lint_gmm_t *gmm, const lint_halos_t *halos,
+                   const int32_t *open_ids_dev, int64_t n_open, int64_t first_new, double *summary_dev,
+                   uint32_t *flags_dev, lint_stream_t stream) {
+    if (!t) return fail(LINT_ERR_BAD_ARG, "lint_tree_open: NULL tree");
+    if (int rc = check_pdf("lint_tree_open", t->dim, gmm, halos)) return rc;
+    if (!t->origin_dev || !t->level_dev || !t->parent_dev || !t->corners_dev || !t->mass_raw_dev || !t->est_dev ||
+        !summary_dev || !flags_dev)
+        return fail(LINT_ERR_BAD_ARG, "lint_tree_open: NULL table / summary / flags pointer");
+    if (n_open < 0 || first_new < 0 || (n_open > 0 && !open_ids_dev) || (n_open == 0 && first_new != 0))
+        return fail(LINT_ERR_BAD_ARG, "lint_tree_open: bad batch (n_open=%lld, first_new=%lld)", (long long)n_open,
+                    (long long)first_new);
+    const int64_t n_new = n_open == 0 ? 1 : n_open << t->dim;
+    if (first_new + n_new > t->capacity || first_new + n_new >= (1ll << 31))
+        return fail(LINT_ERR_BAD_ARG, "lint_tree_open: %lld new cells do not fit the table (capacity %lld)",
+                    (long long)n_new, (long long)t->capacity);
+    for (int d = 0; d < t->dim; ++d)
+        if (!(t->maxs[d] > t->mins[d])) return fail(LINT_ERR_BAD_ARG, "lint_tree_open: empty box along dimension %d", d);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (t->dim) {
+        case 1: return tree_open_k<1>(t, gmm, halos, open_ids_dev, n_open, first_new, summary_dev, flags_dev, st);
+        case 2: return tree_open_k<2>(t, gmm, halos, open_ids_dev, n_open, first_new, summary_dev, flags_dev, st);
+        case 3: return tree_open_k<3>(t, gmm, halos, open_ids_dev, n_open, first_new, summary_dev, flags_dev, st);
+        case 4: return tree_open_k<4>(t, gmm, halos, open_ids_dev, n_open, first_new, summary_dev, flags_dev, st);
+        case 5: return tree_open_k<5>(t, gmm, halos, open_ids_dev, n_open, first_new, summary_dev, flags_dev, st);
+        default: return tree_open_k<6>(t, gmm, halos, open_ids_dev, n_open, first_new, summary_dev, flags_dev, st);
+    }
+}
+
+int lint_points_eval(int dim, const lint_gmm_t *gmm, const lint_halos_t *halos, const double *points_dev, int64_t n,
+                     double *out_dev, lint_stream_t stream) {
+    if (int rc = check_pdf("lint_points_eval", dim, gmm, halos)) return rc;
+    if (n < 0 || n >= (1ll << 32) || (n > 0 && (!points_dev || !out_dev)))
+        return fail(LINT_ERR_BAD_ARG, "lint_points_eval: bad point list");
+    if (n == 0) return LINT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dim) {
+        case 1: return points_eval_k<1>(gmm, halos, points_dev, n, out_dev, st);
+        case 2: return points_eval_k<2>(gmm, halos, points_dev, n, out_dev, st);
+        case 3: return points_eval_k<3>(gmm, halos, points_dev, n, out_dev, st);
+        case 4: return points_eval_k<4>(gmm, halos, points_dev, n, out_dev, st);
+        case 5: return points_eval_k<5>(gmm, halos, points_dev, n, out_dev, st);
+        default: return points_eval_k<6>(gmm, halos, points_dev, n, out_dev, st);
+    }
+}
+
+}  // extern "C"

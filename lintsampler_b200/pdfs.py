@@ -19,6 +19,27 @@ import numpy as np
 from . import _capi
 
 
+def _eval_points(self, x, device=None):
+    """The pdf at points ``x`` (n, k) — or (n,) when k = 1 — evaluated by the device code that also
+    fills grid vertices and tree corners (``lint_points_eval``); returns a NumPy array (n,).
+    A vectorised pdf with exactly the library's arithmetic, e.g. to cross-check a device-built
+    tree against the host builder."""
+    import torch
+    from . import _device
+    dev = _device.require_cuda(device)
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1, self.dim))
+    with torch.cuda.device(dev):
+        pts = torch.as_tensor(x, device=dev)
+        out = torch.empty(len(x), dtype=torch.float64, device=dev)
+        st, keep = self._as_struct()
+        gmm = C.byref(st) if isinstance(st, _capi.LintGmm) else None
+        halos = C.byref(st) if isinstance(st, _capi.LintHalos) else None
+        _capi.call("lint_points_eval", self.dim, gmm, halos, _device.ptr(pts), len(x), _device.ptr(out),
+                   _device.stream_ptr(dev))
+        del keep
+        return out.cpu().numpy()
+
+
 class GaussianMixture:
     """``sum_j w_j N(x; mu_j, Sigma_j)`` in k dimensions.
 
@@ -84,6 +105,8 @@ class GaussianMixture:
         gs, keep = self._as_struct()
         _capi.call("lint_grid_eval_gmm", C.byref(desc), C.byref(gs), scale, stream)
         del keep
+
+    eval_points = _eval_points
 
     def _as_struct(self):
         """(LintGmm, keepalive) for the C ABI (host arrays)."""
@@ -162,7 +185,8 @@ class DoublePowerLaw:
             total += self.rho0[h] * float(self._profile(np.asarray(np.sqrt(d2) / self.scale_radii[h])))
         return total
 
-    def _eval_on_grid(self, desc, scale, stream):
+    def _as_struct(self):
+        """(LintHalos, keepalive) for the C ABI (host arrays)."""
         s = _capi.LintHalos()
         s.dim, s.ncomp = self.dim, self.ncomp
         dp = C.POINTER(C.c_double)
@@ -170,8 +194,14 @@ class DoublePowerLaw:
                 np.ascontiguousarray(self.scale_radii))
         s.rho0, s.centre, s.r_s = (a.ctypes.data_as(dp) for a in keep)
         s.alpha, s.beta, s.gamma, s.eps, s.q_cut = self.alpha, self.beta, self.gamma, self.eps, self.q_cut
+        return s, keep
+
+    def _eval_on_grid(self, desc, scale, stream):
+        s, keep = self._as_struct()
         _capi.call("lint_grid_eval_halos", C.byref(desc), C.byref(s), scale, stream)
         del keep
+
+    eval_points = _eval_points
 
 
 FUSED_PDFS = (GaussianMixture, DoublePowerLaw)

@@ -5,11 +5,15 @@ same constructor, ``refine`` / ``get_leaf_at_pos`` / ``choose_cells`` contract,
 exceptions, warnings and — crucially — the same *leaf order*, because the order
 of ``tree.leaves`` defines the leaf CDF (tree.py:335-338).
 
-Construction and Romberg refinement are sequential, user-pdf-bound host logic
-(SURVEY.md §2 row 4 keeps them on the host); this implementation batches the
-pdf evaluations of every cell opened in a sweep and keeps per-leaf data in flat
-arrays.  Sampling runs on the device over the flattened leaf table
-(``lint_cells_sample_*``).
+Two builders produce the same tree.  For an arbitrary Python pdf, construction
+and Romberg refinement are host logic that batches the pdf evaluations of every
+cell opened in a sweep.  For the pdf families the library evaluates itself
+(``GaussianMixture``, ``DoublePowerLaw``) the cells live in a device table and
+``lint_tree_open`` evaluates corner densities, trapezoid masses and Romberg
+chains of every batch of new cells (``_DeviceTree``); only the choice of the
+cells to open — which fixes the leaf order — is made on the host, from three
+numbers per new cell.  Sampling runs on the device over the flattened leaf
+table (``lint_cells_sample_*``).
 """
 import ctypes as C
 from warnings import warn
@@ -114,6 +118,137 @@ class _VertexEvaluator:
         return out
 
 
+class _DeviceTree:
+    """Cell table of a tree on the device (``lint_tree_t``) and the host mirror of the per-cell
+    scalars the refinement logic reads (tree.py:413-488): level, parent, first child, raw mass,
+    Romberg mass, last Romberg correction."""
+
+    def __init__(self, mins, maxs, pdf, device):
+        import torch
+        self.device = _device.require_cuda(device)
+        self.k = len(mins)
+        self.nc = 2 ** self.k
+        self.mins = np.asarray(mins, dtype=np.float64)
+        self.maxs = np.asarray(maxs, dtype=np.float64)
+        self.pdf = pdf
+        self.stride = int(_capi.load().lint_tree_est_stride())
+        self.max_level = self.stride - 2
+        self.n = 0
+        self.cap = 0
+        self._t = {}
+        self.level = np.empty(0, dtype=np.int32)
+        self.parent = np.empty(0, dtype=np.int64)
+        self.first_child = np.empty(0, dtype=np.int64)
+        self.mass_raw = np.empty(0)
+        self.mass_rom = np.empty(0)
+        self.err = np.empty(0)
+        self._flags = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._grow(4096)
+        self._launch(None)                                       # the root
+
+    # per-cell device arrays: name -> (columns, dtype)
+    def _layout(self):
+        import torch
+        return {"origin": (self.k, torch.int32), "level": (1, torch.int32), "parent": (1, torch.int32),
+                "corners": (self.nc, torch.float64), "mass_raw": (1, torch.float64),
+                "est": (self.stride, torch.float64)}
+
+    def _grow(self, need):
+        import torch
+        if need <= self.cap:
+            return
+        cap = max(need, 2 * self.cap)
+        with torch.cuda.device(self.device):
+            for name, (cols, dt) in self._layout().items():
+                new = torch.empty((cap, cols), dtype=dt, device=self.device)
+                if self.n:
+                    new[:self.n] = self._t[name][:self.n]
+                self._t[name] = new
+        for name in ("level", "parent", "first_child", "mass_raw", "mass_rom", "err"):
+            old = getattr(self, name)
+            new = np.empty(cap, dtype=old.dtype)
+            new[:self.n] = old[:self.n]
+            setattr(self, name, new)
+        self.cap = cap
+
+    def _struct(self):
+        t = _capi.LintTree()
+        t.dim = self.k
+        for d in range(self.k):
+            t.mins[d], t.maxs[d] = float(self.mins[d]), float(self.maxs[d])
+        t.capacity = self.cap
+        for name in self._layout():
+            setattr(t, name + "_dev", self._t[name].data_ptr())
+        return t
+
+    def _pdf_structs(self):
+        from .pdfs import GaussianMixture
+        if isinstance(self.pdf, GaussianMixture):
+            gs, keep = self.pdf._as_struct()
+            return C.byref(gs), None, (gs, keep)
+        hs, keep = self.pdf._as_struct()
+        return None, C.byref(hs), (hs, keep)
+
+    def _launch(self, ids):
+        """Create the root (ids None) or the children of the cells ``ids``; returns the new ids."""
+        import torch
+        with torch.cuda.device(self.device):
+            n_open = 0 if ids is None else len(ids)
+            n_new = 1 if ids is None else n_open * self.nc
+            first = self.n
+            self._grow(first + n_new)
+            ids_t = None if ids is None else torch.as_tensor(np.asarray(ids, dtype=np.int32), device=self.device)
+            summary = torch.empty((n_new, 3), dtype=torch.float64, device=self.device)
+            gmm, halos, keep = self._pdf_structs()
+            t = self._struct()
+            _capi.call("lint_tree_open", C.byref(t), gmm, halos, _device.ptr(ids_t), n_open, first,
+                       _device.ptr(summary), _device.ptr(self._flags), _device.stream_ptr(self.device))
+            del keep
+            s = summary.cpu().numpy()
+        new = np.arange(first, first + n_new, dtype=np.int64)
+        if ids is None:
+            self.level[0], self.parent[0] = 0, -1
+        else:
+            ids = np.asarray(ids, dtype=np.int64)
+            self.level[new] = np.repeat(self.level[ids] + 1, self.nc)
+            self.parent[new] = np.repeat(ids, self.nc)
+            self.first_child[ids] = first + self.nc * np.arange(n_open, dtype=np.int64)
+        self.first_child[new] = -1
+        self.mass_raw[new], self.mass_rom[new], self.err[new] = s[:, 0], s[:, 1], s[:, 2]
+        self.n = first + n_new
+        return new
+
+    def open(self, ids):
+        ids = np.asarray(ids, dtype=np.int64)
+        if len(ids) and int(self.level[ids].max()) >= self.max_level:
+            raise ValueError(f"DensityTree: the device builder refines to level {self.max_level} at most")
+        return self._launch(ids)
+
+    def check(self):
+        """Density checks of tree.py:598-605 for everything evaluated so far."""
+        bad = int(self._flags.item())
+        if bad & _capi.LINT_FLAG_NEGATIVE:
+            raise ValueError("DensityTree: Densities can't be negative")
+        if bad & _capi.LINT_FLAG_NONFINITE:
+            raise ValueError("DensityTree: Detected non-finite density")
+
+    def fetch(self, name, ids=None):
+        """Host copy of a per-cell device array (rows ``ids``, default all cells)."""
+        import torch
+        t = self._t[name][:self.n]
+        if ids is not None:
+            t = t[torch.as_tensor(np.asarray(ids, dtype=np.int64), device=self.device)]
+        return t.cpu().numpy()
+
+    def geometry(self, ids):
+        """(x, dx) of cells ``ids`` with the reference's arithmetic: dx = span / 2^level,
+        x = mins + origin * dx  [tree.py:585-591]."""
+        org = self.fetch("origin", ids).astype(np.int64)
+        lev = self.level[np.asarray(ids, dtype=np.int64)]
+        dx = (self.maxs - self.mins)[None, :] / (2.0 ** lev)[:, None]
+        return self.mins[None, :] + org * dx, dx
+
+
 class DensityTree(DensityStructure):
     """Tree-like domain over the box ``[mins, maxs]``.
 
@@ -125,12 +260,15 @@ class DensityTree(DensityStructure):
     usecache : memoise pdf evaluations on shared vertices.
     batch : evaluate all vertices of a cell's children in one vectorised call.
 
-    Keyword-only extensions: ``dtype``, ``device``, ``cdf_mode`` as ``DensityGrid``.
+    Keyword-only extensions: ``dtype``, ``device``, ``cdf_mode`` as ``DensityGrid``;
+    ``build``: "device" builds the tree in a device cell table (``lint_tree_open``; needs one
+    of the library's own pdf families), "host" keeps the host builder, None (default) picks
+    the device builder whenever the pdf allows it and a CUDA device is present.
     """
 
     def __init__(self, mins, maxs, pdf, vectorizedpdf=False, pdf_args=(), pdf_kwargs={},
                  min_openings=1, usecache=True, batch=False,
-                 *, dtype=np.float64, device=None, cdf_mode="parallel"):
+                 *, dtype=np.float64, device=None, cdf_mode="parallel", build=None):
         if not hasattr(mins, "__len__"):
             mins, maxs = np.array([mins]), np.array([maxs])
         else:
@@ -155,15 +293,89 @@ class DensityTree(DensityStructure):
         self._device_arg = device
         self._table = None          # device leaf table, rebuilt lazily
         self._corners01 = _unit_corners(self._dim)
+        self._dt = None             # device cell table (device builder)
+        self._leaf_ids = None       # its leaves, in the reference's leaf order
+        self._cells = None          # TreeCell objects of a device-built tree, made on demand
+        if self._wants_device_build(pdf, pdf_args, pdf_kwargs, build):
+            self._dt = _DeviceTree(mins, maxs, pdf, device)
+            ids = np.zeros(1, dtype=np.int64)
+            for _ in range(min_openings):                       # tree.py:285-291
+                ids = self._dt.open(ids)                        # children of leaf i follow those of leaf i-1
+            self._leaf_ids = ids
+            self._dt.check()
+            return
         self._eval = _VertexEvaluator(mins, maxs, pdf, vectorizedpdf or batch, pdf_args, pdf_kwargs,
                                       usecache and not batch)
-        self.root = TreeCell(None, 0, 0, np.zeros(self._dim, dtype=np.int64))
-        self._finish_cells([self.root])
-        leaves = [self.root]
+        self._root = TreeCell(None, 0, 0, np.zeros(self._dim, dtype=np.int64))
+        self._finish_cells([self._root])
+        leaves = [self._root]
         for _ in range(min_openings):                           # tree.py:285-291
             self._open(leaves)
             leaves = [child for leaf in leaves for child in leaf.children]
-        self.leaves = leaves
+        self._leaves = leaves
+
+    @staticmethod
+    def _wants_device_build(pdf, pdf_args, pdf_kwargs, build):
+        from .pdfs import FUSED_PDFS
+        if build not in (None, "host", "device"):
+            raise ValueError(f"DensityTree: build must be None, 'host' or 'device', got {build!r}")
+        fused = isinstance(pdf, FUSED_PDFS) and not pdf_args and not pdf_kwargs
+        if build == "device":
+            if not fused:
+                raise ValueError("DensityTree: build='device' needs a GaussianMixture or DoublePowerLaw pdf "
+                                 "without extra arguments")
+            return True
+        if build == "host" or not fused:
+            return False
+        import torch
+        return torch.cuda.is_available()
+
+    # ------------------------------------------------------------------ cells as objects
+    @property
+    def leaves(self):
+        """Leaf cells in the reference's order (tree.py:290-291, 440-446, 479-481)."""
+        if self._dt is not None:
+            cells = self._materialise()
+            return [cells[i] for i in self._leaf_ids]
+        return self._leaves
+
+    @leaves.setter
+    def leaves(self, value):
+        if self._dt is not None:
+            raise AttributeError("DensityTree: the leaves of a device-built tree cannot be reassigned")
+        self._leaves = value
+
+    @property
+    def root(self):
+        return self._materialise()[0] if self._dt is not None else self._root
+
+    def _materialise(self):
+        """TreeCell objects for every cell of the device table (API compatibility: ``leaves``,
+        ``root``, ``get_leaf_at_pos``); built once per state of the tree."""
+        if self._cells is not None and len(self._cells) == self._dt.n:
+            return self._cells
+        dt, k = self._dt, self._dim
+        ids = np.arange(dt.n)
+        org = dt.fetch("origin").astype(np.int64)
+        x, dx = dt.geometry(ids)
+        corners, est = dt.fetch("corners"), dt.fetch("est")
+        cells = []
+        for i in range(dt.n):
+            par = cells[dt.parent[i]] if dt.parent[i] >= 0 else None
+            j = 0 if par is None else i - dt.first_child[dt.parent[i]]
+            c = TreeCell(par, 0 if par is None else par.idx * 2 ** k + int(j), int(dt.level[i]), org[i])
+            c.x, c.dx, c.vol = x[i], dx[i], np.prod(dx[i])
+            c.corner_densities = corners[i]
+            c.mass_raw = dt.mass_raw[i]
+            c.romberg_estimates = list(est[i, :dt.level[i] + 1])
+            c.mass_romberg = dt.mass_rom[i]
+            cells.append(c)
+        for i in range(dt.n):
+            fc = dt.first_child[i]
+            if fc >= 0:
+                cells[i].children = tuple(cells[fc:fc + 2 ** k])
+        self._cells = cells
+        return cells
 
     # ------------------------------------------------------------------ properties
     @property
@@ -180,6 +392,8 @@ class DensityTree(DensityStructure):
 
     @property
     def _leaf_masses(self):
+        if self._dt is not None:
+            return self._dt.mass_raw[self._leaf_ids].copy()
         return np.array([leaf.mass_raw for leaf in self.leaves])
 
     @property
@@ -284,10 +498,12 @@ class DensityTree(DensityStructure):
         opens the single worst leaf until the tree-wide fractional error drops
         below ``tree_tol``.
         """
-        if len(self.leaves) == 1:
+        if (len(self._leaf_ids) if self._dt is not None else len(self.leaves)) == 1:
             raise RuntimeError(
                 "DensityTree.refine: Romberg refinement needs at least two tree levels "
                 "to estimate mass errors. Instantiate tree with min_openings>0.")
+        if self._dt is not None:
+            return self._refine_device(tree_tol, leaf_tol, leaf_mass_contribution_tol, verbose)
         if verbose:
             print(f"Pre-loop: {len(self.leaves)} leaves on tree. Total mass={self.total_mass}")
 
@@ -334,6 +550,52 @@ class DensityTree(DensityStructure):
                       f"Total mass={m_tot}. Fractional error={err_tot / m_tot}.")
         self._table = None
 
+    def _refine_device(self, tree_tol, leaf_tol, leaf_mass_contribution_tol, verbose):
+        """``refine`` over the device cell table: the same two stages and the same open order on
+        arrays of cell ids; every batch of new cells is one ``lint_tree_open`` launch."""
+        dt = self._dt
+        ids = self._leaf_ids
+        if verbose:
+            print(f"Pre-loop: {len(ids)} leaves on tree. Total mass={self.total_mass}")
+        m_rom, errs = dt.mass_rom[ids].copy(), dt.err[ids].copy()
+        sweep = 0
+        while True:
+            sweep += 1
+            sel = np.where((errs > leaf_tol * m_rom)
+                           & (m_rom > leaf_mass_contribution_tol * np.nanmean(m_rom)))[0]
+            if len(sel):
+                keep = np.ones(len(ids), dtype=bool)
+                keep[sel] = False
+                fresh = dt.open(ids[sel[::-1]])                    # reversed index order (tree.py:440-446)
+                ids = np.concatenate((ids[keep], fresh))
+                m_rom = np.concatenate((m_rom[keep], dt.mass_rom[fresh]))
+                errs = np.concatenate((errs[keep], dt.err[fresh]))
+            if verbose:
+                print(f"End of leaf iteration {sweep}: {len(ids)} leaves on tree. "
+                      f"Total mass={np.sum(m_rom)}, with mean leaf mass={np.nanmean(m_rom)}")
+            if not len(sel):
+                break
+        m_raw = dt.mass_raw[ids].copy()
+        it = 0
+        while True:
+            it += 1
+            m_tot = np.sum(m_rom)
+            sq = (m_rom - m_raw) ** 2
+            err_tot = np.sqrt(np.sum(sq))
+            if err_tot / m_tot < tree_tol:
+                break
+            worst = int(np.argmax(sq))
+            fresh = dt.open(ids[worst:worst + 1])
+            ids = np.concatenate((np.delete(ids, worst), fresh))
+            m_rom = np.concatenate((np.delete(m_rom, worst), dt.mass_rom[fresh]))
+            m_raw = np.concatenate((np.delete(m_raw, worst), dt.mass_raw[fresh]))
+            if verbose:
+                print(f"End of tree iteration {it}: {len(ids)} leaves on tree. "
+                      f"Total mass={m_tot}. Fractional error={err_tot / m_tot}.")
+        self._leaf_ids = ids
+        self._table = None
+        dt.check()
+
     def get_leaf_at_pos(self, pos):
         """Leaf containing ``pos``  [tree.py:490-541]."""
         pos = np.array([pos]) if not hasattr(pos, "__len__") else np.array(pos)
@@ -354,6 +616,10 @@ class DensityTree(DensityStructure):
     # ------------------------------------------------------------------ device leaf table
     def leaf_table(self):
         """Host arrays ``(x (L,k), dx (L,k), corners (L,2^k), mass (L,))`` in leaf order."""
+        if self._dt is not None:
+            ids = self._leaf_ids
+            x, dx = self._dt.geometry(ids)
+            return x, dx, self._dt.fetch("corners", ids), self._dt.mass_raw[ids].copy()
         L, k = len(self.leaves), self._dim
         x = np.array([leaf.x for leaf in self.leaves], dtype=np.float64).reshape(L, k)
         dx = np.array([leaf.dx for leaf in self.leaves], dtype=np.float64).reshape(L, k)

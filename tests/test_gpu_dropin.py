@@ -409,3 +409,58 @@ def test_device_resident_inputs_and_updates(lb):
         b.update_densities(-V)
     with pytest.raises(ValueError):
         lb.DensityGrid.from_densities(edges, V[:-1])
+
+
+# ---------------------------------------------------------------------------
+# device tree builder: lint_tree_open against the host builder
+# ---------------------------------------------------------------------------
+def _fused_pdf(lb, kind, k):
+    rng = np.random.default_rng(7 + k)
+    if kind == "gmm":
+        return lb.GaussianMixture(rng.dirichlet(np.ones(3)), rng.uniform(-2, 2, (3, k)),
+                                  sigmas=rng.uniform(0.15, 0.6, 3))
+    return lb.DoublePowerLaw.nfw(rng.uniform(0.5, 2.0, 2), rng.uniform(-2, 2, (2, k)) + 0.01234,
+                                 rng.uniform(0.3, 0.8, 2))
+
+
+@pytest.mark.parametrize("kind,k,openings", [("gmm", 1, 3), ("gmm", 2, 3), ("gmm", 3, 2), ("nfw", 2, 3),
+                                             ("nfw", 3, 2), ("gmm", 4, 1)])
+def test_device_tree_build_equals_host_builder(lb, kind, k, openings):
+    """A tree built in the device cell table (lint_tree_open: corner densities, trapezoid masses,
+    Romberg chains) and refined by the array version of `refine` is, bit for bit, the tree the host
+    builder makes from the same densities (the pdf evaluated through lint_points_eval): same
+    leaves in the same order, same corner tables, raw and Romberg masses, Romberg chains."""
+    pdf = _fused_pdf(lb, kind, k)
+    mins, maxs = np.full(k, -4.0), np.full(k, 4.25)
+    dev = lb.DensityTree(mins, maxs, pdf, min_openings=openings)
+    host = lb.DensityTree(mins, maxs, pdf.eval_points, vectorizedpdf=True, min_openings=openings)
+    assert dev._dt is not None and host._dt is None
+    for stage in range(2):
+        a, b = dev.leaf_table(), host.leaf_table()
+        for x, y in zip(a, b):
+            assert x.shape == y.shape and np.array_equal(x, y)
+        la, lb_ = dev.leaves, host.leaves
+        assert [c.idx for c in la] == [c.idx for c in lb_] and [c.level for c in la] == [c.level for c in lb_]
+        assert all(np.array_equal(p.romberg_estimates, q.romberg_estimates) for p, q in zip(la, lb_))
+        assert all(p.mass_romberg == q.mass_romberg and p.vol == q.vol for p, q in zip(la, lb_))
+        assert dev.total_mass == host.total_mass
+        if stage == 0:
+            dev.refine(2e-3, leaf_tol=2e-2)
+            host.refine(2e-3, leaf_tol=2e-2)
+            assert len(dev.leaves) > len(la)                       # the refinement did open cells
+    pos = np.full(k, 0.3)
+    p, q = dev.get_leaf_at_pos(pos), host.get_leaf_at_pos(pos)
+    assert p.idx == q.idx and np.array_equal(p.x, q.x) and np.array_equal(p.corner_densities, q.corner_densities)
+    # and it samples like any other tree
+    s1 = lb.LintSampler(dev, seed=3, rng_backend="numpy").sample(500)
+    s2 = lb.LintSampler(host, seed=3, rng_backend="numpy").sample(500)
+    assert np.array_equal(s1, s2)
+
+
+def test_device_tree_build_checks_densities(lb):
+    """tree.py:602-605 on the device path: an unsoftened halo centred on a lattice vertex is infinite there."""
+    halo = lb.DoublePowerLaw(1.0, [[0.0, 0.0]], 0.5, eps=0.0)
+    with pytest.raises(ValueError, match="non-finite"):
+        lb.DensityTree([-4.0, -4.0], [4.0, 4.0], halo, min_openings=2)
+    with pytest.raises(ValueError):
+        lb.DensityTree([-4.0, -4.0], [4.0, 4.0], lambda x: x.sum(-1), vectorizedpdf=True, build="device")
