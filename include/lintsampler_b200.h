@@ -391,6 +391,23 @@ int lint_tree_open(const lint_tree_t *t, const lint_gmm_t *gmm, const lint_halos
                    const int32_t *open_ids_dev, int64_t n_open, int64_t first_new, double *summary_dev,
                    uint32_t *flags_dev, lint_stream_t stream);
 
+/* == stage 2 of DensityTree.refine [tree.py:448-488] in one launch: while
+ * sqrt(sum((m_romberg - m_raw)^2)) / sum(m_romberg) >= tree_tol over the leaves (both sums NumPy's
+ * pairwise np.sum of the current leaf arrays), open the leaf with the largest squared difference
+ * (np.argmax: first of equals), delete it from the leaf arrays and append its children — the cells
+ * and the order of the reference's loop.  leaf_ids_dev / m_romberg_dev / m_raw_dev: the leaves in
+ * leaf order, device arrays of leaf_capacity entries; scratch_dev: leaf_capacity doubles.
+ * state_dev (4 x uint32): in  [0] leaves, [1] cells in the table;
+ *                         out [0], [1] updated, [2] openings done, [3] 0 converged, 1 stopped for room
+ * (a table or leaf array full, max_openings reached, more than lint_tree_max_refine_leaves() leaves:
+ * grow and call again, or finish on the host), 2 level limit reached.  New cells are appended to the
+ * table as by lint_tree_open. */
+int lint_tree_refine_worst(const lint_tree_t *t, const lint_gmm_t *gmm, const lint_halos_t *halos,
+                           int32_t *leaf_ids_dev, double *m_romberg_dev, double *m_raw_dev, double *scratch_dev,
+                           int64_t leaf_capacity, double tree_tol, int64_t max_openings, uint32_t *state_dev,
+                           uint32_t *flags_dev, lint_stream_t stream);
+int lint_tree_max_refine_leaves(void);
+
 /* The same pdf at a list of points, points_dev (n, dim) fp64 -> out_dev (n) fp64: what a
  * vectorised `pdf(x)` call of the reference returns (grid.py:398, tree.py:816), with the
  * arithmetic of lint_grid_eval_* / lint_tree_open. */

@@ -22,7 +22,7 @@ SOURCES = [("lint_build.cu", "lint_build", []), ("lint_sample.cu", "lint_sample"
 _DIMS = [int(d) for d in os.environ.get("LINT_DIMS", "1,2,3,4,5,6").split(",")]
 SOURCES += [("lint_cellmajor_inst.cu", f"lint_cellmajor_k{k}",
              [f"-DLINT_K={k}"] + ([] if k in _DIMS else ["-DLINT_STUB"])) for k in range(1, 7)]
-HEADERS = ["lint_device.cuh", "lint_pdf.cuh", "lint_cellmajor.cuh", "lint_cellmajor_plan.h",
+HEADERS = ["lint_device.cuh", "lint_pdf.cuh", "lint_pairwise.cuh", "lint_cellmajor.cuh", "lint_cellmajor_plan.h",
            os.path.join("..", "..", "include", "lintsampler_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -99,6 +99,9 @@ PROTOTYPES = {
     "lint_tree_est_stride": (C.c_int, []),
     "lint_tree_open": (C.c_int, [C.POINTER(LintTree), C.POINTER(LintGmm), C.POINTER(LintHalos), _P, _I64, _I64, _P,
                                  _P, _P]),
+    "lint_tree_refine_worst": (C.c_int, [C.POINTER(LintTree), C.POINTER(LintGmm), C.POINTER(LintHalos), _P, _P, _P,
+                                         _P, _I64, C.c_double, _I64, _P, _P, _P]),
+    "lint_tree_max_refine_leaves": (C.c_int, []),
     "lint_points_eval": (C.c_int, [C.c_int, C.POINTER(LintGmm), C.POINTER(LintHalos), _P, _I64, _P, _P]),
     "lint_grid_masses": (C.c_int, [C.POINTER(LintGrid), _P, _P, _P]),
     "lint_grid_records": (C.c_int, [C.POINTER(LintGrid), _P, _P]),

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include "lint_device.cuh"
 #include "lint_pdf.cuh"
+#include "lint_pairwise.cuh"
 
 namespace lint {
 
@@ -64,6 +65,92 @@ __device__ __forceinline__ double cell_volume(const double (&span)[K], int level
     return vol;
 }
 
+// Creates cell `id`: child `c` (corner order) of cell `par`, or the root (par < 0).  Returns its
+// raw mass, Romberg mass and last Romberg correction; ORs density findings into `bad`.
+template <int K, typename Pdf>
+__device__ void tree_new_cell(const TreeTable<K> &tb, const Pdf &pdf, uint32_t id, int par, uint32_t c,
+                              double &raw_out, double &rom_out, double &err_out, uint32_t &bad) {
+    constexpr int NC = 1 << K;
+    int32_t org[K];
+    int level = 0;
+    if (par < 0) {
+#pragma unroll
+        for (int d = 0; d < K; ++d) org[d] = 0;
+    } else {
+        level = tb.level[par] + 1;
+#pragma unroll
+        for (int d = 0; d < K; ++d)                                          // tree.py:632-640
+            org[d] = 2 * tb.origin[(size_t)par * K + d] + (int32_t)((c >> (K - 1 - d)) & 1u);
+    }
+    // corner densities at mins + coords * (span / 2^level)                [tree.py:593-596, 866-867]
+    double f[NC];
+#pragma unroll
+    for (int cc = 0; cc < NC; ++cc) {
+        double x[K];
+#pragma unroll
+        for (int d = 0; d < K; ++d) {
+            const int32_t coord = org[d] + (int32_t)((cc >> (K - 1 - d)) & 1);
+            x[d] = __dadd_rn(tb.mins[d], __dmul_rn((double)coord, scalbn(tb.span[d], -level)));
+        }
+        f[cc] = pdf(x);
+        if (f[cc] < 0.0) bad |= LINT_FLAG_NEGATIVE;                          // tree.py:598-601
+        if (!isfinite(f[cc])) bad |= LINT_FLAG_NONFINITE;                    // tree.py:602-605
+    }
+    const double vol = cell_volume<K>(tb.span, level);
+    const double raw = __dmul_rn(vol, __ddiv_rn(numpy_sum<NC>(f), (double)NC));         // tree.py:608
+    tb.level[id] = level;
+    tb.parent[id] = par;
+#pragma unroll
+    for (int d = 0; d < K; ++d) tb.origin[(size_t)id * K + d] = org[d];
+#pragma unroll
+    for (int cc = 0; cc < NC; ++cc) tb.corners[(size_t)id * NC + cc] = f[cc];
+    tb.mass_raw[id] = raw;
+
+    // Romberg chain [tree.py:649-703]: cur[0] the cell's own trapezoid mass, cur[j] the mass its
+    // j-th ancestor's multilinear interpolant gives it (value at the cell's midpoint x volume)
+    double cur[TREE_MAX_LEVEL + 1];
+    cur[0] = raw;
+    int anc = par;
+    for (int j = 1; j <= level; ++j) {
+        double w[NC];
+        w[0] = 1.0;
+        // midpoint of the cell in the ancestor's unit cube (dyadic, exact); weights built dimension
+        // by dimension, ((w0 * w1) * w2) ..., corner index with dim 0 as the most significant bit
+#pragma unroll
+        for (int d = 0; d < K; ++d) {
+            const double mid = scalbn((double)org[d] + 0.5, -j) - (double)tb.origin[(size_t)anc * K + d];
+            const int have = 1 << d;
+#pragma unroll
+            for (int cc = have - 1; cc >= 0; --cc) {
+                const double base = w[cc];
+                w[2 * cc + 1] = d == 0 ? mid : __dmul_rn(base, mid);
+                w[2 * cc] = d == 0 ? 1.0 - mid : __dmul_rn(base, 1.0 - mid);
+            }
+        }
+        double prod[NC];
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc) prod[cc] = __dmul_rn(tb.corners[(size_t)anc * NC + cc], w[cc]);
+        const double fmid = numpy_sum<NC>(prod);
+        const double avol = cell_volume<K>(tb.span, level - j);
+        cur[j] = scalbn(__dmul_rn(fmid, avol), -(j * K));                    // fmid * anc.vol / 2^(j k)
+        anc = tb.parent[anc];
+    }
+    double *est = tb.est + (size_t)id * TREE_EST;
+    est[0] = raw;
+    double prev = raw, last = raw;
+    for (int i = 0; i < level; ++i) {                                        // Richardson extrapolation
+        const double denom = scalbn(1.0, 2 * (i + 1)) - 1.0;                 // 4^(i+1) - 1
+        for (int j = 0; j < level - i; ++j)
+            cur[j] = __dsub_rn(cur[j], __ddiv_rn(__dsub_rn(cur[j + 1], cur[j]), denom));
+        prev = last;
+        last = cur[0];
+        est[i + 1] = last;
+    }
+    raw_out = raw;
+    rom_out = last;                                                          // mass_romberg
+    err_out = fabs(__dsub_rn(last, prev));                                   // |e[-1] - e[-2]| (0 for the root)
+}
+
 // One thread per new cell.  Cell `first + t` is child `t mod 2^K` of open_ids[t / 2^K]
 // (root: the single cell 0 with no parent, n_open == 0).
 template <int K, typename Pdf>
@@ -73,89 +160,157 @@ tree_open_kernel(TreeTable<K> tb, Pdf pdf, const int32_t *__restrict__ open_ids,
     constexpr int NC = 1 << K;
     uint32_t bad = 0;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_new; t += gridDim.x * blockDim.x) {
-        const uint32_t id = first + t;
-        int32_t org[K];
-        int level = 0, par = -1;
-        if (root) {
-#pragma unroll
-            for (int d = 0; d < K; ++d) org[d] = 0;
-        } else {
-            par = open_ids[t >> K];
-            const uint32_t c = t & (NC - 1);
-            level = tb.level[par] + 1;
-#pragma unroll
-            for (int d = 0; d < K; ++d)                                      // tree.py:632-640
-                org[d] = 2 * tb.origin[(size_t)par * K + d] + (int32_t)((c >> (K - 1 - d)) & 1u);
-        }
-        // corner densities at mins + coords * (span / 2^level)            [tree.py:593-596, 866-867]
-        double f[NC];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            double x[K];
-#pragma unroll
-            for (int d = 0; d < K; ++d) {
-                const int32_t coord = org[d] + (int32_t)((c >> (K - 1 - d)) & 1);
-                x[d] = __dadd_rn(tb.mins[d], __dmul_rn((double)coord, scalbn(tb.span[d], -level)));
-            }
-            f[c] = pdf(x);
-            if (f[c] < 0.0) bad |= LINT_FLAG_NEGATIVE;                       // tree.py:598-601
-            if (!isfinite(f[c])) bad |= LINT_FLAG_NONFINITE;                 // tree.py:602-605
-        }
-        const double vol = cell_volume<K>(tb.span, level);
-        const double raw = __dmul_rn(vol, __ddiv_rn(numpy_sum<NC>(f), (double)NC));     // tree.py:608
-        tb.level[id] = level;
-        tb.parent[id] = par;
-#pragma unroll
-        for (int d = 0; d < K; ++d) tb.origin[(size_t)id * K + d] = org[d];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) tb.corners[(size_t)id * NC + c] = f[c];
-        tb.mass_raw[id] = raw;
-
-        // Romberg chain [tree.py:649-703]: cur[0] the cell's own trapezoid mass, cur[j] the mass its
-        // j-th ancestor's multilinear interpolant gives it (value at the cell's midpoint x volume)
-        double cur[TREE_MAX_LEVEL + 1];
-        cur[0] = raw;
-        int anc = par;
-        for (int j = 1; j <= level; ++j) {
-            double w[NC];
-            w[0] = 1.0;
-            // midpoint of the cell in the ancestor's unit cube (dyadic, exact); weights built dimension
-            // by dimension, ((w0 * w1) * w2) ..., corner index with dim 0 as the most significant bit
-#pragma unroll
-            for (int d = 0; d < K; ++d) {
-                const double mid = scalbn((double)org[d] + 0.5, -j) - (double)tb.origin[(size_t)anc * K + d];
-                const int have = 1 << d;
-#pragma unroll
-                for (int c = have - 1; c >= 0; --c) {
-                    const double base = w[c];
-                    w[2 * c + 1] = d == 0 ? mid : __dmul_rn(base, mid);
-                    w[2 * c] = d == 0 ? 1.0 - mid : __dmul_rn(base, 1.0 - mid);
-                }
-            }
-            double prod[NC];
-#pragma unroll
-            for (int c = 0; c < NC; ++c) prod[c] = __dmul_rn(tb.corners[(size_t)anc * NC + c], w[c]);
-            const double fmid = numpy_sum<NC>(prod);
-            const double avol = cell_volume<K>(tb.span, level - j);
-            cur[j] = scalbn(__dmul_rn(fmid, avol), -(j * K));                // fmid * anc.vol / 2^(j k)
-            anc = tb.parent[anc];
-        }
-        double *est = tb.est + (size_t)id * TREE_EST;
-        est[0] = raw;
-        double prev = raw, last = raw;
-        for (int i = 0; i < level; ++i) {                                    // Richardson extrapolation
-            const double denom = scalbn(1.0, 2 * (i + 1)) - 1.0;             // 4^(i+1) - 1
-            for (int j = 0; j < level - i; ++j)
-                cur[j] = __dsub_rn(cur[j], __ddiv_rn(__dsub_rn(cur[j + 1], cur[j]), denom));
-            prev = last;
-            last = cur[0];
-            est[i + 1] = last;
-        }
+        double raw, rom, err;
+        tree_new_cell<K>(tb, pdf, first + t, root ? -1 : open_ids[t >> K], t & (NC - 1), raw, rom, err, bad);
         summary[(size_t)t * 3 + 0] = raw;
-        summary[(size_t)t * 3 + 1] = last;                                   // mass_romberg
-        summary[(size_t)t * 3 + 2] = fabs(__dsub_rn(last, prev));            // |e[-1] - e[-2]| (0 for the root)
+        summary[(size_t)t * 3 + 1] = rom;
+        summary[(size_t)t * 3 + 2] = err;
     }
     if (bad) atomicOr(flags, bad);
+}
+
+// Stage 2 of refine [tree.py:448-488] as one launch: while the tree-wide fractional error
+// sqrt(sum((m_romberg - m_raw)^2)) / sum(m_romberg) is not below tree_tol, open the single leaf with
+// the largest squared difference (np.argmax: the first of equals), drop it from the leaf list and
+// append its children.  One CTA; the two sums are NumPy's pairwise np.sum over the current leaf
+// arrays (recomputed every iteration, as the reference does), so the loop opens exactly the cells
+// the host loop would.  Stops early, to be relaunched or finished by the caller, when a table
+// runs out of room, after max_iters openings, or at the level limit.
+// state: [0] leaves, [1] cells, [2] openings done by this launch, [3] status (TREE_* below)
+enum { TREE_CONVERGED = 0, TREE_OUT_OF_ROOM = 1, TREE_LEVEL_LIMIT = 2, TREE_MORE = 3 };
+constexpr int REFINE_THREADS = 1024;
+constexpr uint32_t REFINE_MAX_LEAVES = 128u * 1024u;      // pairwise tree of at most 1024 nodes per array
+
+template <int K, typename Pdf>
+__global__ void __launch_bounds__(REFINE_THREADS)
+tree_refine_worst_kernel(TreeTable<K> tb, Pdf pdf, int32_t *leaf_ids, double *m_rom, double *m_raw, double *sq,
+                         uint32_t leaf_cap, uint32_t cell_cap, double tree_tol, uint32_t max_iters,
+                         uint32_t *state, uint32_t *flags) {
+    constexpr int NC = 1 << K;
+    constexpr uint32_t MAKERS = REFINE_THREADS - (NC > 32 ? NC : 32);   // first of the threads that create cells
+    constexpr int SHIFT = 8;                               // elements per thread and round of the shift
+    __shared__ double part[2][2][REFINE_THREADS];         // [ping-pong][array][node]
+    __shared__ double s_val[REFINE_THREADS / 32];
+    __shared__ uint32_t s_idx[REFINE_THREADS / 32];
+    __shared__ uint32_t s_worst, s_stop, s_bad;
+    __shared__ int s_par;
+    __shared__ double s_new[2][NC];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t n = state[0], ncell = state[1], done = 0, status = TREE_MORE, bad = 0;
+    while (true) {
+        // (1) squared differences and the largest of them (np.argmax: the first of equals)
+        double best = -1.0;
+        uint32_t best_i = 0xffffffffu;
+        for (uint32_t i = tid; i < n; i += REFINE_THREADS) {
+            const double d = __dsub_rn(m_rom[i], m_raw[i]);
+            const double q = __dmul_rn(d, d);
+            sq[i] = q;
+            if (q > best) { best = q; best_i = i; }       // ascending i per thread: keeps the first
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const uint32_t oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+            if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+        }
+        if (lane == 0) { s_val[wid] = best; s_idx[wid] = best_i; }
+        __syncthreads();
+        if (tid == 0) {
+            double bv = s_val[0];
+            uint32_t bi = s_idx[0];
+            for (int w = 1; w < REFINE_THREADS / 32; ++w)
+                if (s_val[w] > bv || (s_val[w] == bv && s_idx[w] < bi)) { bv = s_val[w]; bi = s_idx[w]; }
+            // can that leaf be opened at all?  (decided before the sums: its children are made beside them)
+            uint32_t stop = TREE_MORE;
+            int par = -1;
+            if (done >= max_iters || n + NC - 1 > leaf_cap || ncell + NC > cell_cap || n + NC - 1 > REFINE_MAX_LEAVES ||
+                bi >= n)
+                stop = TREE_OUT_OF_ROOM;
+            else {
+                par = leaf_ids[bi];
+                if (tb.level[par] >= TREE_MAX_LEVEL) stop = TREE_LEVEL_LIMIT;
+            }
+            s_worst = bi;
+            s_stop = stop;
+            s_par = par;
+            s_bad = 0;
+        }
+        __syncthreads();
+        const uint32_t worst = s_worst;
+        const bool can_open = s_stop == TREE_MORE;
+        // (2) np.sum(m_rom) and np.sum(sq): nodes of the pairwise tree at depth `depth` (one thread per
+        // node and array), folded below; beside them the last warps make the children of the worst
+        // leaf — speculatively: the sums may say the tree has converged, then they are never adopted
+        const int depth = pw_depth(n);
+        const uint32_t nnodes = 1u << depth;
+        const bool two = 2 * nnodes <= MAKERS;             // one thread per (node, array)
+        if (tid < (two ? 2 * nnodes : nnodes)) {
+            const uint32_t p = tid < nnodes ? tid : tid - nnodes;
+            uint64_t start = 0, len = n;
+            for (int b = depth - 1; b >= 0; --b) {
+                const uint64_t n2 = pw_left(len);
+                if ((p >> b) & 1) { start += n2; len -= n2; } else { len = n2; }
+            }
+            if (tid < nnodes) part[0][0][p] = pw_node(m_rom + start, len);
+            if (!two || tid >= nnodes) part[0][1][p] = pw_node(sq + start, len);
+        } else if (can_open && tid >= MAKERS && tid < MAKERS + NC) {
+            const uint32_t c = tid - MAKERS;
+            double raw, rom, err;
+            uint32_t my_bad = 0;
+            tree_new_cell<K>(tb, pdf, ncell + c, s_par, c, raw, rom, err, my_bad);
+            s_new[0][c] = raw;
+            s_new[1][c] = rom;
+            if (my_bad) atomicOr(&s_bad, my_bad);
+        }
+        __syncthreads();
+        int src = 0;
+        for (uint32_t w = nnodes >> 1; w >= 1; w >>= 1) {
+            if (tid < w) {
+                part[src ^ 1][0][tid] = __dadd_rn(part[src][0][2 * tid], part[src][0][2 * tid + 1]);
+                part[src ^ 1][1][tid] = __dadd_rn(part[src][1][2 * tid], part[src][1][2 * tid + 1]);
+            }
+            src ^= 1;
+            __syncthreads();
+        }
+        const double m_tot = part[src][0][0], err_tot = sqrt(part[src][1][0]);
+        if (__ddiv_rn(err_tot, m_tot) < tree_tol) { status = TREE_CONVERGED; break; }     // uniform: shared values
+        if (!can_open) { status = s_stop; break; }
+        bad |= s_bad;
+        // (3) np.delete(a, worst) — the tail moves left by one, SHIFT elements per thread and round
+        // (loads of a round, barrier, stores) — and np.concatenate((a, children))
+        for (uint32_t base = worst + 1; base < n; base += REFINE_THREADS * SHIFT) {
+            int32_t vi[SHIFT];
+            double vr[SHIFT], vw[SHIFT];
+#pragma unroll
+            for (int j = 0; j < SHIFT; ++j) {
+                const uint32_t i = base + j * REFINE_THREADS + tid;
+                if (i < n) { vi[j] = leaf_ids[i]; vr[j] = m_rom[i]; vw[j] = m_raw[i]; }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < SHIFT; ++j) {
+                const uint32_t i = base + j * REFINE_THREADS + tid;
+                if (i < n) { leaf_ids[i - 1] = vi[j]; m_rom[i - 1] = vr[j]; m_raw[i - 1] = vw[j]; }
+            }
+        }
+        __syncthreads();
+        if (tid < NC) {
+            leaf_ids[n - 1 + tid] = (int32_t)(ncell + tid);
+            m_raw[n - 1 + tid] = s_new[0][tid];
+            m_rom[n - 1 + tid] = s_new[1][tid];
+        }
+        __syncthreads();
+        n += NC - 1;
+        ncell += NC;
+        ++done;
+    }
+    if (tid == 0) {
+        if (bad) atomicOr(flags, bad);
+        state[0] = n;
+        state[1] = ncell;
+        state[2] = done;
+        state[3] = status;
+    }
 }
 
 // pdf on a list of points (the host tree builder's vectorised pdf call; parity tests)
@@ -170,9 +325,8 @@ points_eval_kernel(Pdf pdf, const double *__restrict__ pts, uint32_t n, double *
     }
 }
 
-template <int K, typename Pdf>
-int tree_open_launch(const lint_tree_t *t, const Pdf &pdf, const int32_t *open_ids, int64_t n_open,
-                     int64_t first, double *summary, uint32_t *flags, cudaStream_t st) {
+template <int K>
+TreeTable<K> make_tree_table(const lint_tree_t *t) {
     TreeTable<K> tb;
     for (int d = 0; d < K; ++d) {
         tb.mins[d] = t->mins[d];
@@ -184,6 +338,13 @@ int tree_open_launch(const lint_tree_t *t, const Pdf &pdf, const int32_t *open_i
     tb.corners = t->corners_dev;
     tb.mass_raw = t->mass_raw_dev;
     tb.est = t->est_dev;
+    return tb;
+}
+
+template <int K, typename Pdf>
+int tree_open_launch(const lint_tree_t *t, const Pdf &pdf, const int32_t *open_ids, int64_t n_open,
+                     int64_t first, double *summary, uint32_t *flags, cudaStream_t st) {
+    TreeTable<K> tb = make_tree_table<K>(t);
     const bool root = n_open == 0;
     const uint32_t n_new = root ? 1u : (uint32_t)(n_open << K);
     const int blocks = (int)std::min<uint32_t>((n_new + 127) / 128, 148 * 8);
@@ -196,6 +357,28 @@ int tree_open_k(const lint_tree_t *t, const lint_gmm_t *gmm, const lint_halos_t 
                 int64_t n_open, int64_t first, double *summary, uint32_t *flags, cudaStream_t st) {
     if (gmm) return tree_open_launch<K>(t, fill_gmm<K>(gmm), open_ids, n_open, first, summary, flags, st);
     return tree_open_launch<K>(t, fill_halos<K>(halos), open_ids, n_open, first, summary, flags, st);
+}
+
+template <int K, typename Pdf>
+int tree_refine_launch(const lint_tree_t *t, const Pdf &pdf, int32_t *leaf_ids, double *m_rom, double *m_raw,
+                       double *sq, int64_t leaf_cap, double tree_tol, int64_t max_iters, uint32_t *state,
+                       uint32_t *flags, cudaStream_t st) {
+    TreeTable<K> tb = make_tree_table<K>(t);
+    tree_refine_worst_kernel<K, Pdf><<<1, REFINE_THREADS, 0, st>>>(
+        tb, pdf, leaf_ids, m_rom, m_raw, sq, (uint32_t)std::min<int64_t>(leaf_cap, REFINE_MAX_LEAVES),
+        (uint32_t)t->capacity, tree_tol, (uint32_t)std::min<int64_t>(max_iters, 0x7fffffff), state, flags);
+    return check_launch("lint_tree_refine_worst");
+}
+
+template <int K>
+int tree_refine_k(const lint_tree_t *t, const lint_gmm_t *gmm, const lint_halos_t *halos, int32_t *leaf_ids,
+                  double *m_rom, double *m_raw, double *sq, int64_t leaf_cap, double tree_tol, int64_t max_iters,
+                  uint32_t *state, uint32_t *flags, cudaStream_t st) {
+    if (gmm)
+        return tree_refine_launch<K>(t, fill_gmm<K>(gmm), leaf_ids, m_rom, m_raw, sq, leaf_cap, tree_tol, max_iters,
+                                     state, flags, st);
+    return tree_refine_launch<K>(t, fill_halos<K>(halos), leaf_ids, m_rom, m_raw, sq, leaf_cap, tree_tol, max_iters,
+                                 state, flags, st);
 }
 
 template <int K>
@@ -253,6 +436,30 @@ int lint_tree_open(const lint_tree_t *t, const lint_gmm_t *gmm, const lint_halos
         default: return tree_open_k<6>(t, gmm, halos, open_ids_dev, n_open, first_new, summary_dev, flags_dev, st);
     }
 }
+
+int lint_tree_refine_worst(const lint_tree_t *t, const lint_gmm_t *gmm, const lint_halos_t *halos,
+                           int32_t *leaf_ids_dev, double *m_romberg_dev, double *m_raw_dev, double *scratch_dev,
+                           int64_t leaf_capacity, double tree_tol, int64_t max_openings, uint32_t *state_dev,
+                           uint32_t *flags_dev, lint_stream_t stream) {
+    if (!t) return fail(LINT_ERR_BAD_ARG, "lint_tree_refine_worst: NULL tree");
+    if (int rc = check_pdf("lint_tree_refine_worst", t->dim, gmm, halos)) return rc;
+    if (!t->origin_dev || !t->level_dev || !t->parent_dev || !t->corners_dev || !t->mass_raw_dev || !t->est_dev ||
+        !leaf_ids_dev || !m_romberg_dev || !m_raw_dev || !scratch_dev || !state_dev || !flags_dev)
+        return fail(LINT_ERR_BAD_ARG, "lint_tree_refine_worst: NULL pointer");
+    if (leaf_capacity < 1 || max_openings < 0 || t->capacity >= (1ll << 31) || !(tree_tol == tree_tol))
+        return fail(LINT_ERR_BAD_ARG, "lint_tree_refine_worst: bad capacity / tolerance");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (t->dim) {
+        case 1: return tree_refine_k<1>(t, gmm, halos, leaf_ids_dev, m_romberg_dev, m_raw_dev, scratch_dev, leaf_capacity, tree_tol, max_openings, state_dev, flags_dev, st);
+        case 2: return tree_refine_k<2>(t, gmm, halos, leaf_ids_dev, m_romberg_dev, m_raw_dev, scratch_dev, leaf_capacity, tree_tol, max_openings, state_dev, flags_dev, st);
+        case 3: return tree_refine_k<3>(t, gmm, halos, leaf_ids_dev, m_romberg_dev, m_raw_dev, scratch_dev, leaf_capacity, tree_tol, max_openings, state_dev, flags_dev, st);
+        case 4: return tree_refine_k<4>(t, gmm, halos, leaf_ids_dev, m_romberg_dev, m_raw_dev, scratch_dev, leaf_capacity, tree_tol, max_openings, state_dev, flags_dev, st);
+        case 5: return tree_refine_k<5>(t, gmm, halos, leaf_ids_dev, m_romberg_dev, m_raw_dev, scratch_dev, leaf_capacity, tree_tol, max_openings, state_dev, flags_dev, st);
+        default: return tree_refine_k<6>(t, gmm, halos, leaf_ids_dev, m_romberg_dev, m_raw_dev, scratch_dev, leaf_capacity, tree_tol, max_openings, state_dev, flags_dev, st);
+    }
+}
+
+int lint_tree_max_refine_leaves(void) { return (int)REFINE_MAX_LEAVES; }
 
 int lint_points_eval(int dim, const lint_gmm_t *gmm, const lint_halos_t *halos, const double *points_dev, int64_t n,
                      double *out_dev, lint_stream_t stream) {

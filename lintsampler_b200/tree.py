@@ -123,6 +123,8 @@ class _DeviceTree:
     scalars the refinement logic reads (tree.py:413-488): level, parent, first child, raw mass,
     Romberg mass, last Romberg correction."""
 
+    room_override = None        # (tests) openings per launch of the stage-2 loop
+
     def __init__(self, mins, maxs, pdf, device):
         import torch
         self.device = _device.require_cuda(device)
@@ -223,6 +225,65 @@ class _DeviceTree:
         if len(ids) and int(self.level[ids].max()) >= self.max_level:
             raise ValueError(f"DensityTree: the device builder refines to level {self.max_level} at most")
         return self._launch(ids)
+
+    def refine_worst(self, ids, tree_tol):
+        """Stage 2 of ``refine`` (tree.py:448-488) on the device, one launch per batch of openings
+        (``lint_tree_refine_worst``).  Returns ``(leaf ids, finished)``; not finished means the
+        leaf list outgrew what the single-CTA loop handles and the caller carries on."""
+        import torch
+        lib = _capi.load()
+        max_leaves = int(lib.lint_tree_max_refine_leaves())
+        ids = np.asarray(ids, dtype=np.int64)
+        with torch.cuda.device(self.device):
+            while True:
+                n = len(ids)
+                room = self.room_override or max(512, n // 2)        # openings this launch has room for
+                if n + room * (self.nc - 1) + self.nc > max_leaves:
+                    return ids, False
+                self._grow(self.n + room * self.nc)
+                leaf_cap = n + room * (self.nc - 1) + self.nc
+                dev = self.device
+                ids_t = torch.empty(leaf_cap, dtype=torch.int32, device=dev)
+                ids_t[:n] = torch.as_tensor(ids.astype(np.int32), device=dev)
+                rom_t = torch.empty(leaf_cap, dtype=torch.float64, device=dev)
+                raw_t = torch.empty(leaf_cap, dtype=torch.float64, device=dev)
+                rom_t[:n] = torch.as_tensor(self.mass_rom[ids], device=dev)
+                raw_t[:n] = torch.as_tensor(self.mass_raw[ids], device=dev)
+                sq_t = torch.empty(leaf_cap, dtype=torch.float64, device=dev)
+                state = torch.tensor([n, self.n, 0, 0], dtype=torch.int32, device=dev)
+                gmm, halos, keep = self._pdf_structs()
+                t = self._struct()
+                _capi.call("lint_tree_refine_worst", C.byref(t), gmm, halos, _device.ptr(ids_t), _device.ptr(rom_t),
+                           _device.ptr(raw_t), _device.ptr(sq_t), leaf_cap, float(tree_tol), room,
+                           _device.ptr(state), _device.ptr(self._flags), _device.stream_ptr(dev))
+                del keep
+                n_leaves, n_cells, done, status = (int(v) for v in state.cpu().numpy())
+                self._adopt(n_cells)
+                ids = ids_t[:n_leaves].cpu().numpy().astype(np.int64)
+                if status == 0:
+                    return ids, True
+                if status == 2:
+                    raise ValueError(f"DensityTree: the device builder refines to level {self.max_level} at most")
+                if done == 0:                                        # no room at all although we just made some
+                    return ids, False
+
+    def _adopt(self, n_cells):
+        """Bring the host mirror up to date with cells [self.n, n_cells) made by a device-side loop."""
+        if n_cells == self.n:
+            return
+        new = np.arange(self.n, n_cells, dtype=np.int64)
+        n_before, self.n = self.n, n_cells                           # fetch() reads up to self.n
+        lev = self.fetch("level", new)[:, 0]
+        par = self.fetch("parent", new)[:, 0].astype(np.int64)
+        est = self.fetch("est", new)
+        rows = np.arange(len(new))
+        self.level[new], self.parent[new] = lev, par
+        self.first_child[new] = -1
+        self.first_child[par[::self.nc]] = new[::self.nc]
+        self.mass_raw[new] = self.fetch("mass_raw", new)[:, 0]
+        self.mass_rom[new] = est[rows, lev]
+        self.err[new] = np.abs(est[rows, lev] - est[rows, np.maximum(lev - 1, 0)])
+        assert n_before + len(new) == n_cells
 
     def check(self):
         """Density checks of tree.py:598-605 for everything evaluated so far."""
@@ -575,6 +636,14 @@ class DensityTree(DensityStructure):
                       f"Total mass={np.sum(m_rom)}, with mean leaf mass={np.nanmean(m_rom)}")
             if not len(sel):
                 break
+        if not verbose:                                            # stage 2 in one launch per batch of openings
+            ids, finished = dt.refine_worst(ids, tree_tol)
+            if finished:
+                self._leaf_ids = ids
+                self._table = None
+                dt.check()
+                return
+            m_rom = dt.mass_rom[ids].copy()
         m_raw = dt.mass_raw[ids].copy()
         it = 0
         while True:

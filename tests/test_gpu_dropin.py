@@ -448,6 +448,16 @@ def test_device_tree_build_equals_host_builder(lb, kind, k, openings):
             dev.refine(2e-3, leaf_tol=2e-2)
             host.refine(2e-3, leaf_tol=2e-2)
             assert len(dev.leaves) > len(la)                       # the refinement did open cells
+    # the same refinement with stage 2 cut into launches of three openings, and with the host-side
+    # stage-2 loop over the device table (verbose mode): the same leaves again
+    for variant in ("batches", "verbose"):
+        other = lb.DensityTree(mins, maxs, pdf, min_openings=openings, build="device")
+        if variant == "batches":
+            other._dt.room_override = 3
+        other.refine(2e-3, leaf_tol=2e-2, verbose=variant == "verbose")
+        assert np.array_equal(other._leaf_ids, dev._leaf_ids)
+        for x, y in zip(other.leaf_table(), dev.leaf_table()):
+            assert np.array_equal(x, y)
     pos = np.full(k, 0.3)
     p, q = dev.get_leaf_at_pos(pos), host.get_leaf_at_pos(pos)
     assert p.idx == q.idx and np.array_equal(p.x, q.x) and np.array_equal(p.corner_densities, q.corner_densities)
