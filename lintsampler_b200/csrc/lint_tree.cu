@@ -65,37 +65,43 @@ __device__ __forceinline__ double cell_volume(const double (&span)[K], int level
     return vol;
 }
 
-// Creates cell `id`: child `c` (corner order) of cell `par`, or the root (par < 0).  Returns its
-// raw mass, Romberg mass and last Romberg correction; ORs density findings into `bad`.
-template <int K, typename Pdf>
-__device__ void tree_new_cell(const TreeTable<K> &tb, const Pdf &pdf, uint32_t id, int par, uint32_t c,
-                              double &raw_out, double &rom_out, double &err_out, uint32_t &bad) {
-    constexpr int NC = 1 << K;
-    int32_t org[K];
-    int level = 0;
+// Lattice origin and level of child `c` (corner order) of cell `par`, or of the root (par < 0).
+template <int K>
+__device__ __forceinline__ int tree_child_origin(const TreeTable<K> &tb, int par, uint32_t c, int32_t (&org)[K]) {
     if (par < 0) {
 #pragma unroll
         for (int d = 0; d < K; ++d) org[d] = 0;
-    } else {
-        level = tb.level[par] + 1;
-#pragma unroll
-        for (int d = 0; d < K; ++d)                                          // tree.py:632-640
-            org[d] = 2 * tb.origin[(size_t)par * K + d] + (int32_t)((c >> (K - 1 - d)) & 1u);
+        return 0;
     }
-    // corner densities at mins + coords * (span / 2^level)                [tree.py:593-596, 866-867]
-    double f[NC];
 #pragma unroll
-    for (int cc = 0; cc < NC; ++cc) {
-        double x[K];
+    for (int d = 0; d < K; ++d)                                              // tree.py:632-640
+        org[d] = 2 * tb.origin[(size_t)par * K + d] + (int32_t)((c >> (K - 1 - d)) & 1u);
+    return tb.level[par] + 1;
+}
+
+// Density at corner `cc` of the cell at (org, level): mins + coords * (span / 2^level)
+// [tree.py:593-596, 866-867]; ORs the findings of tree.py:598-605 into `bad`.
+template <int K, typename Pdf>
+__device__ __forceinline__ double tree_corner_density(const TreeTable<K> &tb, const Pdf &pdf, const int32_t (&org)[K],
+                                                      int level, uint32_t cc, uint32_t &bad) {
+    double x[K];
 #pragma unroll
-        for (int d = 0; d < K; ++d) {
-            const int32_t coord = org[d] + (int32_t)((cc >> (K - 1 - d)) & 1);
-            x[d] = __dadd_rn(tb.mins[d], __dmul_rn((double)coord, scalbn(tb.span[d], -level)));
-        }
-        f[cc] = pdf(x);
-        if (f[cc] < 0.0) bad |= LINT_FLAG_NEGATIVE;                          // tree.py:598-601
-        if (!isfinite(f[cc])) bad |= LINT_FLAG_NONFINITE;                    // tree.py:602-605
+    for (int d = 0; d < K; ++d) {
+        const int32_t coord = org[d] + (int32_t)((cc >> (K - 1 - d)) & 1u);
+        x[d] = __dadd_rn(tb.mins[d], __dmul_rn((double)coord, scalbn(tb.span[d], -level)));
     }
+    const double f = pdf(x);
+    if (f < 0.0) bad |= LINT_FLAG_NEGATIVE;
+    if (!isfinite(f)) bad |= LINT_FLAG_NONFINITE;
+    return f;
+}
+
+// Enters cell `id` (child of `par` at (org, level), corner densities f) into the table: trapezoid
+// mass and Romberg chain.  Returns raw mass, Romberg mass and last Romberg correction.
+template <int K>
+__device__ void tree_finish_cell(const TreeTable<K> &tb, uint32_t id, int par, const int32_t (&org)[K], int level,
+                                 const double (&f)[1 << K], double &raw_out, double &rom_out, double &err_out) {
+    constexpr int NC = 1 << K;
     const double vol = cell_volume<K>(tb.span, level);
     const double raw = __dmul_rn(vol, __ddiv_rn(numpy_sum<NC>(f), (double)NC));         // tree.py:608
     tb.level[id] = level;
@@ -151,6 +157,19 @@ __device__ void tree_new_cell(const TreeTable<K> &tb, const Pdf &pdf, uint32_t i
     err_out = fabs(__dsub_rn(last, prev));                                   // |e[-1] - e[-2]| (0 for the root)
 }
 
+// Creates cell `id`: child `c` (corner order) of cell `par`, or the root (par < 0), by one thread.
+template <int K, typename Pdf>
+__device__ void tree_new_cell(const TreeTable<K> &tb, const Pdf &pdf, uint32_t id, int par, uint32_t c,
+                              double &raw_out, double &rom_out, double &err_out, uint32_t &bad) {
+    constexpr int NC = 1 << K;
+    int32_t org[K];
+    const int level = tree_child_origin<K>(tb, par, c, org);
+    double f[NC];
+#pragma unroll
+    for (int cc = 0; cc < NC; ++cc) f[cc] = tree_corner_density<K>(tb, pdf, org, level, cc, bad);
+    tree_finish_cell<K>(tb, id, par, org, level, f, raw_out, rom_out, err_out);
+}
+
 // One thread per new cell.  Cell `first + t` is child `t mod 2^K` of open_ids[t / 2^K]
 // (root: the single cell 0 with no parent, n_open == 0).
 template <int K, typename Pdf>
@@ -187,14 +206,19 @@ tree_refine_worst_kernel(TreeTable<K> tb, Pdf pdf, int32_t *leaf_ids, double *m_
                          uint32_t leaf_cap, uint32_t cell_cap, double tree_tol, uint32_t max_iters,
                          uint32_t *state, uint32_t *flags) {
     constexpr int NC = 1 << K;
-    constexpr uint32_t MAKERS = REFINE_THREADS - (NC > 32 ? NC : 32);   // first of the threads that create cells
-    constexpr int SHIFT = 8;                               // elements per thread and round of the shift
+    // the threads that create the children of the leaf being opened: one per (child, corner) for
+    // the densities (up to four dimensions; one per child beyond), one per child for the rest
+    constexpr bool WIDE = K <= 4;
+    constexpr uint32_t NMAKE = WIDE ? (NC * NC > 32 ? NC * NC : 32) : (NC > 32 ? NC : 32);
+    constexpr uint32_t MAKERS = REFINE_THREADS - NMAKE;
+    constexpr int SHIFT = 4;                               // elements per thread and round of the shift
     __shared__ double part[2][2][REFINE_THREADS];         // [ping-pong][array][node]
     __shared__ double s_val[REFINE_THREADS / 32];
     __shared__ uint32_t s_idx[REFINE_THREADS / 32];
     __shared__ uint32_t s_worst, s_stop, s_bad;
     __shared__ int s_par;
     __shared__ double s_new[2][NC];
+    __shared__ double s_f[WIDE ? NC : 1][WIDE ? NC : 1];   // corner densities of the children
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint32_t n = state[0], ncell = state[1], done = 0, status = TREE_MORE, bad = 0;
     while (true) {
@@ -253,16 +277,36 @@ tree_refine_worst_kernel(TreeTable<K> tb, Pdf pdf, int32_t *leaf_ids, double *m_
             }
             if (tid < nnodes) part[0][0][p] = pw_node(m_rom + start, len);
             if (!two || tid >= nnodes) part[0][1][p] = pw_node(sq + start, len);
-        } else if (can_open && tid >= MAKERS && tid < MAKERS + NC) {
-            const uint32_t c = tid - MAKERS;
-            double raw, rom, err;
+        } else if (can_open && tid >= MAKERS && tid < MAKERS + (WIDE ? NC * NC : NC)) {
             uint32_t my_bad = 0;
-            tree_new_cell<K>(tb, pdf, ncell + c, s_par, c, raw, rom, err, my_bad);
-            s_new[0][c] = raw;
-            s_new[1][c] = rom;
+            if constexpr (WIDE) {
+                const uint32_t c = (tid - MAKERS) / NC, cc = (tid - MAKERS) % NC;
+                int32_t org[K];
+                const int level = tree_child_origin<K>(tb, s_par, c, org);
+                s_f[c][cc] = tree_corner_density<K>(tb, pdf, org, level, cc, my_bad);
+            } else {
+                const uint32_t c = tid - MAKERS;
+                double raw, rom, err;
+                tree_new_cell<K>(tb, pdf, ncell + c, s_par, c, raw, rom, err, my_bad);
+                s_new[0][c] = raw;
+                s_new[1][c] = rom;
+            }
             if (my_bad) atomicOr(&s_bad, my_bad);
         }
         __syncthreads();
+        if constexpr (WIDE) {                              // masses and Romberg chains, beside the fold
+            if (can_open && tid >= MAKERS && tid < MAKERS + NC) {
+                const uint32_t c = tid - MAKERS;
+                int32_t org[K];
+                const int level = tree_child_origin<K>(tb, s_par, c, org);
+                double f[NC], raw, rom, err;
+#pragma unroll
+                for (int cc = 0; cc < NC; ++cc) f[cc] = s_f[c][cc];
+                tree_finish_cell<K>(tb, ncell + c, s_par, org, level, f, raw, rom, err);
+                s_new[0][c] = raw;
+                s_new[1][c] = rom;
+            }
+        }
         int src = 0;
         for (uint32_t w = nnodes >> 1; w >= 1; w >>= 1) {
             if (tid < w) {
