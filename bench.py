@@ -69,6 +69,8 @@ class ClockSampler:
         self._t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        if self._run_nvml():
+            return
         while not self._stop.is_set():
             try:
                 out = subprocess.run(
@@ -80,8 +82,39 @@ class ClockSampler:
                 pass
             self._stop.wait(0.05)
 
+    def _run_nvml(self):
+        """The same fields through NVML (what nvidia-smi reads), every 2 ms: a timed region of a few
+        tens of milliseconds still gets a median over many samples.  False if NVML is unusable."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            reasons(h)
+        except Exception:
+            return False
+        bits = [0x8, 0x40, 0x20, 0x4]       # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        while not self._stop.is_set():
+            try:
+                r = int(reasons(h))
+                self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx)]
+                                 + ["Active" if r & b else "Not Active" for b in bits])
+            except Exception:
+                pass
+            self._stop.wait(0.002)
+        self.source = "nvml"
+        return True
+
     def __enter__(self):
         if self.enabled:
+            try:                                # load and initialise NVML before the timed region starts
+                import pynvml
+                pynvml.nvmlInit()
+            except Exception:
+                pass
             self._t.start()
         return self
 
@@ -97,7 +130,8 @@ class ClockSampler:
         reasons = [n for j, n in enumerate(names)
                    if any(len(r) > 2 + j and r[2 + j].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm),
+                "source": getattr(self, "source", "nvidia-smi")}
 
 
 # --------------------------------------------------------------------------- CPU legs (oracle)
@@ -168,7 +202,7 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": "samples/s", "value": val, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "C3: 3-D DensityGrid 256^3, K=4 isotropic GMM on [-4,4]^3",
                    "samples_per_step": n_step, "note": "bounded sample of the N=1e9 workload"},
