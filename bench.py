@@ -65,12 +65,13 @@ class ClockSampler:
         self.index = index
         self.enabled = enabled
         self.rows = []
+        self._nv = None
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
-        if self._run_nvml():
-            return
+        if self._nv is not None:
+            return self._run_nvml()
         while not self._stop.is_set():
             try:
                 out = subprocess.run(
@@ -82,9 +83,9 @@ class ClockSampler:
                 pass
             self._stop.wait(0.05)
 
-    def _run_nvml(self):
-        """The same fields through NVML (what nvidia-smi reads), every 2 ms: a timed region of a few
-        tens of milliseconds still gets a median over many samples.  False if NVML is unusable."""
+    def _setup_nvml(self):
+        """The same fields through NVML (what nvidia-smi reads), so that they can be read every
+        millisecond: a timed region of a few milliseconds still gets a median over several samples."""
         try:
             import pynvml as nv
             nv.nvmlInit()
@@ -94,8 +95,12 @@ class ClockSampler:
             mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
             reasons(h)
+            return nv, h, reasons, mx
         except Exception:
-            return False
+            return None
+
+    def _run_nvml(self):
+        nv, h, reasons, mx = self._nv
         bits = [0x8, 0x40, 0x20, 0x4]       # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
         while not self._stop.is_set():
             try:
@@ -104,17 +109,12 @@ class ClockSampler:
                                  + ["Active" if r & b else "Not Active" for b in bits])
             except Exception:
                 pass
-            self._stop.wait(0.002)
-        self.source = "nvml"
-        return True
+            self._stop.wait(0.001)
 
     def __enter__(self):
         if self.enabled:
-            try:                                # load and initialise NVML before the timed region starts
-                import pynvml
-                pynvml.nvmlInit()
-            except Exception:
-                pass
+            self._nv = self._setup_nvml()       # before the timed region starts
+            self.source = "nvml" if self._nv is not None else "nvidia-smi"
             self._t.start()
         return self
 
@@ -338,6 +338,27 @@ def run_b200(args):
         host_ms = (time.perf_counter() - h0) * 1e3 / args.steps      # host time to enqueue a step
         barrier()
     ms_total = t_beg.elapsed_time(t_end)
+    clock_line = clocks.summary()
+    if rank == 0 and clock_line["samples"] < 5:
+        # a timed region of a few milliseconds is shorter than a handful of NVML reads: sample the same
+        # steps again, untimed, right after it (every rank runs them, so the load is the same)
+        clock_line["note"] = ("timed region %.1f ms: clocks sampled over extra untimed steps right after it"
+                              % ms_total)
+    extra = clock_line["samples"] < 5 if rank == 0 else False
+    if world > 1:
+        flag = torch.tensor([int(extra)], device=dev)
+        dist.broadcast(flag, 0)
+        extra = bool(flag.item())
+    if extra:
+        with ClockSampler(local, enabled=rank == 0) as clocks2:
+            barrier()
+            for i in range(max(args.steps, int(60.0 / max(ms_total / args.steps, 1e-3)))):
+                graph.replay() if graph is not None else body()
+            barrier()
+        if rank == 0:
+            note = clock_line["note"]
+            clock_line = clocks2.summary()
+            clock_line["note"] = note
     # stage breakdown: a few eager steps with events between the stages
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(3)]
     for e in evs:
@@ -479,7 +500,7 @@ def run_b200(args):
                 "rows": ({k: kern[k] for k in ("rows_flat", "rows_general", "rows_grouped")} if kern else None),
                 "step_frac_of_hbm_roofline": step_bytes_per_gpu / (ms_step * 1e-3) / 1e9 / peak,
             },
-            "clocks": clocks.summary(),
+            "clocks": clock_line,
             "gpu_launches": (shard.launches_per_step(args.order) + 1) * args.steps,   # + the offset-counter kernel
         }
         if other_line:

@@ -735,6 +735,10 @@ group_totals_kernel(GridView<K> g, GroupPlan plan, uint32_t ncells, const double
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     uint32_t n_le = 0, n_lt = 0;
+    // (Off[g] <= u total instead of Off[g] / total <= u: one product instead of a division per entry;
+    // the two can differ for an entry within an ulp of a stratum boundary, which the group of margin
+    // on either side of the slab absorbs)
+    const double t_lo = plan.u_lo * run, t_hi = plan.u_hi * run;
     for (uint32_t base = threadIdx.x; base < plan.ngroups; base += blockDim.x * 8) {
         double v[8];                                               // eight L2 loads in flight, not one
 #pragma unroll
@@ -745,9 +749,8 @@ group_totals_kernel(GridView<K> g, GroupPlan plan, uint32_t ncells, const double
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (base + j * blockDim.x < plan.ngroups) {
-                const double f = v[j] / run;
-                n_le += f <= plan.u_lo;
-                n_lt += f < plan.u_hi;
+                n_le += v[j] <= t_lo;
+                n_lt += v[j] < t_hi;
             }
         }
     }

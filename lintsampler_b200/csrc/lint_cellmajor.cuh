@@ -253,7 +253,8 @@ __device__ __forceinline__ unsigned long long pack(uint32_t rows, uint32_t cells
 static __global__ void __launch_bounds__(SCAN_THREADS)
 scan_compact_kernel(const uint32_t *counts, uint32_t ncells_all, const uint32_t *__restrict__ range,
                     uint32_t id_mul, uint32_t id_add, unsigned long long *tile_state, uint32_t *tile_counter,
-                    uint32_t *cid, uint32_t *coff, uint32_t *nnz_out, uint32_t *rows_out) {
+                    uint32_t *cid, uint32_t *coff, uint32_t *nnz_out, uint32_t *rows_out, uint32_t chunk_rows,
+                    uint32_t chunk_slots, uint32_t *__restrict__ chunk0, uint32_t *__restrict__ chunk1) {
     // cells [first, first + ncells) of the count array; ids are global cell indices
     const uint32_t first = range ? range[0] : 0u;
     const uint32_t ncells = range ? range[1] - range[0] : ncells_all;
@@ -327,6 +328,20 @@ scan_compact_kernel(const uint32_t *counts, uint32_t ncells_all, const uint32_t 
             LINT_CHECK(slot < ncells && base + i < ncells);
             cid[slot] = (base + i) * id_mul + id_add;
             coff[slot] = (uint32_t)pre;
+            // Chunk t of the run starts in the segment that holds its first row: t * chunk_rows when
+            // the run begins on an even global row, max(t * chunk_rows, 1) - 1 when on an odd one
+            // (the general run is laid over even rows, see emit_kernel).  This segment holds rows
+            // [lo, hi); almost always it owns no chunk start or one.
+            const uint64_t lo = (uint32_t)pre, hi = lo + c[i];
+            // (t < chunk_slots: the tables are sized for the N rows asked for; an 8-sigma Poisson total
+            // beyond that is clamped away by run_rows and never emitted)
+            for (uint64_t t = (lo + chunk_rows - 1) / chunk_rows; t * chunk_rows < hi && t < chunk_slots; ++t)
+                chunk0[t] = slot;
+            if (chunk1) {
+                if (lo == 0) chunk1[0] = slot;
+                for (uint64_t t = (lo + chunk_rows) / chunk_rows; t * chunk_rows < hi + 1 && t < chunk_slots; ++t)
+                    chunk1[t] = slot;
+            }
         }
         pre += pack(c[i], c[i] != 0);
     }
@@ -338,42 +353,22 @@ scan_compact_kernel(const uint32_t *counts, uint32_t ncells_all, const uint32_t 
     }
 }
 
-// Row budget of the two grouped runs and the first segment of every output chunk, one launch.
-// T_f + T_r <= N but for an 8-sigma event of the Poisson total; clamping keeps every writer
-// inside the output whatever happened.  plan[0] = T_f, plan[1] = T_r, plan[2] = T_f + T_r; the
-// flat emitter's chunk counter is reset.
-// Chunk t of a run holds the rows r with t * chunk_rows <= r + shift < (t + 1) * chunk_rows
-// (shift = T_f & 1 for the general run, whose chunks are laid over even global rows, see
-// emit_kernel; 0 for the flat run); its first segment is the last j with coff[j] <= its first row.
-struct SegTable {
-    const uint32_t *coff, *nnz, *rows;
-    uint32_t *chunk_start;
-};
-static __global__ void plan_chunks_kernel(SegTable flat, SegTable rest, uint32_t n_requested, uint32_t chunk_rows,
-                                          uint32_t *plan, uint32_t *chunk_counter) {
-    const uint32_t tf = flat.rows ? min(*flat.rows, n_requested) : 0u;
-    const uint32_t tr = min(*rest.rows, n_requested - tf);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        plan[0] = tf;
-        plan[1] = tr;
-        plan[2] = tf + tr;
-        *chunk_counter = 0;
-    }
-    const uint32_t shift = tf & 1u;
-    const uint32_t nflat = tf ? (tf + chunk_rows - 1) / chunk_rows : 0u;
-    const uint32_t nrest = tr ? (tr + shift + chunk_rows - 1) / chunk_rows : 0u;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nflat + nrest; i += gridDim.x * blockDim.x) {
-        const bool is_rest = i >= nflat;
-        const SegTable &l = is_rest ? rest : flat;
-        const uint32_t t = is_rest ? i - nflat : i, sh = is_rest ? shift : 0u;
-        const uint32_t r0 = max(t * chunk_rows, sh) - sh;
-        uint32_t lo = 0, hi = *l.nnz;                              // coff[nnz] = rows of the run > r0
-        while (lo < hi) {                                          // first j with coff[j] > r0
-            const uint32_t mid = lo + ((hi - lo) >> 1);
-            if (__ldg(l.coff + mid) > r0) hi = mid; else lo = mid + 1;
-        }
-        l.chunk_start[t] = lo - 1;
+// Row budget of the two grouped runs (for the top-up, which starts at row T, and for callers):
+// plan[0] = T_f, plan[1] = T_r, plan[2] = T = T_f + T_r.  T <= N but for an 8-sigma event of the
+// Poisson total; clamping keeps every writer inside the output whatever happened.  The emitters
+// derive the same numbers themselves (run_rows) so that they need not wait for this kernel.
+__device__ __forceinline__ void run_rows(const uint32_t *flat_rows, const uint32_t *rest_rows, uint32_t n_requested,
+                                         uint32_t &tf, uint32_t &tr) {
+    tf = flat_rows ? min(*flat_rows, n_requested) : 0u;
+    tr = min(*rest_rows, n_requested - tf);
 }
+static __global__ void plan_totals_kernel(const uint32_t *flat_rows, const uint32_t *rest_rows, uint32_t n_requested,
+                                          uint32_t *plan) {
+    uint32_t tf, tr;
+    run_rows(flat_rows, rest_rows, n_requested, tf, tr);
+    plan[0] = tf;
+    plan[1] = tr;
+    plan[2] = tf + tr;
 }
 
 // ---------------------------------------------------------------------------
@@ -586,7 +581,7 @@ flat_boxes_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *_
 template <int K, typename T, bool CELLS>
 __global__ void __launch_bounds__(FLAT_THREADS, LINT_FLAT_MINB)
 emit_flat_kernel(const T *__restrict__ boxes, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
-                 const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ plan,
+                 const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ flat_rows, uint32_t n_requested,
                  const uint32_t *__restrict__ chunk_start, uint32_t chunk_rows, uint32_t *chunk_counter,
                  const __grid_constant__ PhiloxKeys key, StreamPos pos, T *__restrict__ out,
                  int64_t *__restrict__ cell_idx) {
@@ -606,7 +601,7 @@ emit_flat_kernel(const T *__restrict__ boxes, const uint32_t *__restrict__ cid, 
     T *s_box = s_box_all[warp];
     uint32_t *s_end = s_end_all[warp];
     const uint32_t nnz = *nnz_p;
-    const uint32_t N = plan[0];                        // rows of the flat run
+    const uint32_t N = min(*flat_rows, n_requested);   // rows of the flat run (T_f)
     const uint32_t nchunks = (N + chunk_rows - 1) / chunk_rows;
     const uint32_t olo = (uint32_t)offset, ohi = (uint32_t)(offset >> 32);
     constexpr uint32_t FULL = 0xffffffffu;
@@ -842,8 +837,9 @@ constexpr uint32_t EMIT_PRE_NONE = 0x80000000u;
 template <int K, typename T, typename Cells, bool CELLS>
 __global__ void __launch_bounds__(EMIT_THREADS, sizeof(T) == 4 ? (K <= 3 ? LINT_EMIT_MINB : 2) : 1)
 emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restrict__ coff,
-            const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ plan,
-            const uint32_t *__restrict__ chunk_start, uint32_t chunk_rows, const __grid_constant__ PhiloxKeys key,
+            const uint32_t *__restrict__ nnz_p, const uint32_t *__restrict__ flat_rows,
+            const uint32_t *__restrict__ rest_rows, uint32_t n_requested, const uint32_t *__restrict__ chunk_start0,
+            const uint32_t *__restrict__ chunk_start1, uint32_t chunk_rows, const __grid_constant__ PhiloxKeys key,
             StreamPos pos, uint32_t split, CdfSlice table, double lam_per_unit, T *__restrict__ out,
             int64_t *__restrict__ cell_idx) {
     using FT = FlatTraits<T>;
@@ -865,11 +861,14 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
     const uint32_t nnz = *nnz_p;
     // Rows are counted from the even global row at or before the start of the run: row r of this
     // frame is global row (T_f - shift) + r and belongs to the run when shift <= r < end.
-    const uint32_t shift = plan[0] & 1u, end = plan[1] + shift;
-    out += (size_t)(plan[0] - shift) * K;
-    if (CELLS) cell_idx += plan[0] - shift;
-    const uint32_t pair0 = (plan[0] - shift) >> 1;     // global index of the frame's first pair of rows
-    const uint32_t nchunks = plan[1] ? (end + chunk_rows - 1) / chunk_rows : 0u;      // (an empty run has no chunk)
+    uint32_t t_flat, t_rest;                           // rows of the flat run before this one, rows of this run
+    run_rows(flat_rows, rest_rows, n_requested, t_flat, t_rest);
+    const uint32_t shift = t_flat & 1u, end = t_rest + shift;
+    const uint32_t *__restrict__ chunk_start = shift ? chunk_start1 : chunk_start0;
+    out += (size_t)(t_flat - shift) * K;
+    if (CELLS) cell_idx += t_flat - shift;
+    const uint32_t pair0 = (t_flat - shift) >> 1;      // global index of the frame's first pair of rows
+    const uint32_t nchunks = t_rest ? (end + chunk_rows - 1) / chunk_rows : 0u;       // (an empty run has no chunk)
     const uint32_t nwarps = gridDim.x * (EMIT_THREADS / 32);
     const uint32_t olo = (uint32_t)offset, ohi = (uint32_t)(offset >> 32);
     constexpr uint32_t FULL = 0xffffffffu;
@@ -1055,13 +1054,18 @@ inline int env_int(const char *name, int fallback) {
 // host orchestration
 // ---------------------------------------------------------------------------
 static void scan_list(const uint32_t *counts, uint32_t n, const uint32_t *range, uint32_t id_mul, uint32_t id_add,
-                      const SegList &l, cudaStream_t st) {
+                      const SegList &l, uint32_t chunk_rows, uint32_t chunk_slots, bool odd_frame_too,
+                      cudaStream_t st) {
     const uint32_t nscan = (n + SCAN_TILE - 1) / SCAN_TILE;
     scan_compact_kernel<<<nscan, SCAN_THREADS, 0, st>>>(counts, n, range, id_mul, id_add, l.tile_state,
-                                                       l.tile_counter, l.cid, l.coff, l.nnz, l.rows);
+                                                       l.tile_counter, l.cid, l.coff, l.nnz, l.rows, chunk_rows,
+                                                       chunk_slots, l.chunk_start,
+                                                       odd_frame_too ? l.chunk_start1 : nullptr);
 }
 
-// counts -> offsets (+ compaction) -> row budget -> chunk starts, for both runs
+// counts -> offsets, compaction and chunk starts, for both runs; the row budget (plan[]) for the
+// top-up on its lane.  Lanes: the flat scan runs on side[0] beside the other scan on the caller's
+// stream; ev[1] = flat scan done, ev[4] = other scan done.
 template <typename Cells>
 static int plan_rows(const Cells &src, const double *cdf, uint64_t ncells, uint64_t N, uint2 key,
                      uint64_t offset, Stratum u, const uint32_t *range, const Scratch &s, cudaStream_t st) {
@@ -1069,35 +1073,36 @@ static int plan_rows(const Cells &src, const double *cdf, uint64_t ncells, uint6
     const CdfSlice t{cdf, (uint32_t)ncells, u.u_lo, u.u_hi};
     const double lam_per_unit = grouped_mean(N) / (u.u_hi - u.u_lo);
     const int cblocks = (int)std::min<uint64_t>((ncells + POISSON_THREADS - 1) / POISSON_THREADS, 148 * 32);
+    const uint32_t chunk_rows = emit_chunk_rows(N);
     poisson_counts_kernel<<<cblocks, POISSON_THREADS, 0, st>>>(
         src, t, lam_per_unit, key, StreamPos{offset, offset_counter()}, split, range, s.counts_flat, s.counts_rest,
         (uint4 *)s.zero_begin, (uint32_t)(s.zero_bytes / 16));
-    Lanes *L = split ? side_lanes() : nullptr;
-    if (L) {                                                   // the two scans side by side
+    Lanes *L = side_lanes();
+    if (L && split) {                                          // the two scans side by side
         cudaEventRecord(L->ev[0], st);
         cudaStreamWaitEvent(L->side[0], L->ev[0], 0);
-        scan_list(s.counts_flat, (uint32_t)ncells, range, 1, 0, s.flat, L->side[0]);
+        scan_list(s.counts_flat, (uint32_t)ncells, range, 1, 0, s.flat, chunk_rows, s.chunk_slots, false, L->side[0]);
         cudaEventRecord(L->ev[1], L->side[0]);
     } else if (split) {
-        scan_list(s.counts_flat, (uint32_t)ncells, range, 1, 0, s.flat, st);
+        scan_list(s.counts_flat, (uint32_t)ncells, range, 1, 0, s.flat, chunk_rows, s.chunk_slots, false, st);
     }
-    scan_list(s.counts_rest, (uint32_t)ncells, range, split ? 2 : 1, split ? 1 : 0, s.rest, st);
-    if (L) cudaStreamWaitEvent(st, L->ev[1], 0);
-    const uint32_t chunk_rows = emit_chunk_rows(N);
-    const uint32_t nchunks = (uint32_t)((N + chunk_rows - 1) / chunk_rows) + 2;
-    const int sblocks = (int)std::max(1u, std::min((nchunks + 255) / 256, 148u * 8));
-    const SegTable tf{s.flat.coff, s.flat.nnz, split ? s.flat.rows : nullptr, s.flat.chunk_start};
-    const SegTable tr{s.rest.coff, s.rest.nnz, s.rest.rows, s.rest.chunk_start};
-    plan_chunks_kernel<<<sblocks, 256, 0, st>>>(tf, tr, (uint32_t)N, chunk_rows, s.plan, s.chunk_counter);
-    if (Lanes *L2 = side_lanes()) cudaEventRecord(L2->ev[4], st);       // the row budget is known: the top-up may start
+    scan_list(s.counts_rest, (uint32_t)ncells, range, split ? 2 : 1, split ? 1 : 0, s.rest, chunk_rows, s.chunk_slots, split, st);
+    // the row budget, for the top-up (rows [T, N)) on its lane: it needs both scans, the emitters
+    // need neither it nor each other's scan (emit_flat: the flat scan; emit_kernel: both)
+    cudaStream_t st_plan = st;
+    if (L) {
+        cudaEventRecord(L->ev[4], st);
+        cudaStreamWaitEvent(L->side[1], L->ev[4], 0);
+        if (split) cudaStreamWaitEvent(L->side[1], L->ev[1], 0);
+        st_plan = L->side[1];
+    }
+    plan_totals_kernel<<<1, 1, 0, st_plan>>>(split ? s.flat.rows : nullptr, s.rest.rows, (uint32_t)N, s.plan);
+    if (L && split) cudaStreamWaitEvent(st, L->ev[1], 0);      // the general emitter reads T_f
     return check_launch("cell-major row planning");
 }
 
-
 // The flat emitter runs on a side lane beside the general one: the first fills the store path,
-// the second the issue slots (profiles/README.md r2g).  The box table is built on that lane just
-// before the flat emitter, which gives the general emitter a few microseconds of head start on
-// the SMs: moving it next to the scans (both emitters starting together) cost 4 % of the step.
+// the second the issue slots (profiles/README.md r2g).
 template <int K, typename T, typename Cells>
 int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t ncells, uint64_t N, uint2 key,
                 uint64_t offset, Stratum u, void *out, int64_t *cell_idx, cudaStream_t st) {
@@ -1113,7 +1118,12 @@ int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t 
         tm.plan_dev = s.plan;
         cudaEventRecord(tm.ev[0], st);
     }
-    Lanes *L = split ? side_lanes() : nullptr;                 // the flat emitter beside the general one
+    // The flat emitter beside the general one.  It needs the flat scan only, but it is held back
+    // until the general emitter is about to be launched (and then builds its box table first): both
+    // kernels are sized to fill the machine, and the step is shortest when the general one, bound by
+    // instruction issue, takes its share of every SM first and the flat one, bound by the store
+    // path, fills what is left — starting them together or the other way round costs 4 % of the step.
+    Lanes *L = split ? side_lanes() : nullptr;
     cudaStream_t st_main = st;
     if (L) {
         cudaEventRecord(L->ev[2], st);
@@ -1129,11 +1139,11 @@ int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t 
             src, s.flat.cid, s.flat.nnz, boxes);
         if (cell_idx)
             emit_flat_kernel<K, T, true><<<fblocks, FLAT_THREADS, 0, st>>>(
-                boxes, s.flat.cid, s.flat.coff, s.flat.nnz, s.plan, s.flat.chunk_start, chunk_rows, s.chunk_counter,
+                boxes, s.flat.cid, s.flat.coff, s.flat.nnz, s.flat.rows, (uint32_t)N, s.flat.chunk_start, chunk_rows, s.chunk_counter,
                 philox_round_keys(key), StreamPos{offset, offset_counter()}, (T *)out, cell_idx);
         else
             emit_flat_kernel<K, T, false><<<fblocks, FLAT_THREADS, 0, st>>>(
-                boxes, s.flat.cid, s.flat.coff, s.flat.nnz, s.plan, s.flat.chunk_start, chunk_rows, s.chunk_counter,
+                boxes, s.flat.cid, s.flat.coff, s.flat.nnz, s.flat.rows, (uint32_t)N, s.flat.chunk_start, chunk_rows, s.chunk_counter,
                 philox_round_keys(key), StreamPos{offset, offset_counter()}, (T *)out, cell_idx);
         if (int rc = check_launch("cell-major flat emission")) return rc;
     }
@@ -1150,11 +1160,13 @@ int launch_emit(const Cells &src, const double *cdf, const Scratch &s, uint64_t 
                                                 148u * env_int("LINT_REST_BPS", 8));
     if (cell_idx)
         emit_kernel<K, T, Cells, true><<<blocks, EMIT_THREADS, smem, st>>>(
-            src, s.rest.cid, s.rest.coff, s.rest.nnz, s.plan, s.rest.chunk_start, chunk_rows,
+            src, s.rest.cid, s.rest.coff, s.rest.nnz, split ? s.flat.rows : nullptr, s.rest.rows, (uint32_t)N,
+            s.rest.chunk_start, s.rest.chunk_start1, chunk_rows,
             philox_round_keys(key), StreamPos{offset, offset_counter()}, split ? 1u : 0u, t, lam_per_unit, (T *)out, cell_idx);
     else
         emit_kernel<K, T, Cells, false><<<blocks, EMIT_THREADS, smem, st>>>(
-            src, s.rest.cid, s.rest.coff, s.rest.nnz, s.plan, s.rest.chunk_start, chunk_rows,
+            src, s.rest.cid, s.rest.coff, s.rest.nnz, split ? s.flat.rows : nullptr, s.rest.rows, (uint32_t)N,
+            s.rest.chunk_start, s.rest.chunk_start1, chunk_rows,
             philox_round_keys(key), StreamPos{offset, offset_counter()}, split ? 1u : 0u, t, lam_per_unit, (T *)out, cell_idx);
     if (tm.enabled) cudaEventRecord(tm.ev[3], st);
     if (L) cudaStreamWaitEvent(st, L->ev[3], 0);

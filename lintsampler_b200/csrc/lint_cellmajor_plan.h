@@ -19,7 +19,7 @@ inline uint32_t emit_chunk_rows(uint64_t N) { return N >= (1ull << 28) ? EMIT_CH
 // One segment list per run: the flat parts (cid = cell) and the rest (cid = 2 cell + 1 with
 // the split, the cell itself without).
 struct SegList {
-    uint32_t *cid, *coff, *chunk_start, *nnz, *rows, *tile_counter;
+    uint32_t *cid, *coff, *chunk_start, *chunk_start1, *nnz, *rows, *tile_counter;
     unsigned long long *tile_state;
 };
 struct Scratch {
@@ -28,6 +28,7 @@ struct Scratch {
     void *boxes;                 // (lo, w) of every flat segment, 2 * LINT_MAX_DIM doubles at most
     uint32_t *plan;              // [0] T_f, [1] T_r, [2] T = first top-up row
     uint32_t *chunk_counter;     // the flat emitter's work counter
+    uint32_t chunk_slots;        // entries of every chunk_start table
     void *zero_begin;            // [zero_begin, zero_begin + zero_bytes): cleared before every draw
     size_t zero_bytes;
     size_t bytes;
@@ -50,18 +51,22 @@ inline Scratch carve(void *base, uint64_t ncells, uint64_t N, size_t box_bytes =
     uintptr_t p = (uintptr_t)base;
     auto take = [&](size_t n) { uintptr_t q = p; p += (n + 255) & ~(size_t)255; return (void *)q; };
     Scratch s;
+    s.chunk_slots = (uint32_t)(nchunks + 2);
     s.counts_flat = (uint32_t *)take(ncells * 4);
     s.counts_rest = (uint32_t *)take(ncells * 4);
     for (SegList *l : {&s.flat, &s.rest}) {
         l->cid = (uint32_t *)take((ncells + 1) * 4);
         l->coff = (uint32_t *)take((ncells + 1) * 4);
-        l->chunk_start = (uint32_t *)take(std::max<uint64_t>(nchunks, 1) * 4);
+        // first segment of every output chunk, written by the scan: for a run that starts on an even
+        // global row, and (chunk_start1) on an odd one — the general run is laid over even rows
+        l->chunk_start = (uint32_t *)take((nchunks + 2) * 4);
+        l->chunk_start1 = (uint32_t *)take((nchunks + 2) * 4);
     }
     const uint64_t nbox = std::min<uint64_t>(ncells, (uint64_t)((double)N / SPLIT_MIN_LAMBDA) + 1);
     s.boxes = take(nbox * box_bytes);
     s.plan = (uint32_t *)take(16);
-    s.chunk_counter = (uint32_t *)take(4);
     s.zero_begin = (void *)p;
+    s.chunk_counter = (uint32_t *)take(4);
     for (SegList *l : {&s.flat, &s.rest}) {
         l->tile_state = (unsigned long long *)take(nscan * 8);
         l->nnz = (uint32_t *)take(4);

@@ -1,9 +1,9 @@
 # Emulated ranks of the 8-way strong-scaling step on one GPU (graph replay per step) + launch list.
 set -x
 TAG=${TAG:-emu}
-python -m pytest tests/test_gpu_kernels.py tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -5 > gpurun_out/${TAG}_tests.txt
+python -m pytest tests/test_gpu_kernels.py tests/test_gpu_multi.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -5 > gpurun_out/${TAG}_tests.txt
 cat gpurun_out/${TAG}_tests.txt
-J=profiles/r2i_bench_8gpu.json
+J=${STRATA:-profiles/r2m_bench_8gpu.json}
 python scripts/emulate_rank.py 0 1 1e9 10 > gpurun_out/${TAG}_w1.json 2> gpurun_out/${TAG}_w1.err
 rm -f gpurun_out/${TAG}_w8.json
 for r in 0 1 3 4 7; do python scripts/emulate_rank.py $r 8 1e9 20 $J >> gpurun_out/${TAG}_w8.json 2>> gpurun_out/${TAG}_w8.err; done
