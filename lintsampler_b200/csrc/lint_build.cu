@@ -780,8 +780,11 @@ group_totals_kernel(GridView<K> g, GroupPlan plan, uint32_t ncells, const double
 // cells: every corner load is coalesced); the tile is transposed through shared memory so that a
 // thread scans eight consecutive cells.
 constexpr int SCAN_PAD = PAR_ITEMS + 1;         // 9 doubles per thread's run: conflict-free 64-bit reads
+#ifndef LINT_GSCAN_MINB
+#define LINT_GSCAN_MINB 6        // 40 registers: 1536 threads per SM (measured best of 4 / 6 / 8)
+#endif
 template <int K, typename DensT>
-__global__ void __launch_bounds__(PAR_THREADS)
+__global__ void __launch_bounds__(PAR_THREADS, LINT_GSCAN_MINB)
 group_scan_kernel(GridView<K> g, GroupPlan plan, uint32_t ncells, const double *__restrict__ Off,
                   const double *__restrict__ total, const uint32_t *__restrict__ range, double *cdf,
                   double *masses) {

@@ -202,8 +202,11 @@ __device__ __forceinline__ uint32_t poisson(double lam, CellRng &rng) {
 // shared-memory queues with full warps was tried twice and lost to this plain form by 30-45 %:
 // profiles/README.md, r2e.)
 constexpr int POISSON_THREADS = 256;
+#ifndef LINT_POISSON_MINB
+#define LINT_POISSON_MINB 6      // 40 registers: 1536 threads per SM (measured best of 4 / 6 / 8)
+#endif
 template <typename Cells>
-__global__ void __launch_bounds__(POISSON_THREADS)
+__global__ void __launch_bounds__(POISSON_THREADS, LINT_POISSON_MINB)
 poisson_counts_kernel(Cells src, CdfSlice t, double lam_per_unit, uint2 key, StreamPos pos, bool split,
                       const uint32_t *__restrict__ range, uint32_t *__restrict__ counts_flat,
                       uint32_t *__restrict__ counts_rest, uint4 *__restrict__ zero, uint32_t nzero) {
