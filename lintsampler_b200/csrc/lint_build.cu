@@ -32,6 +32,14 @@ const uint64_t *offset_counter() { return g_offset_counter; }
 
 __global__ void advance_counter_kernel(uint64_t *counter, uint64_t by) { *counter += by; }
 
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char *v = getenv("LINT_PDL");
+        return v && v[0] == '1';
+    }();
+    return on;
+}
+
 int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LINT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
@@ -600,6 +608,7 @@ __global__ void __launch_bounds__(256)
 vertex_rowsum_kernel(GridView<K> g, GroupPlan plan, double *__restrict__ Q, uint32_t *flags,
                      uint32_t *done_counter) {
     extern __shared__ double s_omega[];                            // n_last + 1 weights
+    pdl_release();
     if (blockIdx.x == 0 && threadIdx.x == 0) *done_counter = 0;    // for group_totals_kernel, next in the stream
     const double *el = g.edges[K - 1];
     for (uint32_t i = threadIdx.x; i <= plan.n_last; i += blockDim.x) {
@@ -662,6 +671,8 @@ group_totals_kernel(GridView<K> g, GroupPlan plan, uint32_t ncells, const double
                     double *total, uint32_t *done_counter, uint32_t *range_out) {
     __shared__ bool s_last;
     const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+    pdl_release();
+    pdl_wait();                                                    // Q, done_counter: vertex_rowsum_kernel
     // plan.sub lanes per group (a power of two >= the rows of a group, at most 32): 32 / sub groups
     // per warp step.  Lanes past the rows hold zero, so the sum is that of a full-warp tree.
     const uint32_t sub = plan.sub, per_warp = 32 / sub, sl = lane & (sub - 1);
@@ -790,6 +801,8 @@ group_scan_kernel(GridView<K> g, GroupPlan plan, uint32_t ncells, const double *
                   double *masses) {
     __shared__ double warp_tot[PAR_THREADS / 32];
     __shared__ double s_m[PAR_THREADS * SCAN_PAD];
+    pdl_release();
+    pdl_wait();                                                    // Off, total, range: group_totals_kernel
     const double inv_tot = 1.0 / *total;
     const uint32_t g_lo = range[2], g_hi = range[3];
     uint32_t unused = 0;
@@ -899,9 +912,10 @@ int group_build_impl(const lint_grid_t *g, uint64_t ncells, double u_lo, double 
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(vertex_rowsum_kernel<K, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         vertex_rowsum_kernel<K, D><<<qblocks, 256, smem, st>>>(v, plan, Q, flags, done);
-        group_totals_kernel<K><<<tblocks, 256, 0, st>>>(v, plan, (uint32_t)ncells, Q, Off, total, done, range);
-        group_scan_kernel<K, D><<<sblocks, PAR_THREADS, 0, st>>>(v, plan, (uint32_t)ncells, Off, total, range, cdf,
-                                                                masses);
+        launch_chained(group_totals_kernel<K>, tblocks, 256, 0, st, v, plan, (uint32_t)ncells, (const double *)Q, Off,
+                       total, done, range);
+        launch_chained(group_scan_kernel<K, D>, sblocks, PAR_THREADS, 0, st, v, plan, (uint32_t)ncells,
+                       (const double *)Off, (const double *)total, (const uint32_t *)range, cdf, masses);
     };
     if (g->dtype == LINT_F32) run(float{}); else run(double{});
     if (guide_bits > 0 && (1ull << guide_bits) * 16 <= ncells) {

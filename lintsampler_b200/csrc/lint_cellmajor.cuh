@@ -210,6 +210,8 @@ __global__ void __launch_bounds__(POISSON_THREADS, LINT_POISSON_MINB)
 poisson_counts_kernel(Cells src, CdfSlice t, double lam_per_unit, uint2 key, StreamPos pos, bool split,
                       const uint32_t *__restrict__ range, uint32_t *__restrict__ counts_flat,
                       uint32_t *__restrict__ counts_rest, uint4 *__restrict__ zero, uint32_t nzero) {
+    pdl_release();
+    pdl_wait();                                            // the CDF and the slab: the build, if it is the kernel before
     // the scans' tile states and totals (Scratch::zero_begin), cleared here instead of by a memset
     // node of its own: the scans are the next kernels in the stream
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nzero; i += gridDim.x * blockDim.x)
@@ -258,6 +260,7 @@ scan_compact_kernel(const uint32_t *counts, uint32_t ncells_all, const uint32_t 
                     uint32_t id_mul, uint32_t id_add, unsigned long long *tile_state, uint32_t *tile_counter,
                     uint32_t *cid, uint32_t *coff, uint32_t *nnz_out, uint32_t *rows_out, uint32_t chunk_rows,
                     uint32_t chunk_slots, uint32_t *__restrict__ chunk0, uint32_t *__restrict__ chunk1) {
+    pdl_wait();                                            // the counts: poisson_counts_kernel
     // cells [first, first + ncells) of the count array; ids are global cell indices
     const uint32_t first = range ? range[0] : 0u;
     const uint32_t ncells = range ? range[1] - range[0] : ncells_all;
@@ -1057,13 +1060,17 @@ inline int env_int(const char *name, int fallback) {
 // host orchestration
 // ---------------------------------------------------------------------------
 static void scan_list(const uint32_t *counts, uint32_t n, const uint32_t *range, uint32_t id_mul, uint32_t id_add,
-                      const SegList &l, uint32_t chunk_rows, uint32_t chunk_slots, bool odd_frame_too,
+                      const SegList &l, uint32_t chunk_rows, uint32_t chunk_slots, bool odd_frame_too, bool chained,
                       cudaStream_t st) {
     const uint32_t nscan = (n + SCAN_TILE - 1) / SCAN_TILE;
-    scan_compact_kernel<<<nscan, SCAN_THREADS, 0, st>>>(counts, n, range, id_mul, id_add, l.tile_state,
-                                                       l.tile_counter, l.cid, l.coff, l.nnz, l.rows, chunk_rows,
-                                                       chunk_slots, l.chunk_start,
-                                                       odd_frame_too ? l.chunk_start1 : nullptr);
+    uint32_t *chunk1 = odd_frame_too ? l.chunk_start1 : nullptr;
+    if (chained)                                               // behind the Poisson kernel on its own stream
+        launch_chained(scan_compact_kernel, nscan, SCAN_THREADS, 0, st, counts, n, range, id_mul, id_add, l.tile_state,
+                       l.tile_counter, l.cid, l.coff, l.nnz, l.rows, chunk_rows, chunk_slots, l.chunk_start, chunk1);
+    else
+        scan_compact_kernel<<<nscan, SCAN_THREADS, 0, st>>>(counts, n, range, id_mul, id_add, l.tile_state,
+                                                           l.tile_counter, l.cid, l.coff, l.nnz, l.rows, chunk_rows,
+                                                           chunk_slots, l.chunk_start, chunk1);
 }
 
 // counts -> offsets, compaction and chunk starts, for both runs; the row budget (plan[]) for the
@@ -1077,19 +1084,19 @@ static int plan_rows(const Cells &src, const double *cdf, uint64_t ncells, uint6
     const double lam_per_unit = grouped_mean(N) / (u.u_hi - u.u_lo);
     const int cblocks = (int)std::min<uint64_t>((ncells + POISSON_THREADS - 1) / POISSON_THREADS, 148 * 32);
     const uint32_t chunk_rows = emit_chunk_rows(N);
-    poisson_counts_kernel<<<cblocks, POISSON_THREADS, 0, st>>>(
-        src, t, lam_per_unit, key, StreamPos{offset, offset_counter()}, split, range, s.counts_flat, s.counts_rest,
-        (uint4 *)s.zero_begin, (uint32_t)(s.zero_bytes / 16));
+    launch_chained(poisson_counts_kernel<Cells>, cblocks, POISSON_THREADS, 0, st, src, t, lam_per_unit, key,
+                   StreamPos{offset, offset_counter()}, split, range, s.counts_flat, s.counts_rest,
+                   (uint4 *)s.zero_begin, (uint32_t)(s.zero_bytes / 16));
     Lanes *L = side_lanes();
     if (L && split) {                                          // the two scans side by side
         cudaEventRecord(L->ev[0], st);
         cudaStreamWaitEvent(L->side[0], L->ev[0], 0);
-        scan_list(s.counts_flat, (uint32_t)ncells, range, 1, 0, s.flat, chunk_rows, s.chunk_slots, false, L->side[0]);
+        scan_list(s.counts_flat, (uint32_t)ncells, range, 1, 0, s.flat, chunk_rows, s.chunk_slots, false, false, L->side[0]);
         cudaEventRecord(L->ev[1], L->side[0]);
     } else if (split) {
-        scan_list(s.counts_flat, (uint32_t)ncells, range, 1, 0, s.flat, chunk_rows, s.chunk_slots, false, st);
+        scan_list(s.counts_flat, (uint32_t)ncells, range, 1, 0, s.flat, chunk_rows, s.chunk_slots, false, true, st);
     }
-    scan_list(s.counts_rest, (uint32_t)ncells, range, split ? 2 : 1, split ? 1 : 0, s.rest, chunk_rows, s.chunk_slots, split, st);
+    scan_list(s.counts_rest, (uint32_t)ncells, range, split ? 2 : 1, split ? 1 : 0, s.rest, chunk_rows, s.chunk_slots, split, true, st);
     // the row budget, for the top-up (rows [T, N)) on its lane: it needs both scans, the emitters
     // need neither it nor each other's scan (emit_flat: the flat scan; emit_kernel: both)
     cudaStream_t st_plan = st;

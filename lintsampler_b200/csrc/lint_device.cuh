@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <utility>
 #include "../../include/lintsampler_b200.h"
 
 namespace lint {
@@ -16,6 +17,37 @@ namespace lint {
 std::string &last_error_slot();
 int fail(int code, const char *fmt, ...);
 int check_launch(const char *what);
+
+// ---------------------------------------------------------------------------
+// Programmatic dependent launch: the small kernels of a step form a chain in which every kernel
+// needs the whole output of the one before it.  Launched with the stream-serialization attribute,
+// a kernel's CTAs are scheduled as soon as the kernel before it lets them (pdl_release, called at
+// its start) and park at pdl_wait until that kernel has finished and its writes are visible: the
+// launch latency and the ramp of the grid are hidden behind the predecessor.  Without the
+// attribute both calls do nothing.  Measured on the 8-way sharded step (0.46 ms, eleven kernels in
+// a CUDA graph): within +-3 us of the ordinary launches, i.e. no gain inside a graph, whose
+// kernel-to-kernel gaps are already short — so it is off unless LINT_PDL=1 is set.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                  Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
 // ---------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011), counter-based: one 128-bit block per call
