@@ -261,6 +261,7 @@ scan_compact_kernel(const uint32_t *counts, uint32_t ncells_all, const uint32_t 
                     uint32_t *cid, uint32_t *coff, uint32_t *nnz_out, uint32_t *rows_out, uint32_t chunk_rows,
                     uint32_t chunk_slots, uint32_t *__restrict__ chunk0, uint32_t *__restrict__ chunk1) {
     pdl_wait();                                            // the counts: poisson_counts_kernel
+    const int chunk_shift = 31 - __clz(chunk_rows);
     // cells [first, first + ncells) of the count array; ids are global cell indices
     const uint32_t first = range ? range[0] : 0u;
     const uint32_t ncells = range ? range[1] - range[0] : ncells_all;
@@ -326,7 +327,23 @@ scan_compact_kernel(const uint32_t *counts, uint32_t ncells_all, const uint32_t 
         if (lane == 0) s_excl = excl;
     }
     __syncthreads();
-    unsigned long long pre = s_excl + wex + (inc - run);           // exclusive prefix of this thread
+    const unsigned long long pre0 = s_excl + wex + (inc - run);    // exclusive prefix of this thread
+    unsigned long long pre = pre0;
+    // Chunk t of the run starts in the segment that holds its first row: t * chunk_rows when the run
+    // begins on an even global row, max(t * chunk_rows, 1) - 1 when on an odd one (the general run
+    // is laid over even rows, see emit_kernel).  A segment of rows [lo, hi) owns the chunks
+    // [ceil(lo / R), ceil(hi / R)) of the first numbering and [(lo + R) / R, (hi + R) / R) — and
+    // chunk 0 if lo = 0 — of the second: none or one for almost every segment, written by its lane;
+    // a segment of more than two chunks' worth of rows (a heavy tree leaf) is left to the whole warp.
+    // (R is a power of two: shifts.  t < chunk_slots: the tables are sized for the N rows asked for;
+    // an 8-sigma Poisson total beyond that is clamped away by run_rows and never emitted.)
+    auto chunk_span = [&](uint64_t lo, uint64_t hi, uint32_t &t0, uint32_t &t1, uint32_t &u0, uint32_t &u1) {
+        t0 = (uint32_t)min((lo + chunk_rows - 1) >> chunk_shift, (uint64_t)chunk_slots);
+        t1 = (uint32_t)min((hi + chunk_rows - 1) >> chunk_shift, (uint64_t)chunk_slots);
+        u0 = (uint32_t)min((lo + chunk_rows) >> chunk_shift, (uint64_t)chunk_slots);
+        u1 = (uint32_t)min((hi + chunk_rows) >> chunk_shift, (uint64_t)chunk_slots);
+    };
+    bool any_wide = false;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
         if (c[i] != 0) {
@@ -334,22 +351,41 @@ scan_compact_kernel(const uint32_t *counts, uint32_t ncells_all, const uint32_t 
             LINT_CHECK(slot < ncells && base + i < ncells);
             cid[slot] = (base + i) * id_mul + id_add;
             coff[slot] = (uint32_t)pre;
-            // Chunk t of the run starts in the segment that holds its first row: t * chunk_rows when
-            // the run begins on an even global row, max(t * chunk_rows, 1) - 1 when on an odd one
-            // (the general run is laid over even rows, see emit_kernel).  This segment holds rows
-            // [lo, hi); almost always it owns no chunk start or one.
             const uint64_t lo = (uint32_t)pre, hi = lo + c[i];
-            // (t < chunk_slots: the tables are sized for the N rows asked for; an 8-sigma Poisson total
-            // beyond that is clamped away by run_rows and never emitted)
-            for (uint64_t t = (lo + chunk_rows - 1) / chunk_rows; t * chunk_rows < hi && t < chunk_slots; ++t)
-                chunk0[t] = slot;
-            if (chunk1) {
-                if (lo == 0) chunk1[0] = slot;
-                for (uint64_t t = (lo + chunk_rows) / chunk_rows; t * chunk_rows < hi + 1 && t < chunk_slots; ++t)
-                    chunk1[t] = slot;
+            if (chunk1 && lo == 0) chunk1[0] = slot;
+            if (c[i] > 2 * chunk_rows) {
+                any_wide = true;
+            } else {
+                uint32_t t0, t1, u0, u1;
+                chunk_span(lo, hi, t0, t1, u0, u1);
+                for (uint32_t t = t0; t < t1; ++t) chunk0[t] = slot;
+                if (chunk1)
+                    for (uint32_t t = u0; t < u1; ++t) chunk1[t] = slot;
             }
         }
         pre += pack(c[i], c[i] != 0);
+    }
+    if (__ballot_sync(0xffffffffu, any_wide)) {                   // rare: second pass, warp per heavy segment
+        unsigned long long q = pre0;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            const bool wide = c[i] > 2 * chunk_rows;
+            uint32_t t0 = 0, t1 = 0, u0 = 0, u1 = 0;
+            if (wide) chunk_span((uint32_t)q, (uint64_t)(uint32_t)q + c[i], t0, t1, u0, u1);
+            const uint32_t slot = (uint32_t)(q >> 32);
+            uint32_t todo = __ballot_sync(0xffffffffu, wide);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t sl = __shfl_sync(0xffffffffu, slot, src);
+                const uint32_t a0 = __shfl_sync(0xffffffffu, t0, src), a1 = __shfl_sync(0xffffffffu, t1, src);
+                const uint32_t b0 = __shfl_sync(0xffffffffu, u0, src), b1 = __shfl_sync(0xffffffffu, u1, src);
+                for (uint32_t t = a0 + lane; t < a1; t += 32) chunk0[t] = sl;
+                if (chunk1)
+                    for (uint32_t t = b0 + lane; t < b1; t += 32) chunk1[t] = sl;
+            }
+            q += pack(c[i], c[i] != 0);
+        }
     }
     if (base <= ncells - 1 && ncells - 1 < base + SCAN_ITEMS) {    // owner of the last cell
         const uint32_t nnz = (uint32_t)(pre >> 32);

@@ -13,7 +13,8 @@ namespace lint {
 constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 // Rows per warp work item ("chunk"): 4096 amortises the per-chunk set-up best (4.64 against
 // 4.73 ms per 1e9 rows with 2048), but a draw needs enough chunks to balance ~9500 resident warps.
-constexpr uint32_t EMIT_CHUNK_MIN = 2048, EMIT_CHUNK_MAX = 4096;
+constexpr uint32_t EMIT_CHUNK_MIN = 2048, EMIT_CHUNK_MAX = 4096;      // powers of two (scan_compact_kernel shifts by them)
+static_assert((EMIT_CHUNK_MIN & (EMIT_CHUNK_MIN - 1)) == 0 && (EMIT_CHUNK_MAX & (EMIT_CHUNK_MAX - 1)) == 0, "chunk sizes");
 inline uint32_t emit_chunk_rows(uint64_t N) { return N >= (1ull << 28) ? EMIT_CHUNK_MAX : EMIT_CHUNK_MIN; }
 
 // One segment list per run: the flat parts (cid = cell) and the rest (cid = 2 cell + 1 with
