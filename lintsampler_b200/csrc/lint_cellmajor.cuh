@@ -334,7 +334,7 @@ scan_compact_kernel(const uint32_t *counts, uint32_t ncells_all, const uint32_t 
     // is laid over even rows, see emit_kernel).  A segment of rows [lo, hi) owns the chunks
     // [ceil(lo / R), ceil(hi / R)) of the first numbering and [(lo + R) / R, (hi + R) / R) — and
     // chunk 0 if lo = 0 — of the second: none or one for almost every segment, written by its lane;
-    // a segment of more than two chunks' worth of rows (a heavy tree leaf) is left to the whole warp.
+    // a segment of more than eight chunks' worth of rows (a heavy tree leaf) is left to the whole warp.
     // (R is a power of two: shifts.  t < chunk_slots: the tables are sized for the N rows asked for;
     // an 8-sigma Poisson total beyond that is clamped away by run_rows and never emitted.)
     auto chunk_span = [&](uint64_t lo, uint64_t hi, uint32_t &t0, uint32_t &t1, uint32_t &u0, uint32_t &u1) {
@@ -343,6 +343,7 @@ scan_compact_kernel(const uint32_t *counts, uint32_t ncells_all, const uint32_t 
         u0 = (uint32_t)min((lo + chunk_rows) >> chunk_shift, (uint64_t)chunk_slots);
         u1 = (uint32_t)min((hi + chunk_rows) >> chunk_shift, (uint64_t)chunk_slots);
     };
+    constexpr uint32_t WIDE_CHUNKS = 8;                            // up to nine chunk starts per table by the lane itself
     bool any_wide = false;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
@@ -353,7 +354,7 @@ scan_compact_kernel(const uint32_t *counts, uint32_t ncells_all, const uint32_t 
             coff[slot] = (uint32_t)pre;
             const uint64_t lo = (uint32_t)pre, hi = lo + c[i];
             if (chunk1 && lo == 0) chunk1[0] = slot;
-            if (c[i] > 2 * chunk_rows) {
+            if (c[i] > WIDE_CHUNKS * chunk_rows) {
                 any_wide = true;
             } else {
                 uint32_t t0, t1, u0, u1;
@@ -369,7 +370,7 @@ scan_compact_kernel(const uint32_t *counts, uint32_t ncells_all, const uint32_t 
         unsigned long long q = pre0;
 #pragma unroll
         for (int i = 0; i < SCAN_ITEMS; ++i) {
-            const bool wide = c[i] > 2 * chunk_rows;
+            const bool wide = c[i] > WIDE_CHUNKS * chunk_rows;
             uint32_t t0 = 0, t1 = 0, u0 = 0, u1 = 0;
             if (wide) chunk_span((uint32_t)q, (uint64_t)(uint32_t)q + c[i], t0, t1, u0, u1);
             const uint32_t slot = (uint32_t)(q >> 32);
