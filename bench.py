@@ -367,7 +367,11 @@ def run_b200(args):
     ms_build = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
     ms_sample = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
     t = torch.tensor([ms_total, ms_build, ms_sample, host_ms], dtype=torch.float64, device=dev)
+    rank_ms = [ms_total / args.steps]
     if world > 1:
+        every = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(every, t[:1].clone() / args.steps)
+        rank_ms = [float(v) for v in every.tolist()]             # each rank's own step time (the value uses the max)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_build, ms_sample, host_ms = t.tolist()
     ms_step = ms_total / args.steps
@@ -480,6 +484,7 @@ def run_b200(args):
                            "split of N over the ranks is drawn once per run from the shared seed"
                            % (shard.launches_per_step(args.order) + 1)) if graph is not None else "eager launches",
                 "host_ms_per_step": host_ms,
+                "rank_ms_per_step": rank_ms,
                 "order": ("rows grouped by cell: exact multinomial cell counts (Poisson counts + u-driven "
                           "top-up), i.i.d. as a multiset, NOT exchangeable in row order"
                           if args.order == "cell" else

@@ -278,7 +278,7 @@ class ShardedGrid:
 
     # -- reporting -------------------------------------------------------------
     # -- calibration -----------------------------------------------------------
-    def calibrate(self, n_rows, seed=0, iters=3, fixed_ms=0.08):
+    def calibrate(self, n_rows, seed=0, iters=4, fixed_ms=0.07):
         """Re-cut the strata from MEASURED step times (multi-GPU, collective).  The analytic cost
         model of ``cost_balanced_strata`` misjudges the ranks that own the tails of the density
         (their rows are dearer than the model's average).  Every iteration each rank times its
@@ -298,16 +298,35 @@ class ShardedGrid:
             n = int(counts[self.rank])
             out = torch.empty((max(n, 1), self.grid.dim), dtype=_device.torch_dtype(self.grid.dtype),
                               device=self.device)
-            best = float("inf")
-            for rep in range(3):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
+            first = int(counts[:self.rank].sum())
+
+            def step():
                 self.enqueue_build(gather=False)
-                self.sample_cellmajor_into(out[:n], seed=seed, offset=int(counts[:self.rank].sum()))
-                b.record()
-                torch.cuda.synchronize(self.device)
-                if rep:
-                    best = min(best, a.elapsed_time(b))
+                self.sample_cellmajor_into(out[:n], seed=seed, offset=first)
+
+            step()                                                 # scratch allocated, kernels loaded
+            torch.cuda.synchronize(self.device)
+            # timed as the benchmark runs it: one CUDA graph replay per step (eager launches add
+            # host-side gaps that differ from rank to rank and hide the differences that matter)
+            graph = None
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    step()
+            except Exception:
+                graph = None
+            run = graph.replay if graph is not None else step
+            for _ in range(2):
+                run()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 8
+            a.record()
+            for _ in range(reps):
+                run()
+            b.record()
+            torch.cuda.synchronize(self.device)
+            best = a.elapsed_time(b) / reps
+            del graph
             times = torch.tensor([best], dtype=torch.float64, device=self.device)
             gathered = torch.empty(self.world, dtype=torch.float64, device=self.device)
             dist.all_gather_into_tensor(gathered, times, group=self.group)
