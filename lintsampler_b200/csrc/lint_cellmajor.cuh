@@ -661,6 +661,7 @@ emit_flat_kernel(const T *__restrict__ boxes, const uint32_t *__restrict__ cid, 
         if (chunk >= nchunks) break;
         const uint32_t r0 = chunk * chunk_rows, r1 = min(r0 + chunk_rows, N);
         uint32_t j = __ldg(chunk_start + chunk);                           // segment that holds row r0
+        LINT_CHECK(j < nnz && coff[j] <= r0 && r0 < coff[j + 1]);          // (the scan wrote the right owner)
         // 32-entry register window of the segment table: lane i holds segment jbase + i
         uint32_t jbase = j, w_off = 0xffffffffu;
         auto reload = [&](uint32_t jb) {
@@ -934,6 +935,7 @@ emit_kernel(Cells src, const uint32_t *__restrict__ cid, const uint32_t *__restr
         const bool more = chunk + nwarps < nchunks;
         if (more) prefetch(j0_next, buf ^ 1);
         uint32_t jbase = j0;                             // segment held in window slot 0
+        LINT_CHECK(j0 < nnz && coff[j0] <= max(r0, shift) - shift && max(r0, shift) - shift < coff[j0 + 1]);
         j0 = j0_next;
         if (chunk + 2 * (uint64_t)nwarps < nchunks) j0_next = __ldg(chunk_start + chunk + 2 * nwarps);
         if (more) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
