@@ -412,6 +412,39 @@ def test_hierarchical_grid_build(lb, name, dtype):
             part._sample_philox(10, 5, 0, stratum=(0.0, 1.0))
 
 
+@pytest.mark.parametrize("shape", [(1024,), (5, 512), (3, 4, 256), (2, 3, 2, 256)])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_hierarchical_build_masses_on_wide_rows(lb, shape, dtype):
+    """Grids whose last dimension is a multiple of the scan's 256 threads (every round of a CTA
+    lies in one cell row — the benchmark's shape): the masses lint_grid_build computes on the way
+    must be the very masses of the per-cell kernel (lint_grid_masses, pinned bit for bit to the
+    oracle elsewhere), and the CDF the NumPy-sequential table of those masses to 1e-13 — on
+    non-uniform edges, so that every width matters."""
+    import torch
+    import ctypes as C
+    from lintsampler_b200 import _capi, _device
+    rng = np.random.default_rng(len(shape))
+    edges = tuple(np.concatenate([[0.0], np.cumsum(rng.uniform(0.5, 1.5, n))]) for n in shape)
+    dens = rng.uniform(0.0, 2.0, tuple(n + 1 for n in shape))
+    dens[tuple(slice(0, 2) for _ in shape)] = 0.0                  # a zero-mass corner of the domain
+    grid = lb.DensityGrid.from_densities(edges if len(shape) > 1 else edges[0], dens, dtype=dtype)
+    n = int(grid.ncells)
+    ref = grid._masses.clone()                                     # lint_grid_masses
+    got = torch.empty(n, dtype=torch.float64, device="cuda")
+    cdf = torch.empty(n, dtype=torch.float64, device="cuda")
+    desc = grid._descriptor()
+    _capi.call("lint_grid_build", C.byref(desc), C.c_double(0.0), C.c_double(1.0), _device.ptr(cdf),
+               _device.ptr(grid._total), _device.ptr(grid._guide), 0, _device.ptr(got), _device.ptr(grid._flags),
+               _device.ptr(grid._range), _device.ptr(grid._scratch), grid._scratch.numel(),
+               _device.stream_ptr(grid.device))
+    assert torch.equal(got, ref)
+    assert torch.equal(cdf, grid._cdf)
+    m = ref.cpu().numpy()
+    V = dens.astype(dtype).astype(np.float64) * grid._scale
+    assert np.array_equal(m, O.cell_masses(edges, V).ravel())
+    assert np.max(np.abs(cdf.cpu().numpy() - O.cdf_from_masses(m))) < 1e-13
+
+
 @pytest.mark.parametrize("name", ["g2d_fullcov", "g3d_holes", "g1d_nonuniform"])
 def test_grid_without_a_guide_table(lb, name):
     """guide_bits=0: no guide table is built; the u-driven kernels search the whole CDF (same cells
