@@ -826,13 +826,19 @@ group_scan_kernel(GridView<K> g, GroupPlan plan, uint32_t ncells, const double *
             for (int j = 0; j < PAR_ITEMS; ++j) x[j] = s_m[threadIdx.x * SCAN_PAD + j];
             const uint32_t base = tb + threadIdx.x * PAR_ITEMS;
             const double tile_total = tile_scan(x, warp_tot);
+            // back through shared memory: a thread holds eight consecutive entries, and eight-byte stores
+            // at a 64-byte stride reach L2 as partial sectors; transposed, a warp stores 256 contiguous bytes
 #pragma unroll
             for (int j = 0; j < PAR_ITEMS; ++j) {
-                if (base + j < c_end) {
-                    const double s = fmin(__dadd_rn(off, tb == c_begin ? x[j] : __dadd_rn(run, x[j])), off_next);
-                    // (a product, not a division: twenty-odd instructions per cell less; monotone all the same)
-                    cdf[base + j] = base + j == ncells - 1 ? 1.0 : fmin(__dmul_rn(s, inv_tot), 1.0);
-                }
+                const double s = fmin(__dadd_rn(off, tb == c_begin ? x[j] : __dadd_rn(run, x[j])), off_next);
+                // (a product, not a division: twenty-odd instructions per cell less; monotone all the same)
+                s_m[threadIdx.x * SCAN_PAD + j] = base + j == ncells - 1 ? 1.0 : fmin(__dmul_rn(s, inv_tot), 1.0);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < PAR_ITEMS; ++j) {
+                const uint32_t k = threadIdx.x + j * PAR_THREADS;
+                if (tb + k < c_end) cdf[tb + k] = s_m[(k / PAR_ITEMS) * SCAN_PAD + (k % PAR_ITEMS)];
             }
             run = tb == c_begin ? tile_total : __dadd_rn(run, tile_total);
         }
