@@ -372,3 +372,28 @@ def test_sobol_advance_equals_fast_forward():
                 sobol_advance(b, n2)
             assert a.num_generated == b.num_generated
             assert np.array_equal(a.random(m), b.random(m)), (n1, n2)
+
+
+def test_tree_builder_choice_without_cuda():
+    """Which builder a DensityTree uses: the device table only for the library's own pdf families
+    and only where a CUDA device exists; explicit requests are validated."""
+    import torch
+    from lintsampler_b200.tree import DensityTree
+    gmm = lb.GaussianMixture([0.5, 0.5], [[-1.0, 0.0], [1.0, 0.5]], sigmas=[0.5, 0.4])
+    assert DensityTree._wants_device_build(gmm, (), {}, "host") is False
+    assert DensityTree._wants_device_build(lambda x: x, (), {}, None) is False
+    assert DensityTree._wants_device_build(gmm, (1,), {}, None) is False          # extra pdf arguments: host callable
+    assert DensityTree._wants_device_build(gmm, (), {}, "device") is True
+    with pytest.raises(ValueError):
+        DensityTree._wants_device_build(lambda x: x, (), {}, "device")
+    with pytest.raises(ValueError):
+        DensityTree._wants_device_build(gmm, (), {}, "gpu")
+    assert DensityTree._wants_device_build(gmm, (), {}, None) is torch.cuda.is_available()
+    if not torch.cuda.is_available():
+        # the host builder takes over: same class, same API, the pdf evaluated by its NumPy __call__
+        t = DensityTree([-4.0, -4.0], [4.0, 4.0], gmm, vectorizedpdf=True, min_openings=3)
+        assert t._dt is None and len(t.leaves) == 64 and abs(t.total_mass - 1.0) < 0.2
+        t.refine(1e-2, leaf_tol=5e-2)
+        assert len(t.leaves) > 64
+        with pytest.raises(RuntimeError, match="CUDA"):
+            DensityTree([-4.0, -4.0], [4.0, 4.0], gmm, build="device")
