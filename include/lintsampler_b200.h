@@ -324,9 +324,11 @@ int lint_multi_grid_sample_sobol(const lint_grid_t *grids, int ndomains, const d
 
 /* N i.i.d. draws as a multiset, emitted grouped by cell (C order of the flat cell
  * index) instead of in draw order.  The per-cell counts are an exact
- * Multinomial(N, p) draw (binomial splitting over the CDF of grid.py:431 /
- * utils.py:195-196 — the distribution `_choice` realises one row at a time,
- * utils.py:179-198); each cell's rows are then drawn from its k-linear
+ * Multinomial(N, p) draw over the CDF of grid.py:431 / utils.py:195-196 — the
+ * distribution `_choice` realises one row at a time, utils.py:179-198: independent
+ * Poisson counts of total mean N - 8 sqrt(N) (given their total T they are
+ * Multinomial(T, p)) plus N - T rows drawn one by one, the "top-up" (T > N is an
+ * 8-sigma event and is clamped); each cell's rows are then drawn from its k-linear
  * interpolant (sampling.py:41-94, 126) with the box and corners loaded once per
  * cell.  No per-sample search or gather.  Row order is NOT exchangeable: apply a
  * row permutation (lintsampler.py:309-311) when the caller relies on it.
@@ -335,7 +337,8 @@ int lint_multi_grid_sample_sobol(const lint_grid_t *grids, int ndomains, const d
  * lint_grid_sample_philox ((0, 1) = whole domain; a cell straddling a stratum
  * boundary is shared in proportion to the overlap).
  * cell_range_dev (grid only): NULL, or the slab written by lint_grid_build for this stratum — the
- * count and scan passes then visit those cells only.
+ * count and scan passes then visit those cells only, and the top-up rows search that slab.  The
+ * guide table is optional here (guide_bits 0): only the top-up rows search the CDF at all.
  * Row order: the flat parts of the split cells grouped by cell, then all other counted rows
  * grouped by cell, then the top-up rows in draw order (see csrc/lint_cellmajor.cuh).
  * N <= 2^32 - 2^16, fewer than 2^29 cells, out_dev 16-byte aligned.
