@@ -397,3 +397,34 @@ def test_tree_builder_choice_without_cuda():
         assert len(t.leaves) > 64
         with pytest.raises(RuntimeError, match="CUDA"):
             DensityTree([-4.0, -4.0], [4.0, 4.0], gmm, build="device")
+
+
+def test_chunk_start_ownership_rule():
+    """The rule by which the scans of the grouped path write chunk starts (scan_compact_kernel):
+    a segment of rows [lo, hi) owns the chunks [ceil(lo/R), ceil(hi/R)) when the run starts on an even
+    global row, and [(lo+R)//R, (hi+R)//R) — plus chunk 0 if lo = 0 — when it starts on an odd one
+    (the first row of chunk t is then max(t R, 1) - 1).  Restated here and checked against the
+    definition 'the segment that holds the chunk's first row' on random segment lists."""
+    rng = np.random.default_rng(0)
+    for R in (2048, 4096):
+        for trial in range(20):
+            counts = rng.integers(1, 3 * R, size=rng.integers(1, 60))
+            if trial % 4 == 0:
+                counts[rng.integers(len(counts))] = rng.integers(5 * R, 40 * R)      # one heavy segment
+            off = np.concatenate([[0], np.cumsum(counts)])
+            total = int(off[-1])
+            for shift in (0, 1):
+                nchunks = -(-(total + shift) // R)
+                table = np.full(nchunks + 2, -1)
+                for j, (lo, hi) in enumerate(zip(off[:-1], off[1:])):
+                    lo, hi = int(lo), int(hi)
+                    if shift == 0:
+                        table[-(-lo // R):-(-hi // R)] = j
+                    else:
+                        if lo == 0:
+                            table[0] = j
+                        table[(lo + R) // R:(hi + R) // R] = j
+                for t in range(nchunks):
+                    first = max(t * R, shift) - shift
+                    owner = int(np.searchsorted(off, first, side="right")) - 1
+                    assert table[t] == owner, (R, shift, t)
